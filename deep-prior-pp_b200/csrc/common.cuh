@@ -1,0 +1,69 @@
+// Shared helpers for the dpp_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/dpp_b200.h"
+
+namespace dpp {
+
+extern thread_local char g_err[512];
+
+inline int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define DPP_CHECK_ARG(cond)                                                                  \
+    do {                                                                                     \
+        if (!(cond)) return dpp::fail(DPP_EINVAL, "%s: argument check failed: %s", __func__, #cond); \
+    } while (0)
+
+#define DPP_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) return dpp::fail(DPP_ECUDA, "%s: %s", __func__, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define DPP_LAUNCH_CHECK() DPP_CUDA(cudaGetLastError())
+
+inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- BN prologue coefficients ---------------------------------------------------------
+// a = max(x*scale + shift, 0) with scale = gamma*inv_std, shift = beta - mean*scale.
+// mean / inv_std come from fp64 batch sums (train) or stored running stats (test).
+__device__ __forceinline__ void bn_mean_istd(const dpp_bn_ref &bn, int c, int C, float &mean, float &inv_std) {
+    if (bn.sums != nullptr) {
+        double m = bn.sums[c] / bn.count;
+        double var = bn.sums[C + c] / bn.count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        inv_std = (float)(1.0 / sqrt(var + (double)bn.eps));
+    } else {
+        mean = bn.mean[c];
+        inv_std = bn.inv_std[c];
+    }
+}
+
+__device__ __forceinline__ void bn_scale_shift(const dpp_bn_ref &bn, int c, int C, float &scale, float &shift) {
+    float mean, istd;
+    bn_mean_istd(bn, c, C, mean, istd);
+    scale = bn.gamma[c] * istd;
+    shift = bn.beta[c] - mean * scale;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dpp

@@ -1,0 +1,679 @@
+"""Graph executor: lowers a network object built by the reference-surface classes (``net.*``) to
+calls into libdpp_b200.so and owns the device buffers (torch CUDA tensors used as storage only).
+
+What it replaces in the reference: the three ``theano.function`` compilations -
+``compute_output`` (src/net/netbase.py:257-282), ``train_model`` and the validation functions
+(src/trainer/poseregnettrainer.py:146-209) - i.e. Theano's graph compilation, ``T.grad`` and the
+``updates`` mechanism.  The graph recorded by ``net.sym.Sym`` is pattern-matched onto the fused
+kernels:
+
+  BN -> ReLU -> ConvLayer          => dpp_conv2d_fwd with in_bn prologue   (BN/ReLU never stored)
+  ConvLayer -> (+ identity/shortcut) => residual epilogue of dpp_conv2d_fwd
+  tensor -> BN                      => fp64 sum/sumsq in the producer's epilogue (out_stats)
+  BN -> ReLU -> flatten -> Hidden   => dpp_bn_apply (materialised once), dpp_fc_fwd
+  Hidden -> Dropout                 => mask / 0.7 scale in dpp_fc_fwd's epilogue
+
+The backward program is the reverse walk of the forward op list (dgrad/wgrad/bn_bwd_apply), i.e.
+what ``T.grad(cost, params)`` (poseregnettrainer.py:111) produced symbolically.
+
+There is NO CPU path: constructing an Engine without CUDA raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from .lib import lib, BnRef, ConvDesc, BnEmaItem, DppError
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Tensor(object):
+    """A materialised activation: NHWC (4-D) or (B, n) (2-D) fp32 device buffer."""
+
+    def __init__(self, name, shape_nchw):
+        self.name = name
+        self.shape = tuple(int(v) for v in shape_nchw)    # reference (NCHW or (B,n)) shape
+        self.buf = None
+        self.grad = None
+        self.bn = None              # BatchNormLayer normalising this tensor (if any)
+        self.is_input = False
+        self.chw = None             # (C,H,W) if a 2-D tensor is the flatten of a 4-D one
+
+    @property
+    def numel(self):
+        return int(np.prod(self.shape))
+
+    @property
+    def pixels(self):
+        s = self.shape
+        return s[0] * s[2] * s[3]
+
+
+class Slot(object):
+    def __init__(self, var, arena, offset):
+        self.var = var
+        self.arena = arena          # 'w' (trainable) or 'r' (non-trained)
+        self.offset = offset
+        self.shape = tuple(var.shape)
+        self.size = int(np.prod(self.shape)) if len(self.shape) else 1
+        self.chw = None             # FC rows permuted from (c,h,w) to (h,w,c)
+
+    # reference layout <-> device layout
+    def to_device_layout(self, v):
+        v = np.asarray(v, np.float32)
+        if self.var.kind == 'convW':                   # (O,I,kh,kw) -> KC [(r,s,c)][o], flipped
+            w = v[:, :, ::-1, ::-1].transpose(2, 3, 1, 0)
+            return np.ascontiguousarray(w).reshape(-1)
+        if self.var.kind == 'fcW' and self.chw is not None:
+            c, h, w = self.chw
+            return np.ascontiguousarray(v.reshape(c, h, w, -1).transpose(1, 2, 0, 3)).reshape(-1)
+        return np.ascontiguousarray(v).reshape(-1)
+
+    def from_device_layout(self, flat):
+        if self.var.kind == 'convW':
+            o, i, kh, kw = self.shape
+            w = flat.reshape(kh, kw, i, o).transpose(3, 2, 0, 1)[:, :, ::-1, ::-1]
+            return np.ascontiguousarray(w)
+        if self.var.kind == 'fcW' and self.chw is not None:
+            c, h, w = self.chw
+            return np.ascontiguousarray(flat.reshape(h, w, c, -1).transpose(2, 0, 1, 3)).reshape(self.shape)
+        return flat.reshape(self.shape).copy()
+
+
+class Engine(object):
+    def __init__(self, net, precision=None, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise DppError("dpp_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        lib.load()
+        self.torch = torch
+        self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self.net = net
+        self.output_sym = net.output
+        self.B = int(net.cfgParams.batch_size)
+        if precision is None:
+            precision = int(os.environ.get('DPP_PRECISION', '0'))
+        self.precision = precision
+        self.world = 1
+        self.allreduce_fn = None
+        self._graphs = {}
+        self._masks_injected = None
+        self._lower()
+        self._alloc_params()
+        self._alloc_activations()
+        self._train_ready = False
+
+    # ---------------------------------------------------------------------------------
+    # lowering
+    # ---------------------------------------------------------------------------------
+    def _lower(self):
+        from net.convlayer import ConvLayer
+        from net.convpoollayer import ConvPoolLayer
+        from net.batchnormlayer import BatchNormLayer
+        from net.nonlinearitylayer import NonlinearityLayer
+        from net.hiddenlayer import HiddenLayer
+        from net.dropoutlayer import DropoutLayer
+
+        out = self.output_sym
+        order, seen = [], set()
+
+        def visit(s):
+            if id(s) in seen:
+                return
+            seen.add(id(s))
+            for i in s.inputs:
+                visit(i)
+            order.append(s)
+        visit(out)
+        consumers = {}
+        for s in order:
+            for i in s.inputs:
+                consumers.setdefault(id(i), []).append(s)
+        pos = {id(s): k for k, s in enumerate(order)}
+
+        def lay(s, cls):
+            return s.op == 'layer' and isinstance(s.layer, cls)
+
+        self.tensors = []
+        self.ops = []
+        self.bns = []                 # BatchNormLayer objects in use, in forward order
+        val = {}                      # id(sym) -> Tensor
+        virt = {}                     # id(relu sym) -> (bn layer, raw Tensor) not materialised
+        inputs = [s for s in order if s.op == 'input']
+        if len(inputs) != 1:
+            raise NotImplementedError("engine handles single-input graphs (ScaleNet towers are run per tower)")
+        tin = Tensor('input', self.net.cfgParams.inputDim)
+        tin.is_input = True
+        self.tensors.append(tin)
+        self.t_in = tin
+        val[id(inputs[0])] = tin
+
+        def new_tensor(name, shape):
+            t = Tensor(name, shape)
+            self.tensors.append(t)
+            return t
+
+        # which conv fuses which add
+        fused_add = {}      # id(conv sym) -> (add sym, residual operand sym)
+        for s in order:
+            if s.op == 'add':
+                a, b = s.inputs
+                cands = [x for x in (a, b) if lay(x, ConvLayer) and len(consumers[id(x)]) == 1]
+                if not cands:
+                    raise NotImplementedError("add without a ConvLayer operand")
+                conv = max(cands, key=lambda x: pos[id(x)])
+                other = b if conv is a else a
+                fused_add[id(conv)] = (s, other)
+
+        self.dropout_layers = []
+        for s in order:
+            if s.op == 'input':
+                continue
+            if s.op == 'add':
+                continue                      # value assigned by the fusing conv
+            if s.op == 'flatten':
+                src = s.inputs[0]
+                if id(src) in virt:           # BN->ReLU->flatten: materialise
+                    bn, raw = virt[id(src)]
+                    t = new_tensor('bnrelu%d' % bn.layerNum, raw.shape)
+                    self.ops.append(dict(kind='bn_apply', bn=bn, src=raw, dst=t, relu=1))
+                    val[id(src)] = t
+                t4 = val[id(src)]
+                t2 = Tensor(t4.name + '_flat', (t4.shape[0], int(np.prod(t4.shape[1:]))))
+                t2.alias = t4
+                t2.chw = t4.shape[1:]
+                val[id(s)] = t2
+                continue
+            if s.op == 'reshape':
+                raise NotImplementedError("reshape hidden->conv is unused on the hot path")
+            L = s.layer
+            src = s.inputs[0]
+            if isinstance(L, BatchNormLayer):
+                raw = val[id(src)]
+                if raw.bn is not None and raw.bn is not L:
+                    raise NotImplementedError("two BN layers on one tensor")
+                raw.bn = L
+                self.bns.append(L)
+                val[id(s)] = ('bn', L, raw)
+                continue
+            if isinstance(L, NonlinearityLayer):
+                v = val[id(src)]
+                if not (isinstance(v, tuple) and v[0] == 'bn'):
+                    raise NotImplementedError("ReLU layer without a preceding BN")
+                virt[id(s)] = (v[1], v[2])
+                continue
+            if isinstance(L, ConvLayer):
+                p = L.cfgParams
+                if id(src) in virt:
+                    bn, raw = virt[id(src)]
+                    xin, in_bn = raw, bn
+                else:
+                    xin, in_bn = val[id(src)], None
+                t = new_tensor('conv%d' % L.layerNum, p.outputDim)
+                op = dict(kind='conv', layer=L, src=xin, in_bn=in_bn, dst=t, residual=None)
+                self.ops.append(op)
+                val[id(s)] = t
+                if id(s) in fused_add:
+                    add_sym, other = fused_add[id(s)]
+                    op['residual'] = val[id(other)]
+                    val[id(add_sym)] = t
+                continue
+            if isinstance(L, ConvPoolLayer):
+                p = L.cfgParams
+                xin = val[id(src)]
+                t = new_tensor('convpool%d' % L.layerNum, p.outputDim)
+                self.ops.append(dict(kind='convpool', layer=L, src=xin, dst=t))
+                val[id(s)] = t
+                continue
+            if isinstance(L, HiddenLayer):
+                xin = val[id(src)]
+                t = new_tensor('fc%d' % L.layerNum, (self.B, int(L.cfgParams.outputDim[1])))
+                op = dict(kind='fc', layer=L, src=xin, dst=t, dropout=None)
+                self.ops.append(op)
+                val[id(s)] = t
+                continue
+            if isinstance(L, DropoutLayer):
+                xin = val[id(src)]
+                prod = [o for o in self.ops if o['kind'] == 'fc' and o['dst'] is xin]
+                if not prod or len(consumers[id(src)]) != 1:
+                    raise NotImplementedError("Dropout must directly follow a HiddenLayer")
+                prod[0]['dropout'] = L
+                self.dropout_layers.append(L)
+                val[id(s)] = xin
+                continue
+            raise NotImplementedError("layer %r" % L)
+        self.t_out = val[id(out)]
+        if not isinstance(self.t_out, Tensor):
+            raise NotImplementedError("network output must be a materialised tensor")
+        # stats producers: every tensor with a BN must be produced by conv / convpool
+        for op in self.ops:
+            if op['kind'] in ('conv', 'convpool') and op['dst'].bn is not None:
+                op['out_bn'] = op['dst'].bn
+            else:
+                op['out_bn'] = None
+        for t in self.tensors:
+            if t.bn is not None and not any(o.get('out_bn') is t.bn for o in self.ops):
+                raise NotImplementedError("BN on a tensor not produced by a conv layer")
+        # consumers of each BN's normalised output (for the backward accumulation order)
+        self.bn_consumers = {}
+        for op in self.ops:
+            if op['kind'] == 'conv' and op['in_bn'] is not None:
+                self.bn_consumers.setdefault(id(op['in_bn']), []).append(op)
+            if op['kind'] == 'bn_apply':
+                self.bn_consumers.setdefault(id(op['bn']), []).append(op)
+
+    # ---------------------------------------------------------------------------------
+    # parameters
+    # ---------------------------------------------------------------------------------
+    def _alloc_params(self):
+        torch = self.torch
+        self.slots = {}
+        off = 0
+        order = []
+        for p in self.net.all_params:
+            s = Slot(p, 'w', off)
+            self.slots[id(p)] = s
+            order.append(s)
+            off += (s.size + 3) // 4 * 4          # 16-byte aligned slots
+        self.n_w = off
+        self.w_slots = order
+        roff = 0
+        self.r_slots = []
+        for l in self.net.layers:
+            for p in l.params_nontrained:
+                s = Slot(p, 'r', roff)
+                self.slots[id(p)] = s
+                self.r_slots.append(s)
+                roff += (s.size + 3) // 4 * 4
+        self.n_r = max(roff, 4)
+        # FC layers fed by a flattened NHWC tensor: permute rows
+        for op in self.ops:
+            if op['kind'] == 'fc' and getattr(op['src'], 'chw', None) is not None:
+                self.slots[id(op['layer'].W)].chw = tuple(op['src'].chw)
+        self.W = torch.zeros(self.n_w, dtype=torch.float32, device=self.dev)
+        self.R = torch.zeros(self.n_r, dtype=torch.float32, device=self.dev)
+        self.G = self.M = self.V = None
+        host = np.zeros(self.n_w, np.float32)
+        for s in order:
+            host[s.offset:s.offset + s.size] = s.to_device_layout(s.var._host)
+        self.W.copy_(torch.from_numpy(host))
+        hostr = np.zeros(self.n_r, np.float32)
+        for s in self.r_slots:
+            hostr[s.offset:s.offset + s.size] = s.to_device_layout(s.var._host)
+        self.R.copy_(torch.from_numpy(hostr))
+        for s in list(order) + self.r_slots:
+            s.var._binding = (self, s)
+        # BN statistic arena (fp64): per BN forward sums [2C] + backward sums [2C]
+        soff = 0
+        self.bn_stat_off = {}
+        for bn in self.bns:
+            c = int(bn.cfgParams.inputDim[1])
+            self.bn_stat_off[id(bn)] = (soff, soff + 2 * c, c)
+            soff += 4 * c
+        self.n_stats = max(soff, 2)
+        self.STATS = torch.zeros(self.n_stats, dtype=torch.float64, device=self.dev)
+
+    def release(self):
+        """Detach variables from the device arenas (values are pulled back to the host)."""
+        for s in list(self.w_slots) + self.r_slots:
+            if s.var._binding is not None and s.var._binding[0] is self:
+                s.var._host = self.download_param(s)
+                s.var._binding = None
+        self._graphs = {}
+
+    def _arena(self, slot):
+        return self.W if slot.arena == 'w' else self.R
+
+    def download_param(self, slot):
+        flat = self._arena(slot)[slot.offset:slot.offset + slot.size].cpu().numpy()
+        return slot.from_device_layout(flat)
+
+    def upload_param(self, slot, value):
+        flat = self.torch.from_numpy(slot.to_device_layout(value))
+        self._arena(slot)[slot.offset:slot.offset + slot.size].copy_(flat)
+
+    def pview(self, var, arena=None):
+        s = self.slots[id(var)]
+        a = self._arena(s) if arena is None else arena
+        return a[s.offset:s.offset + s.size]
+
+    # ---------------------------------------------------------------------------------
+    # activations
+    # ---------------------------------------------------------------------------------
+    def _nhwc_shape(self, t):
+        s = t.shape
+        return (s[0], s[2], s[3], s[1]) if len(s) == 4 else s
+
+    def _alloc_activations(self):
+        torch = self.torch
+        for t in self.tensors:
+            t.buf = torch.zeros(self._nhwc_shape(t), dtype=torch.float32, device=self.dev)
+        for op in self.ops:
+            if op['kind'] == 'convpool':
+                op['argmax'] = torch.zeros(self._nhwc_shape(op['dst']), dtype=torch.uint8, device=self.dev)
+        self.x_nchw = torch.zeros(self.t_in.shape, dtype=torch.float32, device=self.dev)
+        self.cost = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+    def _alloc_training(self):
+        if self._train_ready:
+            return
+        torch = self.torch
+        self.G = torch.zeros_like(self.W)
+        self.M = torch.zeros_like(self.W)
+        self.V = torch.zeros_like(self.W)
+        for t in self.tensors:
+            if not t.is_input:
+                t.grad = torch.zeros_like(t.buf)
+        self.dz = {}
+        for bn in self.bns:
+            raw = [t for t in self.tensors if t.bn is bn][0]
+            self.dz[id(bn)] = torch.zeros_like(raw.buf)
+        for op in self.ops:
+            if op['kind'] == 'fc':
+                op['scratch'] = torch.zeros_like(op['dst'].buf)
+                if op['dropout'] is not None:
+                    op['mask'] = torch.ones_like(op['dst'].buf)
+                    g = torch.Generator(device=self.dev)
+                    g.manual_seed(op['dropout'].mask_seed)
+                    op['mask_gen'] = g
+        self.y_in = torch.zeros((self.B, int(np.prod(self.t_out.shape[1:]))), dtype=torch.float32, device=self.dev)
+        # hyper: lr, t, -, grad_scale
+        self.hyper = torch.tensor([0.0, 1.0, 0.0, 1.0], dtype=torch.float32, device=self.dev)
+        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        items = (BnEmaItem * max(len(self.bns), 1))()
+        for i, bn in enumerate(self.bns):
+            f0, _, c = self.bn_stat_off[id(bn)]
+            raw = [t for t in self.tensors if t.bn is bn][0]
+            items[i].sums = self.STATS.data_ptr() + 8 * f0
+            items[i].mean = self.pview(bn.mean).data_ptr()
+            items[i].inv_std = self.pview(bn.inv_std).data_ptr()
+            items[i].count = float(raw.pixels)
+            items[i].C = c
+            items[i].eps = float(bn.cfgParams.epsilon)
+        raw_bytes = bytes(items)
+        self.ema_items = torch.frombuffer(bytearray(raw_bytes), dtype=torch.uint8).to(self.dev)
+        self._train_ready = True
+
+    # ---------------------------------------------------------------------------------
+    # kernels
+    # ---------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def _bnref(self, bn, raw, train, relu=1):
+        r = BnRef()
+        f0, _, c = self.bn_stat_off[id(bn)]
+        r.sums = (self.STATS.data_ptr() + 8 * f0) if train else None
+        r.mean = self.pview(bn.mean).data_ptr()
+        r.inv_std = self.pview(bn.inv_std).data_ptr()
+        r.gamma = self.pview(bn.gamma).data_ptr()
+        r.beta = self.pview(bn.beta).data_ptr()
+        r.count = float(raw.pixels)
+        r.eps = float(bn.cfgParams.epsilon)
+        r.relu = relu
+        return r
+
+    def _conv_desc(self, op):
+        L = op['layer']
+        p = L.cfgParams
+        n, ci, h, w = p.inputDim
+        d = ConvDesc()
+        d.N, d.H, d.W, d.Cin = int(n), int(h), int(w), int(ci)
+        d.Cout = int(p.nFilters)
+        d.k = int(p.filterDim[0])
+        d.stride = int(p.stride[0])
+        if p.border_mode != 'half':
+            raise NotImplementedError("ConvLayer border_mode %s" % p.border_mode)
+        d.pad = d.k // 2
+        d.Ho, d.Wo = int(p.outputDim[2]), int(p.outputDim[3])
+        d.precision = self.precision
+        return d
+
+    def _stats_ptr(self, bn, which=0):
+        f0, b0, _ = self.bn_stat_off[id(bn)]
+        return C.c_void_p(self.STATS.data_ptr() + 8 * (f0 if which == 0 else b0))
+
+    def _run_forward(self, train):
+        st = self._stream()
+        for op in self.ops:
+            k = op['kind']
+            if k == 'convpool':
+                L = op['layer']
+                p = L.cfgParams
+                n, ci, h, w = p.inputDim
+                pad = p.filterDim[0] // 2 if p.border_mode == 'half' else 0
+                if p.stride != (1, 1) and tuple(p.stride) != (1, 1):
+                    raise NotImplementedError("strided ConvPoolLayer")
+                relu = 1 if p.activation_str == 'ReLU' else 0
+                stats = self._stats_ptr(op['out_bn']) if (op['out_bn'] is not None and train) else None
+                lib.dpp_convpool_fwd(_ptr(op['src'].buf), _ptr(self.pview(L.W)), _ptr(self.pview(L.b)),
+                                     _ptr(op['dst'].buf), _ptr(op['argmax']), stats, int(n), int(h), int(w), int(ci),
+                                     int(p.nFilters), int(p.filterDim[0]), int(pad), int(p.poolsize[0]), relu, st)
+            elif k == 'conv':
+                L = op['layer']
+                d = self._conv_desc(op)
+                bnref = self._bnref(op['in_bn'], op['src'], train) if op['in_bn'] is not None else None
+                stats = self._stats_ptr(op['out_bn']) if (op['out_bn'] is not None and train) else None
+                lib.dpp_conv2d_fwd(C.byref(d), _ptr(op['src'].buf), C.byref(bnref) if bnref else None,
+                                   _ptr(self.pview(L.W)), _ptr(self.pview(L.b)),
+                                   _ptr(op['residual'].buf) if op['residual'] is not None else None,
+                                   _ptr(op['dst'].buf), stats, st)
+            elif k == 'bn_apply':
+                bnref = self._bnref(op['bn'], op['src'], train, relu=op['relu'])
+                c = op['src'].shape[1]
+                lib.dpp_bn_apply(_ptr(op['src'].buf), C.byref(bnref), _ptr(op['dst'].buf), op['src'].pixels, int(c), st)
+            elif k == 'fc':
+                L = op['layer']
+                src = op['src']
+                xbuf = src.alias.buf if hasattr(src, 'alias') else src.buf
+                n_in, n_out = int(L.cfgParams.inputDim[1]), int(L.cfgParams.outputDim[1])
+                relu = 1 if L.cfgParams.activation_str == 'ReLU' else 0
+                mask, scale = None, 1.0
+                if op['dropout'] is not None:
+                    if train:
+                        mask = op['mask']
+                    else:
+                        scale = float(op['dropout'].prob_keep)
+                lib.dpp_fc_fwd(_ptr(xbuf), _ptr(self.pview(L.W)), _ptr(self.pview(L.b)), _ptr(op['dst'].buf),
+                               self.B, n_in, n_out, relu, _ptr(mask), scale, self.precision, st)
+            else:
+                raise NotImplementedError(k)
+
+    def _run_backward(self):
+        """Reverse walk.  t.grad of the output tensor must hold dCost/dOut on entry."""
+        st = self._stream()
+        G = self.G
+        pending = {}          # id(bn) -> number of consumers still to contribute
+        for bn in self.bns:
+            pending[id(bn)] = len(self.bn_consumers.get(id(bn), []))
+        # a tensor used as residual operand receives the fusing conv's output gradient as `skip`
+        skip_of = {}
+        for op in self.ops:
+            if op['kind'] == 'conv' and op['residual'] is not None:
+                skip_of[id(op['residual'])] = op['dst']
+
+        def finish_bn(bn, raw):
+            """all consumers contributed dz (+stats): apply the BN backward, producing raw.grad"""
+            bnref = self._bnref(bn, raw, True)
+            c = raw.shape[1]
+            sk = skip_of.get(id(raw))
+            lib.dpp_bn_bwd_apply(_ptr(self.dz[id(bn)]), _ptr(raw.buf), C.byref(bnref), self._stats_ptr(bn, 1),
+                                 _ptr(sk.grad) if sk is not None else None, _ptr(raw.grad),
+                                 _ptr(self.pview(bn.gamma, G)), _ptr(self.pview(bn.beta, G)), None,
+                                 raw.pixels, int(c), st)
+
+        for op in reversed(self.ops):
+            k = op['kind']
+            if k == 'fc':
+                L = op['layer']
+                src = op['src']
+                base = src.alias if hasattr(src, 'alias') else src
+                n_in, n_out = int(L.cfgParams.inputDim[1]), int(L.cfgParams.outputDim[1])
+                relu = 1 if L.cfgParams.activation_str == 'ReLU' else 0
+                mask = op['mask'] if op['dropout'] is not None else None
+                dx = None if base.is_input else base.grad
+                lib.dpp_fc_bwd(_ptr(base.buf), _ptr(self.pview(L.W)), _ptr(op['dst'].buf), _ptr(op['dst'].grad),
+                               _ptr(self.pview(L.W, G)), _ptr(self.pview(L.b, G)), _ptr(dx), _ptr(op['scratch']),
+                               self.B, n_in, n_out, relu, _ptr(mask), 1.0, self.precision, st)
+            elif k == 'bn_apply':
+                bn, raw = op['bn'], op['src']
+                bnref = self._bnref(bn, raw, True, relu=op['relu'])
+                c = raw.shape[1]
+                lib.dpp_bn_relu_bwd_reduce(_ptr(op['dst'].grad), _ptr(raw.buf), C.byref(bnref), _ptr(self.dz[id(bn)]),
+                                           self._stats_ptr(bn, 1), raw.pixels, int(c), st)
+                pending[id(bn)] -= 1
+                if pending[id(bn)] == 0:
+                    finish_bn(bn, raw)
+            elif k == 'conv':
+                L = op['layer']
+                d = self._conv_desc(op)
+                dst = op['dst']
+                # a conv output that is only the residual operand of a later conv (projection
+                # block: conv3 feeding the shortcut conv's epilogue) shares that conv's gradient
+                dy = skip_of[id(dst)].grad if (id(dst) in skip_of and dst.bn is None) else dst.grad
+                bn, raw = op['in_bn'], op['src']
+                bnref = self._bnref(bn, raw, True) if bn is not None else None
+                lib.dpp_conv2d_wgrad(C.byref(d), _ptr(raw.buf), C.byref(bnref) if bnref else None, _ptr(dy),
+                                     _ptr(self.pview(L.W, G)), _ptr(self.pview(L.b, G)), st)
+                if bn is not None:
+                    total = len(self.bn_consumers[id(bn)])
+                    first = (pending[id(bn)] == total)
+                    last = (pending[id(bn)] == 1)
+                    dzbuf = self.dz[id(bn)]
+                    if first and d.stride != 1:
+                        lib.dpp_fill_f32(_ptr(dzbuf), 0.0, dzbuf.numel(), st)
+                    lib.dpp_conv2d_dgrad(C.byref(d), _ptr(dy), _ptr(self.pview(L.W)), _ptr(dzbuf), 0 if first else 1,
+                                         C.byref(bnref) if last else None, _ptr(raw.buf) if last else None,
+                                         self._stats_ptr(bn, 1) if last else None, st)
+                    pending[id(bn)] -= 1
+                    if last:
+                        finish_bn(bn, raw)
+                elif not raw.is_input:
+                    lib.dpp_conv2d_dgrad(C.byref(d), _ptr(dy), _ptr(self.pview(L.W)), _ptr(raw.grad), 0, None, None,
+                                         None, st)
+            elif k == 'convpool':
+                L = op['layer']
+                p = L.cfgParams
+                n, ci, h, w = p.inputDim
+                pad = p.filterDim[0] // 2 if p.border_mode == 'half' else 0
+                relu = 1 if p.activation_str == 'ReLU' else 0
+                dx = None if op['src'].is_input else op['src'].grad
+                lib.dpp_convpool_bwd(_ptr(op['src'].buf), _ptr(self.pview(L.W)), _ptr(op['dst'].buf),
+                                     _ptr(op['argmax']), _ptr(op['dst'].grad), _ptr(self.pview(L.W, G)),
+                                     _ptr(self.pview(L.b, G)), _ptr(dx), int(n), int(h), int(w), int(ci),
+                                     int(p.nFilters), int(p.filterDim[0]), int(pad), int(p.poolsize[0]), relu, st)
+            else:
+                raise NotImplementedError(k)
+
+    # ---------------------------------------------------------------------------------
+    # public API
+    # ---------------------------------------------------------------------------------
+    def forward_device(self, deterministic=True):
+        """Run the forward pass on the NHWC input already in ``self.t_in.buf``; returns the device
+        output tensor (B, n_out)."""
+        st = self._stream()
+        if not deterministic:
+            lib.dpp_fill_f64(_ptr(self.STATS), 0.0, self.STATS.numel(), st)
+        self._run_forward(train=not deterministic)
+        return self.t_out.buf
+
+    def set_input_nchw(self, x_host_or_dev):
+        torch = self.torch
+        if isinstance(x_host_or_dev, np.ndarray):
+            x_host_or_dev = torch.from_numpy(np.ascontiguousarray(x_host_or_dev, np.float32))
+        self.x_nchw.copy_(x_host_or_dev.reshape(self.x_nchw.shape), non_blocking=True)
+        n, c, h, w = self.t_in.shape
+        lib.dpp_nchw_to_nhwc(_ptr(self.x_nchw), _ptr(self.t_in.buf), n, c, h, w, self._stream())
+
+    def forward_host(self, batch_list, deterministic=True):
+        """computeOutput's inner step: numpy NCHW batch in, numpy output out."""
+        self.set_input_nchw(batch_list[0])
+        out = self.forward_device(deterministic=deterministic)
+        return out.cpu().numpy()
+
+    def set_dropout_masks(self, masks):
+        """Inject explicit dropout masks (list of numpy (B, n) arrays, forward order) - parity
+        tests only; production masks are drawn on the device each step."""
+        self._alloc_training()
+        self._masks_injected = True
+        fcs = [o for o in self.ops if o['kind'] == 'fc' and o['dropout'] is not None]
+        for o, m in zip(fcs, masks):
+            o['mask'].copy_(self.torch.from_numpy(np.ascontiguousarray(m, np.float32)))
+
+    def _draw_masks(self):
+        if self._masks_injected:
+            return
+        for o in self.ops:
+            if o['kind'] == 'fc' and o['dropout'] is not None:
+                keep = float(o['dropout'].prob_keep)
+                o['mask'].bernoulli_(keep, generator=o['mask_gen'])
+
+    def _step_body(self):
+        """zero -> forward(train) -> cost -> backward -> (allreduce) -> ADAM -> EMA"""
+        st = self._stream()
+        lib.dpp_fill_f64(_ptr(self.STATS), 0.0, self.STATS.numel(), st)
+        lib.dpp_fill_f32(_ptr(self.G), 0.0, self.G.numel(), st)
+        self._run_forward(train=True)
+        d = int(self.y_in.shape[1])
+        lib.dpp_loss_sqerr(_ptr(self.t_out.buf), _ptr(self.y_in), _ptr(self.t_out.grad), _ptr(self.cost), self.B, d, st)
+        self._run_backward()
+        if self.allreduce_fn is not None:
+            self.allreduce_fn(self.G)
+        lib.dpp_adam_step(_ptr(self.W), _ptr(self.G), _ptr(self.M), _ptr(self.V), _ptr(self.hyper), self.n_w, st)
+        lib.dpp_adam_tick(_ptr(self.hyper), st)
+        if self.bns:
+            lib.dpp_bn_ema_update(_ptr(self.ema_items), len(self.bns), float(self.bns[0].cfgParams.alpha), st)
+
+    def set_lr(self, lr):
+        self.hyper[0:1].fill_(float(lr))
+
+    def set_world(self, world, allreduce_fn):
+        self._alloc_training()
+        self.world = world
+        self.allreduce_fn = allreduce_fn
+        self.hyper[3:4].fill_(1.0 / world)
+
+    def train_step(self, lr=None, use_graph=True):
+        """One ``train_model`` call (poseregnettrainer.py:146-160) on the batch in
+        ``t_in.buf`` (NHWC) / ``y_in``.  Returns the device scalar holding the minibatch cost."""
+        self._alloc_training()
+        torch = self.torch
+        if lr is not None:
+            self.set_lr(lr)
+        self._draw_masks()
+        if not use_graph:
+            self._step_body()
+            return self.cost
+        g = self._graphs.get('train')
+        if g is None:
+            # eager warm-up (sets kernel attributes, allocates nothing new), then capture
+            w0, r0, m0, v0, h0 = self.W.clone(), self.R.clone(), self.M.clone(), self.V.clone(), self.hyper.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._step_body()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.W.copy_(w0); self.R.copy_(r0); self.M.copy_(m0); self.V.copy_(v0); self.hyper.copy_(h0)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()
+            # the capture itself does not execute; state is untouched
+            self._graphs['train'] = g
+        g.replay()
+        return self.cost
+
+    def gradients(self):
+        """dict var-id -> numpy gradient in the reference layout (parity tests)."""
+        out = {}
+        for s in self.w_slots:
+            flat = self.G[s.offset:s.offset + s.size].cpu().numpy()
+            out[id(s.var)] = s.from_device_layout(flat)
+        return out

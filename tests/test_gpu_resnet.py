@@ -1,0 +1,116 @@
+"""GPU parity: ResNet forward / cost / gradients / ADAM step through the reference-surface
+classes + libdpp_b200.so, against the CPU oracle (oracle/nets.py) on the same seeded inputs.
+Tolerance: regressed outputs within 1e-4 relative (north_star), gradients 2e-3 of each tensor's
+max (fp32 summation-order noise through 61 batch-norms)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def _build(net_type, B, J, D, seed=23455, precision=0):
+    from net.resnet import ResNet, ResNetParams
+    from oracle import nets as O
+    net = ResNet(np.random.RandomState(seed), cfgParams=ResNetParams(type=net_type, batchSize=B, numJoints=J, nDims=D))
+    onet = O.build_resnet(np.random.RandomState(seed), type=net_type, batchSize=B, numJoints=J, nDims=D)
+    from dpp_b200.engine import Engine
+    eng = Engine(net, precision=precision)
+    net._eng = eng
+    return net, onet, eng
+
+
+def _data(B, D, seed=1):
+    rng = np.random.RandomState(seed)
+    x = rng.uniform(-1, 1, (B, 1, 128, 128)).astype(np.float32)
+    x[:, :, :20] = 1.0
+    y = rng.randn(B, D).astype(np.float32)
+    return x, y
+
+
+def test_forward_train_mode_matches_oracle():
+    from oracle import nets as O
+    B, D = 4, 30
+    net, onet, eng = _build(0, B, 1, D)
+    x, y = _data(B, D)
+    eng.set_input_nchw(x)
+    out = eng.forward_device(deterministic=False).cpu().numpy()
+    with torch.no_grad():
+        oout, _ = onet.forward(torch.from_numpy(x), deterministic=False)
+    r = _rel(out, oout.numpy())
+    print("forward(train) rel err", r)
+    assert r < 1e-4
+
+
+def test_forward_deterministic_matches_oracle():
+    B, D = 4, 30
+    net, onet, eng = _build(0, B, 1, D)
+    x, y = _data(B, D)
+    out = net.computeOutput(x[:3])          # exercises padding to the batch size
+    net.setDeterministic()
+    with torch.no_grad():
+        oout, _ = onet.forward(torch.from_numpy(np.concatenate([x[:3], x[2:3]])), deterministic=True)
+    r = _rel(out, oout.numpy()[:3])
+    print("forward(det) rel err", r)
+    assert out.shape == (3, D)
+    assert r < 1e-4
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_matches_oracle(use_graph):
+    from oracle import nets as O
+    B, D = 4, 30
+    net, onet, eng = _build(0, B, 1, D)
+    x, y = _data(B, D)
+    adam = O.Adam(onet.params)
+    lr = 1e-3
+    for step in range(2):
+        eng.set_input_nchw(x)
+        eng._alloc_training()
+        eng.y_in.copy_(torch.from_numpy(y))
+        cost = float(eng.train_step(lr, use_graph=use_graph).cpu()[0])
+        ocost, oout, ograds = O.train_step(onet, adam, torch.from_numpy(x), torch.from_numpy(y), lr, 1, D)
+        print("step", step, "cost", cost, ocost)
+        assert abs(cost - ocost) < 1e-4 * abs(ocost)
+        grads = eng.gradients()
+        worst = 0.0
+        for p, og, l in zip(net.params, ograds, [l for l in onet.layers for _ in l.params]):
+            g = grads[id(p)]
+            og = og.numpy()
+            if l.kind in ('conv', 'convpool') and g.ndim == 1:
+                continue            # conv biases feed only BNs: true gradient is exactly 0 (roundoff only)
+            scale = np.abs(og).max() + 1e-12
+            e = float(np.abs(g - og).max() / scale)
+            worst = max(worst, e)
+            assert e < 2e-3, (p.name, e, scale)
+        print("worst grad rel err", worst)
+    # parameters after two ADAM steps (skip the zero-gradient conv biases)
+    for p, op_, l in zip(net.params, onet.params, [l for l in onet.layers for _ in l.params]):
+        if l.kind in ('conv', 'convpool') and p.shape == (p.shape[0],) and len(p.shape) == 1:
+            continue
+        a, b = p.get_value(), op_.detach().numpy()
+        assert np.abs(a - b).max() < 2.5e-3 * max(1.0, np.abs(b).max()), p.name   # |step| <= lr each
+    # BN running statistics (EMA of mean and inv_std)
+    for l, ol in zip(net.layers, onet.layers):
+        if ol.kind == 'bn':
+            assert _rel(l.params_nontrained[0].get_value(), ol.nontrained[0].numpy()) < 1e-3 or \
+                np.abs(ol.nontrained[0].numpy()).max() < 1e-3
+            assert _rel(l.params_nontrained[1].get_value(), ol.nontrained[1].numpy()) < 1e-4
+
+
+def test_type1_with_pca_tail_forward():
+    B, J = 4, 14
+    net, onet, eng = _build(1, B, J, 3)
+    x, _ = _data(B, 3 * J)
+    eng.set_input_nchw(x)
+    out = eng.forward_device(deterministic=False).cpu().numpy()
+    with torch.no_grad():
+        oout, _ = onet.forward(torch.from_numpy(x), deterministic=False)
+    assert out.shape == (B, 3 * J)
+    assert _rel(out, oout.numpy()) < 1e-4
