@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py - the driver's measurement contract for the DeepPrior++ hot path on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic NYU crops:
+  dpp_augment_fwd (rot/com/none, from the HBM-resident ORIGINAL crops) -> ResNet (type 0,
+  nDims 30) forward -> cost -> backward -> [NCCL all-reduce] -> ADAM -> BN running-stat EMA.
+Workload = BASELINE.json configs[1]: "NYU posereg_embedding ResNet training, batch 128 synthetic
+depth, 1xB200".  For N > 1 every rank runs the same per-GPU batch (weak scaling, global batch
+128*N) with one gradient all-reduce per step.
+
+  value : whole-job frames/s with all inputs resident in HBM when the timed region starts
+  e2e   : the same metric through the reference-facing API with HOST buffers: per step the
+          batch's crops + augmentation records + labels are copied from pinned host memory and
+          the cost is read back (what trainer.train_model() returns to the caller)
+  --impl reference : the CPU oracle restatement (torch-CPU + cv2) of the same step on the host
+          cores (the reference's own Theano path cannot run here: no Theano/Python 2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'deep-prior-pp_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "training frames/sec, 128x128 depth crops (augment + ResNet fwd/bwd + ADAM)"
+UNIT = "frames/s"
+TRAIN_GFLOP_PER_FRAME = 0.7229     # BASELINE.md section 2 (fwd + dgrad + wgrad, no stem dgrad)
+B = 128
+E = 30
+N_RESIDENT = 2048                  # crops resident in HBM: 2048 * 64 KiB = 134 MB > 126 MB L2
+AUG_MODES = ['com', 'rot', 'none']
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', 1400.0), d.get('hbm_gbs', 6650.0), 'measured'
+    return 1590.0, 1400.0, 6650.0, 'fallback'
+
+
+class ClockSampler(object):
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(seed=23455):
+    """synthetic NYU set + PCA stand-in + per-sample augmentation records for many steps"""
+    from data import synthetic
+    ds = synthetic.generate('NYU', N_RESIDENT, seed=seed)
+    comp, mean = synthetic.random_orthonormal_pca(E, ds['gt3D'].shape[1] * 3, seed=1)
+    return ds, comp, mean
+
+
+def records_for(ds, comp, mean, idxs, rng):
+    """host side of one batch: draws in the reference order, dpp_aug_rec records, embedded labels"""
+    hd, di = ds['hd'], ds['importer']
+    recs, ys, draws = [], [], []
+    for i in idxs:
+        mode = rng.randint(0, len(AUG_MODES)); off = rng.randn(3) * 5.; rot = rng.uniform(-180., 180.)
+        sc = abs(1. + rng.randn() * 0.02)
+        draws.append((mode, off, rot, sc))
+        com = di.joint3DToImg(ds['com3D'][i])
+        rec, lab, _, _, _ = hd.aug_record(i, AUG_MODES[mode], off, rot, sc, com, ds['cube'][i].copy(),
+                                          ds['M'][i].copy(), ds['gt3Dcrop'][i].copy())
+        recs.append(rec)
+        ys.append(np.dot(lab.reshape(-1).astype(np.float64) - mean, comp.T))
+    return np.array(recs), np.asarray(ys, np.float32), draws
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle restatement (reference-equivalent CPU path)
+# ---------------------------------------------------------------------------------------------
+def cpu_step_time(ds, comp, mean, steps, threads):
+    import torch
+    from oracle import nets as ON, augment as OA
+    torch.set_num_threads(threads)
+    onet = ON.build_resnet(np.random.RandomState(23455), type=0, batchSize=B, numJoints=1, nDims=E)
+    adam = ON.Adam(onet.params)
+    cam = OA.Camera(**OA.NYU_CAM)
+    ohd = OA.Hand(cam, use_cv2=True)
+    rng = np.random.RandomState(99)
+    times = []
+    for s in range(steps):
+        idxs = rng.randint(0, N_RESIDENT, B)
+        draws = [OA.draw_aug_params(rng, len(AUG_MODES)) for _ in idxs]
+        t0 = time.time()
+        x, y = OA.augment_poses(ds['x'], ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], list(idxs), draws,
+                                AUG_MODES, cam, ohd, pca_mean=mean, pca_components=comp)
+        ON.train_step(onet, adam, torch.from_numpy(x), torch.from_numpy(y), 1e-4, 1, E)
+        times.append(time.time() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ds, comp, mean = make_workload()
+    steps = max(1, min(args.steps, 6))
+    warm = 1 if args.warmup > 0 else 0
+    times = cpu_step_time(ds, comp, mean, steps + warm, threads)[warm:]
+    ms = 1000. * float(np.mean(times))
+    val = B / (ms / 1000.)
+    sample = "%d step(s) of the batch-128 workload (cv2 augmentation + torch-CPU ResNet fwd/bwd/ADAM), %d thread(s)" % (
+        len(times), threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "NYU posereg_embedding ResNet(type 0, 30-D embedding) training, batch 128, "
+                               "aug rot/com/none", "global_batch": B, "note": "CPU oracle restatement of the "
+                   "reference path (Theano cannot run here); host cores only"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import ctypes as C
+    from dpp_b200.lib import lib, AUG_REC_DTYPE
+    from dpp_b200.engine import Engine
+    from net.resnet import ResNet, ResNetParams
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    precision = int(os.environ.get('DPP_PRECISION', '0'))
+    ds, comp, mean = make_workload(seed=23455 + rank)
+    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=B, numJoints=1, nDims=E))
+    eng = Engine(net, precision=precision)
+    net._eng = eng
+    eng._alloc_training()
+    if world > 1:
+        eng.set_world(world, lambda g: dist.all_reduce(g))
+    total = args.warmup + args.steps
+    rng = np.random.RandomState(1234 + rank)
+    nrec = min(total, 64)                    # distinct record sets, cycled
+    recs_all, ys_all = [], []
+    for s in range(nrec):
+        idxs = rng.randint(0, N_RESIDENT, B)
+        r, y, _ = records_for(ds, comp, mean, idxs, rng)
+        recs_all.append(r); ys_all.append(y)
+    crops_dev = torch.from_numpy(ds['x'][:, 0].copy()).to(dev)
+    recs_np = np.concatenate(recs_all)
+    recs_dev = torch.from_numpy(recs_np.view(np.uint8).reshape(len(recs_np), -1).copy()).to(dev)
+    ys_dev = torch.from_numpy(np.concatenate(ys_all)).to(dev)
+    rec_bytes = np.dtype(AUG_REC_DTYPE).itemsize
+    eng.set_lr(1e-4)
+    launches = {'n': 0}
+
+    def step_resident(s):
+        k = s % nrec
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lib.dpp_augment_fwd(C.c_void_p(crops_dev.data_ptr()), C.c_void_p(recs_dev.data_ptr() + k * B * rec_bytes),
+                            C.c_void_p(eng.t_in.buf.data_ptr()), B, 128, 128, st)
+        eng.y_in.copy_(ys_dev[k * B:(k + 1) * B], non_blocking=True)
+        eng.train_step(None, use_graph=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for s in range(warmup):
+            fn(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(warmup + s)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms / steps
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_step = timed(step_resident, args.steps, max(args.warmup, 3))
+    value = B * world / (ms_step / 1000.)
+
+    # ---- e2e: host buffers in, cost out, every step
+    pin_x = torch.from_numpy(ds['x'][:, 0].copy()).pin_memory()
+    pin_r = torch.from_numpy(recs_np.view(np.uint8).reshape(len(recs_np), -1).copy()).pin_memory()
+    pin_y = torch.from_numpy(np.concatenate(ys_all)).pin_memory()
+    stage_x = torch.empty((B, 128, 128), dtype=torch.float32, device=dev)
+    stage_r = torch.empty((B, rec_bytes), dtype=torch.uint8, device=dev)
+    idx_sets = [np.sort(np.asarray(recs_all[k]['src_index'])) for k in range(nrec)]
+    host_batches = []
+    for k in range(nrec):
+        r = recs_all[k].copy()
+        src = r['src_index'].copy()
+        r['src_index'] = np.arange(B, dtype=np.int32)        # records index the staged batch
+        host_batches.append((torch.from_numpy(ds['x'][src, 0].copy()).pin_memory(),
+                             torch.from_numpy(r.view(np.uint8).reshape(B, -1).copy()).pin_memory(),
+                             torch.from_numpy(ys_all[k].copy()).pin_memory()))
+    cost_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def step_e2e(s):
+        hx, hr, hy = host_batches[s % nrec]
+        stage_x.copy_(hx, non_blocking=True)
+        stage_r.copy_(hr, non_blocking=True)
+        eng.y_in.copy_(hy, non_blocking=True)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lib.dpp_augment_fwd(C.c_void_p(stage_x.data_ptr()), C.c_void_p(stage_r.data_ptr()),
+                            C.c_void_p(eng.t_in.buf.data_ptr()), B, 128, 128, st)
+        cost = eng.train_step(None, use_graph=True)
+        cost_host.copy_(cost, non_blocking=False)            # the float train_model() returns
+
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    e2e_val = B * world / (ms_e2e / 1000.)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel class, timed live with CUDA events on this stream
+    roof = measure_dominant_kernel(eng, torch)
+    # ---- kernel launches per step (counted from the engine's op list)
+    n_launch = count_launches(eng) + 1
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t = cpu_step_time(ds, comp, mean, 3, threads)[1:]
+        v = B / float(np.mean(t))
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "2 steps of the batch-128 workload (cv2 augmentation + torch-CPU ResNet fwd/bwd/ADAM) after "
+                         "1 warm-up step"}
+    h2d = B * 128 * 128 * 4 + B * rec_bytes + B * E * 4
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {0: "f32", 1: "tf32x3", 2: "tf32"}[precision], "data": "synthetic",
+        "config": {"workload": "NYU posereg_embedding ResNet(type 0, 30-D embedding) training, batch 128/GPU, "
+                               "aug rot/com/none, %d resident crops" % N_RESIDENT,
+                   "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "l2": "inputs (134 MB of crops + 0.9 GB of activations per step) exceed the 126 MB L2",
+                   "precision_mode": precision},
+        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": n_launch * args.steps,
+        "clocks": clk,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "tensor_fraction_whole_step": value / world * TRAIN_GFLOP_PER_FRAME / 1000. / peaks()[1],
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def count_launches(eng):
+    n = 2 + 1 + 2 + 1      # fills, loss, adam + tick, ema
+    for op in eng.ops:
+        k = op['kind']
+        if k == 'conv':
+            n += 1 + 2 + (1 if op['in_bn'] is not None else 0)   # fwd, wgrad, dgrad, bn_bwd_apply
+        elif k == 'convpool':
+            n += 2
+        elif k == 'fc':
+            n += 2 + 3 + 2
+        elif k == 'bn_apply':
+            n += 3
+    return n
+
+
+def measure_dominant_kernel(eng, torch):
+    """Time the heaviest conv class of the step in isolation (20 launches, CUDA events on the
+    launching stream) and express it against the tensor-pipe peak.  The dominant kernels of the
+    fp32 path are the implicit-GEMM convolutions (k_igemm / k_wgrad): we time the forward launch of
+    the layer with the most MACs."""
+    import ctypes as C
+    from dpp_b200.lib import lib
+    best = None
+    for op in eng.ops:
+        if op['kind'] != 'conv':
+            continue
+        d = eng._conv_desc(op)
+        macs = d.N * d.Ho * d.Wo * d.Cout * d.k * d.k * d.Cin
+        if best is None or macs > best[0]:
+            best = (macs, op, d)
+    macs, op, d = best
+    L = op['layer']
+    bnref = eng._bnref(op['in_bn'], op['src'], True) if op['in_bn'] is not None else None
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=eng.dev)     # 256 MB > L2
+
+    def launch():
+        lib.dpp_conv2d_fwd(C.byref(d), C.c_void_p(op['src'].buf.data_ptr()), C.byref(bnref) if bnref else None,
+                           C.c_void_p(eng.pview(L.W).data_ptr()), C.c_void_p(eng.pview(L.b).data_ptr()), None,
+                           C.c_void_p(op['dst'].buf.data_ptr()), None, st)
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    tot = 0.0
+    reps = 10
+    for _ in range(reps):
+        flush.fill_(1.0)                     # evict L2 between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); launch(); e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / reps
+    burst, sustained, hbm, how = peaks()
+    tflops = 2.0 * macs / (ms * 1e-3) / 1e12
+    bytes_alg = 4.0 * (d.N * d.H * d.W * d.Cin + d.N * d.Ho * d.Wo * d.Cout)
+    return {"bound": "tensor", "kernel": "conv2d_fwd %dx%d %d->%d @%dx%d (precision %d)" % (
+                d.k, d.k, d.Cin, d.Cout, d.H, d.W, d.precision),
+            "achieved": tflops, "peak": burst, "unit": "TFLOP/s", "frac": tflops / burst, "traffic": None,
+            "peak_source": "%s bf16 burst (MEASURED_PEAKS.json); TF32 peak is half of it" % how,
+            "ms_per_launch": ms, "hbm_gbs_algorithmic": bytes_alg / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -19,6 +19,7 @@ namespace {
 constexpr int AUG_THREADS = 512;
 
 __device__ __forceinline__ float finalize_px(float v, float premax, const dpp_aug_rec &r) {
+    if (r.mode & 16) return v;   // raw: warp only (HandDetector.rotateHand/recropHand called directly)
     // nettrainer.py:990-995, applied in the reference's order
     if (v == premax) v = r.bg;
     if (v == 0.f) v = r.bg;
@@ -60,7 +61,8 @@ k_augment(const float *__restrict__ crops, const dpp_aug_rec *__restrict__ recs,
     if ((tid & 31) == 0) red[tid >> 5] = mx;
 
     // 2. per-sample tables
-    if (r.mode == 2) {
+    const int wmode = r.mode & 15;
+    if (wmode == 2) {
         if (tid < 3) {                       // running fp64 row sums r(0)=c, r(y+1)=r(y)+b
             double b = r.m[tid * 3 + 1], v = r.m[tid * 3 + 2];
             for (int y = 0; y < H; ++y) {
@@ -68,7 +70,7 @@ k_augment(const float *__restrict__ crops, const dpp_aug_rec *__restrict__ recs,
                 v = __dadd_rn(v, b);
             }
         }
-    } else if (r.mode == 1) {
+    } else if (wmode == 1) {
         // AB_BITS = 10 fixed point (cv2 warpAffine): adelta/bdelta per x, X0/Y0 per y
         for (int i = tid; i < W; i += AUG_THREADS) {
             itab[i] = (int)rint(__dmul_rn(__dmul_rn(r.m[0], (double)i), 1024.0));
@@ -88,9 +90,9 @@ k_augment(const float *__restrict__ crops, const dpp_aug_rec *__restrict__ recs,
     __syncthreads();
     const float premax = s_premax;
 
-    if (r.mode == 0) {
+    if (wmode == 0) {
         for (int i = tid; i < npx; i += AUG_THREADS) o[i] = finalize_px(src[i], premax, r);
-    } else if (r.mode == 1) {
+    } else if (wmode == 1) {
         for (int i = tid; i < npx; i += AUG_THREADS) {
             int y = i / W, x = i - y * W;
             int X = (itab[2 * W + y] + itab[x]) >> 10;

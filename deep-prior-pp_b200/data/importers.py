@@ -1,0 +1,117 @@
+"""Camera models of the dataset importers (reference: src/data/importers.py: DepthImporter
+:51-150, ICVLImporter :186-210, MSRA15Importer :536-570 + :756-793, NYUImporter :880-920 +
+:1187-1224).  Only the pin-hole projections and per-dataset constants are on the hot path
+(augmentation label math); the file readers are out of scope (datasets are absent - synthetic
+inputs come from ``data.synthetic``).
+
+dtype discipline: the reference ran on NumPy 1.x value-based casting, where
+``np.float32 scalar (op) python float`` is computed in float64 and only the store into the
+``np.float32`` result array rounds.  NumPy 2 would keep float32, so every expression below casts
+explicitly."""
+import numpy as np
+
+f64 = np.float64
+
+
+class DepthImporter(object):
+    def __init__(self, fx, fy, ux, uy, hand=None):
+        self.fx = fx
+        self.fy = fy
+        self.ux = ux
+        self.uy = uy
+        self.depth_map_size = (320, 240)
+        self.refineNet = None
+        self.crop_joint_idx = 0
+        self.hand = hand
+        self.flip_y = False
+
+    def jointsImgTo3D(self, sample):
+        ret = np.zeros((sample.shape[0], 3), np.float32)
+        for i in range(sample.shape[0]):
+            ret[i] = self.jointImgTo3D(sample[i])
+        return ret
+
+    def jointImgTo3D(self, sample):
+        ret = np.zeros((3,), np.float32)
+        ret[0] = (f64(sample[0]) - self.ux) * f64(sample[2]) / self.fx
+        if self.flip_y:
+            ret[1] = (self.uy - f64(sample[1])) * f64(sample[2]) / self.fy
+        else:
+            ret[1] = (f64(sample[1]) - self.uy) * f64(sample[2]) / self.fy
+        ret[2] = sample[2]
+        return ret
+
+    def joints3DToImg(self, sample):
+        ret = np.zeros((sample.shape[0], 3), np.float32)
+        for i in range(sample.shape[0]):
+            ret[i] = self.joint3DToImg(sample[i])
+        return ret
+
+    def joint3DToImg(self, sample):
+        ret = np.zeros((3,), np.float32)
+        if sample[2] == 0.:
+            ret[0] = self.ux
+            ret[1] = self.uy
+            return ret
+        sample = np.asarray(sample)
+        if sample.dtype == np.float32:          # f32/f32 stays f32 before meeting the python floats
+            q0 = f64(np.float32(sample[0]) / np.float32(sample[2]))
+            q1 = f64(np.float32(sample[1]) / np.float32(sample[2]))
+        else:
+            q0 = f64(sample[0]) / f64(sample[2])
+            q1 = f64(sample[1]) / f64(sample[2])
+        ret[0] = q0 * self.fx + self.ux
+        ret[1] = (self.uy - q1 * self.fy) if self.flip_y else (q1 * self.fy + self.uy)
+        ret[2] = sample[2]
+        return ret
+
+    def getCameraProjection(self):
+        ret = np.zeros((4, 4), np.float32)
+        ret[0, 0] = self.fx
+        ret[1, 1] = -self.fy if self.flip_y else self.fy
+        ret[2, 2] = 1.
+        ret[0, 2] = self.ux
+        ret[1, 2] = self.uy
+        ret[3, 2] = 1.
+        return ret
+
+
+class ICVLImporter(DepthImporter):
+    def __init__(self, basepath=None, useCache=True, cacheDir='./cache/', refineNet=None, hand=None):
+        super(ICVLImporter, self).__init__(241.42, 241.42, 160., 120., hand)
+        self.depth_map_size = (320, 240)
+        self.basepath = basepath
+        self.numJoints = 16
+        self.crop_joint_idx = 0
+        self.refineNet = refineNet
+        self.default_cubes = {'train': (250, 250, 250), 'test_seq_1': (250, 250, 250), 'test_seq_2': (250, 250, 250)}
+
+
+class MSRA15Importer(DepthImporter):
+    def __init__(self, basepath=None, useCache=True, cacheDir='./cache/', refineNet=None, detectorNet=None,
+                 derotNet=None, hand=None):
+        super(MSRA15Importer, self).__init__(241.42, 241.42, 160., 120., hand)
+        self.flip_y = True
+        self.depth_map_size = (320, 240)
+        self.basepath = basepath
+        self.refineNet = refineNet
+        self.numJoints = 21
+        self.crop_joint_idx = 5
+        self.default_cubes = {'P0': (200, 200, 200), 'P1': (200, 200, 200), 'P2': (200, 200, 200),
+                              'P3': (180, 180, 180), 'P4': (180, 180, 180), 'P5': (180, 180, 180),
+                              'P6': (170, 170, 170), 'P7': (160, 160, 160), 'P8': (150, 150, 150)}
+
+
+class NYUImporter(DepthImporter):
+    def __init__(self, basepath=None, useCache=True, cacheDir='./cache/', refineNet=None, allJoints=False, hand=None):
+        super(NYUImporter, self).__init__(588.03, 587.07, 320., 240., hand)
+        self.flip_y = True
+        self.depth_map_size = (640, 480)
+        self.basepath = basepath
+        self.allJoints = allJoints
+        self.numJoints = 36
+        self.crop_joint_idx = 32 if allJoints else 13
+        self.default_cubes = {'train': (300, 300, 300), 'test_1': (300, 300, 300), 'test_2': (250, 250, 250),
+                              'test': (300, 300, 300)}
+        self.restrictedJointsEval = [0, 3, 6, 9, 12, 15, 18, 21, 24, 25, 27, 30, 31, 32]
+        self.refineNet = refineNet

@@ -1,0 +1,394 @@
+"""NetTrainer (reference: src/trainer/nettrainer.py:47-997): training-data residency, the
+epoch/minibatch loop with the learning-rate schedule, validation and best-weights snapshot, and
+``augmentCrop``.
+
+B200 redesign of the data path: the reference splits host RAM into macro batches
+that are copied to the GPU one at a time while 8 worker processes augment the next one with cv2.
+Here the whole (aligned) training set lives in HBM once; per epoch the host only prepares one
+112-byte ``dpp_aug_rec`` per sample (in ``para_num_proc`` worker processes when ``para_augment`` is
+set, mirroring nettrainer.py:666-689) and ``dpp_augment_fwd`` regenerates the augmented set on the
+device from the ORIGINAL crops.  What is kept: ceil(N/B) minibatches per epoch, the tail-padding
+rule with ``RandomState(N)`` (:365-413), fresh augmentation per epoch swapped in when the last
+minibatch of an epoch is requested (:528-529), ``lr_of_ep`` (:54), validation every
+``validation_frequency`` iterations on full batches only (:796,859), ``net_last.pkl`` snapshots,
+NaN abort, best-weights restore."""
+import time
+import multiprocessing
+import numpy
+
+from net.convpoollayer import ConvPoolLayer
+from net.convlayer import ConvLayer
+
+
+class NetTrainerParams(object):
+    def __init__(self):
+        self.batch_size = 128
+        self.momentum = 0.9
+        self.learning_rate = 0.01
+        self.weightreg_factor = 0.001
+        self.use_early_stopping = True
+        # nettrainer.py:54
+        self.lr_of_ep = lambda ep: numpy.float32(self.learning_rate / 10.) if ep <= 1 else \
+            numpy.float32(self.learning_rate / 3.) if 1 < ep <= 2 else \
+            numpy.float32(self.learning_rate * numpy.exp(-0.04 * ep))
+        self.snapshot_last = 5
+        self.snapshot_freq = None
+        self.para_augment = False
+        self.para_num_proc = 8
+        self.augment_fun_params = {'fun': None, 'args': {}}
+        self.para_load = False
+        self.load_fun_params = {'fun': None, 'args': {}}
+        self.force_macrobatch_reload = False
+        self.pad_random = True
+        self.validation_frequency = 1000
+        self.pre_epoch_fn = None
+        self.post_epoch_fn = None
+        self.pre_minibatch_fn = None
+        self.post_minibatch_fn = None
+
+
+def _records_chunk(args):
+    """worker: build augmentation records + labels for a slice of samples"""
+    trainer_state, idxs, draws = args
+    hd, di, aug_modes, comDB, cubeDB, MDB, gtDB, proj = trainer_state
+    recs, labels = [], []
+    for i, (mode, off, rot, sc) in zip(idxs, draws):
+        com = di.joint3DToImg(comDB[i])
+        rec, lab, _, _, _ = hd.aug_record(i, aug_modes[mode], off, rot, sc, com, cubeDB[i].copy(), MDB[i].copy(),
+                                          gtDB[i].copy())
+        recs.append(rec)
+        if proj is not None:
+            labels.append(proj.transform(lab.reshape(1, -1))[0])
+        else:
+            labels.append(lab.reshape(-1))
+    return numpy.array(recs), numpy.asarray(labels, dtype='float32')
+
+
+class NetTrainer(object):
+    def __init__(self, cfgParams, memory_factor, subfolder='./eval/', numChunks=1):
+        self.subfolder = subfolder
+        self.cfgParams = cfgParams
+        self.rng = numpy.random.RandomState(23455)
+        if not isinstance(cfgParams, NetTrainerParams):
+            raise ValueError("cfgParams must be an instance of NetTrainerParams")
+        # nettrainer.py:100-112: a fraction of the free device memory bounds one resident array
+        try:
+            import torch
+            free = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else None
+        except Exception:
+            free = None
+        if free is None:
+            import psutil
+            free = psutil.virtual_memory().available
+        self.memorySize = (free / 1024 ** 2) / float(memory_factor)
+        if cfgParams.para_load is True:
+            raise NotImplementedError("para_load (chunked loading from disk) is out of scope: the set is HBM resident")
+        self.currentMacroBatch = -1
+        self.numChunks = numChunks
+        self.trainSize = 0
+        self.sampleSize = 0
+        self.numTrainSamplesMB = 0
+        self.numTrainSamples = 0
+        self.numValSamples = 0
+        self.epoch = 0
+        self.managedVar = []
+        self.trainingVar = []
+        self.validation_observer = []
+        self._pool = None
+        self._dev = {}
+
+    # -- data registration ------------------------------------------------------------------
+    def setData(self, train_data, train_y, val_data, val_y, max_train_size=0):
+        if (train_data.shape[0] != train_y.shape[0]) or (val_data.shape[0] != val_y.shape[0]):
+            raise ValueError("Number of samples must be the same as number of labels.")
+        self.trainSize = max(train_data.nbytes, train_y.nbytes, max_train_size) / 1024. / 1024.
+        self.numTrainSamplesMB = train_data.shape[0]
+        self.numTrainSamples = self.numTrainSamplesMB
+        self.numValSamples = val_data.shape[0]
+        self.sampleSize = self.trainSize / self.numTrainSamplesMB
+        assert self.memorySize > self.sampleSize * self.cfgParams.batch_size
+        if self.getNumMacroBatches() != 1:
+            raise NotImplementedError("training set larger than the HBM budget (%.0f MB > %.0f MB): sharding over "
+                                      "data-parallel ranks is the supported way to scale" % (self.trainSize, self.memorySize))
+        # shrink to the smallest whole number of minibatches (nettrainer.py:257-258)
+        self.memorySize = self.sampleSize * numpy.ceil(self.numTrainSamplesMB / float(self.cfgParams.batch_size)) \
+            * self.cfgParams.batch_size
+        self.train_data_xDB = self.alignData(train_data)
+        self.train_data_yDB = self.alignData(train_y)
+        self.trainingVar += ['train_data_x', 'train_data_y']
+        self.val_data_xDB = val_data
+        self.val_data_yDB = val_y
+        print("{} train samples, {} val samples, batch size {}".format(train_data.shape[0], val_data.shape[0],
+                                                                       self.cfgParams.batch_size))
+        print("{} macro batches, {} mini batches per macro, {} full mini batches total".format(
+            self.getNumMacroBatches(), self.getNumMiniBatchesPerMacroBatch(), self.getNumMiniBatches()))
+        self._dev_dirty = True
+
+    def addData(self, data):
+        if not isinstance(data, dict):
+            raise ValueError("Error: expected dictionary for data!")
+        for key in data:
+            setattr(self, key + 'DB', self.alignData(data[key]))
+        self._dev_dirty = True
+
+    def addStaticData(self, data):
+        if not isinstance(data, dict):
+            raise ValueError("Error: expected dictionary for data!")
+        for key in data:
+            setattr(self, key + 'DB', data[key])
+        self._dev_dirty = True
+
+    def addManagedData(self, data):
+        if not isinstance(data, dict):
+            raise ValueError("Error: expected dictionary for data!")
+        for key in data:
+            if data[key].shape[0] != self.numTrainSamplesMB:
+                raise ValueError("Number of samples must be the same as number of labels.")
+            setattr(self, key + 'DB', self.alignData(data[key]))
+            self.trainingVar.append(key)
+
+    def alignData(self, data, alignSize=None, out=None, fillData=None):
+        """nettrainer.py:365-413: pad to the macro-batch size; the tail is filled with random real
+        samples drawn with RandomState(N) so that x / y / side arrays stay aligned."""
+        if alignSize is None:
+            alignSize = self.getNumSamplesPerMacroBatch()
+        if data.shape[0] == alignSize:
+            topad = 0
+        else:
+            topad = alignSize - data.shape[0] % alignSize
+        sz = [(0, topad)] + [(0, 0)] * (len(data.shape) - 1)
+        padded = numpy.pad(data, sz, mode='constant', constant_values=0)
+        if fillData is None:
+            fillData = data
+        if (data.shape[0] % alignSize) != 0:
+            if self.cfgParams.pad_random:
+                rng = numpy.random.RandomState(data.shape[0])
+                for i in range(0, alignSize - (data.shape[0] % alignSize)):
+                    padded[data.shape[0] + i] = fillData[rng.randint(0, fillData.shape[0])]
+            else:
+                for i in range(0, alignSize - (data.shape[0] % alignSize)):
+                    padded[data.shape[0] + i] = padded[data.shape[0] - 1]
+        return padded
+
+    # -- batch arithmetic (nettrainer.py:415-487) ------------------------------------------------
+    def getSizeMiniBatch(self):
+        return self.cfgParams.batch_size * self.sampleSize
+
+    def getNumFullMiniBatches(self):
+        return self.getNumMiniBatches()
+
+    def getNumMiniBatches(self):
+        return int(numpy.ceil(self.numTrainSamples / float(self.cfgParams.batch_size)))
+
+    def getNumMacroBatches(self):
+        return int(numpy.ceil(self.trainSize / float(self.getGPUMemAligned())))
+
+    def getNumMiniBatchesPerMacroBatch(self):
+        return int(self.getGPUMemAligned() / self.sampleSize / self.cfgParams.batch_size)
+
+    def getNumSamplesPerMacroBatch(self):
+        return int(self.getNumMiniBatchesPerMacroBatch() * self.cfgParams.batch_size)
+
+    def getNumMiniBatchesPerChunk(self):
+        return int(self.getNumMiniBatchesPerMacroBatch() * self.getNumMacroBatches())
+
+    def getNumSamplesPerChunk(self):
+        return self.getNumMiniBatchesPerChunk() * self.cfgParams.batch_size
+
+    def getGPUMemAligned(self):
+        return self.sampleSize * self.cfgParams.batch_size * int(
+            self.memorySize / float(self.sampleSize * self.cfgParams.batch_size))
+
+    # -- device residency -------------------------------------------------------------------------
+    def _to_device(self):
+        """Upload the (aligned) training set, the validation set and the static arrays once."""
+        import torch
+        if not getattr(self, '_dev_dirty', True):
+            return
+        dev = self.poseNet._engine().dev
+        f = lambda a: torch.from_numpy(numpy.ascontiguousarray(a, dtype='float32')).to(dev)
+        d = self._dev
+        d['train_x_orig'] = f(self.train_data_xDB.reshape((self.train_data_xDB.shape[0],) + self.train_data_xDB.shape[-2:])) \
+            if self.train_data_xDB.shape[1] == 1 else None
+        if d['train_x_orig'] is None:
+            raise NotImplementedError("multi-channel training crops")
+        d['train_x'] = d['train_x_orig'].clone()
+        d['train_y'] = f(self.train_data_yDB.reshape(self.train_data_yDB.shape[0], -1))
+        nb = self.val_data_xDB.shape[0] // self.cfgParams.batch_size * self.cfgParams.batch_size
+        d['val_x'] = f(self.val_data_xDB[:nb].reshape((nb,) + self.val_data_xDB.shape[-2:]))
+        d['val_y'] = f(self.val_data_yDB[:nb].reshape(nb, -1))
+        if hasattr(self, 'val_data_y3DDB'):
+            d['val_y3D'] = f(self.val_data_y3DDB[:nb].reshape(nb, -1))
+        self._dev_dirty = False
+
+    # -- augmentation pipeline ----------------------------------------------------------------------
+    def setupDataLoading(self):
+        """nettrainer.py:666-699: start the record workers and prepare the first augmented set."""
+        if self.cfgParams.para_augment and self.cfgParams.para_num_proc > 1 and self._pool is None:
+            ctx = multiprocessing.get_context('fork')
+            self._pool = ctx.Pool(self.cfgParams.para_num_proc)
+        self._pending = self._request_augmentation()
+        self._swap_augmentation()
+        self._pending = self._request_augmentation()
+
+    def unsetDataLoading(self):
+        if self._pool is not None:
+            self._pool.terminate()
+            self._pool = None
+        self._pending = None
+
+    def _draw(self, n):
+        a = self.cfgParams.augment_fun_params['args']
+        sigma_com = a.get('sigma_com') or 5.
+        sigma_sc = a.get('sigma_sc') or 0.02
+        rot_range = a.get('rot_range') or 180.
+        draws = []
+        for _ in range(n):                                    # nettrainer.py:954-957 draw order
+            mode = self.rng.randint(0, len(a['aug_modes']))
+            off = self.rng.randn(3) * sigma_com
+            rot = self.rng.uniform(-rot_range, rot_range)
+            sc = abs(1. + self.rng.randn() * sigma_sc)
+            draws.append((mode, off, rot, sc))
+        return draws
+
+    def _request_augmentation(self):
+        a = self.cfgParams.augment_fun_params['args']
+        n = self.train_data_xDB.shape[0]
+        draws = self._draw(n)
+        state = (a['hd'], a['di'], a['aug_modes'], self.train_data_comDB, self.train_data_cubeDB,
+                 self.train_data_MDB, self.train_gt3DcropDB, a.get('proj'))
+        idxs = list(range(n))
+        if self._pool is not None:
+            k = self.cfgParams.para_num_proc
+            step = (n + k - 1) // k
+            jobs = [(state, idxs[s:s + step], draws[s:s + step]) for s in range(0, n, step)]
+            return ('async', self._pool.map_async(_records_chunk, jobs))
+        return ('sync', [_records_chunk((state, idxs, draws))])
+
+    def _swap_augmentation(self):
+        """wait for the records, regenerate train_x/train_y on the device (one kernel launch)"""
+        import torch
+        from dpp_b200.augment import run_records_device
+        kind, res = self._pending
+        parts = res.get() if kind == 'async' else res
+        recs = numpy.concatenate([p[0] for p in parts])
+        labels = numpy.concatenate([p[1] for p in parts])
+        self._to_device()
+        d = self._dev
+        run_records_device(d['train_x_orig'], recs, out_dev=d['train_x'])
+        d['train_y'].copy_(torch.from_numpy(labels.reshape(d['train_y'].shape)))
+
+    def loadMiniBatch(self, mini_idx):
+        """nettrainer.py:489-599 for the single-macro-batch case: when the last minibatch of an
+        epoch is requested and force_macrobatch_reload is set, the freshly augmented set is swapped
+        in and the next one is requested."""
+        n = self.getNumMiniBatchesPerMacroBatch()
+        aug = self.cfgParams.augment_fun_params['fun'] is not None
+        if aug and self.cfgParams.force_macrobatch_reload and (mini_idx % n) == n - 1:
+            self._swap_augmentation()
+            self._pending = self._request_augmentation()
+        return mini_idx % n
+
+    # -- training loop (nettrainer.py:778-907) -------------------------------------------------------
+    def train(self, n_epochs=50, storeFilters=False):
+        if len(self.validation_observer) < 1:
+            raise ValueError("Require at least 1 validation function, that monitors validation cost!")
+        self._to_device()
+        if self.cfgParams.augment_fun_params['fun'] is not None:
+            self.setupDataLoading()
+        wvals = []
+        n_val_batches = self.val_data_xDB.shape[0] // self.cfgParams.batch_size
+        best_validation_loss = numpy.inf
+        bestParams = None
+        bestParamsEp = -1
+        start_time = time.time()
+        train_costs = []
+        validation_obs = [[] for x in range(1, len(self.validation_observer))]
+        self.epoch = 0
+        self.poseNet.setDeterministic()
+        for vi in range(1, len(self.validation_observer)):
+            validation_obs[vi - 1].append(numpy.nanmean([self.validation_observer[vi](i) for i in range(n_val_batches)]))
+        self.poseNet.unsetDeterministic()
+        while self.epoch < n_epochs:
+            if self.epoch % self.cfgParams.snapshot_last == 0:
+                self.poseNet.save(self.subfolder + '/net_last.pkl')
+            if self.cfgParams.snapshot_freq is not None:
+                if self.epoch % self.cfgParams.snapshot_freq == 0:
+                    self.poseNet.save(self.subfolder + '/net_{}.pkl'.format(self.epoch))
+            if self.cfgParams.pre_epoch_fn is not None:
+                getattr(self, self.cfgParams.pre_epoch_fn)()
+            self.epoch += 1
+            learning_rate = self.cfgParams.lr_of_ep(self.epoch)
+            for minibatch_index in range(self.getNumFullMiniBatches()):
+                if self.cfgParams.pre_minibatch_fn is not None:
+                    getattr(self, self.cfgParams.pre_minibatch_fn)()
+                self.poseNet.unsetDeterministic()
+                mini_idx = self.loadMiniBatch(minibatch_index)
+                minibatch_avg_cost = self.train_model(mini_idx, learning_rate)
+                if getattr(self, 'verbose', True):
+                    print("minibatch {0:4d}, average cost: {1}".format(minibatch_index, minibatch_avg_cost))
+                if numpy.any(numpy.isnan(minibatch_avg_cost)):
+                    self.checkNaNs()
+                    assert False
+                train_costs.append(minibatch_avg_cost)
+                if self.cfgParams.post_minibatch_fn is not None:
+                    getattr(self, self.cfgParams.post_minibatch_fn)()
+                iter_count = (self.epoch - 1) * self.getNumFullMiniBatches() + minibatch_index
+                if (iter_count + 1) % self.cfgParams.validation_frequency == 0:
+                    if storeFilters:
+                        for lay in self.poseNet.layers:
+                            if isinstance(lay, (ConvPoolLayer, ConvLayer)):
+                                wvals.append(lay.W.get_value())
+                    self.poseNet.setDeterministic()
+                    this_validation_loss = numpy.nanmean([self.validation_observer[0](i) for i in range(n_val_batches)])
+                    for vi in range(1, len(self.validation_observer)):
+                        validation_obs[vi - 1].append(
+                            numpy.nanmean([self.validation_observer[vi](i) for i in range(n_val_batches)]))
+                    self.poseNet.unsetDeterministic()
+                    print("{}: epoch {}, LR {}, minibatch {}/{}, validation cost {} error {}".format(
+                        time.ctime(), self.epoch, learning_rate, minibatch_index + 1, self.getNumFullMiniBatches(),
+                        this_validation_loss, [vo[-1] for vo in validation_obs]))
+                    if this_validation_loss < best_validation_loss:
+                        best_validation_loss = this_validation_loss
+                        print("Best validation loss so far, store network weights!")
+                        bestParams = self.poseNet.weightVals
+                        bestParamsEp = self.epoch
+            if self.cfgParams.post_epoch_fn is not None:
+                getattr(self, self.cfgParams.post_epoch_fn)()
+        end_time = time.time()
+        print('Optimization complete with best validation score of %f,' % best_validation_loss)
+        print('The code run for %d epochs, with %f epochs/sec' % (self.epoch, self.epoch / (end_time - start_time)))
+        if bestParams is not None and self.cfgParams.use_early_stopping is True:
+            self.poseNet.weightVals = bestParams
+            print('Best params at epoch %d' % bestParamsEp)
+        if self.cfgParams.augment_fun_params['fun'] is not None:
+            self.unsetDataLoading()
+        return train_costs, wvals, validation_obs[0] if len(validation_obs) == 1 else validation_obs
+
+    def checkNaNs(self):
+        for param_i in self.params:
+            if numpy.any(numpy.isnan(param_i.get_value())):
+                print("NaN in weights", param_i.name)
+
+    # -- augmentCrop with the reference signature (per sample; slow path) ------------------------------
+    def augmentCrop(self, img, gt3Dcrop, com, cube, M, aug_modes, hd, normZeroOne=False, sigma_com=None,
+                    sigma_sc=None, rot_range=None):
+        """nettrainer.py:919-997.  The four random numbers are always drawn, in the reference's
+        order; the pixel work runs in dpp_augment_fwd."""
+        from dpp_b200.augment import run_records
+        assert len(img.shape) == 2
+        assert isinstance(aug_modes, list)
+        if normZeroOne is True:
+            raise NotImplementedError("normZeroOne=True is unused by the reference's entry scripts")
+        sigma_com = 5. if sigma_com is None else sigma_com
+        sigma_sc = 0.02 if sigma_sc is None else sigma_sc
+        rot_range = 180. if rot_range is None else rot_range
+        mode = self.rng.randint(0, len(aug_modes))
+        off = self.rng.randn(3) * sigma_com
+        rot = self.rng.uniform(-rot_range, rot_range)
+        sc = abs(1. + self.rng.randn() * sigma_sc)
+        name = aug_modes[mode]
+        rec, curLabel, cube2, com2, M2 = hd.aug_record(0, name, off, rot, sc, com, cube, M, gt3Dcrop)
+        imgD = run_records(numpy.ascontiguousarray(img, dtype='float32')[None], numpy.array([rec]))[0]
+        rot_out = numpy.mod(rot, 360) if (name == 'rot' and not numpy.allclose(rot, 0.)) else (rot if name == 'rot' else 0.)
+        return imgD, None, curLabel, numpy.asarray(cube2), com2, M2, rot_out

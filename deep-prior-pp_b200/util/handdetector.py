@@ -1,0 +1,210 @@
+"""HandDetector - the augmentation subset (reference: src/util/handdetector.py: comToBounds
+:204-226, comToTransform :228-258, moveCoM :678-710, rotateHand :712-747, scaleHand :750-780,
+recropHand :782-803).  The geometry (3x3 matrices, crop bounds, label transforms) stays on the
+host in fp64 exactly as the reference computes it; every pixel operation - the cv2.warpAffine /
+cv2.warpPerspective nearest-neighbour gathers, the z-thresholds and the CoM normalisation - runs
+in ``dpp_augment_fwd`` (csrc/augment.cu).  ``aug_record`` turns one sample's draw into the
+``dpp_aug_rec`` the kernel consumes; ``NetTrainer`` batches those records per macro batch.
+
+Hand detection (detect/track/cropArea3D/...) is out of scope (CPU, serial)."""
+import math
+import numpy as np
+
+from data.transformations import rotatePoint2D
+from dpp_b200.lib import AUG_REC_DTYPE
+
+f32 = np.float32
+f64 = np.float64
+
+
+def invert3x3_cv(S):
+    """cv::invert of a 3x3 CV_64F matrix (closed-form cofactors) - the inverse
+    cv2.warpPerspective applies to the forward matrix; its last bits decide NN ties."""
+    S = np.asarray(S, f64)
+    d = S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0]) \
+        + S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0])
+    d = 1. / d
+    t = np.empty(9, f64)
+    t[0] = (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * d
+    t[1] = (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d
+    t[2] = (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d
+    t[3] = (S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d
+    t[4] = (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d
+    t[5] = (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d
+    t[6] = (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * d
+    t[7] = (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d
+    t[8] = (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d
+    return t
+
+
+def rotation_inverse_affine(center, angle_deg):
+    """cv2.getRotationMatrix2D(center, angle, 1) followed by the 2x3 inversion cv2.warpAffine
+    performs; returns {i00, i01, b0, i10, i11, b1} (fp64)."""
+    a = float(angle_deg) * (math.pi / 180.)
+    alpha, beta = math.cos(a), math.sin(a)
+    cx, cy = float(center[0]), float(center[1])
+    m00, m01, m02 = alpha, beta, (1 - alpha) * cx - beta * cy
+    m10, m11, m12 = -beta, alpha, beta * cx + (1 - alpha) * cy
+    D = m00 * m11 - m01 * m10
+    D = 1. / D if D != 0 else 0.
+    i00, i11 = m11 * D, m00 * D
+    i01, i10 = -m01 * D, -m10 * D
+    b0 = -i00 * m02 - i01 * m12
+    b1 = -i10 * m02 - i11 * m12
+    return np.array([i00, i01, b0, i10, i11, b1, 0., 0., 0.], f64)
+
+
+class HandDetector(object):
+    RESIZE_BILINEAR = 0
+    RESIZE_CV2_NN = 1
+    RESIZE_CV2_LINEAR = 2
+
+    def __init__(self, dpt, fx, fy, importer=None, refineNet=None):
+        self.dpt = dpt
+        self.maxDepth = min(1500, dpt.max()) if dpt is not None else 1500
+        self.minDepth = max(10, dpt.min()) if dpt is not None else 10
+        self.fx = fx
+        self.fy = fy
+        self.refineNet = refineNet
+        self.importer = importer
+        self.resizeMethod = self.RESIZE_CV2_NN
+
+    # -- crop geometry ------------------------------------------------------------------
+    def comToBounds(self, com, size):
+        """handdetector.py:204-226; ``com[0]*com[2]`` is a float32 product in the reference."""
+        if np.isclose(com[2], 0.):
+            print("Warning: CoM ill-defined!")
+            xstart = self.dpt.shape[0] // 4
+            xend = xstart + self.dpt.shape[0] // 2
+            ystart = self.dpt.shape[1] // 4
+            yend = ystart + self.dpt.shape[1] // 2
+            zstart = self.minDepth
+            zend = self.maxDepth
+        else:
+            c2 = f64(f32(com[2]))
+            zstart = c2 - f64(size[2]) / 2.
+            zend = c2 + f64(size[2]) / 2.
+            p0 = f64(f32(com[0]) * f32(com[2]))
+            p1 = f64(f32(com[1]) * f32(com[2]))
+            xstart = int(np.floor((p0 / self.fx - f64(size[0]) / 2.) / c2 * self.fx + 0.5))
+            xend = int(np.floor((p0 / self.fx + f64(size[0]) / 2.) / c2 * self.fx + 0.5))
+            ystart = int(np.floor((p1 / self.fy - f64(size[1]) / 2.) / c2 * self.fy + 0.5))
+            yend = int(np.floor((p1 / self.fy + f64(size[1]) / 2.) / c2 * self.fy + 0.5))
+        return xstart, xend, ystart, yend, zstart, zend
+
+    def comToTransform(self, com, size, dsize=(128, 128)):
+        """handdetector.py:228-258 (py2 integer division; the sz[1]/sz[0] swap is the reference's)."""
+        xstart, xend, ystart, yend, _, _ = self.comToBounds(com, size)
+        trans = np.eye(3)
+        trans[0, 2] = -xstart
+        trans[1, 2] = -ystart
+        wb = (xend - xstart)
+        hb = (yend - ystart)
+        if wb > hb:
+            scale = np.eye(3) * dsize[0] / float(wb)
+            sz = (dsize[0], hb * dsize[0] // wb)
+        else:
+            scale = np.eye(3) * dsize[1] / float(hb)
+            sz = (wb * dsize[1] // hb, dsize[1])
+        scale[2, 2] = 1
+        xstart = int(np.floor(dsize[0] / 2. - sz[1] / 2.))
+        ystart = int(np.floor(dsize[1] / 2. - sz[0] / 2.))
+        off = np.eye(3)
+        off[0, 2] = xstart
+        off[1, 2] = ystart
+        return np.dot(off, np.dot(scale, trans))
+
+    # -- one sample's augmentation record + labels ---------------------------------------
+    def aug_record(self, src_index, mode_name, off, rot, sc, com, cube, M, gt3Dcrop, raw=False):
+        """Geometry of NetTrainer.augmentCrop for one sample (nettrainer.py:948-995 + the
+        HandDetector methods it calls).  Returns (record, curLabel (J,3) f32, cube', com', M')."""
+        di = self.importer
+        rec = np.zeros((), dtype=AUG_REC_DTYPE)
+        rec['src_index'] = src_index
+        half = f32(f64(cube[2]) / 2.)
+        rec['half_old'] = half
+        rec['comz_old'] = f32(com[2])
+        new_com, new_cube, Mnew = com, cube, M
+        mode = 0
+        joints = gt3Dcrop
+        if mode_name == 'com' and not np.allclose(off, 0.):
+            new_com = di.joint3DToImg(di.jointImgTo3D(com).astype(f64) + np.asarray(off, f64))
+            if not (np.allclose(com[2], 0.) or np.allclose(new_com[2], 0.)):
+                Mnew = self.comToTransform(new_com, cube, (128, 128))
+                H = np.dot(Mnew, np.linalg.inv(M))           # inv of the float32 M, as in moveCoM
+                rec['m'] = invert3x3_cv(H)
+                _, _, _, _, zs, ze = self.comToBounds(new_com, cube)
+                rec['zstart'], rec['zend'] = f32(zs), f32(ze)
+                mode = 2
+            joints = ((gt3Dcrop + di.jointImgTo3D(com)) - di.jointImgTo3D(new_com)).astype(f32)
+        elif mode_name == 'rot' and not np.allclose(rot, 0.):
+            rot = np.mod(rot, 360)
+            rec['m'] = rotation_inverse_affine((64, 64), -rot)
+            mode = 1
+            com3D = di.jointImgTo3D(com)
+            joint_2D = di.joints3DToImg((gt3Dcrop + com3D).astype(f32))
+            data_2D = np.zeros_like(joint_2D)
+            for k in range(data_2D.shape[0]):
+                data_2D[k] = rotatePoint2D(joint_2D[k], com[0:2], rot)
+            joints = (di.jointsImgTo3D(data_2D) - com3D).astype(f32)
+        elif mode_name == 'sc' and not np.allclose(sc, 1.):
+            new_cube = [f64(s) * f64(sc) for s in cube]
+            if not np.allclose(com[2], 0.):
+                Mnew = self.comToTransform(com, new_cube, (128, 128))
+                H = np.dot(Mnew, np.linalg.inv(M))
+                rec['m'] = invert3x3_cv(H)
+                _, _, _, _, zs, ze = self.comToBounds(com, cube)     # z-threshold with the OLD cube
+                rec['zstart'], rec['zend'] = f32(zs), f32(ze)
+                mode = 2
+        elif mode_name not in ('com', 'rot', 'sc', 'none'):
+            raise NotImplementedError()
+        rec['mode'] = mode + (16 if raw else 0)
+        rec['bg'] = f32(f64(new_com[2]) + f64(new_cube[2]) / 2.)
+        rec['lo'] = f32(f64(new_com[2]) - f64(new_cube[2]) / 2.)
+        rec['comz_new'] = f32(new_com[2])
+        rec['half_new'] = f32(f64(new_cube[2]) / 2.)
+        curLabel = (joints / f32(f64(new_cube[2]) / 2.)).astype(f32)
+        return rec, curLabel, np.asarray(new_cube), new_com, Mnew
+
+    # -- reference-signature methods on single images (slow path: one launch per call) ----
+    def _warp_raw(self, dpt, rec):
+        import torch
+        from dpp_b200.augment import run_records
+        rec = rec.copy()
+        rec['src_index'] = 0
+        rec['half_old'] = 1.0
+        rec['comz_old'] = 0.0
+        rec['mode'] = (int(rec['mode']) & 15) | 16
+        out = run_records(np.ascontiguousarray(dpt, f32)[None], np.array([rec]))
+        return out[0]
+
+    def moveCoM(self, dpt, cube, com, off, joints3D, M, pad_value=0):
+        if np.allclose(off, 0.):
+            return dpt, joints3D, com, M
+        rec, _, _, new_com, Mnew = self.aug_record(0, 'com', off, 0., 1., com, cube, M, joints3D, raw=True)
+        new_dpt = self._warp_raw(dpt, rec) if (int(rec['mode']) & 15) == 2 else dpt
+        di = self.importer
+        new_joints3D = ((joints3D + di.jointImgTo3D(com)) - di.jointImgTo3D(new_com)).astype(f32)
+        return new_dpt, new_joints3D, new_com, Mnew
+
+    def rotateHand(self, dpt, cube, com, rot, joints3D, pad_value=0):
+        if np.allclose(rot, 0.):
+            return dpt, joints3D, rot
+        rec, lab, _, _, _ = self.aug_record(0, 'rot', np.zeros(3), rot, 1., com, cube, np.eye(3, dtype=f32), joints3D,
+                                            raw=True)
+        new_dpt = self._warp_raw(dpt, rec)
+        # labels in mm: undo the /(cube_z/2) of aug_record exactly is not possible in f32, recompute
+        rotm = np.mod(rot, 360)
+        com3D = self.importer.jointImgTo3D(com)
+        joint_2D = self.importer.joints3DToImg((joints3D + com3D).astype(f32))
+        data_2D = np.zeros_like(joint_2D)
+        for k in range(data_2D.shape[0]):
+            data_2D[k] = rotatePoint2D(joint_2D[k], com[0:2], rotm)
+        return new_dpt, (self.importer.jointsImgTo3D(data_2D) - com3D).astype(f32), rotm
+
+    def scaleHand(self, dpt, cube, com, sc, joints3D, M, pad_value=0):
+        if np.allclose(sc, 1.):
+            return dpt, joints3D, cube, M
+        rec, _, new_cube, _, Mnew = self.aug_record(0, 'sc', np.zeros(3), 0., sc, com, cube, M, joints3D, raw=True)
+        new_dpt = self._warp_raw(dpt, rec) if (int(rec['mode']) & 15) == 2 else dpt
+        return new_dpt, joints3D, list(new_cube), Mnew

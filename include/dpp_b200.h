@@ -75,7 +75,8 @@ int dpp_nhwc_to_nchw(const float *src, float *dst, int N, int C, int H, int W, v
  * (util/handdetector.py:730-738, :791-801).  One record per output sample; the host side
  * (util/handdetector.py mirror) prepares it in fp64 exactly as the reference computes the
  * matrices.  mode: 0 = none, 1 = affine NN (rotateHand), 2 = perspective NN + z-threshold
- * (moveCoM / scaleHand via recropHand).
+ * (moveCoM / scaleHand via recropHand); +16 = raw (skip the final CoM re-normalisation:
+ * the warp alone, for direct HandDetector.rotateHand / recropHand calls).
  * Bit-exact against the oracle's index rules (oracle/augment.py).                        */
 typedef struct dpp_aug_rec {
     int32_t src_index;   /* row of `crops` to read (the ORIGINAL normalised crop)        */

@@ -1,0 +1,56 @@
+"""Generates the committed golden vectors from the CPU oracle (run in the build container:
+`python tests/golden/make_golden.py`).  The reference has no tests/fixtures of its own and cannot
+run here (Theano), so these oracle outputs - produced from the reference-following restatement in
+oracle/ with cv2 4.13.0 as the executable ground truth for the warps - are the pins."""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'deep-prior-pp_b200'))
+
+
+def augment_case(name, cam_name, aug_modes, n, seed):
+    from oracle import augment as A
+    from data import synthetic
+    ds = synthetic.generate(name, n, seed=seed)
+    cam = A.Camera(**getattr(A, cam_name))
+    rng = np.random.RandomState(seed + 1)
+    draws = [A.draw_aug_params(rng, len(aug_modes)) for _ in range(n)]
+    ox, oy = A.augment_poses(ds['x'], ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], list(range(n)), draws,
+                             aug_modes, cam, A.Hand(cam, use_cv2=False))
+    cx, cy = A.augment_poses(ds['x'], ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], list(range(n)), draws,
+                             aug_modes, cam, A.Hand(cam, use_cv2=True))
+    return dict(x=ds['x'], com3D=ds['com3D'], cube=ds['cube'], M=ds['M'], gt3Dcrop=ds['gt3Dcrop'],
+                mode=np.array([d[0] for d in draws]), off=np.array([d[1] for d in draws]),
+                rot=np.array([d[2] for d in draws]), sc=np.array([d[3] for d in draws]),
+                out_x=ox, out_y=oy, cv2_x=cx, cv2_y=cy)
+
+
+def resnet_case():
+    import torch
+    from oracle import nets as O
+    B, D = 2, 30
+    rng = np.random.RandomState(4242)
+    x = rng.uniform(-1, 1, (B, 1, 128, 128)).astype(np.float32)
+    y = rng.randn(B, D).astype(np.float32)
+    net = O.build_resnet(np.random.RandomState(23455), type=0, batchSize=B, numJoints=1, nDims=D)
+    adam = O.Adam(net.params)
+    with torch.no_grad():
+        out_det, _ = net.forward(torch.from_numpy(x), deterministic=True)
+    cost, out, grads = O.train_step(net, adam, torch.from_numpy(x), torch.from_numpy(y), 1e-3, 1, D)
+    gn = np.array([float(g.norm()) for g in grads], np.float64)
+    with torch.no_grad():
+        out2, _ = net.forward(torch.from_numpy(x), deterministic=False)
+    return dict(x=x, y=y, out_det=out_det.numpy(), out_train=out.numpy(), cost=np.float64(cost), grad_norms=gn,
+                fc2_grad=grads[-2].numpy(), out_after_step=out2.numpy())
+
+
+if __name__ == '__main__':
+    np.savez_compressed(os.path.join(HERE, 'augment_nyu.npz'), **augment_case('NYU', 'NYU_CAM', ['com', 'rot', 'none'], 8, 11))
+    np.savez_compressed(os.path.join(HERE, 'augment_msra.npz'),
+                        **augment_case('MSRA15', 'MSRA_CAM', ['com', 'rot', 'sc', 'none'], 8, 13))
+    np.savez_compressed(os.path.join(HERE, 'resnet_b2.npz'), **resnet_case())
+    print("golden vectors written to", HERE)

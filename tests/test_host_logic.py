@@ -1,0 +1,176 @@
+"""CPU tests of the host side: reference-surface classes, layer bookkeeping, checkpoints,
+trainer batch arithmetic, the C-ABI library's exported symbols (no compute without a GPU)."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+
+from net.resnet import ResNet, ResNetParams
+from net.poseregnet import PoseRegNet, PoseRegNetParams
+from net.hiddenlayer import HiddenLayer, HiddenLayerParams
+from net.batchnormlayer import BatchNormLayer
+from net.convlayer import ConvLayer, ConvLayerParams
+from net.convpoollayer import ConvPoolLayerParams
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_resnet_layer_numbering_and_param_order():
+    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=2, numJoints=1, nDims=30))
+    assert len(net.layers) == 189
+    assert [l.layerNum for l in net.layers] == list(range(189))
+    assert sum(isinstance(l, BatchNormLayer) for l in net.layers) == 61
+    assert sum(isinstance(l, ConvLayer) for l in net.layers) == 63
+    # projection block = 10 layers, identity = 9; stage-1 block 0 starts at layer 1
+    assert isinstance(net.layers[10], ConvLayer) and net.layers[10].cfgParams.stride == (2, 2)   # shortcut conv
+    assert net.layers[10].cfgParams.inputDim == (2, 32, 64, 64)
+    assert net.layers[-1].cfgParams.outputDim == (2, 30)
+    n = sum(int(np.prod(p.get_value().shape)) for p in net.params)
+    assert n == 18713150
+    names = [p.name for p in net.params[:6]]
+    assert names == ['convW0', 'convB0', 'beta1', 'gamma1', 'convW3', 'convB3']
+    assert ResNet(np.random.RandomState(1), cfgParams=ResNetParams(type=1, batchSize=2, numJoints=14, nDims=3)).layers[-1] \
+        .cfgParams.outputDim == (2, 42)
+
+
+def test_stage4_ignores_stride_like_the_reference():
+    net = ResNet(np.random.RandomState(0), cfgParams=ResNetParams(type=0, batchSize=1, numJoints=1, nDims=30))
+    convs = [l for l in net.layers if isinstance(l, ConvLayer)]
+    assert convs[-1].cfgParams.outputDim == (1, 256, 8, 8)      # stage 4 stays at 8x8 (resnet.py:353)
+
+
+def test_init_matches_oracle_draw_for_draw():
+    from oracle import nets as O
+    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=4, batchSize=2, numJoints=14, nDims=3))
+    onet = O.build_resnet(np.random.RandomState(23455), type=4, batchSize=2, numJoints=14, nDims=3)
+    assert len(net.params) == len(onet.params)
+    for a, b in zip(net.params, onet.params):
+        assert np.array_equal(a.get_value(), b.detach().numpy())
+    p = PoseRegNet(np.random.RandomState(5), cfgParams=PoseRegNetParams(type=11, batchSize=2, numJoints=1, nDims=30))
+    op = O.build_poseregnet(np.random.RandomState(5), type=11, batchSize=2, numJoints=1, nDims=30)
+    for a, b in zip(p.params, op.params):
+        assert np.array_equal(a.get_value(), b.detach().numpy())
+
+
+def test_layer_dims():
+    p = ConvPoolLayerParams(inputDim=(4, 1, 128, 128), nFilters=8, filterDim=(5, 5), poolsize=(4, 4))
+    assert p.outputDim == (4, 8, 31, 31)
+    c = ConvLayerParams(inputDim=(4, 32, 64, 64), nFilters=16, filterDim=(1, 1), stride=(2, 2), border_mode='same')
+    assert c.outputDim == (4, 16, 32, 32) and c.border_mode == 'half'
+    pn = PoseRegNetParams(type=0, batchSize=4, numJoints=1, nDims=30)
+    assert [l.outputDim for l in pn.layers[:4]] == [(4, 8, 31, 31), (4, 8, 13, 13), (4, 8, 11, 11), (4, 1024)]
+
+
+def test_save_load_roundtrip_and_pca_layer_append(tmp_path):
+    rng = np.random.RandomState(3)
+    net = PoseRegNet(rng, cfgParams=PoseRegNetParams(type=0, batchSize=2, numJoints=1, nDims=30))
+    f = str(tmp_path / 'net.pkl')
+    net.save(f)
+    net2 = PoseRegNet(np.random.RandomState(99), cfgParams=PoseRegNetParams(type=0, batchSize=2, numJoints=1, nDims=30))
+    assert not np.array_equal(net.layers[0].W.get_value(), net2.layers[0].W.get_value())
+    net2.load(f)
+    for a, b in zip(net.params, net2.params):
+        assert np.array_equal(a.get_value(), b.get_value())
+    # main_nyu_posereg_embedding.py:148-158
+    pca_w, pca_b = rng.randn(30, 42).astype('float32'), rng.randn(42).astype('float32')
+    cfg = HiddenLayerParams(inputDim=(2, 30), outputDim=(2, 42), activation=None)
+    pcalayer = HiddenLayer(rng, net.layers[-1].output, cfg, layerNum=len(net.layers))
+    pcalayer.W.set_value(pca_w)
+    pcalayer.b.set_value(pca_b)
+    net.layers.append(pcalayer)
+    net.output = pcalayer.output
+    net.cfgParams.numJoints, net.cfgParams.nDims, net.cfgParams.outputDim = 14, 3, pcalayer.cfgParams.outputDim
+    assert len(net.params) == 14 and np.array_equal(net.params[-2].get_value(), pca_w)
+    net.save(str(tmp_path / 'net_prior.pkl.gz'))
+
+
+def test_deterministic_switch_and_dropout():
+    net = PoseRegNet(np.random.RandomState(3), cfgParams=PoseRegNetParams(type=0, batchSize=2, numJoints=1, nDims=30))
+    assert net.hasDropout() and not net.isDeterministic()
+    net.setDeterministic()
+    assert net.isDeterministic()
+    net.unsetDeterministic()
+    assert not net.isDeterministic()
+    r = ResNet(np.random.RandomState(0), cfgParams=ResNetParams(type=0, batchSize=1, numJoints=1, nDims=30))
+    assert not r.hasDropout()
+
+
+def test_trainer_batch_arithmetic_and_padding():
+    from trainer.poseregnettrainer import PoseRegNetTrainer, PoseRegNetTrainerParams
+    net = PoseRegNet(np.random.RandomState(3), cfgParams=PoseRegNetParams(type=0, batchSize=8, numJoints=1, nDims=30))
+    cfg = PoseRegNetTrainerParams()
+    cfg.batch_size = 8
+    cfg.weightreg_factor = 0.0
+    tr = PoseRegNetTrainer(net, cfg, np.random.RandomState(1), '/tmp')
+    N = 21
+    x = np.arange(N * 4, dtype='float32').reshape(N, 1, 2, 2)
+    y = np.arange(N * 30, dtype='float32').reshape(N, 30)
+    tr.setData(x, y, x[:16], y[:16])
+    assert tr.getNumMiniBatches() == 3 and tr.getNumMacroBatches() == 1 and tr.getNumSamplesPerMacroBatch() == 24
+    assert tr.train_data_xDB.shape[0] == 24
+    rng = np.random.RandomState(N)                        # nettrainer.py:401-407
+    for i in range(3):
+        j = rng.randint(0, N)
+        assert np.array_equal(tr.train_data_xDB[N + i], x[j])
+    # x and y padded with the same draws
+    rng = np.random.RandomState(N)
+    for i in range(3):
+        assert np.array_equal(tr.train_data_yDB[N + i], y[rng.randint(0, N)])
+    lr = cfg.lr_of_ep
+    cfg.learning_rate = 1e-3
+    assert lr(1) == np.float32(1e-4) and lr(2) == np.float32(1e-3 / 3.) and abs(lr(10) - 1e-3 * np.exp(-0.4)) < 1e-9
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from dpp_b200.lib import library_path, EXPORTED_SYMBOLS
+    hdr = open(os.path.join(ROOT, 'include', 'dpp_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(dpp_[a-z0-9_]+)\s*\(', hdr)))
+    assert declared, "no declarations found"
+    dll = ctypes.CDLL(library_path())
+    for name in declared:
+        assert hasattr(dll, name), name
+    assert set(EXPORTED_SYMBOLS) == set(declared)
+    dll.dpp_abi_version.restype = ctypes.c_int
+    assert dll.dpp_abi_version() == 1
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dpp_b200 import DppError
+    net = PoseRegNet(np.random.RandomState(3), cfgParams=PoseRegNetParams(type=0, batchSize=2, numJoints=1, nDims=30))
+    with pytest.raises(DppError):
+        net.computeOutput(np.zeros((2, 1, 128, 128), 'float32'))
+
+
+def test_aug_record_layout_matches_c_struct():
+    from dpp_b200.lib import AUG_REC_DTYPE, AugRec
+    dt = np.dtype(AUG_REC_DTYPE)
+    assert dt.itemsize == ctypes.sizeof(AugRec) == 112
+    for name in dt.names:
+        assert dt.fields[name][1] == getattr(AugRec, name).offset
+
+
+def test_host_augmentation_geometry_matches_oracle():
+    """labels, matrices and thresholds of the dpp_aug_rec records vs the oracle (pixels are the
+    GPU test's job)"""
+    from oracle import augment as A
+    from data import synthetic
+    ds = synthetic.generate('MSRA15', 40, seed=5)
+    cam = A.Camera(**A.MSRA_CAM)
+    ohd = A.Hand(cam)
+    hd, di = ds['hd'], ds['importer']
+    modes = ['com', 'rot', 'sc', 'none']
+    rng = np.random.RandomState(2)
+    for i in range(40):
+        mode, off, rot, sc = A.draw_aug_params(rng, 4)
+        com = di.joint3DToImg(ds['com3D'][i])
+        assert np.array_equal(com, cam.joint3DToImg(ds['com3D'][i]))
+        rec, lab, cube2, com2, M2 = hd.aug_record(i, modes[mode], off, rot, sc, com, ds['cube'][i].copy(),
+                                                  ds['M'][i].copy(), ds['gt3Dcrop'][i].copy())
+        _, olab, ocube, ocom, oM = A.augment_crop(ds['x'][i, 0], ds['gt3Dcrop'][i].copy(), com, ds['cube'][i].copy(),
+                                                   ds['M'][i].copy(), modes[mode], off, rot, sc, ohd)
+        assert np.array_equal(lab, olab)
+        assert np.allclose(cube2, ocube, rtol=0, atol=0) and np.array_equal(com2, ocom) and np.array_equal(M2, oM)
