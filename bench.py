@@ -119,6 +119,11 @@ def records_for(ds, comp, mean, idxs, rng):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: oracle restatement (reference-equivalent CPU path)
 # ---------------------------------------------------------------------------------------------
+def cpu_threads():
+    # torch-CPU convolutions on 8x8..64x64 maps stop scaling (and regress) beyond ~16 threads
+    return min(os.cpu_count() or 1, int(os.environ.get('DPP_CPU_THREADS', '16')))
+
+
 def cpu_step_time(ds, comp, mean, steps, threads):
     import torch
     from oracle import nets as ON, augment as OA
@@ -144,7 +149,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     ds, comp, mean = make_workload()
     steps = max(1, min(args.steps, 6))
     warm = 1 if args.warmup > 0 else 0
@@ -286,7 +291,7 @@ def run_b200(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         t = cpu_step_time(ds, comp, mean, 3, threads)[1:]
         v = B / float(np.mean(t))
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -363,6 +363,8 @@ int check_desc(const dpp_conv_desc *d) {
 // tcgen05 path (conv_tc.cu); returns DPP_ENOTSUP when it does not take the shape
 int dpp_conv2d_fwd_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *w,
                       const float *bias, const float *residual, float *y, double *out_stats, void *stream);
+int dpp_conv2d_dgrad_tc(const dpp_conv_desc *d, const float *dy, float *dx, int accumulate, const dpp_bn_ref *mask_bn,
+                        const float *x_pre, double *dz_stats, void *stream);
 
 extern "C" int dpp_conv2d_fwd(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *w,
                               const float *bias, const float *residual, float *y, double *out_stats,
@@ -390,6 +392,10 @@ extern "C" int dpp_conv2d_dgrad(const dpp_conv_desc *d, const float *dy, const f
                                 const dpp_bn_ref *mask_bn, const float *x_pre, double *dz_stats, void *stream) {
     DPP_CHECK_ARG(check_desc(d) == 0 && dy && w && dx);
     DPP_CHECK_ARG(!mask_bn || (x_pre && dz_stats));
+    if (d->precision != 0) {
+        int rc = dpp_conv2d_dgrad_tc(d, dy, dx, accumulate, mask_bn, x_pre, dz_stats, stream);
+        if (rc != DPP_ENOTSUP) return rc;
+    }
     IGArgs a;
     memset(&a, 0, sizeof(a));
     a.in = dy; a.w = w; a.out = dx;

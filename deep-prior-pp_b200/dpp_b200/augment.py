@@ -14,6 +14,8 @@ def run_records_device(crops_dev, recs_np, out_dev=None):
     recs_np = np.ascontiguousarray(recs_np, dtype=AUG_REC_DTYPE)
     n = recs_np.shape[0]
     H, W = int(crops_dev.shape[-2]), int(crops_dev.shape[-1])
+    if n == 0:
+        return torch.empty((0, H, W), dtype=torch.float32, device=crops_dev.device)
     rec_dev = torch.from_numpy(recs_np.view(np.uint8).reshape(n, -1).copy()).to(crops_dev.device)
     if out_dev is None:
         out_dev = torch.empty((n, H, W), dtype=torch.float32, device=crops_dev.device)

@@ -22,7 +22,7 @@ import ctypes as C
 import os
 import numpy as np
 
-from .lib import lib, BnRef, ConvDesc, BnEmaItem, DppError
+from .lib import lib, BnRef, ConvDesc, BnEmaItem, PackItem, DppError
 
 
 def _torch():
@@ -109,6 +109,7 @@ class Engine(object):
         self._alloc_params()
         self._alloc_activations()
         self._train_ready = False
+        self._alloc_packs()
 
     # ---------------------------------------------------------------------------------
     # lowering
@@ -338,6 +339,48 @@ class Engine(object):
     def upload_param(self, slot, value):
         flat = self.torch.from_numpy(slot.to_device_layout(value))
         self._arena(slot)[slot.offset:slot.offset + slot.size].copy_(flat)
+        if slot.var.kind == 'convW':
+            self._packs_dirty = True
+
+    # ---------------------------------------------------------------------------------
+    # tcgen05 weight images (precision 1|2): re-packed after every optimiser step
+    # ---------------------------------------------------------------------------------
+    def _alloc_packs(self):
+        torch = self.torch
+        self._packs_dirty = False
+        self.pack_items = None
+        convs = [op for op in self.ops if op['kind'] == 'conv']
+        if self.precision == 0 or not convs:
+            return
+        passes = 2 if self.precision == 1 else 1
+        sizes, total = [], 0
+        for op in convs:
+            p = op['layer'].cfgParams
+            cin, cout, k = int(p.inputDim[1]), int(p.nFilters), int(p.filterDim[0])
+            f, g = C.c_int64(), C.c_int64()
+            lib.dpp_conv_pack_size(cin, cout, k, self.precision, C.byref(f), C.byref(g))
+            sizes.append((total, total + f.value, cin, cout, k))
+            total += f.value + g.value
+        self.WPACK = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        items = (PackItem * len(convs))()
+        for i, (op, (o_f, o_g, cin, cout, k)) in enumerate(zip(convs, sizes)):
+            op['wpack_fwd'] = self.WPACK.data_ptr() + 4 * o_f
+            op['wpack_dgrad'] = self.WPACK.data_ptr() + 4 * o_g
+            items[i].w = self.pview(op['layer'].W).data_ptr()
+            items[i].img_fwd = op['wpack_fwd']
+            items[i].img_dgrad = op['wpack_dgrad']
+            items[i].Cin, items[i].Cout, items[i].k = cin, cout, k
+            items[i].bn_fwd = min(cout, 128)
+            items[i].bn_dgrad = min(cin, 128)
+            items[i].passes = passes
+        self.pack_items = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
+        self.n_pack = len(convs)
+        self._packs_dirty = True
+
+    def _repack(self):
+        if self.pack_items is not None:
+            lib.dpp_conv_pack_all(_ptr(self.pack_items), self.n_pack, self._stream())
+        self._packs_dirty = False
 
     def pview(self, var, arena=None):
         s = self.slots[id(var)]
@@ -433,7 +476,9 @@ class Engine(object):
             raise NotImplementedError("ConvLayer border_mode %s" % p.border_mode)
         d.pad = d.k // 2
         d.Ho, d.Wo = int(p.outputDim[2]), int(p.outputDim[3])
-        d.precision = self.precision
+        d.precision = self.precision if 'wpack_fwd' in op else 0
+        d.wpack_fwd = op.get('wpack_fwd')
+        d.wpack_dgrad = op.get('wpack_dgrad')
         return d
 
     def _stats_ptr(self, bn, which=0):
@@ -579,6 +624,8 @@ class Engine(object):
         """Run the forward pass on the NHWC input already in ``self.t_in.buf``; returns the device
         output tensor (B, n_out)."""
         st = self._stream()
+        if self._packs_dirty:
+            self._repack()
         if not deterministic:
             lib.dpp_fill_f64(_ptr(self.STATS), 0.0, self.STATS.numel(), st)
         self._run_forward(train=not deterministic)
@@ -628,6 +675,8 @@ class Engine(object):
             self.allreduce_fn(self.G)
         lib.dpp_adam_step(_ptr(self.W), _ptr(self.G), _ptr(self.M), _ptr(self.V), _ptr(self.hyper), self.n_w, st)
         lib.dpp_adam_tick(_ptr(self.hyper), st)
+        if self.pack_items is not None:
+            lib.dpp_conv_pack_all(_ptr(self.pack_items), self.n_pack, st)
         if self.bns:
             lib.dpp_bn_ema_update(_ptr(self.ema_items), len(self.bns), float(self.bns[0].cfgParams.alpha), st)
 
@@ -647,6 +696,8 @@ class Engine(object):
         torch = self.torch
         if lr is not None:
             self.set_lr(lr)
+        if self._packs_dirty:
+            self._repack()
         self._draw_masks()
         if not use_graph:
             self._step_body()

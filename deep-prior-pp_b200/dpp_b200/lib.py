@@ -30,7 +30,13 @@ class AugRec(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
                 ('Cout', C.c_int), ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int),
-                ('Ho', C.c_int), ('Wo', C.c_int), ('precision', C.c_int)]
+                ('Ho', C.c_int), ('Wo', C.c_int), ('precision', C.c_int),
+                ('wpack_fwd', C.c_void_p), ('wpack_dgrad', C.c_void_p)]
+
+
+class PackItem(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('img_fwd', C.c_void_p), ('img_dgrad', C.c_void_p), ('Cin', C.c_int),
+                ('Cout', C.c_int), ('k', C.c_int), ('bn_fwd', C.c_int), ('bn_dgrad', C.c_int), ('passes', C.c_int)]
 
 
 class BnEmaItem(C.Structure):
@@ -53,6 +59,8 @@ _SIGS = {
     'dpp_augment_fwd': (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, P]),
     'dpp_convpool_fwd': (C.c_int, [P, P, P, P, P, P] + [C.c_int] * 9 + [P]),
     'dpp_convpool_bwd': (C.c_int, [P, P, P, P, P, P, P, P] + [C.c_int] * 9 + [P]),
+    'dpp_conv_pack_size': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'dpp_conv_pack_all': (C.c_int, [P, C.c_int, P]),
     'dpp_conv2d_fwd': (C.c_int, [C.POINTER(ConvDesc), P, C.POINTER(BnRef), P, P, P, P, P, P]),
     'dpp_conv2d_dgrad': (C.c_int, [C.POINTER(ConvDesc), P, P, P, C.c_int, C.POINTER(BnRef), P, P, P]),
     'dpp_conv2d_wgrad': (C.c_int, [C.POINTER(ConvDesc), P, C.POINTER(BnRef), P, P, P, P]),

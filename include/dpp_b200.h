@@ -122,7 +122,26 @@ typedef struct dpp_conv_desc {
     int Cout, k, stride, pad;
     int Ho, Wo;
     int precision;
+    /* tcgen05 path only (precision 1|2): the layer's weights pre-packed by dpp_conv_pack_all
+     * into shared-memory images; NULL selects the fp32 SIMT kernels. */
+    const float *wpack_fwd;
+    const float *wpack_dgrad;
 } dpp_conv_desc;
+
+/* ---- weight packing for the tcgen05 path ------------------------------------------------
+ * Sizes (in floats) of the forward / dgrad images of one layer; precision as in dpp_conv_desc. */
+int dpp_conv_pack_size(int Cin, int Cout, int k, int precision, int64_t *fwd_floats,
+                       int64_t *dgrad_floats);
+/* One launch re-packs every conv layer after the optimiser step.  items_dev: device array of
+ * n_items records {const float* w; float* img_fwd; float* img_dgrad; int Cin, Cout, k,
+ * bn_fwd, bn_dgrad, passes;} (bn = min(channels,128) n-tile, passes = 2 for 3xTF32 else 1). */
+typedef struct dpp_pack_item {
+    const float *w;
+    float *img_fwd;
+    float *img_dgrad;
+    int Cin, Cout, k, bn_fwd, bn_dgrad, passes;
+} dpp_pack_item;
+int dpp_conv_pack_all(const void *items_dev, int n_items, void *stream);
 
 int dpp_conv2d_fwd(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn,
                    const float *w, const float *bias, const float *residual, float *y,
