@@ -208,6 +208,161 @@ __global__ void k_convpool_bwd_x(const float *__restrict__ w, const float *__res
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// ResNet stem specialisation: 5x5 'half' conv, Cin = 1, Cout = 32, 2x2 max-pool (net/resnet.py:128-133).
+// Everything is compile-time: a thread owns one pooled pixel x 8 channels, keeps its 6x6 input window
+// in registers and runs 25 taps x 4 pool cells x 8 channels of FMAs against broadcast weight reads.
+// -------------------------------------------------------------------------------------------------
+constexpr int SP = 20;   // stem input patch edge: 8*2 + 5 - 1
+
+__global__ void __launch_bounds__(256)
+k_stem_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+           float *__restrict__ y, uint8_t *__restrict__ argmax, double *__restrict__ stats, int N, int H, int W) {
+    __shared__ __align__(16) float ws[25 * 32];
+    __shared__ float patch[SP * SP];
+    __shared__ double ssum[64];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 25 * 32; i += 256) ws[i] = w[i];
+    if (tid < 64) ssum[tid] = 0.0;
+    const int Hp = H / 2, Wp = W / 2;
+    const int tilesY = (Hp + 7) / 8, tilesX = (Wp + 7) / 8;
+    const int tiles = N * tilesY * tilesX;
+    const int pix = tid & 63, grp = tid >> 6;
+    const int ly = pix >> 3, lx = pix & 7;
+    const int o0 = grp * 8;
+    float bq[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) bq[q] = bias[o0 + q];
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int n = tile / (tilesY * tilesX), tr = tile % (tilesY * tilesX);
+        const int ty0 = tr / tilesX, tx0 = tr % tilesX;
+        __syncthreads();
+        for (int i = tid; i < SP * SP; i += 256) {
+            int py = i / SP, px = i - py * SP;
+            int yy = ty0 * 16 - 2 + py, xx = tx0 * 16 - 2 + px;
+            patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * H + yy) * W + xx] : 0.f;
+        }
+        __syncthreads();
+        float win[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int s = 0; s < 6; ++s) win[r][s] = patch[(ly * 2 + r) * SP + lx * 2 + s];
+        float acc[4][8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[c][q] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(&ws[(r * 5 + s) * 32 + o0]);
+                const float4 w1 = *reinterpret_cast<const float4 *>(&ws[(r * 5 + s) * 32 + o0 + 4]);
+                const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float xv = win[(c >> 1) + r][(c & 1) + s];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[c][q] = fmaf(xv, wq[q], acc[c][q]);
+                }
+            }
+        const int ph = ty0 * 8 + ly, pw = tx0 * 8 + lx;
+        const bool valid = ph < Hp && pw < Wp;
+        float v[8];
+        uint8_t am[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float b = acc[0][q];
+            uint8_t bi = 0;
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+                if (acc[c][q] > b) { b = acc[c][q]; bi = (uint8_t)c; }       // first max wins
+            v[q] = b + bq[q];
+            am[q] = bi;
+        }
+        if (valid) {
+            size_t ob = (((size_t)n * Hp + ph) * Wp + pw) * 32 + o0;
+            *reinterpret_cast<float4 *>(y + ob) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(y + ob + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            if (argmax) {
+                uint2 pk;
+                pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                *reinterpret_cast<uint2 *>(argmax + ob) = pk;
+            }
+        }
+        if (stats) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float s0 = warp_sum(valid ? v[q] : 0.f), s1 = warp_sum(valid ? v[q] * v[q] : 0.f);
+                if ((tid & 31) == 0) { atomicAdd(&ssum[o0 + q], (double)s0); atomicAdd(&ssum[32 + o0 + q], (double)s1); }
+            }
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        if (tid < 64) atomicAdd(&stats[tid], ssum[tid]);
+    }
+}
+
+// stem weight/bias gradients.  Thread = (output channel o, tap group): it walks the tile's 64 pooled
+// pixels and accumulates g * x[argmax cell + tap] for its own taps in registers - no reductions until the
+// single atomicAdd per (tap, o) per CTA at the end.
+__global__ void __launch_bounds__(256)
+k_stem_bwd_w(const float *__restrict__ x, const uint8_t *__restrict__ argmax, const float *__restrict__ dy,
+             float *__restrict__ dw, float *__restrict__ db, int N, int H, int W) {
+    __shared__ float patch[SP * SP];
+    __shared__ float gs[64 * 32];
+    __shared__ uint8_t cs[64 * 32];
+    const int tid = threadIdx.x;
+    const int o = tid & 31, tg = tid >> 5;      // taps tg, tg+8, tg+16, tg+24
+    const int Hp = H / 2, Wp = W / 2;
+    const int tilesY = (Hp + 7) / 8, tilesX = (Wp + 7) / 8;
+    const int tiles = N * tilesY * tilesX;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
+    int toff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int t = tg + 8 * j;
+        toff[j] = t < 25 ? (t / 5) * SP + (t % 5) : -1;
+    }
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int n = tile / (tilesY * tilesX), tr = tile % (tilesY * tilesX);
+        const int ty0 = tr / tilesX, tx0 = tr % tilesX;
+        __syncthreads();
+        for (int i = tid; i < SP * SP; i += 256) {
+            int py = i / SP, px = i - py * SP;
+            int yy = ty0 * 16 - 2 + py, xx = tx0 * 16 - 2 + px;
+            patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * H + yy) * W + xx] : 0.f;
+        }
+        for (int i = tid; i < 64 * 32; i += 256) {
+            int p = i >> 5, c = i & 31;
+            int ph = ty0 * 8 + (p >> 3), pw = tx0 * 8 + (p & 7);
+            bool valid = ph < Hp && pw < Wp;
+            size_t ob = (((size_t)n * Hp + (valid ? ph : 0)) * Wp + (valid ? pw : 0)) * 32 + c;
+            gs[i] = valid ? dy[ob] : 0.f;
+            cs[i] = valid ? argmax[ob] : 0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = 0; p < 64; ++p) {
+            const float g = gs[p * 32 + o];
+            const int cell = cs[p * 32 + o];
+            const int base = ((p >> 3) * 2 + (cell >> 1)) * SP + (p & 7) * 2 + (cell & 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (toff[j] >= 0) acc[j] = fmaf(g, patch[base + toff[j]], acc[j]);
+            accb += g;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (toff[j] >= 0) atomicAdd(&dw[(tg + 8 * j) * 32 + o], acc[j]);
+    if (tg == 0) atomicAdd(&db[o], accb);
+}
+
 int make_dims(CPDims &d, int N, int H, int W, int Cin, int Cout, int k, int pad, int pool) {
     d.N = N; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.k = k; d.pad = pad; d.pool = pool;
     int Hc = H + 2 * pad - k + 1, Wc = W + 2 * pad - k + 1;
@@ -229,6 +384,12 @@ extern "C" int dpp_convpool_fwd(const float *x, const float *w, const float *bia
     DPP_CHECK_ARG(smem <= 200 * 1024);
     DPP_CUDA(cudaFuncSetAttribute(k_convpool_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int tiles = N * d.tilesY * d.tilesX;
+    if (k == 5 && pool == 2 && Cin == 1 && Cout == 32 && pad == 2 && !relu && H % 2 == 0 && W % 2 == 0) {
+        int g2 = tiles < 148 * 4 ? tiles : 148 * 4;
+        k_stem_fwd<<<g2, 256, 0, S(stream)>>>(x, w, bias, y, argmax, stats, N, H, W);
+        DPP_LAUNCH_CHECK();
+        return DPP_OK;
+    }
     int grid = tiles < 148 * 4 ? tiles : 148 * 4;
     k_convpool_fwd<<<grid, CP_THREADS, smem, S(stream)>>>(x, w, bias, y, argmax, stats, d, relu);
     DPP_LAUNCH_CHECK();
@@ -245,6 +406,12 @@ extern "C" int dpp_convpool_bwd(const float *x, const float *w, const float *y, 
     DPP_CHECK_ARG(smem <= 200 * 1024);
     DPP_CUDA(cudaFuncSetAttribute(k_convpool_bwd_w, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int tiles = N * d.tilesY * d.tilesX;
+    if (k == 5 && pool == 2 && Cin == 1 && Cout == 32 && pad == 2 && !relu && !dx && H % 2 == 0 && W % 2 == 0) {
+        int g2 = tiles < 148 * 4 ? tiles : 148 * 4;
+        k_stem_bwd_w<<<g2, 256, 0, S(stream)>>>(x, argmax, dy, dw, db, N, H, W);
+        DPP_LAUNCH_CHECK();
+        return DPP_OK;
+    }
     int grid = tiles < 148 * 2 ? tiles : 148 * 2;
     k_convpool_bwd_w<<<grid, CP_THREADS, smem, S(stream)>>>(x, y, argmax, dy, dw, db, d, relu);
     DPP_LAUNCH_CHECK();
