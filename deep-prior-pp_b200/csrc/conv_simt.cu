@@ -365,6 +365,8 @@ int dpp_conv2d_fwd_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *
                       const float *bias, const float *residual, float *y, double *out_stats, void *stream);
 int dpp_conv2d_dgrad_tc(const dpp_conv_desc *d, const float *dy, float *dx, int accumulate, const dpp_bn_ref *mask_bn,
                         const float *x_pre, double *dz_stats, void *stream);
+int dpp_conv2d_wgrad_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
+                        float *db, void *stream);
 
 extern "C" int dpp_conv2d_fwd(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *w,
                               const float *bias, const float *residual, float *y, double *out_stats,
@@ -415,6 +417,10 @@ extern "C" int dpp_conv2d_dgrad(const dpp_conv_desc *d, const float *dy, const f
 extern "C" int dpp_conv2d_wgrad(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy,
                                 float *dw, float *db, void *stream) {
     DPP_CHECK_ARG(check_desc(d) == 0 && x && dy && dw);
+    if (d->precision != 0) {
+        int rc = dpp_conv2d_wgrad_tc(d, x, in_bn, dy, dw, db, stream);
+        if (rc != DPP_ENOTSUP) return rc;
+    }
     WGArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x; a.dy = dy; a.dw = dw; a.db = db;

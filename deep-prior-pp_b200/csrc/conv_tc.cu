@@ -389,6 +389,223 @@ k_conv_tc(TCArgs a) {
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Backward-weights on tcgen05:  dW[(r,s,c)][o] += sum_p a[p*stride - pad + (r,s)][c] * dy[p][o]
+// GEMM with the PIXELS as the reduction dimension: D[128 rows (r,s,c)][BN cols o], K = pixels.
+// Both operands are K-major with K = pixel, i.e. transposed w.r.t. NHWC memory: the producers load
+// channel-contiguous 16-byte pieces (BN+ReLU prologue recomputed on the activations), split hi/lo and
+// scatter 4-byte elements into the swizzled rows (a warp = 32 consecutive pixels = one 128-byte row
+// segment per store instruction, conflict-free).  Each CTA reduces a slice of the pixels into TMEM and
+// its epilogue adds the tile to dW with fp32 reductions (red.global.add); db rides on the dy loads.
+// -------------------------------------------------------------------------------------------------
+struct WGTArgs {
+    const float *x; const float *dy; float *dw; float *db;
+    int N, H, W, Cin, Cout, k, stride, pad, Ho, Wo;
+    dpp_bn_ref in_bn; int has_in_bn;
+    int mtiles, ntiles, splits, chunks_per_split;   // pixel chunks of 32
+};
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_wgrad_tc(WGTArgs a) {
+    using L = SmemLayout<BN, PASSES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
+    float *scr = reinterpret_cast<float *>(smem + L::SCR_OFF);
+    float *s_scale = scr + 4 * 32 * 33;
+    float *s_shift = s_scale + 256;
+    constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
+
+    const int tile = blockIdx.x % (a.mtiles * a.ntiles), split = blockIdx.x / (a.mtiles * a.ntiles);
+    const int mt = tile / a.ntiles, nt = tile % a.ntiles;
+    const int kd0 = mt * TM, o0 = nt * BN;
+    const int Kw = a.k * a.k * a.Cin;
+    const int P = a.N * a.Ho * a.Wo;
+    const int total_chunks = (P + 31) / 32;
+    const int c_begin = split * a.chunks_per_split;
+    int c_end = c_begin + a.chunks_per_split; if (c_end > total_chunks) c_end = total_chunks;
+    const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NSTAGE + s), 1); }
+        mbar_init(bar(2 * NSTAGE), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (a.has_in_bn)
+        for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // producers: thread = (pixel j of the chunk, row quarter q)
+        const int j = tid & 31, q = tid >> 5;
+        float dbp[BN / 4];
+#pragma unroll
+        for (int i = 0; i < BN / 4; ++i) dbp[i] = 0.f;
+        uint32_t stage = 0, phase = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int p = (c_begin + ch) * 32 + j;
+            const bool pv = p < P;
+            const int pp = pv ? p : 0;
+            const int wo = pp % a.Wo, ho = (pp / a.Wo) % a.Ho, n = pp / (a.Wo * a.Ho);
+            // ---- gather: 8 float4 of the activation rows, BN/16 float4 of dy
+            float4 va[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int kd = kd0 + q * 32 + g * 4;
+                va[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pv && kd < Kw) {
+                    const int tap = kd / a.Cin, c = kd - tap * a.Cin;
+                    const int r = tap / a.k, s = tap - r * a.k;
+                    const int hi = ho * a.stride - a.pad + r, wi = wo * a.stride - a.pad + s;
+                    if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+                        float4 xv = *reinterpret_cast<const float4 *>(a.x + (((size_t)n * a.H + hi) * a.W + wi) * a.Cin + c);
+                        if (a.has_in_bn) {
+                            xv.x = fmaf(xv.x, s_scale[c], s_shift[c]);
+                            xv.y = fmaf(xv.y, s_scale[c + 1], s_shift[c + 1]);
+                            xv.z = fmaf(xv.z, s_scale[c + 2], s_shift[c + 2]);
+                            xv.w = fmaf(xv.w, s_scale[c + 3], s_shift[c + 3]);
+                            if (a.in_bn.relu) {
+                                xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f);
+                                xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f);
+                            }
+                        }
+                        va[g] = xv;
+                    }
+                }
+            }
+            float4 vb[BN / 16];
+#pragma unroll
+            for (int g = 0; g < BN / 16; ++g) {
+                vb[g] = pv ? *reinterpret_cast<const float4 *>(a.dy + (size_t)p * a.Cout + o0 + q * (BN / 4) + g * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                dbp[g * 4] += vb[g].x; dbp[g * 4 + 1] += vb[g].y; dbp[g * 4 + 2] += vb[g].z; dbp[g * 4 + 3] += vb[g].w;
+            }
+            mbar_wait(bar(NSTAGE + stage), phase ^ 1);
+            unsigned char *sA = smem + stage * L::STAGE_BYTES;
+            unsigned char *sB = sA + L::A_BYTES;
+            // element (row, col j): row block (row>>3)*1024 + (row&7)*128, 16B chunk (j>>2)^(row&7), + (j&3)*4
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float e[4] = {va[g].x, va[g].y, va[g].z, va[g].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int row = q * 32 + g * 4 + t;
+                    const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((j >> 2) ^ (row & 7)) << 4) + ((j & 3) << 2);
+                    const uint32_t h = to_tf32(e[t]);
+                    *reinterpret_cast<uint32_t *>(sA + off) = h;
+                    if (PASSES > 1) *reinterpret_cast<uint32_t *>(sA + TM * 128 + off) = to_tf32(e[t] - __uint_as_float(h));
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < BN / 16; ++g) {
+                const float e[4] = {vb[g].x, vb[g].y, vb[g].z, vb[g].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int row = q * (BN / 4) + g * 4 + t;
+                    const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((j >> 2) ^ (row & 7)) << 4) + ((j & 3) << 2);
+                    const uint32_t h = to_tf32(e[t]);
+                    *reinterpret_cast<uint32_t *>(sB + off) = h;
+                    if (PASSES > 1) *reinterpret_cast<uint32_t *>(sB + BN * 128 + off) = to_tf32(e[t] - __uint_as_float(h));
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(bar(stage));
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        if (a.db != nullptr && mt == 0) {
+#pragma unroll
+            for (int i = 0; i < BN / 4; ++i) {
+                float t = warp_sum(dbp[i]);
+                if (j == 0) atomicAdd(&a.db[o0 + q * (BN / 4) + i], t);
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0 && nchunks > 0) {
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            uint32_t stage = 0, phase = 0;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                mbar_wait(bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = sbase + stage * L::STAGE_BYTES;
+                const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < KC / 8; ++ks) {
+                    const uint64_t ah = make_desc(sa + ks * 32), bh = make_desc(sb + ks * 32);
+                    const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
+                    if (PASSES > 1) {
+                        const uint64_t al = make_desc(sa + TM * 128 + ks * 32), bl = make_desc(sb + BN * 128 + ks * 32);
+                        mma_tf32(tmem_base, ah, bl, IDESC, first);
+                        mma_tf32(tmem_base, al, bh, IDESC, 1u);
+                        mma_tf32(tmem_base, ah, bh, IDESC, 1u);
+                    } else {
+                        mma_tf32(tmem_base, ah, bh, IDESC, first);
+                    }
+                }
+                mma_commit(bar(NSTAGE + stage));
+                if (ch == nchunks - 1) mma_commit(bar(2 * NSTAGE));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (nchunks > 0) {
+        // epilogue: row = (tap, c) index, columns = output channels
+        const int ew = warp - 4;
+        const int kd = kd0 + ew * 32 + lane;
+        mbar_wait(bar(2 * NSTAGE), 0);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < BN; cb += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + cb, v);
+            if (kd < Kw) {
+                float *dst = a.dw + (size_t)kd * a.Cout + o0 + cb;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) atomicAdd(dst + t, v[t]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
+    }
+}
+
+template <int BN, int PASSES>
+int launch_wgrad_tc(WGTArgs &a, cudaStream_t st) {
+    using L = SmemLayout<BN, PASSES>;
+    static bool done = false;
+    if (!done) {
+        if (cudaFuncSetAttribute(k_wgrad_tc<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+            return -1;
+        done = true;
+    }
+    const int Kw = a.k * a.k * a.Cin;
+    a.mtiles = (Kw + TM - 1) / TM;
+    a.ntiles = a.Cout / BN;
+    const int tiles = a.mtiles * a.ntiles;
+    const int P = a.N * a.Ho * a.Wo;
+    const int total_chunks = (P + 31) / 32;
+    int splits = (148 * 2) / tiles; if (splits < 1) splits = 1;
+    if (splits > total_chunks) splits = total_chunks;
+    a.chunks_per_split = (total_chunks + splits - 1) / splits;
+    a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+    k_wgrad_tc<BN, PASSES><<<tiles * a.splits, NTHREADS, L::TOTAL, st>>>(a);
+    return 0;
+}
+
 // ---- weight packing: KC fp32 weights -> per-(n-tile, k-chunk) shared-memory images (hi/lo, swizzled)
 struct PackItem {
     const float *w; float *img_fwd; float *img_dgrad;
@@ -520,6 +737,27 @@ int dpp_conv2d_dgrad_tc(const dpp_conv_desc *d, const float *dy, float *dx, int 
     a.accumulate = accumulate;
     if (mask_bn) { a.mask_bn = *mask_bn; a.has_mask = 1; a.x_pre = x_pre; a.dz_stats = dz_stats; }
     if (dispatch_tc(a, d->precision == 1 ? 2 : 1, S(stream)) != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
+    DPP_LAUNCH_CHECK();
+    return DPP_OK;
+}
+
+int dpp_conv2d_wgrad_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
+                        float *db, void *stream) {
+    if (!tc_supported(d, d->Cout)) return DPP_ENOTSUP;
+    WGTArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.dy = dy; a.dw = dw; a.db = db;
+    a.N = d->N; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout;
+    a.k = d->k; a.stride = d->stride; a.pad = d->pad; a.Ho = d->Ho; a.Wo = d->Wo;
+    if (in_bn) { a.in_bn = *in_bn; a.has_in_bn = 1; }
+    const int bn = d->Cout > 128 ? 128 : d->Cout;
+    const bool p3 = d->precision == 1;
+    int rc = -1;
+    if (bn == 16) rc = p3 ? launch_wgrad_tc<16, 2>(a, S(stream)) : launch_wgrad_tc<16, 1>(a, S(stream));
+    else if (bn == 32) rc = p3 ? launch_wgrad_tc<32, 2>(a, S(stream)) : launch_wgrad_tc<32, 1>(a, S(stream));
+    else if (bn == 64) rc = p3 ? launch_wgrad_tc<64, 2>(a, S(stream)) : launch_wgrad_tc<64, 1>(a, S(stream));
+    else if (bn == 128) rc = p3 ? launch_wgrad_tc<128, 2>(a, S(stream)) : launch_wgrad_tc<128, 1>(a, S(stream));
+    if (rc != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }

@@ -105,3 +105,24 @@ def test_dgrad_tc_vs_simt(shape, precision, tol):
     print(shape, precision, "dgrad rel err", err)
     assert err < tol
     assert np.allclose(s1, s0, rtol=max(tol * 20, 1e-4), atol=np.abs(s0).max() * tol * 10)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("precision,tol", [(1, 2e-5), (2, 4e-3)])
+def test_wgrad_tc_vs_simt(shape, precision, tol):
+    N, H, Cin, Cout, k, stride = shape
+    outs = []
+    for prec in (0, precision):
+        d, x, w, bias, bn, Ho, keep = _setup(N, H, Cin, Cout, k, stride, prec)
+        g = torch.Generator(device='cuda').manual_seed(11)
+        dy = torch.randn(N, Ho, Ho, Cout, device='cuda', generator=g)
+        dw = torch.zeros(k * k * Cin, Cout, device='cuda')
+        db = torch.zeros(Cout, device='cuda')
+        lib.dpp_conv2d_wgrad(C.byref(d), P(x), C.byref(bn), P(dy), P(dw), P(db), None)
+        torch.cuda.synchronize()
+        outs.append((dw.cpu().numpy(), db.cpu().numpy()))
+    (w0, b0), (w1, b1) = outs
+    err = np.abs(w1 - w0).max() / np.abs(w0).max()
+    print(shape, precision, "wgrad rel err", err)
+    assert err < tol
+    assert np.allclose(b1, b0, rtol=1e-4, atol=1e-4 * np.abs(b0).max())

@@ -62,11 +62,12 @@ def test_forward_deterministic_matches_oracle():
     assert r < 1e-4
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_train_step_matches_oracle(use_graph):
+@pytest.mark.parametrize("use_graph,precision", [(False, 0), (True, 0), (True, 1)])
+def test_train_step_matches_oracle(use_graph, precision):
+    """precision 0 = fp32 SIMT kernels, 1 = 3xTF32 tcgen05 kernels (conv fwd/dgrad/wgrad)"""
     from oracle import nets as O
     B, D = 4, 30
-    net, onet, eng = _build(0, B, 1, D)
+    net, onet, eng = _build(0, B, 1, D, precision=precision)
     x, y = _data(B, D)
     adam = O.Adam(onet.params)
     lr = 1e-3
@@ -103,6 +104,19 @@ def test_train_step_matches_oracle(use_graph):
             assert _rel(l.params_nontrained[0].get_value(), ol.nontrained[0].numpy()) < 1e-3 or \
                 np.abs(ol.nontrained[0].numpy()).max() < 1e-3
             assert _rel(l.params_nontrained[1].get_value(), ol.nontrained[1].numpy()) < 1e-4
+
+
+def test_forward_tc_3xtf32_matches_oracle():
+    B, D = 4, 30
+    net, onet, eng = _build(0, B, 1, D, precision=1)
+    x, y = _data(B, D)
+    eng.set_input_nchw(x)
+    out = eng.forward_device(deterministic=False).cpu().numpy()
+    with torch.no_grad():
+        oout, _ = onet.forward(torch.from_numpy(x), deterministic=False)
+    r = _rel(out, oout.numpy())
+    print("forward(train, 3xTF32 tcgen05) rel err", r)
+    assert r < 1e-4
 
 
 def test_type1_with_pca_tail_forward():
