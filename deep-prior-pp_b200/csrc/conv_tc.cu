@@ -28,7 +28,7 @@ namespace {
 
 constexpr int TM = 128;          // pixels per tile (TMEM lanes)
 constexpr int KC = 32;           // floats of K per stage: 128-byte rows
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 3;           // stages of the wgrad kernel (k_conv_tc uses SmemLayout::NS)
 constexpr int NTHREADS = 288;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,22 +121,38 @@ struct SmemLayout {
     static constexpr int A_BYTES = PASSES * TM * 128;
     static constexpr int B_BYTES = PASSES * BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = NSTAGE * STAGE_BYTES;
-    static constexpr int SCR_OFF = BAR_OFF + 256;
     static constexpr int SCR_BYTES = 4 * 32 * 33 * 4 + 2 * 256 * 4 + 4 * 128 * 4;   // transpose tiles + BN coefficients
+    static constexpr int NS = (4 * STAGE_BYTES + 256 + SCR_BYTES + 1024 <= 225 * 1024) ? 4 : 3;   // pipeline stages
+    static constexpr int BAR_OFF = NS * STAGE_BYTES;
+    static constexpr int SCR_OFF = BAR_OFF + 256;
     static constexpr int TOTAL = SCR_OFF + SCR_BYTES + 1024;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// pixel-row cursor of a producer thread: walks (tile, k-chunk) in launch order
+struct RowCursor {
+    int tile, kc;                 // current tile (global index) and k-chunk
+    int ho, wo; bool rvalid;      // this thread's pixel of the tile
+    const float *img;
 };
 
 template <int BN, int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_conv_tc(TCArgs a) {
     using L = SmemLayout<BN, PASSES>;
+    constexpr int NS = L::NS;
+    constexpr int D = NS - 1;                       // cp.async prefetch distance (chunks in flight)
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::BAR_OFF);
-    // bar index: full[s] = s, empty[s] = NSTAGE + s, tfull[a] = 2*NSTAGE + a, tempty[a] = 2*NSTAGE + 2 + a
+    // bar index: full[s] = s, empty[s] = NS + s, tfull[a] = 2*NS + a, tempty[a] = 2*NS + 2 + a
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
     float *scr = reinterpret_cast<float *>(smem + L::SCR_OFF);
@@ -146,7 +162,6 @@ k_conv_tc(TCArgs a) {
     float *s_msh = s_msc + 128;                  // [BN] mask-BN shift
     float *s_mmean = s_msh + 128;                // [BN]
     float *s_mistd = s_mmean + 128;              // [BN]
-    (void)bars;
 
     const int M = a.N * a.Hg * a.Wg;
     const int mtiles = (M + TM - 1) / TM;
@@ -157,8 +172,8 @@ k_conv_tc(TCArgs a) {
     constexpr uint32_t TCOLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(s), 129); mbar_init(bar(NSTAGE + s), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NSTAGE + i), 1); mbar_init(bar(2 * NSTAGE + 2 + i), 128); }
+        for (int s = 0; s < NS; ++s) { mbar_init(bar(s), 129); mbar_init(bar(NS + s), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NS + i), 1); mbar_init(bar(2 * NS + 2 + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -180,85 +195,111 @@ k_conv_tc(TCArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
     if (warp < 4) {
         // =========================== producers ===========================
-        const int row = tid;                       // 0..127
+        // cp.async (LDGSTS, zero-fill for padding) lands the raw 128-byte row of chunk it+D in the
+        // 'hi' tile while chunk it is transformed in place (BN+ReLU, TF32 hi/lo split) by the same
+        // thread: no register staging, D chunks of loads in flight per thread.
+        const int row = tid;
         const int Kreal = a.k * a.k * a.Cin;
-        uint32_t stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int mt = tile / ntiles, nt = tile % ntiles;
-            const int m = mt * TM + row;
-            const bool rvalid = m < M;
-            const int mm = rvalid ? m : 0;
-            const int wo = mm % a.Wg, ho = (mm / a.Wg) % a.Hg, n = mm / (a.Wg * a.Hg);
-            const float *img = a.in + (size_t)n * a.Hin * a.Win * a.Cin;
-            for (int kc = 0; kc < a.kchunks; ++kc) {
-                mbar_wait(bar(NSTAGE + stage), phase ^ 1);
-                unsigned char *sA = smem + stage * L::STAGE_BYTES;
-                if (tid == 0) {
-                    const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
-                    mbar_expect_tx(bar(stage), L::B_BYTES);
-                    bulk_g2s(sbase + stage * L::STAGE_BYTES + L::A_BYTES, src, L::B_BYTES, bar(stage));
-                }
-                // gather 8 x 16-byte sub-chunks of this pixel row
-                float4 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k0 = kc * KC + j * 4;
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rvalid && k0 < Kreal) {
-                        const int tap = k0 / a.Cin, c = k0 - tap * a.Cin;
-                        const int r = tap / a.k, s = tap - r * a.k;
-                        const int hi = ho * a.in_stride - a.pad + r, wi = wo * a.in_stride - a.pad + s;
-                        if (hi >= 0 && hi < a.Hin && wi >= 0 && wi < a.Win) {
-                            float4 x = *reinterpret_cast<const float4 *>(img + ((size_t)hi * a.Win + wi) * a.Cin + c);
-                            if (a.has_in_bn) {
-                                x.x = fmaf(x.x, s_scale[c], s_shift[c]);
-                                x.y = fmaf(x.y, s_scale[c + 1], s_shift[c + 1]);
-                                x.z = fmaf(x.z, s_scale[c + 2], s_shift[c + 2]);
-                                x.w = fmaf(x.w, s_scale[c + 3], s_shift[c + 3]);
-                                if (a.in_bn.relu) {
-                                    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
-                                    x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-                                }
-                            }
-                            v[j] = x;
-                        }
-                    }
-                }
-                // split + store, K-major SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
-                unsigned char *rowp = sA + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int pj = (j ^ (row & 7)) * 16;
-                    uint4 h;
-                    h.x = to_tf32(v[j].x); h.y = to_tf32(v[j].y); h.z = to_tf32(v[j].z); h.w = to_tf32(v[j].w);
-                    *reinterpret_cast<uint4 *>(rowp + pj) = h;
-                    if (PASSES > 1) {
-                        uint4 l;
-                        l.x = to_tf32(v[j].x - __uint_as_float(h.x));
-                        l.y = to_tf32(v[j].y - __uint_as_float(h.y));
-                        l.z = to_tf32(v[j].z - __uint_as_float(h.z));
-                        l.w = to_tf32(v[j].w - __uint_as_float(h.w));
-                        *reinterpret_cast<uint4 *>(rowp + TM * 128 + pj) = l;
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(bar(stage));
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        const int T = my_tiles * a.kchunks;
+        const uint32_t rowoff = (row >> 3) * 1024 + (row & 7) * 128;
+
+        auto set_tile = [&](RowCursor &c, int tile) {
+            c.tile = tile;
+            const int m = (tile / ntiles) * TM + row;
+            c.rvalid = m < M;
+            const int mm = c.rvalid ? m : 0;
+            c.wo = mm % a.Wg; c.ho = (mm / a.Wg) % a.Hg;
+            c.img = a.in + (size_t)(mm / (a.Wg * a.Hg)) * a.Hin * a.Win * a.Cin;
+        };
+        // source of 16-byte piece j of chunk kc for this row (nullptr = zero / padding)
+        auto piece_src = [&](const RowCursor &c, int kc, int j, int &chan) -> const float * {
+            const int k0 = kc * KC + j * 4;
+            if (!c.rvalid || k0 >= Kreal) return nullptr;
+            const int tap = k0 / a.Cin;
+            chan = k0 - tap * a.Cin;
+            const int r = tap / a.k, s = tap - r * a.k;
+            const int hi = c.ho * a.in_stride - a.pad + r, wi = c.wo * a.in_stride - a.pad + s;
+            if (hi < 0 || hi >= a.Hin || wi < 0 || wi >= a.Win) return nullptr;
+            return c.img + ((size_t)hi * a.Win + wi) * a.Cin + chan;
+        };
+        auto issue = [&](RowCursor &c, int it) {
+            const uint32_t stage = it % NS, phase = (it / NS) & 1;
+            mbar_wait(bar(NS + stage), phase ^ 1);
+            const uint32_t sA = sbase + stage * L::STAGE_BYTES;
+            if (tid == 0) {
+                const int nt = c.tile % ntiles;
+                const float *src = a.wimg + ((size_t)(nt * a.kchunks + c.kc)) * (PASSES * BN * 32);
+                mbar_expect_tx(bar(stage), L::B_BYTES);
+                bulk_g2s(sA + L::A_BYTES, src, L::B_BYTES, bar(stage));
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int chan;
+                const float *src = piece_src(c, c.kc, j, chan);
+                cp_async16(sA + rowoff + ((j ^ (row & 7)) << 4), src ? src : a.in, src ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (++c.kc == a.kchunks) { c.kc = 0; set_tile(c, c.tile + gridDim.x); }
+        };
+        auto process = [&](RowCursor &c, int it) {
+            const uint32_t stage = it % NS;
+            unsigned char *rowp = smem + stage * L::STAGE_BYTES + rowoff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int pj = (j ^ (row & 7)) << 4;
+                int chan = 0;
+                const bool valid = piece_src(c, c.kc, j, chan) != nullptr;
+                float4 x = *reinterpret_cast<const float4 *>(rowp + pj);
+                if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                else if (a.has_in_bn) {
+                    x.x = fmaf(x.x, s_scale[chan], s_shift[chan]);
+                    x.y = fmaf(x.y, s_scale[chan + 1], s_shift[chan + 1]);
+                    x.z = fmaf(x.z, s_scale[chan + 2], s_shift[chan + 2]);
+                    x.w = fmaf(x.w, s_scale[chan + 3], s_shift[chan + 3]);
+                    if (a.in_bn.relu) {
+                        x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+                    }
+                }
+                uint4 h;
+                h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+                *reinterpret_cast<uint4 *>(rowp + pj) = h;
+                if (PASSES > 1) {
+                    uint4 l;
+                    l.x = to_tf32(x.x - __uint_as_float(h.x)); l.y = to_tf32(x.y - __uint_as_float(h.y));
+                    l.z = to_tf32(x.z - __uint_as_float(h.z)); l.w = to_tf32(x.w - __uint_as_float(h.w));
+                    *reinterpret_cast<uint4 *>(rowp + TM * 128 + pj) = l;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(bar(stage));
+            if (++c.kc == a.kchunks) { c.kc = 0; set_tile(c, c.tile + gridDim.x); }
+        };
+        RowCursor ci, cp;
+        ci.kc = cp.kc = 0;
+        set_tile(ci, blockIdx.x);
+        set_tile(cp, blockIdx.x);
+        for (int i = 0; i < D && i < T; ++i) issue(ci, i);
+        for (int it = 0; it < T; ++it) {
+            if (it + D < T) { issue(ci, it + D); cp_async_wait<D>(); }
+            else cp_async_wait<0>();
+            process(cp, it);
         }
     } else if (warp == 8) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            uint32_t stage = 0, phase = 0, acc = 0, aphase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                mbar_wait(bar(2 * NSTAGE + 2 + acc), aphase ^ 1);
+            uint32_t acc = 0, aphase = 0;
+            int it = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                mbar_wait(bar(2 * NS + 2 + acc), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kc = 0; kc < a.kchunks; ++kc) {
+                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                    const uint32_t stage = it % NS, phase = (it / NS) & 1;
                     mbar_wait(bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = sbase + stage * L::STAGE_BYTES;
@@ -276,9 +317,8 @@ k_conv_tc(TCArgs a) {
                             mma_tf32(d_tmem, ah, bh, IDESC, first);
                         }
                     }
-                    mma_commit(bar(NSTAGE + stage));               // frees the smem stage when the MMAs retire
-                    if (kc == a.kchunks - 1) mma_commit(bar(2 * NSTAGE + acc));   // accumulator ready
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    mma_commit(bar(NS + stage));                              // frees the smem stage when the MMAs retire
+                    if (kc == a.kchunks - 1) mma_commit(bar(2 * NS + acc));   // accumulator ready
                 }
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
             }
@@ -292,8 +332,12 @@ k_conv_tc(TCArgs a) {
 #pragma unroll
         for (int i = 0; i < BN / 16; ++i) stacc[i] = 0.0;
         const bool want_stats = (a.out_stats != nullptr) || (a.dz_stats != nullptr);
+        // side operand read by the epilogue: residual (forward) or x_pre (dgrad mask)
+        const float *side = a.wmode == 0 ? a.residual : (a.has_mask ? a.x_pre : nullptr);
+        constexpr int HB = BN > 32 ? 32 : BN;        // columns per prefetch batch
         uint32_t acc = 0, aphase = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = blockIdx.x + t * gridDim.x;
             const int mt = tile / ntiles, nt = tile % ntiles;
             const int n0 = nt * BN;
             const int m = mt * TM + row;
@@ -301,77 +345,77 @@ k_conv_tc(TCArgs a) {
             const int mm = rvalid ? m : 0;
             const int wo = mm % a.Wg, ho = (mm / a.Wg) % a.Hg, n = mm / (a.Wg * a.Hg);
             const size_t ob = (((size_t)n * a.Hout + ho * a.out_stride) * a.Wout + wo * a.out_stride) * a.Cn + n0;
-            mbar_wait(bar(2 * NSTAGE + acc), aphase);
+            // prefetch the first batch of the side operand before waiting for the accumulator
+            float4 sd[HB / 4], ex[HB / 4];
+            auto prefetch = [&](int c0) {
+#pragma unroll
+                for (int q = 0; q < HB / 4; ++q) {
+                    sd[q] = (side && rvalid) ? *reinterpret_cast<const float4 *>(side + ob + c0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ex[q] = (a.wmode == 1 && a.accumulate && rvalid) ? *reinterpret_cast<const float4 *>(a.out + ob + c0 + q * 4)
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            prefetch(0);
+            mbar_wait(bar(2 * NS + acc), aphase);
             tc_fence_after();
 #pragma unroll
-            for (int cb = 0; cb < BN; cb += 16) {
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + cb, v);
-                float s0[16], s1[16];
-                if (a.wmode == 0) {
+            for (int c0 = 0; c0 < BN; c0 += HB) {
+                float sdv[HB], exv[HB];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        if (a.bias) {
-                            float4 b = *reinterpret_cast<const float4 *>(a.bias + n0 + cb + j);
-                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
-                        if (a.residual && rvalid) {
-                            float4 r4 = *reinterpret_cast<const float4 *>(a.residual + ob + cb + j);
-                            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-                        }
-                    }
+                for (int q = 0; q < HB / 4; ++q) {
+                    sdv[q * 4] = sd[q].x; sdv[q * 4 + 1] = sd[q].y; sdv[q * 4 + 2] = sd[q].z; sdv[q * 4 + 3] = sd[q].w;
+                    exv[q * 4] = ex[q].x; exv[q * 4 + 1] = ex[q].y; exv[q * 4 + 2] = ex[q].z; exv[q * 4 + 3] = ex[q].w;
+                }
+                if (c0 + HB < BN) prefetch(c0 + HB);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { s0[j] = rvalid ? v[j] : 0.f; s1[j] = rvalid ? v[j] * v[j] : 0.f; }
-                } else {
+                for (int cb = c0; cb < c0 + HB; cb += 16) {
+                    float v[16], s0[16], s1[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + cb, v);
+                    if (a.wmode == 0) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        if (a.accumulate && rvalid) {
-                            float4 e = *reinterpret_cast<const float4 *>(a.out + ob + cb + j);
-                            v[j] += e.x; v[j + 1] += e.y; v[j + 2] += e.z; v[j + 3] += e.w;
-                        }
-                    }
-                    if (a.has_mask) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 xp = rvalid ? *reinterpret_cast<const float4 *>(a.x_pre + ob + cb + j)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                            float xr[4] = {xp.x, xp.y, xp.z, xp.w};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int cl = cb + j + q;
-                                const float pre = fmaf(xr[q], s_msc[cl], s_msh[cl]);
-                                const float dz = (pre > 0.f && rvalid) ? v[j + q] : 0.f;
-                                v[j + q] = dz;
-                                s0[j + q] = dz;
-                                s1[j + q] = dz * (xr[q] - s_mmean[cl]) * s_mistd[cl];
-                            }
+                        for (int j = 0; j < 16; ++j) {
+                            if (a.bias) v[j] += a.bias[n0 + cb + j];
+                            v[j] += sdv[cb - c0 + j];
+                            s0[j] = rvalid ? v[j] : 0.f;
+                            s1[j] = rvalid ? v[j] * v[j] : 0.f;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+                        for (int j = 0; j < 16; ++j) {
+                            v[j] += exv[cb - c0 + j];
+                            if (a.has_mask) {
+                                const int cl = cb + j;
+                                const float xr = sdv[cb - c0 + j];
+                                const float pre = fmaf(xr, s_msc[cl], s_msh[cl]);
+                                const float dz = (pre > 0.f && rvalid) ? v[j] : 0.f;
+                                v[j] = dz;
+                                s0[j] = dz;
+                                s1[j] = dz * (xr - s_mmean[cl]) * s_mistd[cl];
+                            } else { s0[j] = 0.f; s1[j] = 0.f; }
+                        }
                     }
-                }
-                if (rvalid) {
+                    if (rvalid) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4 *>(a.out + ob + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                if (want_stats) {
-                    // column sums over this warp's 32 rows: transpose through shared memory, 16 columns at a time
-                    // lanes 0-15 own column (cb + lane) sums s0; lanes 16-31 own s1
-                    __syncwarp();
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4 *>(a.out + ob + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (want_stats) {
+                        // column sums over this warp's 32 rows through a 32x33 shared tile: lanes 0-15 end up
+                        // with sum0 of column cb+lane, lanes 16-31 with sum1 of column cb+lane-16
+                        __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { tr[lane * 33 + j] = s0[j]; tr[lane * 33 + 16 + j] = s1[j]; }
-                    __syncwarp();
-                    float t = 0.f;
+                        for (int j = 0; j < 16; ++j) { tr[lane * 33 + j] = s0[j]; tr[lane * 33 + 16 + j] = s1[j]; }
+                        __syncwarp();
+                        float tsum = 0.f;
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) t += tr[r * 33 + lane];
-                    stacc[cb / 16] += (double)t;   // lane<16: sum s0 of column cb+lane; lane>=16: sum s1 of column cb+lane-16
-                    __syncwarp();
+                        for (int r = 0; r < 32; ++r) tsum += tr[r * 33 + lane];
+                        stacc[cb / 16] += (double)tsum;
+                        __syncwarp();
+                    }
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar(2 * NSTAGE + 2 + acc));
+            mbar_arrive(bar(2 * NS + 2 + acc));
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         if (want_stats) {
@@ -405,18 +449,34 @@ struct WGTArgs {
     int mtiles, ntiles, splits, chunks_per_split;   // pixel chunks of 32
 };
 
+// wgrad shared-memory plan: 2 MMA tile stages + RD private raw slots per producer thread
+template <int BN, int PASSES>
+struct WgSmem {
+    static constexpr int A_BYTES = PASSES * TM * 128;
+    static constexpr int B_BYTES = PASSES * BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NST = 2;
+    static constexpr int SLOT = (8 + BN / 16) * 16 + 16;       // bytes per thread per raw stage (+16: bank spread)
+    static constexpr int RAW_BYTES = 128 * SLOT;
+    static constexpr int RD = (NST * STAGE_BYTES + 3 * RAW_BYTES + 4096 <= 225 * 1024) ? 3 : 2;
+    static constexpr int RAW_OFF = NST * STAGE_BYTES;
+    static constexpr int BAR_OFF = RAW_OFF + RD * RAW_BYTES;
+    static constexpr int COEF_OFF = BAR_OFF + 256;
+    static constexpr int TOTAL = COEF_OFF + 2 * 256 * 4 + 1024;
+};
+
 template <int BN, int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_wgrad_tc(WGTArgs a) {
-    using L = SmemLayout<BN, PASSES>;
+    using L = WgSmem<BN, PASSES>;
+    constexpr int NST = L::NST, RD = L::RD, D = RD - 1;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
+    auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };      // full[s]=s, empty[s]=NST+s, done=2*NST
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
-    float *scr = reinterpret_cast<float *>(smem + L::SCR_OFF);
-    float *s_scale = scr + 4 * 32 * 33;
+    float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);
     float *s_shift = s_scale + 256;
     constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
 
@@ -431,8 +491,8 @@ k_wgrad_tc(WGTArgs a) {
     const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NSTAGE + s), 1); }
-        mbar_init(bar(2 * NSTAGE), 1);
+        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NST + s), 1); }
+        mbar_init(bar(2 * NST), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -448,57 +508,64 @@ k_wgrad_tc(WGTArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // producers: thread = (pixel j of the chunk, row quarter q)
+        // producers: thread = (pixel j of the chunk, row quarter q).  cp.async lands the raw activation /
+        // dy pieces of chunk ch+D in this thread's private slot while chunk ch is transposed into the tiles.
         const int j = tid & 31, q = tid >> 5;
         float dbp[BN / 4];
 #pragma unroll
         for (int i = 0; i < BN / 4; ++i) dbp[i] = 0.f;
-        uint32_t stage = 0, phase = 0;
-        for (int ch = 0; ch < nchunks; ++ch) {
+        // source of activation piece g (4 channels of rows kd0 + q*32 + g*4 ..) for pixel p; chan out
+        auto a_src = [&](int p, int g, int &chan) -> const float * {
+            const int kd = kd0 + q * 32 + g * 4;
+            if (p >= P || kd >= Kw) return nullptr;
+            const int wo = p % a.Wo, ho = (p / a.Wo) % a.Ho, n = p / (a.Wo * a.Ho);
+            const int tap = kd / a.Cin;
+            chan = kd - tap * a.Cin;
+            const int r = tap / a.k, s = tap - r * a.k;
+            const int hi = ho * a.stride - a.pad + r, wi = wo * a.stride - a.pad + s;
+            if (hi < 0 || hi >= a.H || wi < 0 || wi >= a.W) return nullptr;
+            return a.x + (((size_t)n * a.H + hi) * a.W + wi) * a.Cin + chan;
+        };
+        auto issue = [&](int ch) {
             const int p = (c_begin + ch) * 32 + j;
-            const bool pv = p < P;
-            const int pp = pv ? p : 0;
-            const int wo = pp % a.Wo, ho = (pp / a.Wo) % a.Ho, n = pp / (a.Wo * a.Ho);
-            // ---- gather: 8 float4 of the activation rows, BN/16 float4 of dy
-            float4 va[8];
+            const uint32_t slot = sbase + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const int kd = kd0 + q * 32 + g * 4;
-                va[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pv && kd < Kw) {
-                    const int tap = kd / a.Cin, c = kd - tap * a.Cin;
-                    const int r = tap / a.k, s = tap - r * a.k;
-                    const int hi = ho * a.stride - a.pad + r, wi = wo * a.stride - a.pad + s;
-                    if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
-                        float4 xv = *reinterpret_cast<const float4 *>(a.x + (((size_t)n * a.H + hi) * a.W + wi) * a.Cin + c);
-                        if (a.has_in_bn) {
-                            xv.x = fmaf(xv.x, s_scale[c], s_shift[c]);
-                            xv.y = fmaf(xv.y, s_scale[c + 1], s_shift[c + 1]);
-                            xv.z = fmaf(xv.z, s_scale[c + 2], s_shift[c + 2]);
-                            xv.w = fmaf(xv.w, s_scale[c + 3], s_shift[c + 3]);
-                            if (a.in_bn.relu) {
-                                xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f);
-                                xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f);
-                            }
-                        }
-                        va[g] = xv;
-                    }
-                }
+                int chan;
+                const float *src = a_src(p, g, chan);
+                cp_async16(slot + g * 16, src ? src : a.x, src ? 16u : 0u);
             }
-            float4 vb[BN / 16];
 #pragma unroll
             for (int g = 0; g < BN / 16; ++g) {
-                vb[g] = pv ? *reinterpret_cast<const float4 *>(a.dy + (size_t)p * a.Cout + o0 + q * (BN / 4) + g * 4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                dbp[g * 4] += vb[g].x; dbp[g * 4 + 1] += vb[g].y; dbp[g * 4 + 2] += vb[g].z; dbp[g * 4 + 3] += vb[g].w;
+                const bool ok = p < P;
+                cp_async16(slot + (8 + g) * 16, ok ? a.dy + (size_t)p * a.Cout + o0 + q * (BN / 4) + g * 4 : a.dy, ok ? 16u : 0u);
             }
-            mbar_wait(bar(NSTAGE + stage), phase ^ 1);
+            cp_async_commit();
+        };
+        auto process = [&](int ch) {
+            const int p = (c_begin + ch) * 32 + j;
+            const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
+            const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
+            mbar_wait(bar(NST + stage), phase ^ 1);
             unsigned char *sA = smem + stage * L::STAGE_BYTES;
             unsigned char *sB = sA + L::A_BYTES;
             // element (row, col j): row block (row>>3)*1024 + (row&7)*128, 16B chunk (j>>2)^(row&7), + (j&3)*4
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const float e[4] = {va[g].x, va[g].y, va[g].z, va[g].w};
+                int chan = 0;
+                const bool valid = a_src(p, g, chan) != nullptr;
+                float4 xv = *reinterpret_cast<const float4 *>(slot + g * 16);
+                if (!valid) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                else if (a.has_in_bn) {
+                    xv.x = fmaf(xv.x, s_scale[chan], s_shift[chan]);
+                    xv.y = fmaf(xv.y, s_scale[chan + 1], s_shift[chan + 1]);
+                    xv.z = fmaf(xv.z, s_scale[chan + 2], s_shift[chan + 2]);
+                    xv.w = fmaf(xv.w, s_scale[chan + 3], s_shift[chan + 3]);
+                    if (a.in_bn.relu) {
+                        xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f);
+                    }
+                }
+                const float e[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int row = q * 32 + g * 4 + t;
@@ -510,7 +577,9 @@ k_wgrad_tc(WGTArgs a) {
             }
 #pragma unroll
             for (int g = 0; g < BN / 16; ++g) {
-                const float e[4] = {vb[g].x, vb[g].y, vb[g].z, vb[g].w};
+                const float4 bv = *reinterpret_cast<const float4 *>(slot + (8 + g) * 16);
+                const float e[4] = {bv.x, bv.y, bv.z, bv.w};
+                dbp[g * 4] += bv.x; dbp[g * 4 + 1] += bv.y; dbp[g * 4 + 2] += bv.z; dbp[g * 4 + 3] += bv.w;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int row = q * (BN / 4) + g * 4 + t;
@@ -522,7 +591,12 @@ k_wgrad_tc(WGTArgs a) {
             }
             fence_proxy_async();
             mbar_arrive(bar(stage));
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        };
+        for (int i = 0; i < D && i < nchunks; ++i) issue(i);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            if (ch + D < nchunks) { issue(ch + D); cp_async_wait<D>(); }
+            else cp_async_wait<0>();
+            process(ch);
         }
         if (a.db != nullptr && mt == 0) {
 #pragma unroll
@@ -534,8 +608,8 @@ k_wgrad_tc(WGTArgs a) {
     } else if (warp == 8) {
         if (lane == 0 && nchunks > 0) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            uint32_t stage = 0, phase = 0;
             for (int ch = 0; ch < nchunks; ++ch) {
+                const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
                 mbar_wait(bar(stage), phase);
                 tc_fence_after();
                 const uint32_t sa = sbase + stage * L::STAGE_BYTES;
@@ -553,16 +627,15 @@ k_wgrad_tc(WGTArgs a) {
                         mma_tf32(tmem_base, ah, bh, IDESC, first);
                     }
                 }
-                mma_commit(bar(NSTAGE + stage));
-                if (ch == nchunks - 1) mma_commit(bar(2 * NSTAGE));
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                mma_commit(bar(NST + stage));
+                if (ch == nchunks - 1) mma_commit(bar(2 * NST));
             }
         }
     } else if (nchunks > 0) {
         // epilogue: row = (tap, c) index, columns = output channels
         const int ew = warp - 4;
         const int kd = kd0 + ew * 32 + lane;
-        mbar_wait(bar(2 * NSTAGE), 0);
+        mbar_wait(bar(2 * NST), 0);
         tc_fence_after();
 #pragma unroll
         for (int cb = 0; cb < BN; cb += 16) {
@@ -585,7 +658,7 @@ k_wgrad_tc(WGTArgs a) {
 
 template <int BN, int PASSES>
 int launch_wgrad_tc(WGTArgs &a, cudaStream_t st) {
-    using L = SmemLayout<BN, PASSES>;
+    using L = WgSmem<BN, PASSES>;
     static bool done = false;
     if (!done) {
         if (cudaFuncSetAttribute(k_wgrad_tc<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)

@@ -6,6 +6,9 @@
 
 using namespace dpp;
 
+int dpp_gemm_tc(const float *A, const float *B, float *C, int M, int N, int K, int64_t lda, int64_t ldb, int a_trans,
+                int b_trans, int precision, void *stream);
+
 namespace {
 
 // C[M][N] (+)= sum_k A(m,k) B(k,n);  A(m,k) = A[m*am + k*ak], B(k,n) = B[k*bk + n*bn].
@@ -75,7 +78,12 @@ k_gemm(GArgs g) {
 }
 
 int run_gemm(const float *A, const float *B, float *C, int M, int N, int K, int64_t am, int64_t ak, int64_t bk,
-             int64_t bn, cudaStream_t st) {
+             int64_t bn, cudaStream_t st, int precision = 0) {
+    if (precision != 0) {
+        const int a_trans = (ak != 1), b_trans = (bn == 1);
+        int rc = dpp_gemm_tc(A, B, C, M, N, K, a_trans ? ak : am, b_trans ? bk : bn, a_trans, b_trans, precision, st);
+        if (rc != DPP_ENOTSUP) return rc;
+    }
     GArgs g{A, B, C, M, N, K, am, ak, bk, bn, K, 0};
     int tiles = cdiv(M, 64) * cdiv(N, 64);
     int split = 1;
@@ -124,9 +132,8 @@ __global__ void k_fc_bwd_pre(const float *__restrict__ y, const float *__restric
 extern "C" int dpp_fc_fwd(const float *x, const float *w, const float *bias, float *y, int B, int n_in, int n_out,
                           int relu, const float *mask, float scale_out, int precision, void *stream) {
     DPP_CHECK_ARG(x && w && bias && y && B > 0 && n_in > 0 && n_out > 0);
-    (void)precision;
     DPP_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)B * n_out, S(stream)));
-    run_gemm(x, w, y, B, n_out, n_in, n_in, 1, n_out, 1, S(stream));
+    run_gemm(x, w, y, B, n_out, n_in, n_in, 1, n_out, 1, S(stream), precision);
     DPP_LAUNCH_CHECK();
     int64_t total = (int64_t)B * n_out;
     int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
@@ -139,16 +146,15 @@ extern "C" int dpp_fc_bwd(const float *x, const float *w, const float *y, const 
                           float *dx, float *scratch, int B, int n_in, int n_out, int relu, const float *mask,
                           float scale_out, int precision, void *stream) {
     DPP_CHECK_ARG(x && w && y && dy && dw && db && scratch && B > 0);
-    (void)precision;
     k_fc_bwd_pre<<<cdiv(n_out, 128), 128, 0, S(stream)>>>(y, dy, mask, scale_out, relu, scratch, db, B, n_out);
     DPP_LAUNCH_CHECK();
     // dW[n_in][n_out] += x^T dpre : A(m=i,k=b) = x[b*n_in + i]
-    run_gemm(x, scratch, dw, n_in, n_out, B, 1, n_in, n_out, 1, S(stream));
+    run_gemm(x, scratch, dw, n_in, n_out, B, 1, n_in, n_out, 1, S(stream), precision);
     DPP_LAUNCH_CHECK();
     if (dx) {
         DPP_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * n_in, S(stream)));
         // dx[B][n_in] = dpre W^T : B(k=o, n=i) = w[i*n_out + o]
-        run_gemm(scratch, w, dx, B, n_in, n_out, n_out, 1, 1, n_out, S(stream));
+        run_gemm(scratch, w, dx, B, n_in, n_out, n_out, 1, 1, n_out, S(stream), precision);
         DPP_LAUNCH_CHECK();
     }
     return DPP_OK;
