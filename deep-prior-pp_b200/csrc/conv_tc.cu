@@ -121,9 +121,11 @@ struct SmemLayout {
     static constexpr int A_BYTES = PASSES * TM * 128;
     static constexpr int B_BYTES = PASSES * BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SCR_BYTES = 4 * 32 * 33 * 4 + 2 * 256 * 4 + 4 * 128 * 4;   // transpose tiles + BN coefficients
-    static constexpr int NS = (4 * STAGE_BYTES + 256 + SCR_BYTES + 1024 <= 225 * 1024) ? 4 : 3;   // pipeline stages
-    static constexpr int BAR_OFF = NS * STAGE_BYTES;
+    static constexpr int SCR_BYTES = 4 * 32 * 33 * 4 + 2 * 256 * 4 + 5 * 128 * 4;   // transpose tiles + BN coefficients + bias
+    static constexpr int NS = PASSES == 2 ? 2 : 3;          // MMA tile stages
+    static constexpr int RD = 4;                            // raw landing slots (cp.async ring), 16 KB each
+    static constexpr int RAW_OFF = NS * STAGE_BYTES;
+    static constexpr int BAR_OFF = RAW_OFF + RD * TM * 128;
     static constexpr int SCR_OFF = BAR_OFF + 256;
     static constexpr int TOTAL = SCR_OFF + SCR_BYTES + 1024;
 };
@@ -138,6 +140,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // pixel-row cursor of a producer thread: walks (tile, k-chunk) in launch order
 struct RowCursor {
     int tile, kc;                 // current tile (global index) and k-chunk
+    int tap, c0, r, s;            // first tap / channel of the chunk, and the tap's (r, s)
     int ho, wo; bool rvalid;      // this thread's pixel of the tile
     const float *img;
 };
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_conv_tc(TCArgs a) {
     using L = SmemLayout<BN, PASSES>;
     constexpr int NS = L::NS;
-    constexpr int D = NS - 1;                       // cp.async prefetch distance (chunks in flight)
+    constexpr int RD = L::RD, D = RD - 1;           // cp.async prefetch distance (chunks in flight)
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
@@ -162,6 +165,7 @@ k_conv_tc(TCArgs a) {
     float *s_msh = s_msc + 128;                  // [BN] mask-BN shift
     float *s_mmean = s_msh + 128;                // [BN]
     float *s_mistd = s_mmean + 128;              // [BN]
+    float *s_bias = s_mistd + 128;               // [BN] forward bias of this CTA's n-tile
 
     const int M = a.N * a.Hg * a.Wg;
     const int mtiles = (M + TM - 1) / TM;
@@ -183,6 +187,7 @@ k_conv_tc(TCArgs a) {
     }
     if (a.has_in_bn)
         for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
+    for (int c = tid; c < BN; c += NTHREADS) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
     if (a.has_mask)
         for (int c = tid; c < BN; c += NTHREADS) {
             float mean, istd;
@@ -199,13 +204,14 @@ k_conv_tc(TCArgs a) {
 
     if (warp < 4) {
         // =========================== producers ===========================
-        // cp.async (LDGSTS, zero-fill for padding) lands the raw 128-byte row of chunk it+D in the
-        // 'hi' tile while chunk it is transformed in place (BN+ReLU, TF32 hi/lo split) by the same
-        // thread: no register staging, D chunks of loads in flight per thread.
+        // cp.async (LDGSTS, zero-fill for padding) lands the raw 128-byte row of chunk it+D in a private
+        // raw slot (no barrier: rows are thread-private) while chunk it is read back, transformed
+        // (BN+ReLU, TF32 hi/lo split) and written into the MMA stage.  All index arithmetic is incremental
+        // (no divisions in the chunk loop).
         const int row = tid;
-        const int Kreal = a.k * a.k * a.Cin;
         const int T = my_tiles * a.kchunks;
         const uint32_t rowoff = (row >> 3) * 1024 + (row & 7) * 128;
+        const int KK = a.k * a.k;
 
         auto set_tile = [&](RowCursor &c, int tile) {
             c.tile = tile;
@@ -214,46 +220,51 @@ k_conv_tc(TCArgs a) {
             const int mm = c.rvalid ? m : 0;
             c.wo = mm % a.Wg; c.ho = (mm / a.Wg) % a.Hg;
             c.img = a.in + (size_t)(mm / (a.Wg * a.Hg)) * a.Hin * a.Win * a.Cin;
+            c.kc = 0; c.tap = 0; c.c0 = 0; c.r = 0; c.s = 0;
         };
-        // source of 16-byte piece j of chunk kc for this row (nullptr = zero / padding)
-        auto piece_src = [&](const RowCursor &c, int kc, int j, int &chan) -> const float * {
-            const int k0 = kc * KC + j * 4;
-            if (!c.rvalid || k0 >= Kreal) return nullptr;
-            const int tap = k0 / a.Cin;
-            chan = k0 - tap * a.Cin;
-            const int r = tap / a.k, s = tap - r * a.k;
+        auto advance = [&](RowCursor &c) {
+            if (++c.kc == a.kchunks) { set_tile(c, c.tile + gridDim.x); return; }
+            c.c0 += KC;
+            while (c.c0 >= a.Cin) { c.c0 -= a.Cin; ++c.tap; if (++c.s == a.k) { c.s = 0; ++c.r; } }
+        };
+        // source of 16-byte piece j of the cursor's chunk (nullptr = zero / padding); chan = its first channel
+        auto piece_src = [&](const RowCursor &c, int j, int &chan) -> const float * {
+            chan = c.c0 + j * 4;
+            int tap = c.tap, r = c.r, s = c.s;
+            if (chan >= a.Cin) { chan -= a.Cin; ++tap; if (++s == a.k) { s = 0; ++r; } }   // Cin = 16: second tap
+            if (!c.rvalid || tap >= KK) return nullptr;
             const int hi = c.ho * a.in_stride - a.pad + r, wi = c.wo * a.in_stride - a.pad + s;
             if (hi < 0 || hi >= a.Hin || wi < 0 || wi >= a.Win) return nullptr;
             return c.img + ((size_t)hi * a.Win + wi) * a.Cin + chan;
         };
         auto issue = [&](RowCursor &c, int it) {
+            const uint32_t raw = sbase + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int chan;
+                const float *src = piece_src(c, j, chan);
+                cp_async16(raw + ((j ^ (row & 7)) << 4), src ? src : a.in, src ? 16u : 0u);
+            }
+            cp_async_commit();
+            advance(c);
+        };
+        auto process = [&](RowCursor &c, int it) {
             const uint32_t stage = it % NS, phase = (it / NS) & 1;
             mbar_wait(bar(NS + stage), phase ^ 1);
-            const uint32_t sA = sbase + stage * L::STAGE_BYTES;
             if (tid == 0) {
                 const int nt = c.tile % ntiles;
                 const float *src = a.wimg + ((size_t)(nt * a.kchunks + c.kc)) * (PASSES * BN * 32);
                 mbar_expect_tx(bar(stage), L::B_BYTES);
-                bulk_g2s(sA + L::A_BYTES, src, L::B_BYTES, bar(stage));
+                bulk_g2s(sbase + stage * L::STAGE_BYTES + L::A_BYTES, src, L::B_BYTES, bar(stage));
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int chan;
-                const float *src = piece_src(c, c.kc, j, chan);
-                cp_async16(sA + rowoff + ((j ^ (row & 7)) << 4), src ? src : a.in, src ? 16u : 0u);
-            }
-            cp_async_commit();
-            if (++c.kc == a.kchunks) { c.kc = 0; set_tile(c, c.tile + gridDim.x); }
-        };
-        auto process = [&](RowCursor &c, int it) {
-            const uint32_t stage = it % NS;
+            const unsigned char *rawp = smem + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
             unsigned char *rowp = smem + stage * L::STAGE_BYTES + rowoff;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int pj = (j ^ (row & 7)) << 4;
                 int chan = 0;
-                const bool valid = piece_src(c, c.kc, j, chan) != nullptr;
-                float4 x = *reinterpret_cast<const float4 *>(rowp + pj);
+                const bool valid = piece_src(c, j, chan) != nullptr;
+                float4 x = *reinterpret_cast<const float4 *>(rawp + pj);
                 if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 else if (a.has_in_bn) {
                     x.x = fmaf(x.x, s_scale[chan], s_shift[chan]);
@@ -276,10 +287,9 @@ k_conv_tc(TCArgs a) {
             }
             fence_proxy_async();
             mbar_arrive(bar(stage));
-            if (++c.kc == a.kchunks) { c.kc = 0; set_tile(c, c.tile + gridDim.x); }
+            advance(c);
         };
         RowCursor ci, cp;
-        ci.kc = cp.kc = 0;
         set_tile(ci, blockIdx.x);
         set_tile(cp, blockIdx.x);
         for (int i = 0; i < D && i < T; ++i) issue(ci, i);
@@ -374,8 +384,7 @@ k_conv_tc(TCArgs a) {
                     if (a.wmode == 0) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (a.bias) v[j] += a.bias[n0 + cb + j];
-                            v[j] += sdv[cb - c0 + j];
+                            v[j] += s_bias[cb + j] + sdv[cb - c0 + j];
                             s0[j] = rvalid ? v[j] : 0.f;
                             s1[j] = rvalid ? v[j] * v[j] : 0.f;
                         }
@@ -514,25 +523,39 @@ k_wgrad_tc(WGTArgs a) {
         float dbp[BN / 4];
 #pragma unroll
         for (int i = 0; i < BN / 4; ++i) dbp[i] = 0.f;
-        // source of activation piece g (4 channels of rows kd0 + q*32 + g*4 ..) for pixel p; chan out
-        auto a_src = [&](int p, int g, int &chan) -> const float * {
+        // per-thread invariants: piece g covers rows kd0 + q*32 + g*4 .. +3 = (tap, 4 channels)
+        int g_r[8], g_s[8], g_ch[8];
+        bool g_ok[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
             const int kd = kd0 + q * 32 + g * 4;
-            if (p >= P || kd >= Kw) return nullptr;
-            const int wo = p % a.Wo, ho = (p / a.Wo) % a.Ho, n = p / (a.Wo * a.Ho);
-            const int tap = kd / a.Cin;
-            chan = kd - tap * a.Cin;
-            const int r = tap / a.k, s = tap - r * a.k;
-            const int hi = ho * a.stride - a.pad + r, wi = wo * a.stride - a.pad + s;
+            g_ok[g] = kd < Kw;
+            const int tap = g_ok[g] ? kd / a.Cin : 0;
+            g_ch[g] = g_ok[g] ? kd - tap * a.Cin : 0;
+            g_r[g] = tap / a.k; g_s[g] = tap - g_r[g] * a.k;
+        }
+        struct Pix { int wo, ho; const float *img; bool ok; };
+        auto decode = [&](int p) {
+            Pix px;
+            px.ok = p < P;
+            const int pp = px.ok ? p : 0;
+            px.wo = pp % a.Wo; px.ho = (pp / a.Wo) % a.Ho;
+            px.img = a.x + (size_t)(pp / (a.Wo * a.Ho)) * a.H * a.W * a.Cin;
+            return px;
+        };
+        auto a_src = [&](const Pix &px, int g) -> const float * {
+            if (!px.ok || !g_ok[g]) return nullptr;
+            const int hi = px.ho * a.stride - a.pad + g_r[g], wi = px.wo * a.stride - a.pad + g_s[g];
             if (hi < 0 || hi >= a.H || wi < 0 || wi >= a.W) return nullptr;
-            return a.x + (((size_t)n * a.H + hi) * a.W + wi) * a.Cin + chan;
+            return px.img + ((size_t)hi * a.W + wi) * a.Cin + g_ch[g];
         };
         auto issue = [&](int ch) {
             const int p = (c_begin + ch) * 32 + j;
             const uint32_t slot = sbase + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
+            const Pix px = decode(p);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                int chan;
-                const float *src = a_src(p, g, chan);
+                const float *src = a_src(px, g);
                 cp_async16(slot + g * 16, src ? src : a.x, src ? 16u : 0u);
             }
 #pragma unroll
@@ -549,11 +572,12 @@ k_wgrad_tc(WGTArgs a) {
             mbar_wait(bar(NST + stage), phase ^ 1);
             unsigned char *sA = smem + stage * L::STAGE_BYTES;
             unsigned char *sB = sA + L::A_BYTES;
+            const Pix px = decode(p);
             // element (row, col j): row block (row>>3)*1024 + (row&7)*128, 16B chunk (j>>2)^(row&7), + (j&3)*4
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                int chan = 0;
-                const bool valid = a_src(p, g, chan) != nullptr;
+                const int chan = g_ch[g];
+                const bool valid = a_src(px, g) != nullptr;
                 float4 xv = *reinterpret_cast<const float4 *>(slot + g * 16);
                 if (!valid) xv = make_float4(0.f, 0.f, 0.f, 0.f);
                 else if (a.has_in_bn) {

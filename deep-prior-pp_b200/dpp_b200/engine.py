@@ -713,6 +713,8 @@ class Engine(object):
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.W.copy_(w0); self.R.copy_(r0); self.M.copy_(m0); self.V.copy_(v0); self.hyper.copy_(h0)
+            self._repack()          # the warm-up step re-packed the post-ADAM weights: restore the images too
+            torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step_body()

@@ -129,3 +129,41 @@ def test_type1_with_pca_tail_forward():
         oout, _ = onet.forward(torch.from_numpy(x), deterministic=False)
     assert out.shape == (B, 3 * J)
     assert _rel(out, oout.numpy()) < 1e-4
+
+
+def test_stem_gradient_diagnostic():
+    """Isolates the stem: (a) engine dW0 vs torch autograd on the engine's own dy_stem, (b) the
+    engine's dy_stem vs the oracle's gradient at the stem output."""
+    import torch.nn.functional as F
+    from oracle import nets as O
+    B, D = 4, 30
+    net, onet, eng = _build(0, B, 1, D)
+    x, y = _data(B, D)
+    eng.set_input_nchw(x)
+    eng._alloc_training()
+    eng.y_in.copy_(torch.from_numpy(y))
+    eng.train_step(0.0, use_graph=False)
+    stem_op = [o for o in eng.ops if o['kind'] == 'convpool'][0]
+    dy = stem_op['dst'].grad.clone()                       # NHWC
+    g_eng = eng.gradients()[id(net.layers[0].W)]
+    # (a)
+    w = torch.from_numpy(net.layers[0].W.get_value()).cuda().requires_grad_(True)
+    xt = torch.from_numpy(x).cuda()
+    o = F.max_pool2d(F.conv2d(xt, w.flip(2, 3), padding=2), 2, 2)
+    o.backward(dy.permute(0, 3, 1, 2).contiguous())
+    ea = float((torch.from_numpy(g_eng).cuda() - w.grad).abs().max() / w.grad.abs().max())
+    # (b)
+    for p in onet.params:
+        p.grad = None
+    col = {}
+    out, _ = onet.forward(torch.from_numpy(x), deterministic=False, collect=col)
+    col[0].retain_grad()
+    O.cost_fn(onet, out, torch.from_numpy(y), B, 1, D).backward()
+    dyo = col[0].grad.permute(0, 2, 3, 1).numpy()
+    eb = float(np.abs(dy.cpu().numpy() - dyo).max() / np.abs(dyo).max())
+    eb2 = float(np.linalg.norm(dy.cpu().numpy() - dyo) / np.linalg.norm(dyo))
+    gw = onet.layers[0].params[0].grad.numpy()
+    ec = float(np.abs(g_eng - gw).max() / np.abs(gw).max())
+    print("stem dW vs torch-GPU autograd on same dy:", ea, "| dy_stem vs oracle: max", eb, "l2", eb2, "| dW vs oracle", ec)
+    assert ea < 1e-3
+    assert eb2 < 2e-3
