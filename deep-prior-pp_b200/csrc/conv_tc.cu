@@ -85,6 +85,10 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     uint32_t r[16];
     asm volatile(
@@ -122,9 +126,11 @@ struct SmemLayout {
     static constexpr int B_BYTES = PASSES * BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SCR_BYTES = 4 * 32 * 33 * 4 + 2 * 256 * 4 + 5 * 128 * 4;   // transpose tiles + BN coefficients + bias
-    static constexpr int NS = PASSES == 2 ? 2 : 3;          // MMA tile stages
-    static constexpr int RD = 4;                            // raw landing slots (cp.async ring), 16 KB each
-    static constexpr int RAW_OFF = NS * STAGE_BYTES;
+    static constexpr int NS = PASSES == 2 ? 2 : 3;          // A (activation) MMA tile stages
+    static constexpr int RB = (BN == 128 && PASSES == 2) ? 2 : 4;   // B (weight image) ring, filled by TMA bulk copies
+    static constexpr int RD = (BN == 128 && PASSES == 2) ? 3 : 4;   // raw landing slots (cp.async ring), 16 KB each
+    static constexpr int B_OFF = NS * A_BYTES;
+    static constexpr int RAW_OFF = B_OFF + RB * B_BYTES;
     static constexpr int BAR_OFF = RAW_OFF + RD * TM * 128;
     static constexpr int SCR_OFF = BAR_OFF + 256;
     static constexpr int TOTAL = SCR_OFF + SCR_BYTES + 1024;
@@ -155,9 +161,10 @@ k_conv_tc(TCArgs a) {
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // bar index: full[s] = s, empty[s] = NS + s, tfull[a] = 2*NS + a, tempty[a] = 2*NS + 2 + a
+    // bar index: full[s] = s, empty[s] = NS + s, tfull[a] = 2*NS + a, tempty[a] = 2*NS + 2 + a,
+    //            bfull[b] = 2*NS + 4 + b, bempty[b] = 2*NS + 4 + RB + b
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 224);
     float *scr = reinterpret_cast<float *>(smem + L::SCR_OFF);
     float *s_scale = scr + 4 * 32 * 33;          // [256] input-BN scale
     float *s_shift = s_scale + 256;              // [256]
@@ -176,8 +183,9 @@ k_conv_tc(TCArgs a) {
     constexpr uint32_t TCOLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(bar(s), 129); mbar_init(bar(NS + s), 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NS + s), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NS + i), 1); mbar_init(bar(2 * NS + 2 + i), 128); }
+        for (int b = 0; b < L::RB; ++b) { mbar_init(bar(2 * NS + 4 + b), 1); mbar_init(bar(2 * NS + 4 + L::RB + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -251,14 +259,8 @@ k_conv_tc(TCArgs a) {
         auto process = [&](RowCursor &c, int it) {
             const uint32_t stage = it % NS, phase = (it / NS) & 1;
             mbar_wait(bar(NS + stage), phase ^ 1);
-            if (tid == 0) {
-                const int nt = c.tile % ntiles;
-                const float *src = a.wimg + ((size_t)(nt * a.kchunks + c.kc)) * (PASSES * BN * 32);
-                mbar_expect_tx(bar(stage), L::B_BYTES);
-                bulk_g2s(sbase + stage * L::STAGE_BYTES + L::A_BYTES, src, L::B_BYTES, bar(stage));
-            }
             const unsigned char *rawp = smem + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
-            unsigned char *rowp = smem + stage * L::STAGE_BYTES + rowoff;
+            unsigned char *rowp = smem + stage * L::A_BYTES + rowoff;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int pj = (j ^ (row & 7)) << 4;
@@ -299,8 +301,21 @@ k_conv_tc(TCArgs a) {
             process(cp, it);
         }
     } else if (warp == 8) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // =========================== MMA issuer (lane 0) + weight-image loader (lane 1) =================
+        constexpr int RB = L::RB;
+        if (lane == 1) {
+            // TMA bulk copies of the packed weight images run RB chunks ahead of the MMAs
+            const int nt = blockIdx.x % ntiles;
+            int it = 0;
+            for (int t = 0; t < my_tiles; ++t)
+                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                    const uint32_t b = it % RB, bphase = (it / RB) & 1;
+                    mbar_wait(bar(2 * NS + 4 + RB + b), bphase ^ 1);
+                    const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
+                    mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
+                    bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
+                }
+        } else if (lane == 0) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t acc = 0, aphase = 0;
             int it = 0;
@@ -310,10 +325,12 @@ k_conv_tc(TCArgs a) {
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
                     const uint32_t stage = it % NS, phase = (it / NS) & 1;
+                    const uint32_t bslot = it % RB, bphase = (it / RB) & 1;
+                    mbar_wait(bar(2 * NS + 4 + bslot), bphase);
                     mbar_wait(bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t sa = sbase + stage * L::STAGE_BYTES;
-                    const uint32_t sb = sa + L::A_BYTES;
+                    const uint32_t sa = sbase + stage * L::A_BYTES;
+                    const uint32_t sb = sbase + L::B_OFF + bslot * L::B_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
                         const uint64_t ah = make_desc(sa + ks * 32), bh = make_desc(sb + ks * 32);
@@ -327,7 +344,8 @@ k_conv_tc(TCArgs a) {
                             mma_tf32(d_tmem, ah, bh, IDESC, first);
                         }
                     }
-                    mma_commit(bar(NS + stage));                              // frees the smem stage when the MMAs retire
+                    mma_commit(bar(NS + stage));                              // frees the A stage when the MMAs retire
+                    mma_commit(bar(2 * NS + 4 + RB + bslot));                 // ... and the weight slot
                     if (kc == a.kchunks - 1) mma_commit(bar(2 * NS + acc));   // accumulator ready
                 }
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
@@ -668,7 +686,7 @@ k_wgrad_tc(WGTArgs a) {
             if (kd < Kw) {
                 float *dst = a.dw + (size_t)kd * a.Cout + o0 + cb;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) atomicAdd(dst + t, v[t]);
+                for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
             }
         }
     }
@@ -695,7 +713,7 @@ int launch_wgrad_tc(WGTArgs &a, cudaStream_t st) {
     const int tiles = a.mtiles * a.ntiles;
     const int P = a.N * a.Ho * a.Wo;
     const int total_chunks = (P + 31) / 32;
-    int splits = (148 * 2) / tiles; if (splits < 1) splits = 1;
+    int splits = 148 / tiles; if (splits < 1) splits = 1;
     if (splits > total_chunks) splits = total_chunks;
     a.chunks_per_split = (total_chunks + splits - 1) / splits;
     a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;

@@ -247,8 +247,11 @@ k_gemm_tc(GTArgs a) {
             if (m < a.M) {
                 float *dst = a.C + (size_t)m * a.N + n0 + cb;
 #pragma unroll
-                for (int t = 0; t < 16; ++t)
-                    if (n0 + cb + t < a.N) atomicAdd(dst + t, v[t]);
+                for (int t = 0; t < 16; t += 4)
+                    if (n0 + cb + t < a.N)      // N % 4 == 0: whole quads are in or out
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + t), "f"(v[t]), "f"(v[t + 1]),
+                                     "f"(v[t + 2]), "f"(v[t + 3])
+                                     : "memory");
             }
         }
     }

@@ -165,5 +165,13 @@ def test_stem_gradient_diagnostic():
     gw = onet.layers[0].params[0].grad.numpy()
     ec = float(np.abs(g_eng - gw).max() / np.abs(gw).max())
     print("stem dW vs torch-GPU autograd on same dy:", ea, "| dy_stem vs oracle: max", eb, "l2", eb2, "| dW vs oracle", ec)
+    d = np.abs(dy.cpu().numpy() - dyo) / np.abs(dyo).max()
+    print("  err even-even", d[:, ::2, ::2].max(), "odd rows", d[:, 1::2].max(), "odd cols", d[:, :, 1::2].max())
+    print("  err flat rows(<9 pooled)", d[:, :9].max(), "rest", d[:, 10:].max())
+    print("  per-channel max err", np.round(d.max(axis=(0, 1, 2)), 4))
+    print("  per-image max err", np.round(d.max(axis=(1, 2, 3)), 4))
+    xs = stem_op['dst'].buf.cpu().numpy()
+    xo = col[0].detach().permute(0, 2, 3, 1).numpy()
+    print("  stem output err", np.abs(xs - xo).max() / np.abs(xo).max())
     assert ea < 1e-3
     assert eb2 < 2e-3
