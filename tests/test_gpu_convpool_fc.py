@@ -8,6 +8,9 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+torch.backends.cudnn.allow_tf32 = False        # the torch references must be fp32, not TF32
+torch.backends.cuda.matmul.allow_tf32 = False
+
 from dpp_b200.lib import lib  # noqa: E402
 
 

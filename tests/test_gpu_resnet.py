@@ -170,6 +170,35 @@ def test_stem_gradient_diagnostic():
     print("  err flat rows(<9 pooled)", d[:, :9].max(), "rest", d[:, 10:].max())
     print("  per-channel max err", np.round(d.max(axis=(0, 1, 2)), 4))
     print("  per-image max err", np.round(d.max(axis=(1, 2, 3)), 4))
+    # third opinion: block 0 re-computed with torch GPU ops (fp32) from the engine's stem output and the
+    # engine's gradient at the block output
+    torch.backends.cudnn.allow_tf32 = False
+    blk = [o for o in eng.ops if o['kind'] == 'conv'][:4]          # conv1, conv2, conv3, convS
+    tout = blk[3]['dst']
+    s_in = stem_op['dst'].buf.permute(0, 3, 1, 2).contiguous().clone().requires_grad_(True)
+
+    def bnrelu(t, bn):
+        m = t.mean((0, 2, 3), keepdim=True)
+        v = ((t - m) ** 2).mean((0, 2, 3), keepdim=True)
+        g = torch.from_numpy(bn.gamma.get_value()).cuda().view(1, -1, 1, 1)
+        b = torch.from_numpy(bn.beta.get_value()).cuda().view(1, -1, 1, 1)
+        return torch.relu((t - m) * (g / torch.sqrt(v + 1e-4)) + b)
+
+    def conv(t, L):
+        w = torch.from_numpy(L.W.get_value()).cuda()
+        b = torch.from_numpy(L.b.get_value()).cuda()
+        return F.conv2d(t, w.flip(2, 3), b, stride=L.cfgParams.stride, padding=L.cfgParams.filterDim[0] // 2)
+    a0 = bnrelu(s_in, blk[0]['in_bn'])
+    h = conv(a0, blk[0]['layer'])
+    h = conv(bnrelu(h, blk[1]['in_bn']), blk[1]['layer'])
+    h = conv(bnrelu(h, blk[2]['in_bn']), blk[2]['layer'])
+    outb = h + conv(a0, blk[3]['layer'])
+    print("  block-0 output torch-GPU vs engine", float((outb.detach().permute(0, 2, 3, 1) - tout.buf).abs().max()))
+    outb.backward(tout.grad.permute(0, 3, 1, 2).contiguous())
+    ds = s_in.grad.permute(0, 2, 3, 1)
+    print("  dy_stem engine vs torch-GPU block-0 autograd:", float((ds - dy).abs().max() / ds.abs().max()),
+          "| torch-GPU vs oracle-CPU:", float(np.abs(ds.cpu().numpy() - dyo).max() / np.abs(dyo).max()))
+    go = col[10].grad if 10 in col and col[10].grad is not None else None
     xs = stem_op['dst'].buf.cpu().numpy()
     xo = col[0].detach().permute(0, 2, 3, 1).numpy()
     print("  stem output err", np.abs(xs - xo).max() / np.abs(xo).max())
