@@ -128,6 +128,7 @@ def cpu_step_time(ds, comp, mean, steps, threads):
     import torch
     from oracle import nets as ON, augment as OA
     torch.set_num_threads(threads)
+    ON.set_dtype(torch.float32)          # the timed CPU arm runs in the reference's precision
     onet = ON.build_resnet(np.random.RandomState(23455), type=0, batchSize=B, numJoints=1, nDims=E)
     adam = ON.Adam(onet.params)
     cam = OA.Camera(**OA.NYU_CAM)

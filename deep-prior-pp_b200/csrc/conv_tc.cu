@@ -30,6 +30,7 @@ constexpr int TM = 128;          // pixels per tile (TMEM lanes)
 constexpr int KC = 32;           // floats of K per stage: 128-byte rows
 constexpr int NSTAGE = 3;           // stages of the wgrad kernel (k_conv_tc uses SmemLayout::NS)
 constexpr int NTHREADS = 288;
+constexpr int NTHREADS_CONV = 320;  // k_conv_tc: + warp 9 = weight-image (TMA) loader
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -115,6 +116,9 @@ struct TCArgs {
     dpp_bn_ref in_bn; int has_in_bn;
     const float *bias; const float *residual; double *out_stats;
     int accumulate; dpp_bn_ref mask_bn; int has_mask; const float *x_pre; double *dz_stats;
+    // per k-chunk gather table (host-built): the chunk's 8 16-byte pieces come from tap A (pieces 0-3) and
+    // tap B (pieces 4-7; same tap as A when Cin >= 32): {dr, ds (tap offset incl. -pad), element offset, channel}
+    int tab[18][8];
 };
 
 // smem carve-up (after 1024-byte alignment):
@@ -143,16 +147,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// pixel-row cursor of a producer thread: walks (tile, k-chunk) in launch order
+// pixel-row cursor of a producer thread (issue side): walks (tile, k-chunk) in launch order
 struct RowCursor {
-    int tile, kc;                 // current tile (global index) and k-chunk
-    int tap, c0, r, s;            // first tap / channel of the chunk, and the tap's (r, s)
-    int ho, wo; bool rvalid;      // this thread's pixel of the tile
-    const float *img;
+    int tile, kc;
+    int h0, w0; bool rvalid;      // this thread's pixel of the tile (already multiplied by the stride)
+    const float *base;            // &in[n][h0][w0][0]
 };
 
 template <int BN, int PASSES>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_CONV, 1)
 k_conv_tc(TCArgs a) {
     using L = SmemLayout<BN, PASSES>;
     constexpr int NS = L::NS;
@@ -194,10 +197,10 @@ k_conv_tc(TCArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (a.has_in_bn)
-        for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
-    for (int c = tid; c < BN; c += NTHREADS) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
+        for (int c = tid; c < a.Cin; c += NTHREADS_CONV) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
+    for (int c = tid; c < BN; c += NTHREADS_CONV) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
     if (a.has_mask)
-        for (int c = tid; c < BN; c += NTHREADS) {
+        for (int c = tid; c < BN; c += NTHREADS_CONV) {
             float mean, istd;
             bn_mean_istd(a.mask_bn, cta_n0 + c, a.Cn, mean, istd);
             const float sc = a.mask_bn.gamma[cta_n0 + c] * istd;
@@ -213,66 +216,62 @@ k_conv_tc(TCArgs a) {
     if (warp < 4) {
         // =========================== producers ===========================
         // cp.async (LDGSTS, zero-fill for padding) lands the raw 128-byte row of chunk it+D in a private
-        // raw slot (no barrier: rows are thread-private) while chunk it is read back, transformed
-        // (BN+ReLU, TF32 hi/lo split) and written into the MMA stage.  All index arithmetic is incremental
-        // (no divisions in the chunk loop).
+        // raw slot (rows are thread-private: no barrier) while chunk it is read back, transformed (BN+ReLU,
+        // TF32 hi/lo split) and written into the MMA stage.  Tap offsets come from the host-built chunk
+        // table; the per-thread work is two bounds checks and one base pointer per chunk.
         const int row = tid;
         const int T = my_tiles * a.kchunks;
         const uint32_t rowoff = (row >> 3) * 1024 + (row & 7) * 128;
-        const int KK = a.k * a.k;
+        const uint32_t sw = row & 7;
 
         auto set_tile = [&](RowCursor &c, int tile) {
             c.tile = tile;
+            c.kc = 0;
             const int m = (tile / ntiles) * TM + row;
             c.rvalid = m < M;
             const int mm = c.rvalid ? m : 0;
-            c.wo = mm % a.Wg; c.ho = (mm / a.Wg) % a.Hg;
-            c.img = a.in + (size_t)(mm / (a.Wg * a.Hg)) * a.Hin * a.Win * a.Cin;
-            c.kc = 0; c.tap = 0; c.c0 = 0; c.r = 0; c.s = 0;
+            const int wo = mm % a.Wg, ho = (mm / a.Wg) % a.Hg, n = mm / (a.Wg * a.Hg);
+            c.h0 = ho * a.in_stride; c.w0 = wo * a.in_stride;
+            c.base = a.in + (((size_t)n * a.Hin + c.h0) * a.Win + c.w0) * a.Cin;
         };
-        auto advance = [&](RowCursor &c) {
-            if (++c.kc == a.kchunks) { set_tile(c, c.tile + gridDim.x); return; }
-            c.c0 += KC;
-            while (c.c0 >= a.Cin) { c.c0 -= a.Cin; ++c.tap; if (++c.s == a.k) { c.s = 0; ++c.r; } }
-        };
-        // source of 16-byte piece j of the cursor's chunk (nullptr = zero / padding); chan = its first channel
-        auto piece_src = [&](const RowCursor &c, int j, int &chan) -> const float * {
-            chan = c.c0 + j * 4;
-            int tap = c.tap, r = c.r, s = c.s;
-            if (chan >= a.Cin) { chan -= a.Cin; ++tap; if (++s == a.k) { s = 0; ++r; } }   // Cin = 16: second tap
-            if (!c.rvalid || tap >= KK) return nullptr;
-            const int hi = c.ho * a.in_stride - a.pad + r, wi = c.wo * a.in_stride - a.pad + s;
-            if (hi < 0 || hi >= a.Hin || wi < 0 || wi >= a.Win) return nullptr;
-            return c.img + ((size_t)hi * a.Win + wi) * a.Cin + chan;
-        };
+        uint32_t vbits = 0;           // 2 validity bits per in-flight chunk (ring of RD)
         auto issue = [&](RowCursor &c, int it) {
+            const int *e = a.tab[c.kc];
+            const bool v0 = c.rvalid && (unsigned)(c.h0 + e[0]) < (unsigned)a.Hin && (unsigned)(c.w0 + e[1]) < (unsigned)a.Win;
+            const bool v1 = c.rvalid && (unsigned)(c.h0 + e[4]) < (unsigned)a.Hin && (unsigned)(c.w0 + e[5]) < (unsigned)a.Win;
+            const float *p0 = v0 ? c.base + e[2] : a.in;
+            const float *p1 = v1 ? c.base + e[6] : a.in;
             const uint32_t raw = sbase + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int chan;
-                const float *src = piece_src(c, j, chan);
-                cp_async16(raw + ((j ^ (row & 7)) << 4), src ? src : a.in, src ? 16u : 0u);
+            for (int j = 0; j < 4; ++j) {
+                cp_async16(raw + ((j ^ sw) << 4), p0 + (v0 ? j * 4 : 0), v0 ? 16u : 0u);
+                cp_async16(raw + (((j + 4) ^ sw) << 4), p1 + (v1 ? j * 4 : 0), v1 ? 16u : 0u);
             }
             cp_async_commit();
-            advance(c);
+            const uint32_t sh = 2 * (it % RD);
+            vbits = (vbits & ~(3u << sh)) | (((uint32_t)v0 | ((uint32_t)v1 << 1)) << sh);
+            if (++c.kc == a.kchunks) set_tile(c, c.tile + gridDim.x);
         };
-        auto process = [&](RowCursor &c, int it) {
+        int kc_p = 0;
+        auto process = [&](int it) {
             const uint32_t stage = it % NS, phase = (it / NS) & 1;
+            const int *e = a.tab[kc_p];
+            const uint32_t vb = (vbits >> (2 * (it % RD))) & 3u;
             mbar_wait(bar(NS + stage), phase ^ 1);
             const unsigned char *rawp = smem + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
             unsigned char *rowp = smem + stage * L::A_BYTES + rowoff;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int pj = (j ^ (row & 7)) << 4;
-                int chan = 0;
-                const bool valid = piece_src(c, j, chan) != nullptr;
+                const int pj = (j ^ sw) << 4;
+                const bool valid = (j < 4) ? (vb & 1u) : (vb & 2u);
+                const int chan = (j < 4) ? e[3] + j * 4 : e[7] + (j - 4) * 4;
                 float4 x = *reinterpret_cast<const float4 *>(rawp + pj);
                 if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 else if (a.has_in_bn) {
-                    x.x = fmaf(x.x, s_scale[chan], s_shift[chan]);
-                    x.y = fmaf(x.y, s_scale[chan + 1], s_shift[chan + 1]);
-                    x.z = fmaf(x.z, s_scale[chan + 2], s_shift[chan + 2]);
-                    x.w = fmaf(x.w, s_scale[chan + 3], s_shift[chan + 3]);
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
+                    const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
+                    x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
+                    x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
                     if (a.in_bn.relu) {
                         x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
                     }
@@ -289,33 +288,20 @@ k_conv_tc(TCArgs a) {
             }
             fence_proxy_async();
             mbar_arrive(bar(stage));
-            advance(c);
+            if (++kc_p == a.kchunks) kc_p = 0;
         };
-        RowCursor ci, cp;
+        RowCursor ci;
         set_tile(ci, blockIdx.x);
-        set_tile(cp, blockIdx.x);
         for (int i = 0; i < D && i < T; ++i) issue(ci, i);
         for (int it = 0; it < T; ++it) {
             if (it + D < T) { issue(ci, it + D); cp_async_wait<D>(); }
             else cp_async_wait<0>();
-            process(cp, it);
+            process(it);
         }
     } else if (warp == 8) {
-        // =========================== MMA issuer (lane 0) + weight-image loader (lane 1) =================
+        // =========================== MMA issuer ===========================
         constexpr int RB = L::RB;
-        if (lane == 1) {
-            // TMA bulk copies of the packed weight images run RB chunks ahead of the MMAs
-            const int nt = blockIdx.x % ntiles;
-            int it = 0;
-            for (int t = 0; t < my_tiles; ++t)
-                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
-                    const uint32_t b = it % RB, bphase = (it / RB) & 1;
-                    mbar_wait(bar(2 * NS + 4 + RB + b), bphase ^ 1);
-                    const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
-                    mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
-                    bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
-                }
-        } else if (lane == 0) {
+        if (lane == 0) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t acc = 0, aphase = 0;
             int it = 0;
@@ -350,6 +336,22 @@ k_conv_tc(TCArgs a) {
                 }
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
             }
+        }
+    } else if (warp == 9) {
+        // =========================== weight-image loader ===========================
+        // TMA bulk copies of the packed weight images run up to RB chunks ahead of the MMAs
+        constexpr int RB = L::RB;
+        if (lane == 0) {
+            const int nt = blockIdx.x % ntiles;
+            int it = 0;
+            for (int t = 0; t < my_tiles; ++t)
+                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                    const uint32_t b = it % RB, bphase = (it / RB) & 1;
+                    mbar_wait(bar(2 * NS + 4 + RB + b), bphase ^ 1);
+                    const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
+                    mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
+                    bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
+                }
         }
     } else {
         // =========================== epilogue ===========================
@@ -446,10 +448,23 @@ k_conv_tc(TCArgs a) {
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         if (want_stats) {
-            double *st = a.out_stats ? a.out_stats : a.dz_stats;
-            const int kind = lane >> 4, cl = lane & 15;
+            // combine the four epilogue warps in shared memory, then ONE fp64 atomic per channel per CTA
+            // (same-address fp64 atomics serialise in L2: 4x fewer of them)
+            double *comb = reinterpret_cast<double *>(scr);                 // [4][BN/16][32]
 #pragma unroll
-            for (int i = 0; i < BN / 16; ++i) atomicAdd(&st[kind * a.Cn + cta_n0 + 16 * i + cl], stacc[i]);
+            for (int i = 0; i < BN / 16; ++i) comb[(ew * (BN / 16) + i) * 32 + lane] = stacc[i];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (ew == 0) {
+                double *st = a.out_stats ? a.out_stats : a.dz_stats;
+                const int kind = lane >> 4, cl = lane & 15;
+#pragma unroll
+                for (int i = 0; i < BN / 16; ++i) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) t += comb[(w * (BN / 16) + i) * 32 + lane];
+                    atomicAdd(&st[kind * a.Cn + cta_n0 + 16 * i + cl], t);
+                }
+            }
         }
     }
     tc_fence_before();
@@ -779,11 +794,24 @@ int launch_tc(const TCArgs &a, cudaStream_t st) {
     int ntiles = a.Cn / BN;
     int grid = tiles < 148 ? tiles : 148;
     grid -= grid % ntiles;
-    k_conv_tc<BN, PASSES><<<grid, NTHREADS, L::TOTAL, st>>>(a);
+    k_conv_tc<BN, PASSES><<<grid, NTHREADS_CONV, L::TOTAL, st>>>(a);
     return 0;
 }
 
-int dispatch_tc(const TCArgs &a, int passes, cudaStream_t st) {
+int dispatch_tc(TCArgs &a, int passes, cudaStream_t st) {
+    if (a.kchunks > 18) return -1;
+    const int KK = a.k * a.k;
+    for (int kc = 0; kc < a.kchunks; ++kc)
+        for (int half = 0; half < 2; ++half) {
+            const int k0 = kc * KC + half * 16;
+            const int tap = k0 / a.Cin, chan = k0 - tap * a.Cin;
+            int *e = a.tab[kc] + half * 4;
+            if (tap >= KK) { e[0] = 1 << 28; e[1] = 1 << 28; e[2] = 0; e[3] = 0; continue; }   // beyond K: zero rows
+            const int r = tap / a.k, s = tap - r * a.k;
+            e[0] = r - a.pad; e[1] = s - a.pad;
+            e[2] = ((r - a.pad) * a.Win + (s - a.pad)) * a.Cin + chan;
+            e[3] = chan;
+        }
     const int bn = a.Cn > 128 ? 128 : a.Cn;
 #define DPP_TC_CASE(B_)                                                    \
     if (bn == B_) return passes > 1 ? launch_tc<B_, 2>(a, st) : launch_tc<B_, 1>(a, st);

@@ -1,4 +1,5 @@
-"""CPU oracle: torch-CPU fp32 restatement of the reference networks, cost, gradients and ADAM.
+"""CPU oracle: torch-CPU restatement of the reference networks, cost, gradients and ADAM
+(reference semantics are float32; working precision float64 by default, see DTYPE below).
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED: Theano cannot run
 here; the semantics below follow the reference sources line by line plus SURVEY.md
@@ -41,8 +42,21 @@ def init_vals(rng, shape, mode, act, method=None):
     raise NotImplementedError(method)
 
 
+# Working precision of the oracle's network arithmetic.  The reference computes in float32; the oracle
+# defaults to float64 so that its own rounding - and CPU-dependent reduced-precision kernels inside
+# oneDNN (a B200 host's torch-CPU fp32 conv backward differed from torch-GPU fp32 by 1.4e-2 on one
+# layer while our kernels agreed with torch-GPU to 3e-7) - cannot be mistaken for kernel error.
+# Initial values are always drawn and rounded in float32 exactly as the reference does.
+DTYPE = torch.float64
+
+
+def set_dtype(dt):
+    global DTYPE
+    DTYPE = dt
+
+
 def _t(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).requires_grad_(True)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DTYPE).requires_grad_(True)
 
 
 # --------------------------------------------------------------------------------------
@@ -108,7 +122,7 @@ class OracleNet(object):
         l = L('bn', layerNum=len(self.layers), C=c, eps=1e-4, alpha=0.1)
         # batchnormlayer.py:148-152: trainable [beta, gamma]; non-trained [mean, inv_std]
         l.params = [_t(np.zeros((c,), f32)), _t(np.ones((c,), f32))]
-        l.nontrained = [torch.zeros(c), torch.ones(c)]
+        l.nontrained = [torch.zeros(c, dtype=DTYPE), torch.ones(c, dtype=DTYPE)]
         self.layers.append(l)
         dst = self._newv()
         self.program.append(('layer', l.layerNum, src, dst))
@@ -168,11 +182,14 @@ class OracleNet(object):
         ``collect`` (optional dict) receives every layer output by layerNum."""
         vals = {}
         if isinstance(x, (list, tuple)):
+            x = [xi.to(DTYPE) for xi in x]
             for i, xi in enumerate(x):
                 vals[-(i + 1)] = xi
             vals[0] = x[0]
         else:
-            vals[0] = x
+            vals[0] = x.to(DTYPE)
+        if masks is not None:
+            masks = [m.to(DTYPE) for m in masks]
         bn_stats = {}
         mi = 0
         for st in self.program:
@@ -232,9 +249,9 @@ class OracleNet(object):
         """batchnormlayer.py:164-172: r = 0.9 r + 0.1 stat, for mean and inv_std."""
         for ln, (m, s) in bn_stats.items():
             l = self.layers[ln]
-            a = f32(l.alpha)
-            l.nontrained[0] = (f32(1.) - a) * l.nontrained[0] + a * m
-            l.nontrained[1] = (f32(1.) - a) * l.nontrained[1] + a * s
+            a = float(f32(l.alpha))
+            l.nontrained[0] = (1. - a) * l.nontrained[0] + a * m
+            l.nontrained[1] = (1. - a) * l.nontrained[1] + a * s
 
 
 # --------------------------------------------------------------------------------------
@@ -349,14 +366,14 @@ def cost_fn(net, out, y, batch_size, numJoints, nDims, weightreg=0.0):
     if numJoints == 1 and nDims == 1:
         cost = ((out.reshape(batch_size, nDims) - y) ** 2).mean(dim=1)
     elif numJoints == 1:
-        cost = ((out.reshape(batch_size, nDims) - y) ** 2).sum(dim=1)
+        cost = ((out.reshape(batch_size, nDims) - y.to(out.dtype)) ** 2).sum(dim=1)
     else:
         cost = ((out.reshape(batch_size, numJoints, nDims) - y) ** 2).sum(dim=2).mean(dim=1)
     cost = cost.mean()
     if not net.has_dropout():
         reg = 0.
         for W in net.weights:
-            reg = reg + f32(weightreg) * (W ** 2).sum()
+            reg = reg + float(weightreg) * (W ** 2).sum()
         cost = cost + reg
     return cost
 
@@ -383,10 +400,10 @@ class Adam(object):
             v = b2 * self.v[i] + (one - b2) * (g * g)
             mh = m / c1
             vh = v / c2
-            w = p.detach().numpy() - (lr * mh) / (np.sqrt(vh) + eps)
+            w = p.detach().numpy().astype(f32) - (lr * mh) / (np.sqrt(vh) + eps)
             self.m[i], self.v[i] = m.astype(f32), v.astype(f32)
             with torch.no_grad():
-                p.copy_(torch.from_numpy(w.astype(f32)))
+                p.copy_(torch.from_numpy(w.astype(f32)).to(p.dtype))
         self.t = f32(self.t + one)
 
 
