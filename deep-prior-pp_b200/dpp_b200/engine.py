@@ -716,7 +716,8 @@ class Engine(object):
             self._repack()          # the warm-up step re-packed the post-ADAM weights: restore the images too
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: NCCL's watchdog thread may touch the CUDA API while we capture (world > 1)
+            with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
                 self._step_body()
             # the capture itself does not execute; state is untouched
             self._graphs['train'] = g

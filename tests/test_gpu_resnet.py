@@ -158,6 +158,9 @@ def test_stem_gradient_diagnostic():
     col = {}
     out, _ = onet.forward(torch.from_numpy(x), deterministic=False, collect=col)
     col[0].retain_grad()
+    for k_ in col:
+        if col[k_].requires_grad:
+            col[k_].retain_grad()
     O.cost_fn(onet, out, torch.from_numpy(y), B, 1, D).backward()
     dyo = col[0].grad.permute(0, 2, 3, 1).numpy()
     eb = float(np.abs(dy.cpu().numpy() - dyo).max() / np.abs(dyo).max())
@@ -198,7 +201,22 @@ def test_stem_gradient_diagnostic():
     ds = s_in.grad.permute(0, 2, 3, 1)
     print("  dy_stem engine vs torch-GPU block-0 autograd:", float((ds - dy).abs().max() / ds.abs().max()),
           "| torch-GPU vs oracle-CPU:", float(np.abs(ds.cpu().numpy() - dyo).max() / np.abs(dyo).max()))
-    go = col[10].grad if 10 in col and col[10].grad is not None else None
+    for op in eng.ops:
+        if op['kind'] in ('conv', 'fc') and op['dst'].grad is not None:
+            ln = op['layer'].layerNum
+            if col[ln].grad is None:
+                continue
+            gdst = op['dst']
+            from_skip = [o for o in eng.ops if o['kind'] == 'conv' and o['residual'] is gdst]
+            if from_skip and gdst.bn is None:
+                gdst = from_skip[0]['dst']
+            ge = gdst.grad.cpu().numpy()
+            go_ = col[ln].grad.numpy()
+            go_ = go_.transpose(0, 2, 3, 1) if go_.ndim == 4 else go_
+            dd = np.abs(ge - go_) / (np.abs(go_).max() + 1e-30)
+            per_img = dd.reshape(dd.shape[0], -1).max(axis=1)
+            if ln in (3, 9, 10, 19, 46, 55, 92, 138, 183, 186, 187, 188) or per_img.max() > 2e-3:
+                print("  grad@layer", ln, op['kind'], "per-image max err", np.round(per_img, 5))
     xs = stem_op['dst'].buf.cpu().numpy()
     xo = col[0].detach().permute(0, 2, 3, 1).numpy()
     print("  stem output err", np.abs(xs - xo).max() / np.abs(xo).max())
