@@ -129,7 +129,7 @@ struct SmemLayout {
     static constexpr int A_BYTES = PASSES * TM * 128;
     static constexpr int B_BYTES = PASSES * BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SCR_BYTES = 4 * 32 * 33 * 4 + 2 * 256 * 4 + 5 * 128 * 4;   // transpose tiles + BN coefficients + bias
+    static constexpr int SCR_BYTES = 4 * 32 * 33 * 4 + 2 * 256 * 4 + 5 * 128 * 4 + 18 * 32;   // transpose tiles + BN coefficients + bias + chunk table
     static constexpr int NS = PASSES == 2 ? 2 : 3;          // A (activation) MMA tile stages
     static constexpr int RB = (BN == 128 && PASSES == 2) ? 2 : 4;   // B (weight image) ring, filled by TMA bulk copies
     static constexpr int RD = (BN == 128 && PASSES == 2) ? 3 : 4;   // raw landing slots (cp.async ring), 16 KB each
@@ -176,6 +176,7 @@ k_conv_tc(TCArgs a) {
     float *s_mmean = s_msh + 128;                // [BN]
     float *s_mistd = s_mmean + 128;              // [BN]
     float *s_bias = s_mistd + 128;               // [BN] forward bias of this CTA's n-tile
+    int4 *s_tab = reinterpret_cast<int4 *>(s_bias + 128);   // [18][2] chunk gather table
 
     const int M = a.N * a.Hg * a.Wg;
     const int mtiles = (M + TM - 1) / TM;
@@ -198,6 +199,8 @@ k_conv_tc(TCArgs a) {
     }
     if (a.has_in_bn)
         for (int c = tid; c < a.Cin; c += NTHREADS_CONV) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
+    for (int c = tid; c < a.kchunks * 2; c += NTHREADS_CONV)
+        s_tab[c] = make_int4(a.tab[c >> 1][(c & 1) * 4], a.tab[c >> 1][(c & 1) * 4 + 1], a.tab[c >> 1][(c & 1) * 4 + 2], a.tab[c >> 1][(c & 1) * 4 + 3]);
     for (int c = tid; c < BN; c += NTHREADS_CONV) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
     if (a.has_mask)
         for (int c = tid; c < BN; c += NTHREADS_CONV) {
@@ -217,65 +220,74 @@ k_conv_tc(TCArgs a) {
         // =========================== producers ===========================
         // cp.async (LDGSTS, zero-fill for padding) lands the raw 128-byte row of chunk it+D in a private
         // raw slot (rows are thread-private: no barrier) while chunk it is read back, transformed (BN+ReLU,
-        // TF32 hi/lo split) and written into the MMA stage.  Tap offsets come from the host-built chunk
-        // table; the per-thread work is two bounds checks and one base pointer per chunk.
+        // TF32 hi/lo split) and written into the MMA stage.  Tap offsets come from the chunk table in
+        // shared memory; per thread and chunk: two bounds checks, one base pointer.
         const int row = tid;
-        const int T = my_tiles * a.kchunks;
+        const int kchunks = a.kchunks, Hin = a.Hin, Win = a.Win, gstride = gridDim.x;
+        const int T = my_tiles * kchunks;
         const uint32_t rowoff = (row >> 3) * 1024 + (row & 7) * 128;
         const uint32_t sw = row & 7;
-
-        auto set_tile = [&](RowCursor &c, int tile) {
-            c.tile = tile;
-            c.kc = 0;
-            const int m = (tile / ntiles) * TM + row;
-            c.rvalid = m < M;
-            const int mm = c.rvalid ? m : 0;
-            const int wo = mm % a.Wg, ho = (mm / a.Wg) % a.Hg, n = mm / (a.Wg * a.Hg);
-            c.h0 = ho * a.in_stride; c.w0 = wo * a.in_stride;
-            c.base = a.in + (((size_t)n * a.Hin + c.h0) * a.Win + c.w0) * a.Cin;
-        };
+        const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
+        const float *const gin = a.in;
+        // issue-side cursor
+        int i_tile = blockIdx.x, i_kc = 0, i_h0 = 0, i_w0 = 0;
+        bool i_rv = false;
+        const float *i_base = gin;
+#define DPP_SET_TILE()                                                                         \
+        {                                                                                      \
+            const int m = (i_tile / ntiles) * TM + row;                                        \
+            i_rv = m < M;                                                                      \
+            const int mm = i_rv ? m : 0;                                                       \
+            const int wo = mm % a.Wg, ho = (mm / a.Wg) % a.Hg, n = mm / (a.Wg * a.Hg);         \
+            i_h0 = ho * a.in_stride; i_w0 = wo * a.in_stride;                                  \
+            i_base = gin + (((size_t)n * Hin + i_h0) * Win + i_w0) * a.Cin;                    \
+        }
+        DPP_SET_TILE();
         uint32_t vbits = 0;           // 2 validity bits per in-flight chunk (ring of RD)
-        auto issue = [&](RowCursor &c, int it) {
-            const int *e = a.tab[c.kc];
-            const bool v0 = c.rvalid && (unsigned)(c.h0 + e[0]) < (unsigned)a.Hin && (unsigned)(c.w0 + e[1]) < (unsigned)a.Win;
-            const bool v1 = c.rvalid && (unsigned)(c.h0 + e[4]) < (unsigned)a.Hin && (unsigned)(c.w0 + e[5]) < (unsigned)a.Win;
-            const float *p0 = v0 ? c.base + e[2] : a.in;
-            const float *p1 = v1 ? c.base + e[6] : a.in;
-            const uint32_t raw = sbase + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                cp_async16(raw + ((j ^ sw) << 4), p0 + (v0 ? j * 4 : 0), v0 ? 16u : 0u);
-                cp_async16(raw + (((j + 4) ^ sw) << 4), p1 + (v1 ? j * 4 : 0), v1 ? 16u : 0u);
-            }
-            cp_async_commit();
-            const uint32_t sh = 2 * (it % RD);
-            vbits = (vbits & ~(3u << sh)) | (((uint32_t)v0 | ((uint32_t)v1 << 1)) << sh);
-            if (++c.kc == a.kchunks) set_tile(c, c.tile + gridDim.x);
-        };
         int kc_p = 0;
-        auto process = [&](int it) {
+        for (int it = -D; it < T; ++it) {
+            const int ii = it + D;    // chunk to issue
+            if (ii < T) {
+                const int4 e0 = s_tab[i_kc * 2], e1 = s_tab[i_kc * 2 + 1];
+                const bool v0 = i_rv && (unsigned)(i_h0 + e0.x) < (unsigned)Hin && (unsigned)(i_w0 + e0.y) < (unsigned)Win;
+                const bool v1 = i_rv && (unsigned)(i_h0 + e1.x) < (unsigned)Hin && (unsigned)(i_w0 + e1.y) < (unsigned)Win;
+                const float *p0 = v0 ? i_base + e0.z : gin;
+                const float *p1 = v1 ? i_base + e1.z : gin;
+                const uint32_t raw = sbase + L::RAW_OFF + (ii % RD) * (TM * 128) + rowoff;
+                const uint32_t z0 = v0 ? 16u : 0u, z1 = v1 ? 16u : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cp_async16(raw + ((j ^ sw) << 4), p0 + (v0 ? j * 4 : 0), z0);
+                    cp_async16(raw + (((j + 4) ^ sw) << 4), p1 + (v1 ? j * 4 : 0), z1);
+                }
+                const uint32_t sh = 2 * (ii % RD);
+                vbits = (vbits & ~(3u << sh)) | (((uint32_t)v0 | ((uint32_t)v1 << 1)) << sh);
+                if (++i_kc == kchunks) { i_kc = 0; i_tile += gstride; DPP_SET_TILE(); }
+            }
+            cp_async_commit();        // (possibly empty) group: keeps the wait_group arithmetic uniform
+            if (it < 0) continue;
+            cp_async_wait<D>();       // chunk `it` has landed
             const uint32_t stage = it % NS, phase = (it / NS) & 1;
-            const int *e = a.tab[kc_p];
+            const int4 e0 = s_tab[kc_p * 2], e1 = s_tab[kc_p * 2 + 1];
             const uint32_t vb = (vbits >> (2 * (it % RD))) & 3u;
-            mbar_wait(bar(NS + stage), phase ^ 1);
+            if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);      // one poller per warp
+            __syncwarp();
             const unsigned char *rawp = smem + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
             unsigned char *rowp = smem + stage * L::A_BYTES + rowoff;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int pj = (j ^ sw) << 4;
                 const bool valid = (j < 4) ? (vb & 1u) : (vb & 2u);
-                const int chan = (j < 4) ? e[3] + j * 4 : e[7] + (j - 4) * 4;
+                const int chan = (j < 4) ? e0.w + j * 4 : e1.w + (j - 4) * 4;
                 float4 x = *reinterpret_cast<const float4 *>(rawp + pj);
-                if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
-                else if (a.has_in_bn) {
+                if (pro) {
                     const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
                     const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
                     x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
                     x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
-                    if (a.in_bn.relu) {
-                        x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-                    }
+                    if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                 }
+                if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 uint4 h;
                 h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
                 *reinterpret_cast<uint4 *>(rowp + pj) = h;
@@ -288,16 +300,9 @@ k_conv_tc(TCArgs a) {
             }
             fence_proxy_async();
             mbar_arrive(bar(stage));
-            if (++kc_p == a.kchunks) kc_p = 0;
-        };
-        RowCursor ci;
-        set_tile(ci, blockIdx.x);
-        for (int i = 0; i < D && i < T; ++i) issue(ci, i);
-        for (int it = 0; it < T; ++it) {
-            if (it + D < T) { issue(ci, it + D); cp_async_wait<D>(); }
-            else cp_async_wait<0>();
-            process(it);
+            if (++kc_p == kchunks) kc_p = 0;
         }
+#undef DPP_SET_TILE
     } else if (warp == 8) {
         // =========================== MMA issuer ===========================
         constexpr int RB = L::RB;
@@ -386,7 +391,8 @@ k_conv_tc(TCArgs a) {
                 }
             };
             prefetch(0);
-            mbar_wait(bar(2 * NS + acc), aphase);
+            if (lane == 0) mbar_wait(bar(2 * NS + acc), aphase);       // one poller per warp
+            __syncwarp();
             tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < BN; c0 += HB) {
@@ -450,7 +456,8 @@ k_conv_tc(TCArgs a) {
         if (want_stats) {
             // combine the four epilogue warps in shared memory, then ONE fp64 atomic per channel per CTA
             // (same-address fp64 atomics serialise in L2: 4x fewer of them)
-            double *comb = reinterpret_cast<double *>(scr);                 // [4][BN/16][32]
+            double *comb = reinterpret_cast<double *>(scr);                 // [4][BN/16][32], aliases the transpose tiles
+            asm volatile("bar.sync 1, 128;" ::: "memory");                  // every epilogue warp is done with them
 #pragma unroll
             for (int i = 0; i < BN / 16; ++i) comb[(ew * (BN / 16) + i) * 32 + lane] = stacc[i];
             asm volatile("bar.sync 1, 128;" ::: "memory");
