@@ -21,6 +21,7 @@
 // TMEM allocator.  Persistent CTAs (<= 1 per SM) walk the tile list, so per-channel fp64 statistics
 // leave the CTA once.
 #include "common.cuh"
+#include <stdlib.h>
 
 using namespace dpp;
 
@@ -64,11 +65,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return u;
-}
+// TF32 operand = fp32 with the low 13 mantissa bits cleared (truncation).  hi = trunc(x), lo = trunc(x - hi):
+// x - hi is exact in fp32, so hi + lo reproduces x to 2^-21 relative - the 3xTF32 split in 3 ALU ops per value
+// (cvt.rna.tf32.f32 expands to a ~10-instruction sequence on sm_100a and dominated the producer loop).
+__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (LBO = 16 B, SBO = 1024 B, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -161,7 +161,7 @@ k_conv_tc(TCArgs a) {
     constexpr int NS = L::NS;
     constexpr int RD = L::RD, D = RD - 1;           // cp.async prefetch distance (chunks in flight)
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // bar index: full[s] = s, empty[s] = NS + s, tfull[a] = 2*NS + a, tempty[a] = 2*NS + 2 + a,
@@ -520,7 +520,7 @@ k_wgrad_tc(WGTArgs a) {
     using L = WgSmem<BN, PASSES>;
     constexpr int NST = L::NST, RD = L::RD, D = RD - 1;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };      // full[s]=s, empty[s]=NST+s, done=2*NST
@@ -891,9 +891,16 @@ int dpp_conv2d_dgrad_tc(const dpp_conv_desc *d, const float *dy, float *dx, int 
     return DPP_OK;
 }
 
+int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
+                           float *db, void *stream);
+
 int dpp_conv2d_wgrad_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
                         float *db, void *stream) {
     if (!tc_supported(d, d->Cout)) return DPP_ENOTSUP;
+    {   // MN-major operand layout (wgrad_tc_mn.cu) unless DPP_WGRAD_MN=0 selects the K-major transposing kernel
+        const char *e = getenv("DPP_WGRAD_MN");
+        if (!e || e[0] != '0') return dpp_conv2d_wgrad_tc_mn(d, x, in_bn, dy, dw, db, stream);
+    }
     WGTArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x; a.dy = dy; a.dw = dw; a.db = db;

@@ -107,9 +107,12 @@ def test_dgrad_tc_vs_simt(shape, precision, tol):
     assert np.allclose(s1, s0, rtol=max(tol * 20, 1e-4), atol=np.abs(s0).max() * tol * 10)
 
 
+@pytest.mark.parametrize("mn", ["1", "0"])
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("precision,tol", [(1, 2e-5), (2, 4e-3)])
-def test_wgrad_tc_vs_simt(shape, precision, tol):
+def test_wgrad_tc_vs_simt(shape, precision, tol, mn, monkeypatch):
+    """mn=1: MN-major operand tiles (wgrad_tc_mn.cu); mn=0: K-major transposing kernel (conv_tc.cu)"""
+    monkeypatch.setenv("DPP_WGRAD_MN", mn)
     N, H, Cin, Cout, k, stride = shape
     outs = []
     for prec in (0, precision):
