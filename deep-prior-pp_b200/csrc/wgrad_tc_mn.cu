@@ -99,7 +99,7 @@ struct Lay {
     static constexpr int NPB = BN / 16;                           // dy pieces (16 B) per thread per chunk
     static constexpr int SLOT = (8 + NPB) * 16 + 16;
     static constexpr int RAW_BYTES = 128 * SLOT;
-    static constexpr int RD = 3;
+    static constexpr int RD = (NST * STAGE_BYTES + 3 * RAW_BYTES + 4096 <= 225 * 1024) ? 3 : 2;
     static constexpr int RAW_OFF = NST * STAGE_BYTES;
     static constexpr int BAR_OFF = RAW_OFF + RD * RAW_BYTES;
     static constexpr int COEF_OFF = BAR_OFF + 256;
