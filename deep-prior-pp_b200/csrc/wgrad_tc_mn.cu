@@ -12,6 +12,7 @@
 // Warp roles / pipeline are those of k_wgrad_tc: warps 0-3 producers (cp.async into private raw slots,
 // BN+ReLU, TF32 hi/lo split), warp 8 lane 0 MMA issuer, warps 4-7 epilogue (TMEM -> red.global.add.v4.f32).
 #include "common.cuh"
+#include <stdlib.h>
 
 using namespace dpp;
 
@@ -48,8 +49,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // (cvt.rna.tf32.f32 expands to a ~10-instruction sequence on sm_100a and dominated the producer loop).
 __device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
 // MN-major SWIZZLE_128B descriptor: LBO = 4096 B (next 32-channel block), SBO = 1024 B (next 8 pixels)
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (256ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo16 = 256, uint32_t sbo16 = 64) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -88,6 +89,7 @@ struct WArgs {
     int N, H, W, Cin, Cout, k, stride, pad, Ho, Wo;
     dpp_bn_ref in_bn; int has_in_bn;
     int mtiles, ntiles, splits, chunks_per_split;
+    int lbo16, sbo16, kstep;     // experiment knobs (DPP_MN_LBO / DPP_MN_SBO / DPP_MN_KSTEP), defaults 256 / 64 / 1024
 };
 
 template <int BN, int PASSES>
@@ -271,11 +273,11 @@ k_wgrad_mn(WArgs a) {
                 const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {            // 4 groups of 8 pixels
-                    const uint64_t ah = make_desc_mn(sa + ks * 1024), bh = make_desc_mn(sb + ks * 1024);
+                    const uint64_t ah = make_desc_mn(sa + ks * a.kstep, a.lbo16, a.sbo16), bh = make_desc_mn(sb + ks * a.kstep, a.lbo16, a.sbo16);
                     const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
                     if (PASSES > 1) {
-                        const uint64_t al = make_desc_mn(sa + 4 * 4096 + ks * 1024);
-                        const uint64_t bl = make_desc_mn(sb + (BNP / 32) * 4096 + ks * 1024);
+                        const uint64_t al = make_desc_mn(sa + 4 * 4096 + ks * a.kstep, a.lbo16, a.sbo16);
+                        const uint64_t bl = make_desc_mn(sb + (BNP / 32) * 4096 + ks * a.kstep, a.lbo16, a.sbo16);
                         mma_tf32(tmem_base, ah, bl, IDESC, first);
                         mma_tf32(tmem_base, al, bh, IDESC, 1u);
                         mma_tf32(tmem_base, ah, bh, IDESC, 1u);
@@ -346,6 +348,8 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
     a.N = d->N; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout;
     a.k = d->k; a.stride = d->stride; a.pad = d->pad; a.Ho = d->Ho; a.Wo = d->Wo;
     if (in_bn) { a.in_bn = *in_bn; a.has_in_bn = 1; }
+    { const char *e; a.lbo16 = (e = getenv("DPP_MN_LBO")) ? atoi(e) : 256; a.sbo16 = (e = getenv("DPP_MN_SBO")) ? atoi(e) : 64;
+      a.kstep = (e = getenv("DPP_MN_KSTEP")) ? atoi(e) : 1024; }
     const int bn = d->Cout > 128 ? 128 : d->Cout;
     const bool p3 = d->precision == 1;
     int rc = -1;
