@@ -897,9 +897,9 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
 int dpp_conv2d_wgrad_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
                         float *db, void *stream) {
     if (!tc_supported(d, d->Cout)) return DPP_ENOTSUP;
-    {   // DPP_WGRAD_MN=1 selects the experimental MN-major operand layout (wgrad_tc_mn.cu); default: K-major transposing kernel
+    {   // MN-major operand layout (wgrad_tc_mn.cu, SWIZZLE_128B_BASE32B) unless DPP_WGRAD_MN=0 selects the K-major transposing kernel
         const char *e = getenv("DPP_WGRAD_MN");
-        if (e && e[0] == '1') return dpp_conv2d_wgrad_tc_mn(d, x, in_bn, dy, dw, db, stream);
+        if (!e || e[0] != '0') return dpp_conv2d_wgrad_tc_mn(d, x, in_bn, dy, dw, db, stream);
     }
     WGTArgs a;
     memset(&a, 0, sizeof(a));

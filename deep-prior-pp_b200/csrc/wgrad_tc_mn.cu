@@ -49,8 +49,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // (cvt.rna.tf32.f32 expands to a ~10-instruction sequence on sm_100a and dominated the producer loop).
 __device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
 // MN-major SWIZZLE_128B descriptor: LBO = 4096 B (next 32-channel block), SBO = 1024 B (next 8 pixels)
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo16 = 256, uint32_t sbo16 = 64) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46) | (2ull << 61);
+// MN-major tf32 operands accept only the SWIZZLE_128B_BASE32B layout (type 1): atoms of 4 K-rows x 128 B,
+// 32-byte chunk index XOR (K-row & 3); LBO = stride between 32-element MN blocks, SBO = between 4-row K atoms.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo16 = 256, uint32_t sbo16 = 32, uint32_t lt = 1) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46) | ((uint64_t)lt << 61);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -89,7 +91,7 @@ struct WArgs {
     int N, H, W, Cin, Cout, k, stride, pad, Ho, Wo;
     dpp_bn_ref in_bn; int has_in_bn;
     int mtiles, ntiles, splits, chunks_per_split;
-    int lbo16, sbo16, kstep;     // experiment knobs (DPP_MN_LBO / DPP_MN_SBO / DPP_MN_KSTEP), defaults 256 / 64 / 1024
+    int lbo16, sbo16, kstep;     // experiment knobs (DPP_MN_LBO / DPP_MN_SBO / DPP_MN_KSTEP), defaults 256 / 32 / 1024
 };
 
 template <int BN, int PASSES>
@@ -172,9 +174,9 @@ k_wgrad_mn(WArgs a) {
         float dbp[NPB * 4];
 #pragma unroll
         for (int i = 0; i < NPB * 4; ++i) dbp[i] = 0.f;
-        // within-stage byte offset of (block, pixel row j, 16-byte chunk c): block*4096 + (j>>3)*1024 + (j&7)*128 + ((c^(j&7))<<4)
-        const uint32_t rowoff = (j >> 3) * 1024 + (j & 7) * 128;
-        const uint32_t sw = j & 7;
+        // within-stage byte offset of (block, pixel row j, 16-byte piece c): block*4096 + j*128 + ((c ^ ((j&3)<<1))<<4)
+        const uint32_t rowoff = j * 128;
+        const uint32_t sw = (j & 3) << 1;
         // pixel cursor of the issue side, advanced by 32 pixels per chunk without divisions
         int p_i = c_begin * 32 + j;
         int wo_i = p_i % Wo, ho_i = (p_i / Wo) % Ho, n_i = p_i / (Wo * Ho);
@@ -348,7 +350,7 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
     a.N = d->N; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout;
     a.k = d->k; a.stride = d->stride; a.pad = d->pad; a.Ho = d->Ho; a.Wo = d->Wo;
     if (in_bn) { a.in_bn = *in_bn; a.has_in_bn = 1; }
-    { const char *e; a.lbo16 = (e = getenv("DPP_MN_LBO")) ? atoi(e) : 256; a.sbo16 = (e = getenv("DPP_MN_SBO")) ? atoi(e) : 64;
+    { const char *e; a.lbo16 = (e = getenv("DPP_MN_LBO")) ? atoi(e) : 256; a.sbo16 = (e = getenv("DPP_MN_SBO")) ? atoi(e) : 32;
       a.kstep = (e = getenv("DPP_MN_KSTEP")) ? atoi(e) : 1024; }
     const int bn = d->Cout > 128 ? 128 : d->Cout;
     const bool p3 = d->precision == 1;

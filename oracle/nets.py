@@ -176,7 +176,7 @@ class OracleNet(object):
         return any(l.kind == 'dropout' for l in self.layers)
 
     # -- forward ------------------------------------------------------------------
-    def forward(self, x, deterministic, masks=None, collect=None):
+    def forward(self, x, deterministic, masks=None, collect=None, relu_masks=None):
         """x: torch tensor (B,C,H,W) fp32 or list of tensors (ScaleNet).
         Returns (out, bn_stats) with bn_stats[layerNum] = (batch mean, batch inv_std).
         ``collect`` (optional dict) receives every layer output by layerNum."""
@@ -226,7 +226,12 @@ class OracleNet(object):
                 o = (a - mean.view(1, -1, 1, 1)) * (gamma * inv_std).view(1, -1, 1, 1) \
                     + beta.view(1, -1, 1, 1)
             elif l.kind == 'relu':
-                o = torch.clamp_min(a, 0)                   # T.maximum(x, 0)
+                if relu_masks is not None and l.layerNum in relu_masks:
+                    # test aid: ReLU with the on/off decisions of another implementation imposed, so
+                    # that boundary pre-activations (|z| ~ roundoff) cannot flip between the two
+                    o = a * relu_masks[l.layerNum].to(DTYPE)
+                else:
+                    o = torch.clamp_min(a, 0)               # T.maximum(x, 0)
             elif l.kind == 'fc':
                 W, b = l.params
                 o = a @ W + b
@@ -407,12 +412,12 @@ class Adam(object):
         self.t = f32(self.t + one)
 
 
-def train_step(net, adam, x, y, lr, numJoints, nDims, weightreg=0.0, masks=None):
+def train_step(net, adam, x, y, lr, numJoints, nDims, weightreg=0.0, masks=None, relu_masks=None):
     """One ``train_model`` call (poseregnettrainer.py:146-160): cost on batch statistics,
     T.grad through them, ADAM, BN running-stat EMA; all from the old shared values."""
     for p in net.params:
         p.grad = None
-    out, stats = net.forward(x, deterministic=False, masks=masks)
+    out, stats = net.forward(x, deterministic=False, masks=masks, relu_masks=relu_masks)
     cost = cost_fn(net, out, y, x.shape[0] if not isinstance(x, (list, tuple)) else x[0].shape[0],
                    numJoints, nDims, weightreg)
     grads = torch.autograd.grad(cost, net.params, allow_unused=True)

@@ -9,9 +9,10 @@ from dpp_b200.lib import lib
 shape = (2, 32, 64, 64, 1, 1)
 N, H, Cin, Cout, k, stride = shape
 ref = None
-for var in [('0', 0, 0, 0)] + [('1', l, s, ks) for l, s, ks in itertools.product((256, 64, 8, 1), (64, 256, 8, 1), (1024, 4096, 128, 32))]:
+for var in [('0', 0, 0, 0)] + [('1', l, s, ks) for l, s, ks in [(256, 32, 1024), (32, 256, 1024), (256, 64, 1024), (256, 32, 512), (1, 32, 1024), (256, 8, 1024)]]:
     os.environ['DPP_WGRAD_MN'] = var[0]
     os.environ['DPP_MN_LBO'], os.environ['DPP_MN_SBO'], os.environ['DPP_MN_KSTEP'] = str(var[1]), str(var[2]), str(var[3])
+    print('running', var, flush=True)
     d, x, w, bias, bn, Ho, keep = _setup(N, H, Cin, Cout, k, stride, 2)
     g = torch.Generator(device='cuda').manual_seed(11)
     dy = torch.randn(N, Ho, Ho, Cout, device='cuda', generator=g)

@@ -105,3 +105,33 @@ def test_fc_fwd_bwd_vs_torch(dims, precision, tol):
     print(dims, precision, "fwd", e, "dW", ew, "dx", ex)
     assert e < tol and ew < tol and ex < tol
     assert torch.allclose(db, b.grad, rtol=1e-4, atol=1e-4 * float(b.grad.abs().max()))
+
+
+def test_adam_matches_oracle_on_identical_gradients():
+    """trainer/optimizer.py:58-90 (ADAM v2, fp32 constants): same gradients in, same weights out -
+    three steps, including zero and tiny gradients, against oracle.nets.Adam (numpy fp32)."""
+    from oracle import nets as O
+    rng = np.random.RandomState(3)
+    n = 200003
+    w0 = rng.randn(n).astype(np.float32)
+    op = torch.from_numpy(w0.copy())
+    oadam = O.Adam([op])
+    w = torch.from_numpy(w0).cuda()
+    m = torch.zeros_like(w); v = torch.zeros_like(w)
+    hyper = torch.tensor([0.0, 1.0, 0.0, 1.0], device='cuda')
+    for step, lr in enumerate([1e-4, 3.3e-4, 1e-3]):
+        g = (rng.randn(n) * 10.0 ** rng.uniform(-9, 1, n)).astype(np.float32)
+        g[::97] = 0.0
+        hyper[0:1].fill_(lr)
+        gd = torch.from_numpy(g).cuda()
+        lib.dpp_adam_step(P(w), P(gd), P(m), P(v), P(hyper), n, None)
+        lib.dpp_adam_tick(P(hyper), None)
+        oadam.step([torch.from_numpy(g)], lr)
+        torch.cuda.synchronize()
+        a, b = w.cpu().numpy(), op.numpy()
+        upd = np.abs(b - w0).max()
+        err = np.abs(a - b).max()
+        print("adam step", step, "max |dw| diff", err, "max update", upd)
+        assert err <= 4e-7 * max(1.0, np.abs(b).max())      # a few ulp of w (pow/sqrt/div rounding)
+        assert np.abs(m.cpu().numpy() - oadam.m[0]).max() <= 1e-6 * np.abs(oadam.m[0]).max()
+        assert np.abs(v.cpu().numpy() - oadam.v[0]).max() <= 1e-6 * np.abs(oadam.v[0]).max()

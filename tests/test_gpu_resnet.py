@@ -62,50 +62,110 @@ def test_forward_deterministic_matches_oracle():
     assert r < 1e-4
 
 
+def _engine_relu_masks(net, onet, eng, w_before):
+    """The on/off decision the engine took at every BN->ReLU of the step it just ran (from its own raw
+    buffers, batch statistics and the pre-step gamma/beta, through the library's dpp_bn_apply), keyed by
+    the oracle's ReLU layer number."""
+    import ctypes as C
+    from dpp_b200.lib import lib
+    from dpp_b200.engine import _ptr
+    w_after = eng.W.clone()
+    eng.W.copy_(w_before)
+    masks, done = {}, set()
+    for op in eng.ops:
+        if op['kind'] == 'conv' and op['in_bn'] is not None:
+            bn, raw = op['in_bn'], op['src']
+        elif op['kind'] == 'bn_apply':
+            bn, raw = op['bn'], op['src']
+        else:
+            continue
+        if id(bn) in done:
+            continue
+        done.add(id(bn))
+        i = net.layers.index(bn)
+        assert onet.layers[i + 1].kind == 'relu'
+        tmp = torch.empty_like(raw.buf)
+        ref = eng._bnref(bn, raw, True, relu=1)
+        lib.dpp_bn_apply(_ptr(raw.buf), C.byref(ref), _ptr(tmp), raw.pixels, int(raw.shape[1]), eng._stream())
+        n, c, h, w = raw.shape
+        masks[i + 1] = (tmp.reshape(n, h, w, c) > 0).permute(0, 3, 1, 2).contiguous().cpu()
+    eng.W.copy_(w_after)
+    torch.cuda.synchronize()
+    return masks
+
+
 @pytest.mark.parametrize("use_graph,precision", [(False, 0), (True, 0), (True, 1)])
 def test_train_step_matches_oracle(use_graph, precision):
-    """precision 0 = fp32 SIMT kernels, 1 = 3xTF32 tcgen05 kernels (conv fwd/dgrad/wgrad)"""
+    """precision 0 = fp32 SIMT kernels, 1 = 3xTF32 tcgen05 kernels (conv fwd/dgrad/wgrad).
+
+    Gradient parity is taken with the engine's ReLU decisions imposed on the (fp64) oracle: about 1e-6 of
+    the ~5e6 BN->ReLU inputs lie within fp32 roundoff of 0 and may legitimately land on either side in two
+    correct implementations; ONE such flip in the last stage changes every gradient below it by
+    ~1/sqrt(#units) = 0.4 % in relative L2, which would drown the 1e-4 bar in coin tosses.  With the
+    decisions pinned, the two backward passes compute the same function and must agree to fp32 accuracy.
+    The un-pinned comparison is still made, with the loose bound such flips allow."""
     from oracle import nets as O
     B, D = 4, 30
     net, onet, eng = _build(0, B, 1, D, precision=precision)
     x, y = _data(B, D)
     adam = O.Adam(onet.params)
     lr = 1e-3
+    lays = [l for l in onet.layers for _ in l.params]
     for step in range(2):
         eng.set_input_nchw(x)
         eng._alloc_training()
         eng.y_in.copy_(torch.from_numpy(y))
+        w_before = eng.W.clone()
         cost = float(eng.train_step(lr, use_graph=use_graph).cpu()[0])
-        ocost, oout, ograds = O.train_step(onet, adam, torch.from_numpy(x), torch.from_numpy(y), lr, 1, D)
-        print("step", step, "cost", cost, ocost)
-        assert abs(cost - ocost) < 1e-4 * abs(ocost)
         grads = eng.gradients()
-        worst = 0.0
-        errs = []
-        for p, og, l in zip(net.params, ograds, [l for l in onet.layers for _ in l.params]):
+        masks = _engine_relu_masks(net, onet, eng, w_before)
+        nflip = 0
+        with torch.no_grad():
+            col = {}
+            onet.forward(torch.from_numpy(x), deterministic=False, collect=col)
+            for ln, m in masks.items():
+                nflip += int(((col[ln] > 0) != m).sum())
+        # un-pinned gradients (no state change: plain autograd on the oracle)
+        out_free, _ = onet.forward(torch.from_numpy(x), deterministic=False)
+        cost_free = O.cost_fn(onet, out_free, torch.from_numpy(y), B, 1, D, 0.0)
+        g_free = torch.autograd.grad(cost_free, onet.params, allow_unused=True)
+        ocost, oout, ograds = O.train_step(onet, adam, torch.from_numpy(x), torch.from_numpy(y), lr, 1, D,
+                                           relu_masks=masks)
+        print("step", step, "cost", cost, ocost, "relu decisions differing from the fp64 oracle:", nflip)
+        assert abs(cost - ocost) < 1e-4 * abs(ocost)
+        worst, worst2, worst_free = 0.0, 0.0, 0.0
+        for p, og, gf, l in zip(net.params, ograds, g_free, lays):
             g = grads[id(p)]
-            og = og.numpy()
             if l.kind in ('conv', 'convpool') and g.ndim == 1:
                 continue            # conv biases feed only BNs: true gradient is exactly 0 (roundoff only)
-            scale = np.abs(og).max() + 1e-12
-            e = float(np.abs(g - og).max() / scale)
+            og = og.numpy()
+            e = float(np.abs(g - og).max() / (np.abs(og).max() + 1e-12))
             e2 = float(np.linalg.norm((g - og).ravel()) / (np.linalg.norm(og.ravel()) + 1e-30))
-            worst = max(worst, e)
-            errs.append(e2)
-            # hard bound: a ReLU whose pre-activation is within fp32 roundoff of 0 can flip between two
-            # correct fp32 implementations (about 1e-6 of the 1e7 ReLU inputs); one flip changes the
-            # gradients below it by ~1 % pointwise (test_block0_backward... shows the kernels themselves
-            # agree with torch-GPU fp32 autograd to 3e-7 on identical inputs)
-            assert e < 0.25 and e2 < 5e-2, (p.name, e, e2, scale)
-        errs = np.array(errs)
-        print("worst grad rel err", worst, "median rel-L2", np.median(errs), "share > 2e-3:", (errs > 2e-3).mean())
-        assert np.median(errs) < 1e-3
-    # parameters after two ADAM steps (skip the zero-gradient conv biases)
-    for p, op_, l in zip(net.params, onet.params, [l for l in onet.layers for _ in l.params]):
-        if l.kind in ('conv', 'convpool') and p.shape == (p.shape[0],) and len(p.shape) == 1:
-            continue
-        a, b = p.get_value(), op_.detach().numpy()
-        assert np.abs(a - b).max() < 2.5e-3 * max(1.0, np.abs(b).max()), p.name   # |step| <= lr each
+            worst, worst2 = max(worst, e), max(worst2, e2)
+            assert e < 5e-4 and e2 < 5e-4, (p.name, e, e2)   # fp32 (engine) vs fp64 (oracle) through 189 layers
+            if gf is not None:
+                gf = gf.numpy()
+                ef = float(np.linalg.norm((g - gf).ravel()) / (np.linalg.norm(gf.ravel()) + 1e-30))
+                worst_free = max(worst_free, ef)
+                assert ef < 5e-2, (p.name, ef)
+        print("pinned-ReLU grad err: max-rel %.3g, rel-L2 %.3g; un-pinned rel-L2 %.3g" % (worst, worst2, worst_free))
+        # parameters after this ADAM step.  The first ADAM step is lr*sign(g): an entry whose gradient is
+        # within roundoff of 0 may move the other way (|diff| = 2 lr); such entries must be rare, the rest
+        # must agree closely.  Then hand the engine's weights to the oracle so that the next step again
+        # compares the same function (skip the zero-gradient conv biases).
+        nbad = ntot = 0
+        for p, op_, l in zip(net.params, onet.params, lays):
+            a = p.get_value()
+            if not (l.kind in ('conv', 'convpool') and a.ndim == 1):
+                b = op_.detach().numpy()
+                diff = np.abs(a - b)
+                assert diff.max() < 2.5e-3 * max(1.0, np.abs(b).max()), p.name   # |step| <= lr each
+                nbad += int((diff > 2e-4).sum())
+                ntot += diff.size
+            with torch.no_grad():
+                op_.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(op_.dtype))
+        print("parameters off by > 2e-4 (0.1 lr) after the step: %d of %d" % (nbad, ntot))
+        assert nbad < 2e-2 * ntot       # ADAM itself is checked exactly in test_adam_matches_oracle_on_identical_gradients
     # BN running statistics (EMA of mean and inv_std)
     for l, ol in zip(net.layers, onet.layers):
         if ol.kind == 'bn':
