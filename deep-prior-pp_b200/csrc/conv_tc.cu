@@ -27,11 +27,26 @@ using namespace dpp;
 
 namespace {
 
+#ifdef DPP_PROFILE
+// Debug timeline (tools/conv_probe.py): CTA 0 appends (tag, clock64) pairs per role into a global buffer.
+__device__ long long *g_prof = nullptr;
+#define PROF_DECL(base_) int prof_n_ = (base_); long long *const prof_p_ = blockIdx.x == 0 ? g_prof : nullptr
+#define PROF(tag_)                                                                   \
+    do {                                                                             \
+        if (prof_p_ != nullptr && prof_n_ % 1000 < 990) {                            \
+            prof_p_[prof_n_] = (tag_); prof_p_[prof_n_ + 1] = clock64(); prof_n_ += 2; \
+        }                                                                            \
+    } while (0)
+#else
+#define PROF_DECL(base_)
+#define PROF(tag_)
+#endif
+
 constexpr int TM = 128;          // pixels per tile (TMEM lanes)
 constexpr int KC = 32;           // floats of K per stage: 128-byte rows
 constexpr int NSTAGE = 3;           // stages of the wgrad kernel (k_conv_tc uses SmemLayout::NS)
 constexpr int NTHREADS = 288;
-constexpr int NTHREADS_CONV = 320;  // k_conv_tc: + warp 9 = weight-image (TMA) loader
+constexpr int NTHREADS_CONV = 448;  // k_conv_tc: 8 producer + 4 epilogue warps, MMA issuer, weight-image (TMA) loader
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,6 +118,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct TCArgs {
     const float *in;      // gathered tensor [N, Hin, Win, Cin]
     const float *wimg;    // packed weight image for this mode
@@ -113,6 +135,7 @@ struct TCArgs {
     int k, pad, in_stride, out_stride;
     int wmode;            // 0 forward, 1 dgrad
     int kchunks;          // ceil(k*k*Cin / 32)
+    int wsh, hsh;         // log2(Wg), log2(Hg) when both are powers of two, else -1 (generic division)
     dpp_bn_ref in_bn; int has_in_bn;
     const float *bias; const float *residual; double *out_stats;
     int accumulate; dpp_bn_ref mask_bn; int has_mask; const float *x_pre; double *dz_stats;
@@ -121,55 +144,103 @@ struct TCArgs {
     int tab[18][8];
 };
 
+// Epilogue geometry: the accumulator tile leaves TMEM row-per-thread, is transposed through a per-warp
+// shared staging tile in batches of CB columns, and is then handled column-per-lane-group so that global
+// loads/stores are 16-byte pieces of contiguous NHWC rows (coalesced) and column statistics are plain
+// per-thread sums.
+template <int BN>
+struct EpiGeo {
+    static constexpr int CB = BN < 32 ? 16 : 32;      // columns per batch
+    static constexpr int LPR = CB / 4;                // lanes per row (16 B each)
+    static constexpr int RPI = 32 / LPR;              // rows per warp instruction
+    static constexpr int NIT = 32 / RPI;              // instructions per batch
+    static constexpr int NB = BN / CB;                // batches per tile
+    static constexpr int NSTEP = NB * NIT;
+    static constexpr int PD = NSTEP < 8 ? NSTEP : 8;  // side-operand prefetch distance (steps)
+    static constexpr int ROW_BYTES = CB == 32 ? 144 : 64;
+    static constexpr int WARP_BYTES = 32 * ROW_BYTES;
+    __device__ static __forceinline__ uint32_t addr(int row, int c4) {
+        return CB == 32 ? (uint32_t)(row * 144 + c4 * 16) : (uint32_t)(row * 64 + ((c4 ^ ((row >> 1) & 3)) << 4));
+    }
+};
+
 // smem carve-up (after 1024-byte alignment):
-//   stage s: A tiles [PASSES][128 rows][128 B], B tiles [PASSES][BN rows][128 B]
-//   then barriers, tmem slot, epilogue scratch
+//   A stages [NS][PASSES][128 rows][128 B], B ring [RB][PASSES][BN rows][128 B], barriers, epilogue
+//   staging tiles, BN coefficients, chunk table, per-warp fp64 statistics
 template <int BN, int PASSES>
 struct SmemLayout {
     static constexpr int A_BYTES = PASSES * TM * 128;
     static constexpr int B_BYTES = PASSES * BN * 128;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SCR_BYTES = 4 * 32 * 33 * 4 + 2 * 256 * 4 + 5 * 128 * 4 + 18 * 32;   // transpose tiles + BN coefficients + bias + chunk table
-    static constexpr int NS = PASSES == 2 ? 2 : 3;          // A (activation) MMA tile stages
+    static constexpr int NS = (BN == 128 && PASSES == 2) ? 3 : 4;   // A (activation) MMA tile stages
     static constexpr int RB = (BN == 128 && PASSES == 2) ? 2 : 4;   // B (weight image) ring, filled by TMA bulk copies
-    static constexpr int RD = (BN == 128 && PASSES == 2) ? 3 : 4;   // raw landing slots (cp.async ring), 16 KB each
     static constexpr int B_OFF = NS * A_BYTES;
-    static constexpr int RAW_OFF = B_OFF + RB * B_BYTES;
-    static constexpr int BAR_OFF = RAW_OFF + RD * TM * 128;
-    static constexpr int SCR_OFF = BAR_OFF + 256;
-    static constexpr int TOTAL = SCR_OFF + SCR_BYTES + 1024;
+    static constexpr int BAR_OFF = B_OFF + RB * B_BYTES;
+    static constexpr int STG_OFF = BAR_OFF + 256;
+    static constexpr int COEF_OFF = STG_OFF + 4 * EpiGeo<BN>::WARP_BYTES;
+    static constexpr int COEF_BYTES = 2 * 256 * 4 + 5 * 128 * 4 + 18 * 32;   // in-BN scale/shift, n-tile coefficients, chunk table
+    static constexpr int STAT_OFF = COEF_OFF + COEF_BYTES;
+    static constexpr int TOTAL = STAT_OFF + 4 * 2 * BN * 8 + 1024;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// pixel-row cursor of a producer thread (issue side): walks (tile, k-chunk) in launch order
-struct RowCursor {
-    int tile, kc;
-    int h0, w0; bool rvalid;      // this thread's pixel of the tile (already multiplied by the stride)
-    const float *base;            // &in[n][h0][w0][0]
-};
+// relaxed wait for the non-critical roles (epilogue, weight loader): back off between polls so the
+// spinning warp does not steal issue slots from the producers on the same scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(40);
+    }
+}
+
+constexpr int NPROD_WARPS = 8;
+constexpr int W_EPI = 8, W_MMA = 12, W_LOAD = 13;
+
+// decode a GEMM row (pixel of the gather grid) -> (n, ho, wo)
+__device__ __forceinline__ void decode_pix(const TCArgs &a, int m, int &n, int &ho, int &wo) {
+    if (a.wsh >= 0) {
+        wo = m & (a.Wg - 1); ho = (m >> a.wsh) & (a.Hg - 1); n = m >> (a.wsh + a.hsh);
+    } else {
+        wo = m % a.Wg; ho = (m / a.Wg) % a.Hg; n = m / (a.Wg * a.Hg);
+    }
+}
 
 template <int BN, int PASSES>
 __global__ void __launch_bounds__(NTHREADS_CONV, 1)
-k_conv_tc(TCArgs a) {
+k_conv_tc(const __grid_constant__ TCArgs a) {
     using L = SmemLayout<BN, PASSES>;
-    constexpr int NS = L::NS;
-    constexpr int RD = L::RD, D = RD - 1;           // cp.async prefetch distance (chunks in flight)
+    using G = EpiGeo<BN>;
+    constexpr int NS = L::NS, RB = L::RB;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    PROF_DECL(lane == 0 ? (warp == 0 ? 0 : warp == W_MMA ? 1000 : warp == W_EPI ? 2000 : warp == W_LOAD ? 3000 : 4000) : 4000);
+    PROF(1);
     // bar index: full[s] = s, empty[s] = NS + s, tfull[a] = 2*NS + a, tempty[a] = 2*NS + 2 + a,
     //            bfull[b] = 2*NS + 4 + b, bempty[b] = 2*NS + 4 + RB + b
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 224);
-    float *scr = reinterpret_cast<float *>(smem + L::SCR_OFF);
-    float *s_scale = scr + 4 * 32 * 33;          // [256] input-BN scale
+    float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);   // [256] input-BN scale
     float *s_shift = s_scale + 256;              // [256]
     float *s_msc = s_shift + 256;                // [BN] mask-BN scale   (this CTA's n-tile)
     float *s_msh = s_msc + 128;                  // [BN] mask-BN shift
@@ -177,6 +248,7 @@ k_conv_tc(TCArgs a) {
     float *s_mistd = s_mmean + 128;              // [BN]
     float *s_bias = s_mistd + 128;               // [BN] forward bias of this CTA's n-tile
     int4 *s_tab = reinterpret_cast<int4 *>(s_bias + 128);   // [18][2] chunk gather table
+    double *s_stat = reinterpret_cast<double *>(smem + L::STAT_OFF);   // [4 warps][2 kinds][BN]
 
     const int M = a.N * a.Hg * a.Wg;
     const int mtiles = (M + TM - 1) / TM;
@@ -187,12 +259,12 @@ k_conv_tc(TCArgs a) {
     constexpr uint32_t TCOLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NS + s), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NS + i), 1); mbar_init(bar(2 * NS + 2 + i), 128); }
-        for (int b = 0; b < L::RB; ++b) { mbar_init(bar(2 * NS + 4 + b), 1); mbar_init(bar(2 * NS + 4 + L::RB + b), 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(bar(s), NPROD_WARPS); mbar_init(bar(NS + s), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NS + i), 1); mbar_init(bar(2 * NS + 2 + i), 4); }
+        for (int b = 0; b < RB; ++b) { mbar_init(bar(2 * NS + 4 + b), 1); mbar_init(bar(2 * NS + 4 + RB + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -210,116 +282,128 @@ k_conv_tc(TCArgs a) {
             s_msc[c] = sc; s_msh[c] = a.mask_bn.beta[cta_n0 + c] - mean * sc;
             s_mmean[c] = mean; s_mistd[c] = istd;
         }
+    for (int c = tid; c < 4 * 2 * BN; c += NTHREADS_CONV) s_stat[c] = 0.0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    PROF(2);
 
-    if (warp < 4) {
+    if (warp < NPROD_WARPS) {
         // =========================== producers ===========================
-        // cp.async (LDGSTS, zero-fill for padding) lands the raw 128-byte row of chunk it+D in a private
-        // raw slot (rows are thread-private: no barrier) while chunk it is read back, transformed (BN+ReLU,
-        // TF32 hi/lo split) and written into the MMA stage.  Tap offsets come from the chunk table in
-        // shared memory; per thread and chunk: two bounds checks, one base pointer.
-        const int row = tid;
+        // 8 warps; warp = (row group rg of 32 rows, half of the 128-byte K row).  A lane owns one 16-byte
+        // piece pc of four rows (sp, sp+8, sp+16, sp+24 of the group): 4 adjacent lanes read one pixel's
+        // contiguous 64 bytes (LDG.128, sector-complete), a quarter-warp writes 8 distinct 16-byte bank groups.
+        // Loads run two chunks ahead in a 3-slot register ring; BN+ReLU and the TF32 hi/lo split happen in
+        // registers and go straight into the swizzled MMA stage (generic stores + fence.proxy.async).
+        const int half = warp & 1, rg = warp >> 1;
+        const int pc = lane & 3, sp = ((lane >> 2) & 1) * 4 + (lane >> 3);
+        const uint32_t rbase = (uint32_t)(rg * 4) * 1024u + (uint32_t)sp * 128u + (uint32_t)((((half << 2) | pc) ^ sp) << 4);
         const int kchunks = a.kchunks, Hin = a.Hin, Win = a.Win, gstride = gridDim.x;
         const int T = my_tiles * kchunks;
-        const uint32_t rowoff = (row >> 3) * 1024 + (row & 7) * 128;
-        const uint32_t sw = row & 7;
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
-        const float *const gin = a.in;
-        // issue-side cursor
-        int i_tile = blockIdx.x, i_kc = 0, i_h0 = 0, i_w0 = 0;
-        bool i_rv = false;
-        const float *i_base = gin;
-#define DPP_SET_TILE()                                                                         \
-        {                                                                                      \
-            const int m = (i_tile / ntiles) * TM + row;                                        \
-            i_rv = m < M;                                                                      \
-            const int mm = i_rv ? m : 0;                                                       \
-            const int wo = mm % a.Wg, ho = (mm / a.Wg) % a.Hg, n = mm / (a.Wg * a.Hg);         \
-            i_h0 = ho * a.in_stride; i_w0 = wo * a.in_stride;                                  \
-            i_base = gin + (((size_t)n * Hin + i_h0) * Win + i_w0) * a.Cin;                    \
-        }
-        DPP_SET_TILE();
-        uint32_t vbits = 0;           // 2 validity bits per in-flight chunk (ring of RD)
-        int kc_p = 0;
-        for (int it = -D; it < T; ++it) {
-            const int ii = it + D;    // chunk to issue
-            if (ii < T) {
-                const int4 e0 = s_tab[i_kc * 2], e1 = s_tab[i_kc * 2 + 1];
-                const bool v0 = i_rv && (unsigned)(i_h0 + e0.x) < (unsigned)Hin && (unsigned)(i_w0 + e0.y) < (unsigned)Win;
-                const bool v1 = i_rv && (unsigned)(i_h0 + e1.x) < (unsigned)Hin && (unsigned)(i_w0 + e1.y) < (unsigned)Win;
-                const float *p0 = v0 ? i_base + e0.z : gin;
-                const float *p1 = v1 ? i_base + e1.z : gin;
-                const uint32_t raw = sbase + L::RAW_OFF + (ii % RD) * (TM * 128) + rowoff;
-                const uint32_t z0 = v0 ? 16u : 0u, z1 = v1 ? 16u : 0u;
+        const float *const gin = a.in + pc * 4;
+        int i_tile = blockIdx.x, i_kc = 0;
+        int r_off[4], r_hw[4];        // element offset of the row's pixel (-1: row beyond M), h0 | w0 << 16
+        auto set_tile = [&]() {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    cp_async16(raw + ((j ^ sw) << 4), p0 + (v0 ? j * 4 : 0), z0);
-                    cp_async16(raw + (((j + 4) ^ sw) << 4), p1 + (v1 ? j * 4 : 0), z1);
-                }
-                const uint32_t sh = 2 * (ii % RD);
-                vbits = (vbits & ~(3u << sh)) | (((uint32_t)v0 | ((uint32_t)v1 << 1)) << sh);
-                if (++i_kc == kchunks) { i_kc = 0; i_tile += gstride; DPP_SET_TILE(); }
+            for (int i = 0; i < 4; ++i) {
+                const int m = (i_tile / ntiles) * TM + rg * 32 + i * 8 + sp;
+                int n, ho, wo;
+                decode_pix(a, m < M ? m : 0, n, ho, wo);
+                const int h0 = ho * a.in_stride, w0 = wo * a.in_stride;
+                r_hw[i] = h0 | (w0 << 16);
+                r_off[i] = m < M ? ((n * Hin + h0) * Win + w0) * a.Cin : -1;
             }
-            cp_async_commit();        // (possibly empty) group: keeps the wait_group arithmetic uniform
-            if (it < 0) continue;
-            cp_async_wait<D>();       // chunk `it` has landed
-            const uint32_t stage = it % NS, phase = (it / NS) & 1;
-            const int4 e0 = s_tab[kc_p * 2], e1 = s_tab[kc_p * 2 + 1];
-            const uint32_t vb = (vbits >> (2 * (it % RD))) & 3u;
-            if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);      // one poller per warp
-            __syncwarp();
-            const unsigned char *rawp = smem + L::RAW_OFF + (it % RD) * (TM * 128) + rowoff;
-            unsigned char *rowp = smem + stage * L::A_BYTES + rowoff;
+        };
+        set_tile();
+        // Loads are issued NCH chunks at a time and then consumed: ptxas tracks all LDGs of a warp on one
+        // scoreboard, so a register ring refilled while it is drained would wait for the newest load at every
+        // step; per round the memory latency is paid once for NCH * 16 KB per CTA.
+        constexpr int NCH = 4;
+        float4 buf[NCH][4];
+        uint32_t meta[NCH];           // validity bits 0-3, channel base << 8
+        auto issue = [&](float4 (&b)[4], uint32_t &mt) {
+            const int4 e = s_tab[i_kc * 2 + half];
+            uint32_t vb = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int pj = (j ^ sw) << 4;
-                const bool valid = (j < 4) ? (vb & 1u) : (vb & 2u);
-                const int chan = (j < 4) ? e0.w + j * 4 : e1.w + (j - 4) * 4;
-                float4 x = *reinterpret_cast<const float4 *>(rawp + pj);
+            for (int i = 0; i < 4; ++i) {
+                const int h = (r_hw[i] & 0xffff) + e.x, w = (r_hw[i] >> 16) + e.y;
+                const bool v = r_off[i] >= 0 && (unsigned)h < (unsigned)Hin && (unsigned)w < (unsigned)Win;
+                b[i] = v ? __ldg(reinterpret_cast<const float4 *>(gin + r_off[i] + e.z)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb |= (uint32_t)v << i;
+            }
+            mt = vb | ((uint32_t)e.w << 8);
+            if (++i_kc == kchunks) { i_kc = 0; i_tile += gstride; set_tile(); }
+        };
+        uint32_t stage = 0, phase = 0;
+        auto process = [&](const float4 (&b)[4], uint32_t mt) {
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pro) {
+                const int chan = (int)(mt >> 8) + pc * 4;
+                sc = *reinterpret_cast<const float4 *>(s_scale + chan);
+                sf = *reinterpret_cast<const float4 *>(s_shift + chan);
+            }
+            PROF(11);
+            if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);
+            __syncwarp();
+            PROF(12);
+            unsigned char *dst = smem + stage * L::A_BYTES + rbase;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 x = b[i];
                 if (pro) {
-                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
-                    const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
                     x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
                     x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
                     if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    if (!((mt >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 uint4 h;
                 h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-                *reinterpret_cast<uint4 *>(rowp + pj) = h;
+                *reinterpret_cast<uint4 *>(dst + i * 1024) = h;
                 if (PASSES > 1) {
                     uint4 l;
                     l.x = to_tf32(x.x - __uint_as_float(h.x)); l.y = to_tf32(x.y - __uint_as_float(h.y));
                     l.z = to_tf32(x.z - __uint_as_float(h.z)); l.w = to_tf32(x.w - __uint_as_float(h.w));
-                    *reinterpret_cast<uint4 *>(rowp + TM * 128 + pj) = l;
+                    *reinterpret_cast<uint4 *>(dst + TM * 128 + i * 1024) = l;
                 }
             }
+            PROF(14);
             fence_proxy_async();
-            mbar_arrive(bar(stage));
-            if (++kc_p == kchunks) kc_p = 0;
+            PROF(15);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(stage));
+            PROF(13);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        };
+#pragma unroll 1
+        for (int it0 = 0; it0 < T; it0 += NCH) {
+            PROF(10);
+#pragma unroll
+            for (int s = 0; s < NCH; ++s)
+                if (it0 + s < T) issue(buf[s], meta[s]);
+#pragma unroll
+            for (int s = 0; s < NCH; ++s)
+                if (it0 + s < T) process(buf[s], meta[s]);
         }
-#undef DPP_SET_TILE
-    } else if (warp == 8) {
+    } else if (warp == W_MMA) {
         // =========================== MMA issuer ===========================
-        constexpr int RB = L::RB;
         if (lane == 0) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t acc = 0, aphase = 0;
-            int it = 0;
+            uint32_t stage = 0, phase = 0, bslot = 0, bphase = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 mbar_wait(bar(2 * NS + 2 + acc), aphase ^ 1);
                 tc_fence_after();
+                PROF(20);
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
-                    const uint32_t stage = it % NS, phase = (it / NS) & 1;
-                    const uint32_t bslot = it % RB, bphase = (it / RB) & 1;
+                for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(bar(2 * NS + 4 + bslot), bphase);
+                    PROF(21);
                     mbar_wait(bar(stage), phase);
                     tc_fence_after();
+                    PROF(22);
                     const uint32_t sa = sbase + stage * L::A_BYTES;
                     const uint32_t sb = sbase + L::B_OFF + bslot * L::B_BYTES;
 #pragma unroll
@@ -338,148 +422,171 @@ k_conv_tc(TCArgs a) {
                     mma_commit(bar(NS + stage));                              // frees the A stage when the MMAs retire
                     mma_commit(bar(2 * NS + 4 + RB + bslot));                 // ... and the weight slot
                     if (kc == a.kchunks - 1) mma_commit(bar(2 * NS + acc));   // accumulator ready
+                    PROF(23);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                    if (++bslot == RB) { bslot = 0; bphase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == W_LOAD) {
         // =========================== weight-image loader ===========================
         // TMA bulk copies of the packed weight images run up to RB chunks ahead of the MMAs
-        constexpr int RB = L::RB;
         if (lane == 0) {
             const int nt = blockIdx.x % ntiles;
-            int it = 0;
+            uint32_t b = 0, bphase = 0;
             for (int t = 0; t < my_tiles; ++t)
-                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
-                    const uint32_t b = it % RB, bphase = (it / RB) & 1;
-                    mbar_wait(bar(2 * NS + 4 + RB + b), bphase ^ 1);
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait_relaxed(bar(2 * NS + 4 + RB + b), bphase ^ 1);
                     const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
                     mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
                     bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
+                    if (++b == RB) { b = 0; bphase ^= 1; }
                 }
         }
     } else {
         // =========================== epilogue ===========================
-        const int ew = warp - 4;                     // TMEM lane quarter
-        const int row = ew * 32 + lane;
-        float *tr = scr + ew * (32 * 33);            // per-warp 32x33 transpose tile
-        double stacc[BN / 16];                       // lane l: column 16*i + (l & 15), kind (l >> 4)
-#pragma unroll
-        for (int i = 0; i < BN / 16; ++i) stacc[i] = 0.0;
+        constexpr int CB = G::CB, LPR = G::LPR, RPI = G::RPI, NIT = G::NIT, NB = G::NB;
+        const int ew = warp - W_EPI;                 // TMEM lane quarter (== warp % 4)
+        unsigned char *stg = smem + L::STG_OFF + ew * G::WARP_BYTES;
+        double *stw = s_stat + ew * 2 * BN;
+        const int c4 = lane % LPR, rsub = lane / LPR;
         const bool want_stats = (a.out_stats != nullptr) || (a.dz_stats != nullptr);
-        // side operand read by the epilogue: residual (forward) or x_pre (dgrad mask)
-        const float *side = a.wmode == 0 ? a.residual : (a.has_mask ? a.x_pre : nullptr);
-        constexpr int HB = BN > 32 ? 32 : BN;        // columns per prefetch batch
+        const bool fwd = a.wmode == 0;
+        // side operand streamed by the epilogue: residual (forward) or x_pre (dgrad mask)
+        const float *side = fwd ? a.residual : (a.has_mask ? a.x_pre : nullptr);
+        const bool acc_out = !fwd && a.accumulate;
         uint32_t acc = 0, aphase = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int tile = blockIdx.x + t * gridDim.x;
-            const int mt = tile / ntiles, nt = tile % ntiles;
-            const int n0 = nt * BN;
-            const int m = mt * TM + row;
-            const bool rvalid = m < M;
-            const int mm = rvalid ? m : 0;
-            const int wo = mm % a.Wg, ho = (mm / a.Wg) % a.Hg, n = mm / (a.Wg * a.Hg);
-            const size_t ob = (((size_t)n * a.Hout + ho * a.out_stride) * a.Wout + wo * a.out_stride) * a.Cn + n0;
-            // prefetch the first batch of the side operand before waiting for the accumulator
-            float4 sd[HB / 4], ex[HB / 4];
-            auto prefetch = [&](int c0) {
+            const int mt = tile / ntiles;
+            const int m = mt * TM + ew * 32 + lane;
+            int ob_own = -1;
+            if (m < M) {
+                int n, ho, wo;
+                decode_pix(a, m, n, ho, wo);
+                ob_own = ((n * a.Hout + ho * a.out_stride) * a.Wout + wo * a.out_stride) * a.Cn + cta_n0;
+            }
+            int ob[NIT];                               // element offset of (row i*RPI+rsub, this lane's 4 columns), -1: no row
 #pragma unroll
-                for (int q = 0; q < HB / 4; ++q) {
-                    sd[q] = (side && rvalid) ? *reinterpret_cast<const float4 *>(side + ob + c0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    ex[q] = (a.wmode == 1 && a.accumulate && rvalid) ? *reinterpret_cast<const float4 *>(a.out + ob + c0 + q * 4)
-                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < NIT; ++i) {
+                ob[i] = __shfl_sync(0xffffffffu, ob_own, i * RPI + rsub);
+                if (ob[i] >= 0) ob[i] += c4 * 4;
+            }
+            // side operand: loaded two column batches at a time, issue-all-then-consume (see the producers)
+            constexpr int RND = NB < 2 ? NB : 2;
+            float4 sdq[RND * NIT];
+            auto side_round = [&](int b0) {
+#pragma unroll
+                for (int k = 0; k < RND * NIT; ++k) {
+                    const int b = b0 + k / NIT, i = k % NIT;
+                    sdq[k] = (side != nullptr && ob[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(side + ob[i] + b * CB))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            prefetch(0);
-            if (lane == 0) mbar_wait(bar(2 * NS + acc), aphase);       // one poller per warp
+            side_round(0);
+            PROF(30);
+            if (lane == 0) mbar_wait_relaxed(bar(2 * NS + acc), aphase);
             __syncwarp();
             tc_fence_after();
+            PROF(31);
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += HB) {
-                float sdv[HB], exv[HB];
+            for (int b = 0; b < NB; ++b) {
+                float v[CB];
 #pragma unroll
-                for (int q = 0; q < HB / 4; ++q) {
-                    sdv[q * 4] = sd[q].x; sdv[q * 4 + 1] = sd[q].y; sdv[q * 4 + 2] = sd[q].z; sdv[q * 4 + 3] = sd[q].w;
-                    exv[q * 4] = ex[q].x; exv[q * 4 + 1] = ex[q].y; exv[q * 4 + 2] = ex[q].z; exv[q * 4 + 3] = ex[q].w;
+                for (int q = 0; q < CB / 16; ++q)
+                    tmem_ld16_nowait(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + b * CB + q * 16, v + q * 16);
+                tmem_ld_wait();
+                PROF(33);
+                if (b == NB - 1) {                     // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(2 * NS + 2 + acc));
                 }
-                if (c0 + HB < BN) prefetch(c0 + HB);
 #pragma unroll
-                for (int cb = c0; cb < c0 + HB; cb += 16) {
-                    float v[16], s0[16], s1[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + cb, v);
-                    if (a.wmode == 0) {
+                for (int q = 0; q < CB / 4; ++q)
+                    *reinterpret_cast<float4 *>(stg + G::addr(lane, q)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                __syncwarp();
+                PROF(34);
+                const int cl = b * CB + c4 * 4;        // this lane's 4 columns of the n-tile
+                float4 cf0, cf1, cf2, cf3;
+                if (fwd) {
+                    cf0 = *reinterpret_cast<const float4 *>(s_bias + cl);
+                } else if (a.has_mask) {
+                    cf0 = *reinterpret_cast<const float4 *>(s_msc + cl); cf1 = *reinterpret_cast<const float4 *>(s_msh + cl);
+                    cf2 = *reinterpret_cast<const float4 *>(s_mmean + cl); cf3 = *reinterpret_cast<const float4 *>(s_mistd + cl);
+                }
+                float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            v[j] += s_bias[cb + j] + sdv[cb - c0 + j];
-                            s0[j] = rvalid ? v[j] : 0.f;
-                            s1[j] = rvalid ? v[j] * v[j] : 0.f;
+                for (int i = 0; i < NIT; ++i) {
+                    const float4 sd = sdq[(b % RND) * NIT + i];
+                    float4 y = *reinterpret_cast<const float4 *>(stg + G::addr(i * RPI + rsub, c4));
+                    const bool valid = ob[i] >= 0;
+                    if (fwd) {
+                        y.x += cf0.x + sd.x; y.y += cf0.y + sd.y; y.z += cf0.z + sd.z; y.w += cf0.w + sd.w;
+                        if (valid) {
+                            s0.x += y.x; s0.y += y.y; s0.z += y.z; s0.w += y.w;
+                            s1.x = fmaf(y.x, y.x, s1.x); s1.y = fmaf(y.y, y.y, s1.y); s1.z = fmaf(y.z, y.z, s1.z); s1.w = fmaf(y.w, y.w, s1.w);
                         }
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            v[j] += exv[cb - c0 + j];
-                            if (a.has_mask) {
-                                const int cl = cb + j;
-                                const float xr = sdv[cb - c0 + j];
-                                const float pre = fmaf(xr, s_msc[cl], s_msh[cl]);
-                                const float dz = (pre > 0.f && rvalid) ? v[j] : 0.f;
-                                v[j] = dz;
-                                s0[j] = dz;
-                                s1[j] = dz * (xr - s_mmean[cl]) * s_mistd[cl];
-                            } else { s0[j] = 0.f; s1[j] = 0.f; }
+                        if (acc_out && valid) {
+                            const float4 ex = *reinterpret_cast<const float4 *>(a.out + ob[i] + b * CB);
+                            y.x += ex.x; y.y += ex.y; y.z += ex.z; y.w += ex.w;
+                        }
+                        if (a.has_mask) {
+                            y.x = (fmaf(sd.x, cf0.x, cf1.x) > 0.f && valid) ? y.x : 0.f;
+                            y.y = (fmaf(sd.y, cf0.y, cf1.y) > 0.f && valid) ? y.y : 0.f;
+                            y.z = (fmaf(sd.z, cf0.z, cf1.z) > 0.f && valid) ? y.z : 0.f;
+                            y.w = (fmaf(sd.w, cf0.w, cf1.w) > 0.f && valid) ? y.w : 0.f;
+                            s0.x += y.x; s0.y += y.y; s0.z += y.z; s0.w += y.w;
+                            s1.x += y.x * (sd.x - cf2.x) * cf3.x; s1.y += y.y * (sd.y - cf2.y) * cf3.y;
+                            s1.z += y.z * (sd.z - cf2.z) * cf3.z; s1.w += y.w * (sd.w - cf2.w) * cf3.w;
                         }
                     }
-                    if (rvalid) {
+                    if (valid) *reinterpret_cast<float4 *>(a.out + ob[i] + b * CB) = y;
+                }
+                PROF(35);
+                if (want_stats) {
+                    // lanes with equal c4 hold partial sums of the same 4 columns over different rows
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4 *>(a.out + ob + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int o = LPR; o < 32; o <<= 1) {
+                        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, o); s0.y += __shfl_xor_sync(0xffffffffu, s0.y, o);
+                        s0.z += __shfl_xor_sync(0xffffffffu, s0.z, o); s0.w += __shfl_xor_sync(0xffffffffu, s0.w, o);
+                        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+                        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
                     }
-                    if (want_stats) {
-                        // column sums over this warp's 32 rows through a 32x33 shared tile: lanes 0-15 end up
-                        // with sum0 of column cb+lane, lanes 16-31 with sum1 of column cb+lane-16
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) { tr[lane * 33 + j] = s0[j]; tr[lane * 33 + 16 + j] = s1[j]; }
-                        __syncwarp();
-                        float tsum = 0.f;
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) tsum += tr[r * 33 + lane];
-                        stacc[cb / 16] += (double)tsum;
-                        __syncwarp();
+                    if (rsub == 0) {                   // one owner lane per (warp, column): plain fp64 read-modify-write
+                        stw[cl] += (double)s0.x; stw[cl + 1] += (double)s0.y; stw[cl + 2] += (double)s0.z; stw[cl + 3] += (double)s0.w;
+                        stw[BN + cl] += (double)s1.x; stw[BN + cl + 1] += (double)s1.y;
+                        stw[BN + cl + 2] += (double)s1.z; stw[BN + cl + 3] += (double)s1.w;
                     }
                 }
+                __syncwarp();                          // staging tile is rewritten by the next batch
+                PROF(36);
+                if ((b % RND) == RND - 1 && b + 1 < NB) side_round(b + 1);
             }
-            tc_fence_before();
-            mbar_arrive(bar(2 * NS + 2 + acc));
+            PROF(32);
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         if (want_stats) {
-            // combine the four epilogue warps in shared memory, then ONE fp64 atomic per channel per CTA
-            // (same-address fp64 atomics serialise in L2: 4x fewer of them)
-            double *comb = reinterpret_cast<double *>(scr);                 // [4][BN/16][32], aliases the transpose tiles
-            asm volatile("bar.sync 1, 128;" ::: "memory");                  // every epilogue warp is done with them
-#pragma unroll
-            for (int i = 0; i < BN / 16; ++i) comb[(ew * (BN / 16) + i) * 32 + lane] = stacc[i];
+            // combine the four epilogue warps, then ONE fp64 atomic per channel and kind per CTA
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (ew == 0) {
-                double *st = a.out_stats ? a.out_stats : a.dz_stats;
-                const int kind = lane >> 4, cl = lane & 15;
-#pragma unroll
-                for (int i = 0; i < BN / 16; ++i) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) t += comb[(w * (BN / 16) + i) * 32 + lane];
-                    atomicAdd(&st[kind * a.Cn + cta_n0 + 16 * i + cl], t);
-                }
+            double *st = a.out_stats ? a.out_stats : a.dz_stats;
+            for (int idx = ew * 32 + lane; idx < 2 * BN; idx += 128) {
+                const double tsum = s_stat[idx] + s_stat[2 * BN + idx] + s_stat[4 * BN + idx] + s_stat[6 * BN + idx];
+                const int kind = idx / BN, col = idx - kind * BN;
+                atomicAdd(&st[kind * a.Cn + cta_n0 + col], tsum);
             }
         }
     }
+    PROF(3);
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
+    PROF(4);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -819,6 +926,13 @@ int dispatch_tc(TCArgs &a, int passes, cudaStream_t st) {
             e[2] = ((r - a.pad) * a.Win + (s - a.pad)) * a.Cin + chan;
             e[3] = chan;
         }
+    a.wsh = a.hsh = -1;
+    if ((a.Wg & (a.Wg - 1)) == 0 && (a.Hg & (a.Hg - 1)) == 0) {
+        a.wsh = 0; while ((1 << a.wsh) < a.Wg) ++a.wsh;
+        a.hsh = 0; while ((1 << a.hsh) < a.Hg) ++a.hsh;
+    }
+    // the kernel indexes both tensors with 32-bit element offsets
+    if ((int64_t)a.N * a.Hin * a.Win * a.Cin >= (1ll << 31) || (int64_t)a.N * a.Hout * a.Wout * a.Cn >= (1ll << 31)) return -1;
     const int bn = a.Cn > 128 ? 128 : a.Cn;
 #define DPP_TC_CASE(B_)                                                    \
     if (bn == B_) return passes > 1 ? launch_tc<B_, 2>(a, st) : launch_tc<B_, 1>(a, st);
@@ -918,3 +1032,11 @@ int dpp_conv2d_wgrad_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }
+
+#ifdef DPP_PROFILE
+extern "C" int dpp_debug_set_prof(void *buf) {
+    long long *p = reinterpret_cast<long long *>(buf);
+    DPP_CUDA(cudaMemcpyToSymbol(g_prof, &p, sizeof(p)));
+    return DPP_OK;
+}
+#endif

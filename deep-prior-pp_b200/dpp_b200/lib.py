@@ -4,6 +4,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, '..', 'csrc', 'libdpp_b200.so'))
+if os.environ.get('DPP_LIB'):      # tools/conv_probe.py: the -DDPP_PROFILE debug build
+    _LIB_PATH = os.path.abspath(os.environ['DPP_LIB'])
 
 
 class DppError(RuntimeError):

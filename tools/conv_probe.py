@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Kernel probe (development tool, GPU only): times dpp_conv2d_fwd / dgrad / wgrad on the ResNet's
+batch-128 layer shapes in isolation (CUDA events, warm and L2-flushed) and, with the -DDPP_PROFILE
+build (make -C deep-prior-pp_b200/csrc prof; DPP_LIB=.../libdpp_b200_prof.so), prints the in-kernel
+clock64 timeline of CTA 0 (producer / MMA / epilogue / loader events)."""
+import ctypes as C
+import os
+import sys
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'deep-prior-pp_b200'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from dpp_b200.lib import lib, ConvDesc, BnRef, PackItem  # noqa: E402
+from test_gpu_conv_tc import _setup, P  # noqa: E402
+
+SHAPES = {  # N, H, Cin, Cout, k, stride, residual
+    'A_3x3_16_16@32': (128, 32, 16, 16, 3, 1, 0),
+    'B_1x1_16_64@32+res': (128, 32, 16, 64, 1, 1, 1),
+    'C_1x1_64_16@32': (128, 32, 64, 16, 1, 1, 0),
+    'D_1x1_256_64@8': (128, 8, 256, 64, 1, 1, 0),
+    'E_3x3_64_64@8': (128, 8, 64, 64, 3, 1, 0),
+    'F_1x1_64_256@8+res': (128, 8, 64, 256, 1, 1, 1),
+    'G_1x1s2_32_16@64': (128, 64, 32, 16, 1, 2, 0),
+    'H_3x3_32_32@16': (128, 16, 32, 32, 3, 1, 0),
+    'Z_tiny': (1, 8, 64, 64, 1, 1, 0),
+}
+TAGS = {1: 'entry', 2: 'setup done', 3: 'role done', 4: 'exit', 10: 'P round start', 11: 'P chunk: loads->wait stage',
+        12: 'P stage free', 13: 'P arrived', 20: 'M acc free', 21: 'M B ready', 22: 'M A ready', 23: 'M committed',
+        30: 'E side issued', 31: 'E acc ready', 32: 'E tile done',
+        14: 'P stored', 15: 'P fenced', 33: 'E tmem loaded', 34: 'E staged', 35: 'E batch stored', 36: 'E batch stats done'}
+
+
+def timeline(prof, maxev=60):
+    ev = []
+    for base, role in ((0, 'P'), (1000, 'M'), (2000, 'E'), (3000, 'L')):
+        i = base
+        while i < base + 990 and prof[i] != 0:
+            ev.append((int(prof[i + 1]), role, int(prof[i])))
+            i += 2
+    if not ev:
+        return
+    ev.sort()
+    t0 = ev[0][0]
+    print("    cycles  role event")
+    for t, role, tag in ev[:maxev]:
+        print("    %7d  %s   %s" % (t - t0, role, TAGS.get(tag, tag)))
+    if len(ev) > maxev:
+        print("    ... %d more events; last at %d" % (len(ev) - maxev, ev[-1][0] - t0))
+
+
+def main():
+    precision = int(os.environ.get('DPP_PRECISION', '1'))
+    which = sys.argv[1:] or list(SHAPES)
+    has_prof = False
+    try:
+        setp = lib.raw('dpp_debug_set_prof')
+        setp.restype = C.c_int
+        setp.argtypes = [C.c_void_p]
+        has_prof = True
+    except AttributeError:
+        pass
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device='cuda')
+    for name in which:
+        N, H, Cin, Cout, k, stride, res = SHAPES[name]
+        d, x, w, bias, bn, Ho, keep = _setup(N, H, Cin, Cout, k, stride, precision)
+        y = torch.empty(N, Ho, Ho, Cout, device='cuda')
+        r = torch.randn(N, Ho, Ho, Cout, device='cuda') if res else None
+        stats = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda')
+
+        def launch():
+            lib.dpp_conv2d_fwd(C.byref(d), P(x), C.byref(bn), P(w), P(bias), P(r), P(y), P(stats), None)
+        for _ in range(3):
+            launch()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            launch()
+        e1.record(); torch.cuda.synchronize()
+        warm = e0.elapsed_time(e1) / 20 * 1e3
+        cold = 0.0
+        for _ in range(5):
+            flush.fill_(1.0)
+            e0.record(); launch(); e1.record(); torch.cuda.synchronize()
+            cold += e0.elapsed_time(e1) / 5 * 1e3
+        byt = 4.0 * (x.numel() + y.numel() * (2 if res else 1))
+        print("%-22s fwd warm %7.1f us  cold %7.1f us   alg bytes %6.1f MB -> %5.0f GB/s warm" % (
+            name, warm, cold, byt / 1e6, byt / warm / 1e3))
+        if has_prof:
+            prof = torch.zeros(5000, dtype=torch.int64, device='cuda')
+            setp(prof.data_ptr())
+            launch()
+            torch.cuda.synchronize()
+            setp(None)
+            timeline(prof.cpu().numpy(), int(os.environ.get('PROBE_EVENTS', '70')))
+
+
+if __name__ == '__main__':
+    main()
