@@ -30,6 +30,9 @@ namespace {
 #ifdef DPP_PROFILE
 // Debug timeline (tools/conv_probe.py): CTA 0 appends (tag, clock64) pairs per role into a global buffer.
 __device__ long long *g_prof = nullptr;
+__device__ int g_dbg = 0;     // experiment knobs: 1 no global loads, 2 no transform/STTM, 4 no MMA, 8 no epilogue body, 16 no setup math
+#define DBG(bit_) (g_dbgv & (bit_))
+#define DBG_DECL const int g_dbgv = g_dbg
 #define PROF_DECL(base_) int prof_n_ = (base_); long long *const prof_p_ = blockIdx.x == 0 ? g_prof : nullptr
 #define PROF(tag_)                                                                   \
     do {                                                                             \
@@ -40,13 +43,15 @@ __device__ long long *g_prof = nullptr;
 #else
 #define PROF_DECL(base_)
 #define PROF(tag_)
+#define DBG(bit_) false
+#define DBG_DECL
 #endif
 
 constexpr int TM = 128;          // pixels per tile (TMEM lanes)
 constexpr int KC = 32;           // floats of K per stage: 128-byte rows
 constexpr int NSTAGE = 3;           // stages of the wgrad kernel (k_conv_tc uses SmemLayout::NS)
 constexpr int NTHREADS = 288;
-constexpr int NTHREADS_CONV = 448;  // k_conv_tc: 8 producer + 4 epilogue warps, MMA issuer, weight-image (TMA) loader
+constexpr int NTHREADS_CONV = 576;  // k_conv_tc: 8 producer + 2 x 4 epilogue warps, MMA issuer, weight-image (TMA) loader
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,6 +106,26 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Elected-lane variants: executed by a CONVERGED warp; elect.sync inside the asm lets ptxas emit bare
+// UTCHMMA / UTCBAR instructions (a lane-0 branch around tcgen05.mma costs an ELECT/BRA.U.ANY loop of
+// ~50 stall cycles per instruction, which dominates when the MMAs are small).
+__device__ __forceinline__ void mma_tf32_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_e(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -150,7 +175,7 @@ struct TCArgs {
 // per-thread sums.
 template <int BN>
 struct EpiGeo {
-    static constexpr int CB = BN < 32 ? 16 : 32;      // columns per batch
+    static constexpr int CB = 16;                     // columns per batch (64-byte row segments)
     static constexpr int LPR = CB / 4;                // lanes per row (16 B each)
     static constexpr int RPI = 32 / LPR;              // rows per warp instruction
     static constexpr int NIT = 32 / RPI;              // instructions per batch
@@ -165,21 +190,24 @@ struct EpiGeo {
 };
 
 // smem carve-up (after 1024-byte alignment):
-//   A stages [NS][PASSES][128 rows][128 B], B ring [RB][PASSES][BN rows][128 B], barriers, epilogue
-//   staging tiles, BN coefficients, chunk table, per-warp fp64 statistics
+//   B ring [RB][PASSES][BN rows][128 B] (weight images, TMA bulk copies), barriers, epilogue staging tiles,
+//   BN coefficients, chunk table, per-warp fp64 statistics.  The A operand lives in TENSOR MEMORY.
+// TMEM columns: [0, 2*BN) two accumulators, [256 + s*32*PASSES, ...) A stage s (hi: K = 32 columns, lo: next 32).
 template <int BN, int PASSES>
 struct SmemLayout {
-    static constexpr int A_BYTES = PASSES * TM * 128;
     static constexpr int B_BYTES = PASSES * BN * 128;
-    static constexpr int NS = (BN == 128 && PASSES == 2) ? 3 : 4;   // A (activation) MMA tile stages
-    static constexpr int RB = (BN == 128 && PASSES == 2) ? 2 : 4;   // B (weight image) ring, filled by TMA bulk copies
-    static constexpr int B_OFF = NS * A_BYTES;
-    static constexpr int BAR_OFF = B_OFF + RB * B_BYTES;
+    static constexpr int NS = 4;                                   // A stages (TMEM)
+    static constexpr int RB = (B_BYTES >= 32768) ? 3 : (B_BYTES >= 16384 ? 4 : 6);   // weight-image ring slots
+    static constexpr int RDG = (B_BYTES >= 32768) ? 2 : 3;         // raw landing slots (16 KB chunks) per producer group
+    static constexpr int A_COL0 = 256, A_COLS = 32 * PASSES;
+    static constexpr int B_OFF = 0;
+    static constexpr int RAW_OFF = B_OFF + RB * B_BYTES;
+    static constexpr int BAR_OFF = RAW_OFF + 2 * RDG * TM * 128;
     static constexpr int STG_OFF = BAR_OFF + 256;
-    static constexpr int COEF_OFF = STG_OFF + 4 * EpiGeo<BN>::WARP_BYTES;
+    static constexpr int COEF_OFF = STG_OFF + 8 * EpiGeo<BN>::WARP_BYTES;
     static constexpr int COEF_BYTES = 2 * 256 * 4 + 5 * 128 * 4 + 18 * 32;   // in-BN scale/shift, n-tile coefficients, chunk table
     static constexpr int STAT_OFF = COEF_OFF + COEF_BYTES;
-    static constexpr int TOTAL = STAT_OFF + 4 * 2 * BN * 8 + 1024;
+    static constexpr int TOTAL = STAT_OFF + 8 * 2 * BN * 8 + 1024;
 };
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float *v) {
@@ -194,6 +222,29 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory, B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
 
 // relaxed wait for the non-critical roles (epilogue, weight loader): back off between polls so the
 // spinning warp does not steal issue slots from the producers on the same scheduler
@@ -213,7 +264,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 }
 
 constexpr int NPROD_WARPS = 8;
-constexpr int W_EPI = 8, W_MMA = 12, W_LOAD = 13;
+constexpr int W_EPI = 8, W_MMA = 16, W_LOAD = 17;      // warps 8-11 / 12-15: epilogue warpgroups 0 / 1
 
 // decode a GEMM row (pixel of the gather grid) -> (n, ho, wo)
 __device__ __forceinline__ void decode_pix(const TCArgs &a, int m, int &n, int &ho, int &wo) {
@@ -236,6 +287,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     PROF_DECL(lane == 0 ? (warp == 0 ? 0 : warp == W_MMA ? 1000 : warp == W_EPI ? 2000 : warp == W_LOAD ? 3000 : 4000) : 4000);
     PROF(1);
+    DBG_DECL;
     // bar index: full[s] = s, empty[s] = NS + s, tfull[a] = 2*NS + a, tempty[a] = 2*NS + 2 + a,
     //            bfull[b] = 2*NS + 4 + b, bempty[b] = 2*NS + 4 + RB + b
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
@@ -248,7 +300,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     float *s_mistd = s_mmean + 128;              // [BN]
     float *s_bias = s_mistd + 128;               // [BN] forward bias of this CTA's n-tile
     int4 *s_tab = reinterpret_cast<int4 *>(s_bias + 128);   // [18][2] chunk gather table
-    double *s_stat = reinterpret_cast<double *>(smem + L::STAT_OFF);   // [4 warps][2 kinds][BN]
+    double *s_stat = reinterpret_cast<double *>(smem + L::STAT_OFF);   // [8 warps][2 kinds][BN]
 
     const int M = a.N * a.Hg * a.Wg;
     const int mtiles = (M + TM - 1) / TM;
@@ -256,10 +308,11 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     const int tiles = mtiles * ntiles;
     // gridDim.x is a multiple of ntiles, so every tile of this CTA has the same n-tile
     const int cta_n0 = (blockIdx.x % ntiles) * BN;
-    constexpr uint32_t TCOLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    constexpr uint32_t TCOLS = 512;              // 2 accumulators + the A stages; one CTA per SM
+    const bool resident = a.kchunks <= RB;       // the whole weight image of this n-tile stays in the ring
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(bar(s), NPROD_WARPS); mbar_init(bar(NS + s), 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(bar(s), NPROD_WARPS / 2); mbar_init(bar(NS + s), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NS + i), 1); mbar_init(bar(2 * NS + 2 + i), 4); }
         for (int b = 0; b < RB; ++b) { mbar_init(bar(2 * NS + 4 + b), 1); mbar_init(bar(2 * NS + 4 + RB + b), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -282,7 +335,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
             s_msc[c] = sc; s_msh[c] = a.mask_bn.beta[cta_n0 + c] - mean * sc;
             s_mmean[c] = mean; s_mistd[c] = istd;
         }
-    for (int c = tid; c < 4 * 2 * BN; c += NTHREADS_CONV) s_stat[c] = 0.0;
+    for (int c = tid; c < 8 * 2 * BN; c += NTHREADS_CONV) s_stat[c] = 0.0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -292,104 +345,115 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
 
     if (warp < NPROD_WARPS) {
         // =========================== producers ===========================
-        // 8 warps; warp = (row group rg of 32 rows, half of the 128-byte K row).  A lane owns one 16-byte
-        // piece pc of four rows (sp, sp+8, sp+16, sp+24 of the group): 4 adjacent lanes read one pixel's
-        // contiguous 64 bytes (LDG.128, sector-complete), a quarter-warp writes 8 distinct 16-byte bank groups.
-        // Loads run two chunks ahead in a 3-slot register ring; BN+ReLU and the TF32 hi/lo split happen in
-        // registers and go straight into the swizzled MMA stage (generic stores + fence.proxy.async).
-        const int half = warp & 1, rg = warp >> 1;
-        const int pc = lane & 3, sp = ((lane >> 2) & 1) * 4 + (lane >> 3);
-        const uint32_t rbase = (uint32_t)(rg * 4) * 1024u + (uint32_t)sp * 128u + (uint32_t)((((half << 2) | pc) ^ sp) << 4);
+        // Two independent groups of 4 warps; group g owns the chunks with (chunk index % 2) == g, so the
+        // synchronisation latencies of the two groups overlap.  warp % 4 = TMEM lane quarter; a thread owns
+        // one GEMM row (pixel).  Per chunk it copies the row's 128 bytes (two taps of 64 B) with cp.async into
+        // a private raw slot RDG-1 chunks ahead (exact wait_group tracking, no registers tied up), reads them
+        // back, applies BN+ReLU, splits into TF32 hi/lo and writes 32 + 32 columns of its TMEM lane
+        // (tcgen05.st): the MMA reads A from tensor memory, A never goes through the swizzled smem layout.
+        constexpr int RDG = L::RDG, D = RDG - 1;
+        const int q = warp & 3, grp = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0;
         const int kchunks = a.kchunks, Hin = a.Hin, Win = a.Win, gstride = gridDim.x;
         const int T = my_tiles * kchunks;
+        const int Tg = (T - grp + 1) / 2;             // chunks of this group: grp, grp + 2, ...
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
-        const float *const gin = a.in + pc * 4;
-        int i_tile = blockIdx.x, i_kc = 0;
-        int r_off[4], r_hw[4];        // element offset of the row's pixel (-1: row beyond M), h0 | w0 << 16
+        const float *const gin = a.in;
+        // raw slot layout: [8 pieces][128 rows][16 B] -> conflict-free for cp.async writes and LDS.128 reads
+        const uint32_t raw_u32 = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
+        const unsigned char *raw_ptr = smem + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
+        int i_tile = blockIdx.x, i_kc = grp;
+        int r_off, r_h0, r_w0;        // element offset of the row's pixel (-1: row beyond M)
         auto set_tile = [&]() {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = (i_tile / ntiles) * TM + rg * 32 + i * 8 + sp;
-                int n, ho, wo;
-                decode_pix(a, m < M ? m : 0, n, ho, wo);
-                const int h0 = ho * a.in_stride, w0 = wo * a.in_stride;
-                r_hw[i] = h0 | (w0 << 16);
-                r_off[i] = m < M ? ((n * Hin + h0) * Win + w0) * a.Cin : -1;
-            }
+            const int m = (i_tile / ntiles) * TM + row;
+            int n, ho, wo;
+            decode_pix(a, m < M ? m : 0, n, ho, wo);
+            r_h0 = ho * a.in_stride; r_w0 = wo * a.in_stride;
+            r_off = m < M ? ((n * Hin + r_h0) * Win + r_w0) * a.Cin : -1;
         };
+        while (i_kc >= kchunks) { i_kc -= kchunks; i_tile += gstride; }
         set_tile();
-        // Loads are issued NCH chunks at a time and then consumed: ptxas tracks all LDGs of a warp on one
-        // scoreboard, so a register ring refilled while it is drained would wait for the newest load at every
-        // step; per round the memory latency is paid once for NCH * 16 KB per CTA.
-        constexpr int NCH = 4;
-        float4 buf[NCH][4];
-        uint32_t meta[NCH];           // validity bits 0-3, channel base << 8
-        auto issue = [&](float4 (&b)[4], uint32_t &mt) {
-            const int4 e = s_tab[i_kc * 2 + half];
-            uint32_t vb = 0;
+        uint32_t vring = 0;           // 2 validity bits per in-flight chunk
+        uint32_t cring = 0;           // (kc & 0xff) per in-flight chunk, 8 bits each (RDG <= 3)
+        uint32_t stage = grp, phase = 0;
+        int islot = 0, pslot = 0;
+#pragma unroll 1
+        for (int i = -D; i < Tg; ++i) {
+            if (i + D < Tg) {
+                const int4 e0 = s_tab[i_kc * 2], e1 = s_tab[i_kc * 2 + 1];
+                const bool v0 = r_off >= 0 && (unsigned)(r_h0 + e0.x) < (unsigned)Hin && (unsigned)(r_w0 + e0.y) < (unsigned)Win;
+                const bool v1 = r_off >= 0 && (unsigned)(r_h0 + e1.x) < (unsigned)Hin && (unsigned)(r_w0 + e1.y) < (unsigned)Win;
+                const float *p0 = gin + (v0 ? r_off + e0.z : 0), *p1 = gin + (v1 ? r_off + e1.z : 0);
+                const uint32_t dst = raw_u32 + islot * (TM * 128);
+                const uint32_t z0 = v0 ? 16u : 0u, z1 = v1 ? 16u : 0u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int h = (r_hw[i] & 0xffff) + e.x, w = (r_hw[i] >> 16) + e.y;
-                const bool v = r_off[i] >= 0 && (unsigned)h < (unsigned)Hin && (unsigned)w < (unsigned)Win;
-                b[i] = v ? __ldg(reinterpret_cast<const float4 *>(gin + r_off[i] + e.z)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb |= (uint32_t)v << i;
+                for (int j = 0; j < 4; ++j) {
+                    if (DBG(1)) break;
+                    cp_async16(dst + j * 2048, p0 + j * 4, z0);
+                    cp_async16(dst + (j + 4) * 2048, p1 + j * 4, z1);
+                }
+                const uint32_t sh2 = 2 * islot, sh8 = 8 * islot;
+                vring = (vring & ~(3u << sh2)) | (((uint32_t)v0 | ((uint32_t)v1 << 1)) << sh2);
+                cring = (cring & ~(0xffu << sh8)) | ((uint32_t)i_kc << sh8);
+                if (++islot == RDG) islot = 0;
+                i_kc += 2;
+                if (i_kc >= kchunks) {
+                    do { i_kc -= kchunks; i_tile += gstride; } while (i_kc >= kchunks);
+                    set_tile();
+                }
             }
-            mt = vb | ((uint32_t)e.w << 8);
-            if (++i_kc == kchunks) { i_kc = 0; i_tile += gstride; set_tile(); }
-        };
-        uint32_t stage = 0, phase = 0;
-        auto process = [&](const float4 (&b)[4], uint32_t mt) {
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pro) {
-                const int chan = (int)(mt >> 8) + pc * 4;
-                sc = *reinterpret_cast<const float4 *>(s_scale + chan);
-                sf = *reinterpret_cast<const float4 *>(s_shift + chan);
-            }
+            cp_async_commit();        // (possibly empty) group: keeps the wait_group arithmetic uniform
+            if (i < 0) continue;
+            cp_async_wait<D>();       // this thread's copies of chunk i have landed
+            const uint32_t vb = (vring >> (2 * pslot)) & 3u;
+            const int kc = (int)((cring >> (8 * pslot)) & 0xffu);
+            const unsigned char *rp = raw_ptr + pslot * (TM * 128);
+            if (++pslot == RDG) pslot = 0;
+            const int4 e0 = s_tab[kc * 2], e1 = s_tab[kc * 2 + 1];
             PROF(11);
             if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);
             __syncwarp();
+            tc_fence_after();
             PROF(12);
-            unsigned char *dst = smem + stage * L::A_BYTES + rbase;
+            const uint32_t ta = t_lane + stage * L::A_COLS;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 x = b[i];
-                if (pro) {
-                    x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
-                    x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
-                    if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                    if (!((mt >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int hh = 0; hh < 4; ++hh) {           // 8 columns (two 16-byte pieces) at a time
+                if (DBG(2)) break;
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int pj = hh * 2 + j;         // piece 0-3: tap A, 4-7: tap B
+                    float4 x = *reinterpret_cast<const float4 *>(rp + pj * 2048);
+                    if (pro) {
+                        const int chan = (pj < 4 ? e0.w : e1.w) + (pj & 3) * 4;
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
+                        const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
+                        x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
+                        x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
+                        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        if (!((vb >> (pj >> 2)) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    hi[4 * j] = to_tf32(x.x); hi[4 * j + 1] = to_tf32(x.y); hi[4 * j + 2] = to_tf32(x.z); hi[4 * j + 3] = to_tf32(x.w);
+                    lo[4 * j] = to_tf32(x.x - __uint_as_float(hi[4 * j])); lo[4 * j + 1] = to_tf32(x.y - __uint_as_float(hi[4 * j + 1]));
+                    lo[4 * j + 2] = to_tf32(x.z - __uint_as_float(hi[4 * j + 2])); lo[4 * j + 3] = to_tf32(x.w - __uint_as_float(hi[4 * j + 3]));
                 }
-                uint4 h;
-                h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-                *reinterpret_cast<uint4 *>(dst + i * 1024) = h;
-                if (PASSES > 1) {
-                    uint4 l;
-                    l.x = to_tf32(x.x - __uint_as_float(h.x)); l.y = to_tf32(x.y - __uint_as_float(h.y));
-                    l.z = to_tf32(x.z - __uint_as_float(h.z)); l.w = to_tf32(x.w - __uint_as_float(h.w));
-                    *reinterpret_cast<uint4 *>(dst + TM * 128 + i * 1024) = l;
-                }
+                tmem_st8(ta + hh * 8, hi);
+                if (PASSES > 1) tmem_st8(ta + 32 + hh * 8, lo);
             }
+            tmem_st_wait();
             PROF(14);
-            fence_proxy_async();
-            PROF(15);
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(stage));
             PROF(13);
-            if (++stage == NS) { stage = 0; phase ^= 1; }
-        };
-#pragma unroll 1
-        for (int it0 = 0; it0 < T; it0 += NCH) {
-            PROF(10);
-#pragma unroll
-            for (int s = 0; s < NCH; ++s)
-                if (it0 + s < T) issue(buf[s], meta[s]);
-#pragma unroll
-            for (int s = 0; s < NCH; ++s)
-                if (it0 + s < T) process(buf[s], meta[s]);
+            stage += 2;
+            if (stage >= NS) { stage -= NS; phase ^= 1; }
         }
     } else if (warp == W_MMA) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // the whole warp runs the loop converged; one elected lane issues (see mma_tf32_ts)
+        {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t acc = 0, aphase = 0;
             uint32_t stage = 0, phase = 0, bslot = 0, bphase = 0;
@@ -399,45 +463,50 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 PROF(20);
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
+                    if (resident) { bslot = kc; bphase = 0; }
                     mbar_wait(bar(2 * NS + 4 + bslot), bphase);
                     PROF(21);
                     mbar_wait(bar(stage), phase);
+                    __syncwarp();
                     tc_fence_after();
                     PROF(22);
-                    const uint32_t sa = sbase + stage * L::A_BYTES;
+                    const uint32_t ta = tmem_base + L::A_COL0 + stage * L::A_COLS;
                     const uint32_t sb = sbase + L::B_OFF + bslot * L::B_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
-                        const uint64_t ah = make_desc(sa + ks * 32), bh = make_desc(sb + ks * 32);
+                        if (DBG(4)) break;
+                        const uint64_t bh = make_desc(sb + ks * 32);
                         const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
                         if (PASSES > 1) {
-                            const uint64_t al = make_desc(sa + TM * 128 + ks * 32), bl = make_desc(sb + BN * 128 + ks * 32);
-                            mma_tf32(d_tmem, ah, bl, IDESC, first);
-                            mma_tf32(d_tmem, al, bh, IDESC, 1u);
-                            mma_tf32(d_tmem, ah, bh, IDESC, 1u);
+                            const uint64_t bl = make_desc(sb + BN * 128 + ks * 32);
+                            mma_tf32_ts(d_tmem, ta + ks * 8, bl, IDESC, first);
+                            mma_tf32_ts(d_tmem, ta + 32 + ks * 8, bh, IDESC, 1u);
+                            mma_tf32_ts(d_tmem, ta + ks * 8, bh, IDESC, 1u);
                         } else {
-                            mma_tf32(d_tmem, ah, bh, IDESC, first);
+                            mma_tf32_ts(d_tmem, ta + ks * 8, bh, IDESC, first);
                         }
                     }
-                    mma_commit(bar(NS + stage));                              // frees the A stage when the MMAs retire
-                    mma_commit(bar(2 * NS + 4 + RB + bslot));                 // ... and the weight slot
-                    if (kc == a.kchunks - 1) mma_commit(bar(2 * NS + acc));   // accumulator ready
+                    mma_commit_e(bar(NS + stage));                              // frees the A stage when the MMAs retire
+                    if (!resident) mma_commit_e(bar(2 * NS + 4 + RB + bslot));  // ... and the weight slot
+                    if (kc == a.kchunks - 1) mma_commit_e(bar(2 * NS + acc));   // accumulator ready
                     PROF(23);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
-                    if (++bslot == RB) { bslot = 0; bphase ^= 1; }
+                    if (!resident && ++bslot == RB) { bslot = 0; bphase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
             }
         }
     } else if (warp == W_LOAD) {
         // =========================== weight-image loader ===========================
-        // TMA bulk copies of the packed weight images run up to RB chunks ahead of the MMAs
+        // TMA bulk copies of the packed weight images: once per CTA when the n-tile's image fits the ring,
+        // otherwise streamed up to RB chunks ahead of the MMAs for every tile
         if (lane == 0) {
             const int nt = blockIdx.x % ntiles;
             uint32_t b = 0, bphase = 0;
-            for (int t = 0; t < my_tiles; ++t)
+            const int rounds = resident ? (my_tiles > 0 ? 1 : 0) : my_tiles;
+            for (int t = 0; t < rounds; ++t)
                 for (int kc = 0; kc < a.kchunks; ++kc) {
-                    mbar_wait_relaxed(bar(2 * NS + 4 + RB + b), bphase ^ 1);
+                    if (!resident) mbar_wait_relaxed(bar(2 * NS + 4 + RB + b), bphase ^ 1);
                     const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
                     mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
                     bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
@@ -446,18 +515,21 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         }
     } else {
         // =========================== epilogue ===========================
+        // two warpgroups: group g owns accumulator g and the CTA's tiles t with t % 2 == g
         constexpr int CB = G::CB, LPR = G::LPR, RPI = G::RPI, NIT = G::NIT, NB = G::NB;
-        const int ew = warp - W_EPI;                 // TMEM lane quarter (== warp % 4)
-        unsigned char *stg = smem + L::STG_OFF + ew * G::WARP_BYTES;
-        double *stw = s_stat + ew * 2 * BN;
+        const int ewarp = warp - W_EPI;              // 0..7
+        const int eg = ewarp >> 2, ew = ewarp & 3;   // group, TMEM lane quarter (== warp % 4)
+        unsigned char *stg = smem + L::STG_OFF + ewarp * G::WARP_BYTES;
+        double *stw = s_stat + ewarp * 2 * BN;
         const int c4 = lane % LPR, rsub = lane / LPR;
         const bool want_stats = (a.out_stats != nullptr) || (a.dz_stats != nullptr);
         const bool fwd = a.wmode == 0;
         // side operand streamed by the epilogue: residual (forward) or x_pre (dgrad mask)
         const float *side = fwd ? a.residual : (a.has_mask ? a.x_pre : nullptr);
         const bool acc_out = !fwd && a.accumulate;
-        uint32_t acc = 0, aphase = 0;
-        for (int t = 0; t < my_tiles; ++t) {
+        const uint32_t acc = eg;
+        uint32_t aphase = 0;
+        for (int t = eg; t < my_tiles; t += 2) {
             const int tile = blockIdx.x + t * gridDim.x;
             const int mt = tile / ntiles;
             const int m = mt * TM + ew * 32 + lane;
@@ -473,16 +545,13 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 ob[i] = __shfl_sync(0xffffffffu, ob_own, i * RPI + rsub);
                 if (ob[i] >= 0) ob[i] += c4 * 4;
             }
-            // side operand: loaded two column batches at a time, issue-all-then-consume (see the producers)
-            constexpr int RND = NB < 2 ? NB : 2;
-            float4 sdq[RND * NIT];
-            auto side_round = [&](int b0) {
+            // side operand: one column batch at a time, issue-all-then-consume (see the producers)
+            float4 sdq[NIT];
+            auto side_round = [&](int b) {
 #pragma unroll
-                for (int k = 0; k < RND * NIT; ++k) {
-                    const int b = b0 + k / NIT, i = k % NIT;
-                    sdq[k] = (side != nullptr && ob[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(side + ob[i] + b * CB))
+                for (int i = 0; i < NIT; ++i)
+                    sdq[i] = (side != nullptr && ob[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(side + ob[i] + b * CB))
                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
             };
             side_round(0);
             PROF(30);
@@ -490,12 +559,19 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
             __syncwarp();
             tc_fence_after();
             PROF(31);
+            if (DBG(8)) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(2 * NS + 2 + acc));
+                aphase ^= 1;
+                continue;
+            }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 float v[CB];
 #pragma unroll
-                for (int q = 0; q < CB / 16; ++q)
-                    tmem_ld16_nowait(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + b * CB + q * 16, v + q * 16);
+                for (int qq = 0; qq < CB / 16; ++qq)
+                    tmem_ld16_nowait(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + b * CB + qq * 16, v + qq * 16);
                 tmem_ld_wait();
                 PROF(33);
                 if (b == NB - 1) {                     // accumulator fully read: hand it back to the MMA warp
@@ -504,8 +580,8 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                     if (lane == 0) mbar_arrive(bar(2 * NS + 2 + acc));
                 }
 #pragma unroll
-                for (int q = 0; q < CB / 4; ++q)
-                    *reinterpret_cast<float4 *>(stg + G::addr(lane, q)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                for (int qq = 0; qq < CB / 4; ++qq)
+                    *reinterpret_cast<float4 *>(stg + G::addr(lane, qq)) = make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
                 __syncwarp();
                 PROF(34);
                 const int cl = b * CB + c4 * 4;        // this lane's 4 columns of the n-tile
@@ -519,7 +595,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < NIT; ++i) {
-                    const float4 sd = sdq[(b % RND) * NIT + i];
+                    const float4 sd = sdq[i];
                     float4 y = *reinterpret_cast<const float4 *>(stg + G::addr(i * RPI + rsub, c4));
                     const bool valid = ob[i] >= 0;
                     if (fwd) {
@@ -545,6 +621,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                     }
                     if (valid) *reinterpret_cast<float4 *>(a.out + ob[i] + b * CB) = y;
                 }
+                if (b + 1 < NB) side_round(b + 1);     // in flight during the statistics / next TMEM load
                 PROF(35);
                 if (want_stats) {
                     // lanes with equal c4 hold partial sums of the same 4 columns over different rows
@@ -563,17 +640,18 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 }
                 __syncwarp();                          // staging tile is rewritten by the next batch
                 PROF(36);
-                if ((b % RND) == RND - 1 && b + 1 < NB) side_round(b + 1);
             }
             PROF(32);
-            if (++acc == 2) { acc = 0; aphase ^= 1; }
+            aphase ^= 1;
         }
         if (want_stats) {
-            // combine the four epilogue warps, then ONE fp64 atomic per channel and kind per CTA
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // combine the eight epilogue warps, then ONE fp64 atomic per channel and kind per CTA
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             double *st = a.out_stats ? a.out_stats : a.dz_stats;
-            for (int idx = ew * 32 + lane; idx < 2 * BN; idx += 128) {
-                const double tsum = s_stat[idx] + s_stat[2 * BN + idx] + s_stat[4 * BN + idx] + s_stat[6 * BN + idx];
+            for (int idx = ewarp * 32 + lane; idx < 2 * BN; idx += 256) {
+                double tsum = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tsum += s_stat[w * 2 * BN + idx];
                 const int kind = idx / BN, col = idx - kind * BN;
                 atomicAdd(&st[kind * a.Cn + cta_n0 + col], tsum);
             }
@@ -777,11 +855,12 @@ k_wgrad_tc(WGTArgs a) {
             }
         }
     } else if (warp == 8) {
-        if (lane == 0 && nchunks > 0) {
+        if (nchunks > 0) {      // converged warp, elected issue
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int ch = 0; ch < nchunks; ++ch) {
                 const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
                 mbar_wait(bar(stage), phase);
+                __syncwarp();
                 tc_fence_after();
                 const uint32_t sa = sbase + stage * L::STAGE_BYTES;
                 const uint32_t sb = sa + L::A_BYTES;
@@ -791,15 +870,15 @@ k_wgrad_tc(WGTArgs a) {
                     const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
                     if (PASSES > 1) {
                         const uint64_t al = make_desc(sa + TM * 128 + ks * 32), bl = make_desc(sb + BN * 128 + ks * 32);
-                        mma_tf32(tmem_base, ah, bl, IDESC, first);
-                        mma_tf32(tmem_base, al, bh, IDESC, 1u);
-                        mma_tf32(tmem_base, ah, bh, IDESC, 1u);
+                        mma_tf32_e(tmem_base, ah, bl, IDESC, first);
+                        mma_tf32_e(tmem_base, al, bh, IDESC, 1u);
+                        mma_tf32_e(tmem_base, ah, bh, IDESC, 1u);
                     } else {
-                        mma_tf32(tmem_base, ah, bh, IDESC, first);
+                        mma_tf32_e(tmem_base, ah, bh, IDESC, first);
                     }
                 }
-                mma_commit(bar(NST + stage));
-                if (ch == nchunks - 1) mma_commit(bar(2 * NST));
+                mma_commit_e(bar(NST + stage));
+                if (ch == nchunks - 1) mma_commit_e(bar(2 * NST));
             }
         }
     } else if (nchunks > 0) {
@@ -1034,6 +1113,10 @@ int dpp_conv2d_wgrad_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref
 }
 
 #ifdef DPP_PROFILE
+extern "C" int dpp_debug_set_flags(int flags) {
+    DPP_CUDA(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(flags)));
+    return DPP_OK;
+}
 extern "C" int dpp_debug_set_prof(void *buf) {
     long long *p = reinterpret_cast<long long *>(buf);
     DPP_CUDA(cudaMemcpyToSymbol(g_prof, &p, sizeof(p)));

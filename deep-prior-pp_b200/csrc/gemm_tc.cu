@@ -47,15 +47,23 @@ __device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// executed by a CONVERGED warp: elect.sync inside the asm lets ptxas emit a bare UTCHMMA (a lane-0 branch
+// around tcgen05.mma costs an ELECT/BRA.U.ANY loop of ~50 stall cycles per instruction)
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     uint32_t r[16];
@@ -209,11 +217,12 @@ k_gemm_tc(GTArgs a) {
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 8) {
-        if (lane == 0 && nchunks > 0) {
+        if (nchunks > 0) {      // converged warp, elected issue
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t stage = 0, phase = 0;
             for (int ch = 0; ch < nchunks; ++ch) {
                 mbar_wait(bar(stage), phase);
+                __syncwarp();
                 tc_fence_after();
                 const uint32_t sa = sbase + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll

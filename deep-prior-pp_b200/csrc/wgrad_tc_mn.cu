@@ -54,15 +54,23 @@ __device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x)
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo16 = 256, uint32_t sbo16 = 32, uint32_t lt = 1) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46) | ((uint64_t)lt << 61);
 }
+// executed by a CONVERGED warp: elect.sync inside the asm lets ptxas emit a bare UTCHMMA (a lane-0 branch
+// around tcgen05.mma costs an ELECT/BRA.U.ANY loop of ~50 stall cycles per instruction)
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     uint32_t r[16];
@@ -263,13 +271,14 @@ k_wgrad_mn(WArgs a) {
             }
         }
     } else if (warp == 8) {
-        if (lane == 0 && nchunks > 0) {
+        if (nchunks > 0) {      // converged warp, elected issue
             // c_format F32, a/b TF32, a_major = b_major = MN (bits 15, 16), N = BNP, M = 128
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                        ((uint32_t)(BNP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int ch = 0; ch < nchunks; ++ch) {
                 const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
                 mbar_wait(bar(stage), phase);
+                __syncwarp();
                 tc_fence_after();
                 const uint32_t sa = sbase + stage * L::STAGE_BYTES;
                 const uint32_t sb = sa + L::A_BYTES;

@@ -62,6 +62,13 @@ def main():
     except AttributeError:
         pass
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device='cuda')
+    if os.environ.get('PROBE_FLAGS'):
+        setf = lib.raw('dpp_debug_set_flags')
+        setf.restype = C.c_int
+        setf.argtypes = [C.c_int]
+        setf(int(os.environ['PROBE_FLAGS']))
+        print("debug flags", os.environ['PROBE_FLAGS'])
+        has_prof = has_prof and os.environ.get('PROBE_TIMELINE', '0') == '1'
     for name in which:
         N, H, Cin, Cout, k, stride, res = SHAPES[name]
         d, x, w, bias, bn, Ho, keep = _setup(N, H, Cin, Cout, k, stride, precision)
@@ -80,14 +87,31 @@ def main():
             launch()
         e1.record(); torch.cuda.synchronize()
         warm = e0.elapsed_time(e1) / 20 * 1e3
+        # the same 20 launches replayed from a CUDA graph: no host launch cost between kernels
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        sp = C.c_void_p(side.cuda_stream)
+
+        def launch_on(stp):
+            lib.dpp_conv2d_fwd(C.byref(d), P(x), C.byref(bn), P(w), P(bias), P(r), P(y), P(stats), stp)
+        with torch.cuda.stream(side):
+            launch_on(sp)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(20):
+                launch_on(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        g.replay(); torch.cuda.synchronize()
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        graph_us = e0.elapsed_time(e1) / 20 * 1e3
         cold = 0.0
         for _ in range(5):
             flush.fill_(1.0)
             e0.record(); launch(); e1.record(); torch.cuda.synchronize()
             cold += e0.elapsed_time(e1) / 5 * 1e3
         byt = 4.0 * (x.numel() + y.numel() * (2 if res else 1))
-        print("%-22s fwd warm %7.1f us  cold %7.1f us   alg bytes %6.1f MB -> %5.0f GB/s warm" % (
-            name, warm, cold, byt / 1e6, byt / warm / 1e3))
+        print("%-22s fwd warm %7.1f us  graph %7.1f us  cold %7.1f us   alg bytes %6.1f MB -> %5.0f GB/s (graph)" % (
+            name, warm, graph_us, cold, byt / 1e6, byt / graph_us / 1e3))
         if has_prof:
             prof = torch.zeros(5000, dtype=torch.int64, device='cuda')
             setp(prof.data_ptr())
