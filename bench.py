@@ -189,7 +189,7 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
-    precision = int(os.environ.get('DPP_PRECISION', '0'))
+    precision = int(os.environ.get('DPP_PRECISION', '1'))
     ds, comp, mean = make_workload(seed=23455 + rank)
     net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=B, numJoints=1, nDims=E))
     eng = Engine(net, precision=precision)
@@ -337,50 +337,65 @@ def count_launches(eng):
 
 
 def measure_dominant_kernel(eng, torch):
-    """Time the heaviest conv class of the step in isolation (20 launches, CUDA events on the
-    launching stream) and express it against the tensor-pipe peak.  The dominant kernels of the
-    fp32 path are the implicit-GEMM convolutions (k_igemm / k_wgrad): we time the forward launch of
-    the layer with the most MACs."""
+    """Roofline of the dominant kernel, timed live with CUDA events on the launching stream.
+
+    The dominant kernel of the step is the implicit-GEMM convolution (k_conv_tc in precision 1/2, k_igemm in
+    precision 0: 126 of the ~285 launches and ~half of the GPU time, see profiles/).  All 63 ConvLayer forward
+    launches of the batch-128 net are issued back to back between two events (their 0.9 GB of activations exceed
+    the 126 MB L2, so no flush is needed) and the average launch is compared with HBM speed: per launch the
+    ALGORITHMIC bytes are 4 * (input + output [+ residual]) elements - at ~20 FLOP/B the
+    layers sit far below the tensor ridge, so the bound is HBM; the tensor-pipe fraction is
+    reported next to it."""
     import ctypes as C
     from dpp_b200.lib import lib
-    best = None
-    for op in eng.ops:
-        if op['kind'] != 'conv':
-            continue
-        d = eng._conv_desc(op)
-        macs = d.N * d.Ho * d.Wo * d.Cout * d.k * d.k * d.Cin
-        if best is None or macs > best[0]:
-            best = (macs, op, d)
-    macs, op, d = best
-    L = op['layer']
-    bnref = eng._bnref(op['in_bn'], op['src'], True) if op['in_bn'] is not None else None
+    convs = [op for op in eng.ops if op['kind'] == 'conv']
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=eng.dev)     # 256 MB > L2
+    calls, bytes_alg, macs = [], 0.0, 0.0
+    for op in convs:
+        d = eng._conv_desc(op)
+        L = op['layer']
+        bnref = eng._bnref(op['in_bn'], op['src'], True) if op['in_bn'] is not None else None
+        stats = eng._stats_ptr(op['out_bn']) if op['out_bn'] is not None else None
+        res = op['residual']
+        calls.append((d, op['src'].buf.data_ptr(), bnref, eng.pview(L.W).data_ptr(), eng.pview(L.b).data_ptr(),
+                      res.buf.data_ptr() if res is not None else None, op['dst'].buf.data_ptr(), stats))
+        bytes_alg += 4.0 * (d.N * d.H * d.W * d.Cin + d.N * d.Ho * d.Wo * d.Cout * (2 if res is not None else 1))
+        macs += float(d.N) * d.Ho * d.Wo * d.Cout * d.k * d.k * d.Cin
 
-    def launch():
-        lib.dpp_conv2d_fwd(C.byref(d), C.c_void_p(op['src'].buf.data_ptr()), C.byref(bnref) if bnref else None,
-                           C.c_void_p(eng.pview(L.W).data_ptr()), C.c_void_p(eng.pview(L.b).data_ptr()), None,
-                           C.c_void_p(op['dst'].buf.data_ptr()), None, st)
+    def chain():
+        for d, x, bnref, w, b, r, y, stats in calls:
+            lib.dpp_conv2d_fwd(C.byref(d), C.c_void_p(x), C.byref(bnref) if bnref else None, C.c_void_p(w),
+                               C.c_void_p(b), C.c_void_p(r) if r else None, C.c_void_p(y), stats, st)
     for _ in range(3):
-        launch()
+        chain()
     torch.cuda.synchronize()
-    tot = 0.0
     reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(reps):
-        flush.fill_(1.0)                     # evict L2 between timed launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); launch(); e1.record()
-        torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    ms = tot / reps
+        chain()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * len(calls))          # average launch
     burst, sustained, hbm, how = peaks()
-    tflops = 2.0 * macs / (ms * 1e-3) / 1e12
-    bytes_alg = 4.0 * (d.N * d.H * d.W * d.Cin + d.N * d.Ho * d.Wo * d.Cout)
-    return {"bound": "tensor", "kernel": "conv2d_fwd %dx%d %d->%d @%dx%d (precision %d)" % (
-                d.k, d.k, d.Cin, d.Cout, d.H, d.W, d.precision),
-            "achieved": tflops, "peak": burst, "unit": "TFLOP/s", "frac": tflops / burst, "traffic": None,
-            "peak_source": "%s bf16 burst (MEASURED_PEAKS.json); TF32 peak is half of it" % how,
-            "ms_per_launch": ms, "hbm_gbs_algorithmic": bytes_alg / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm}
+    per_launch_bytes = bytes_alg / len(calls)
+    gbs = per_launch_bytes / (ms * 1e-3) / 1e9
+    tflops = 2.0 * macs / len(calls) / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get('conv_fwd_avg_bytes_per_launch')
+        except Exception:
+            traffic = None
+    kname = {0: 'k_igemm', 1: 'k_conv_tc<*,2>', 2: 'k_conv_tc<*,1>'}[eng.precision]
+    return {"bound": "hbm", "kernel": "%s: the %d ConvLayer forward launches of the step, back to back" % (kname, len(calls)),
+            "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
+            "peak_source": "%s HBM copy bandwidth (MEASURED_PEAKS.json)" % how,
+            "ms_per_launch": ms, "launches_timed": reps * len(calls), "alg_bytes_per_launch": per_launch_bytes,
+            "tensor_tflops": tflops, "tensor_peak_tflops_tf32": burst / 2.0,
+            "tensor_frac_tf32": tflops * (3.0 if eng.precision == 1 else 1.0) / (burst / 2.0),
+            "note": "tensor_frac counts the MMA work actually issued (3 TF32 MMAs per product in 3xTF32 mode)"}
 
 
 def main():

@@ -146,6 +146,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// L1-allocating variant: the taps of a 3x3 window re-read every input pixel 9 times (and the 64-byte row
+// pieces of narrow layers share 32-byte sectors); with .ca those re-reads hit L1 instead of L2
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -161,6 +166,7 @@ struct TCArgs {
     int wmode;            // 0 forward, 1 dgrad
     int kchunks;          // ceil(k*k*Cin / 32)
     int wsh, hsh;         // log2(Wg), log2(Hg) when both are powers of two, else -1 (generic division)
+    int knobs;            // tuning bits (DPP_TC_KNOBS): 1 = L1-allocating gathers for k > 1
     dpp_bn_ref in_bn; int has_in_bn;
     const float *bias; const float *residual; double *out_stats;
     int accumulate; dpp_bn_ref mask_bn; int has_mask; const float *x_pre; double *dz_stats;
@@ -360,6 +366,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         const int Tg = (T - grp + 1) / 2;             // chunks of this group: grp, grp + 2, ...
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
         const float *const gin = a.in;
+        const bool use_ca = (a.knobs & 1) && a.k > 1;
         // raw slot layout: [8 pieces][128 rows][16 B] -> conflict-free for cp.async writes and LDS.128 reads
         const uint32_t raw_u32 = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
         const unsigned char *raw_ptr = smem + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
@@ -390,8 +397,13 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (DBG(1)) break;
-                    cp_async16(dst + j * 2048, p0 + j * 4, z0);
-                    cp_async16(dst + (j + 4) * 2048, p1 + j * 4, z1);
+                    if (use_ca) {
+                        cp_async16_ca(dst + j * 2048, p0 + j * 4, z0);
+                        cp_async16_ca(dst + (j + 4) * 2048, p1 + j * 4, z1);
+                    } else {
+                        cp_async16(dst + j * 2048, p0 + j * 4, z0);
+                        cp_async16(dst + (j + 4) * 2048, p1 + j * 4, z1);
+                    }
                 }
                 const uint32_t sh2 = 2 * islot, sh8 = 8 * islot;
                 vring = (vring & ~(3u << sh2)) | (((uint32_t)v0 | ((uint32_t)v1 << 1)) << sh2);
@@ -991,8 +1003,15 @@ int launch_tc(const TCArgs &a, cudaStream_t st) {
     return 0;
 }
 
+int tc_knobs() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DPP_TC_KNOBS"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 int dispatch_tc(TCArgs &a, int passes, cudaStream_t st) {
     if (a.kchunks > 18) return -1;
+    a.knobs = tc_knobs();
     const int KK = a.k * a.k;
     for (int kc = 0; kc < a.kchunks; ++kc)
         for (int half = 0; half < 2; ++half) {

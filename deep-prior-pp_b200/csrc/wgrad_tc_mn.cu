@@ -87,6 +87,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -100,6 +103,7 @@ struct WArgs {
     dpp_bn_ref in_bn; int has_in_bn;
     int mtiles, ntiles, splits, chunks_per_split;
     int lbo16, sbo16, kstep;     // experiment knobs (DPP_MN_LBO / DPP_MN_SBO / DPP_MN_KSTEP), defaults 256 / 32 / 1024
+    int knobs;                   // tuning bits (DPP_WG_KNOBS): 1 = L1-allocating activation gathers for k > 1
 };
 
 template <int BN, int PASSES>
@@ -167,6 +171,7 @@ k_wgrad_mn(WArgs a) {
         // producers: thread = (pixel j of the 32-pixel chunk, column quarter q)
         const int j = tid & 31, q = tid >> 5;
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
+        const bool use_ca = (a.knobs & 1) && a.k > 1;
         const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, Wo = a.Wo, Ho = a.Ho, stride = a.stride;
         // piece g of this thread covers rows kd0 + q*32 + g*4 .. +3 = one tap, 4 channels
         int g_dr[8], g_ds[8], g_ch[8];
@@ -201,7 +206,9 @@ k_wgrad_mn(WArgs a) {
                 for (int g = 0; g < 8; ++g) {
                     const int hi = h0 + g_dr[g], wi = w0 + g_ds[g];
                     const bool v = pok && g_ok[g] && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
-                    cp_async16(slot + g * 16, v ? img + ((size_t)hi * W + wi) * Cin + g_ch[g] : a.x, v ? 16u : 0u);
+                    const float *src = v ? img + ((size_t)hi * W + wi) * Cin + g_ch[g] : a.x;
+                    if (use_ca) cp_async16_ca(slot + g * 16, src, v ? 16u : 0u);
+                    else cp_async16(slot + g * 16, src, v ? 16u : 0u);
                     vm |= (uint32_t)v << g;
                 }
 #pragma unroll
@@ -360,7 +367,8 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
     a.k = d->k; a.stride = d->stride; a.pad = d->pad; a.Ho = d->Ho; a.Wo = d->Wo;
     if (in_bn) { a.in_bn = *in_bn; a.has_in_bn = 1; }
     { const char *e; a.lbo16 = (e = getenv("DPP_MN_LBO")) ? atoi(e) : 256; a.sbo16 = (e = getenv("DPP_MN_SBO")) ? atoi(e) : 32;
-      a.kstep = (e = getenv("DPP_MN_KSTEP")) ? atoi(e) : 1024; }
+      a.kstep = (e = getenv("DPP_MN_KSTEP")) ? atoi(e) : 1024;
+      a.knobs = (e = getenv("DPP_WG_KNOBS")) ? atoi(e) : 0; }
     const int bn = d->Cout > 128 ? 128 : d->Cout;
     const bool p3 = d->precision == 1;
     int rc = -1;

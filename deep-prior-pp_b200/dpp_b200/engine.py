@@ -99,12 +99,15 @@ class Engine(object):
         self.output_sym = net.output
         self.B = int(net.cfgParams.batch_size)
         if precision is None:
-            precision = int(os.environ.get('DPP_PRECISION', '0'))
+            precision = int(os.environ.get('DPP_PRECISION', '1'))
         self.precision = precision
         self.world = 1
         self.allreduce_fn = None
         self._graphs = {}
         self._masks_injected = None
+        # backward-weights kernels run on a second stream (forked/joined inside the step, also under graph
+        # capture): their results are only needed by ADAM, so they fill the SMs the dgrad chain leaves idle
+        self._wgrad_stream = torch.cuda.Stream(device=self.dev) if os.environ.get('DPP_WGRAD_STREAM', '1') != '0' else None
         self._lower()
         self._alloc_params()
         self._alloc_activations()
@@ -535,6 +538,11 @@ class Engine(object):
         """Reverse walk.  t.grad of the output tensor must hold dCost/dOut on entry."""
         st = self._stream()
         G = self.G
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        side = self._wgrad_stream
+        side_ptr = C.c_void_p(side.cuda_stream) if side is not None else None
+        forked = False
         pending = {}          # id(bn) -> number of consumers still to contribute
         for bn in self.bns:
             pending[id(bn)] = len(self.bn_consumers.get(id(bn), []))
@@ -585,8 +593,11 @@ class Engine(object):
                 dy = skip_of[id(dst)].grad if (id(dst) in skip_of and dst.bn is None) else dst.grad
                 bn, raw = op['in_bn'], op['src']
                 bnref = self._bnref(bn, raw, True) if bn is not None else None
+                if side is not None:
+                    side.wait_stream(main)          # dy (and everything before it) is complete
+                    forked = True
                 lib.dpp_conv2d_wgrad(C.byref(d), _ptr(raw.buf), C.byref(bnref) if bnref else None, _ptr(dy),
-                                     _ptr(self.pview(L.W, G)), _ptr(self.pview(L.b, G)), st)
+                                     _ptr(self.pview(L.W, G)), _ptr(self.pview(L.b, G)), side_ptr if side is not None else st)
                 if bn is not None:
                     total = len(self.bn_consumers[id(bn)])
                     first = (pending[id(bn)] == total)
@@ -616,6 +627,8 @@ class Engine(object):
                                      int(p.nFilters), int(p.filterDim[0]), int(pad), int(p.poolsize[0]), relu, st)
             else:
                 raise NotImplementedError(k)
+        if forked:
+            main.wait_stream(side)                  # join: the gradient arena is complete
 
     # ---------------------------------------------------------------------------------
     # public API

@@ -112,6 +112,30 @@ def main():
         byt = 4.0 * (x.numel() + y.numel() * (2 if res else 1))
         print("%-22s fwd warm %7.1f us  graph %7.1f us  cold %7.1f us   alg bytes %6.1f MB -> %5.0f GB/s (graph)" % (
             name, warm, graph_us, cold, byt / 1e6, byt / graph_us / 1e3))
+        if os.environ.get('PROBE_BWD', '1') == '1':
+            dy = torch.randn(N, Ho, Ho, Cout, device='cuda')
+            dx = torch.zeros(N, H, H, Cin, device='cuda')
+            dzs = torch.zeros(2 * Cin, dtype=torch.float64, device='cuda')
+            dw = torch.zeros(k * k * Cin, Cout, device='cuda')
+            db = torch.zeros(Cout, device='cuda')
+
+            def graph_time(fn):
+                with torch.cuda.stream(side):
+                    fn(sp)
+                torch.cuda.synchronize()
+                gg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gg, stream=side):
+                    for _ in range(20):
+                        fn(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                gg.replay(); torch.cuda.synchronize()
+                e0.record(); gg.replay(); e1.record(); torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 20 * 1e3
+            t_dg = graph_time(lambda stp: lib.dpp_conv2d_dgrad(C.byref(d), P(dy), P(w), P(dx), 0, C.byref(bn), P(x), P(dzs), stp))
+            t_wg = graph_time(lambda stp: lib.dpp_conv2d_wgrad(C.byref(d), P(x), C.byref(bn), P(dy), P(dw), P(db), stp))
+            bd = 4.0 * (dy.numel() + 2 * x.numel())
+            bw = 4.0 * (dy.numel() + x.numel())
+            print("%-22s dgrad graph %7.1f us (%5.0f GB/s)   wgrad graph %7.1f us (%5.0f GB/s)" % (
+                name, t_dg, bd / t_dg / 1e3, t_wg, bw / t_wg / 1e3))
         if has_prof:
             prof = torch.zeros(5000, dtype=torch.int64, device='cuda')
             setp(prof.data_ptr())
