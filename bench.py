@@ -277,12 +277,12 @@ def run_b200(args):
         cost = eng.train_step(None, use_graph=True)
         cost_host.copy_(cost, non_blocking=False)            # the float train_model() returns
 
-    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3)) if not args.no_e2e else float('nan')
     e2e_val = B * world / (ms_e2e / 1000.)
     clk = clocks.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel class, timed live with CUDA events on this stream
-    roof = measure_dominant_kernel(eng, torch)
+    roof = measure_dominant_kernel(eng, torch) if not args.no_roofline else None
     # ---- kernel launches per step (counted from the engine's op list)
     n_launch = count_launches(eng) + 1
 
@@ -405,6 +405,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-roofline', action='store_true', help='skip the live kernel timing (profiler runs)')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiler runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -20,6 +20,8 @@ k_bn_bwd_apply(const float *__restrict__ dz, const float *__restrict__ x, dpp_bn
     __shared__ float s_k1[256], s_mdz[256], s_mdzx[256], s_mean[256], s_istd[256];
     __shared__ float s_red[BT][4];
     const int tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     for (int c = tid; c < C; c += BT) {
         float mean, istd;
         bn_mean_istd(bn, c, C, mean, istd);
@@ -164,8 +166,8 @@ extern "C" int dpp_bn_bwd_apply(const float *dz, const float *x, const dpp_bn_re
                                 int64_t pixels, int C, void *stream) {
     DPP_CHECK_ARG(dz && x && bn && dz_stats && dx && pixels > 0);
     DPP_CHECK_ARG(C % 4 == 0 && C <= 256 && 256 % (C / 4) == 0 && bn->sums != nullptr);
-    k_bn_bwd_apply<<<ew_grid(pixels, C), BT, 0, S(stream)>>>(dz, x, *bn, dz_stats, skip, dx, dgamma, dbeta, dbias_stats,
-                                                            pixels, C);
+    DPP_CUDA(launch_pdl(1, k_bn_bwd_apply, dim3(ew_grid(pixels, C)), dim3(BT), 0, S(stream), dz, x, *bn, dz_stats, skip, dx,
+                        dgamma, dbeta, dbias_stats, pixels, C));
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }

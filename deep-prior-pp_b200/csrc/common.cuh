@@ -32,6 +32,35 @@ inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch ------------------------------------------------------
+// The step is a chain of ~285 short kernels.  A kernel launched through launch_pdl() may start while its
+// stream predecessor is still draining: it runs its private set-up (barriers, TMEM allocation, tables) and then
+// blocks in pdl_wait() until the predecessor grid has completed and its memory is visible.  Contract: a kernel
+// launched with launch_pdl() touches NO global memory before pdl_wait().  pdl_trigger() lets the next kernel
+// start its own set-up.  Both are no-ops in a kernel launched the ordinary way.  DPP_PDL (bit 0: main chain,
+// bit 1: backward-weights kernels) switches the launch attribute; CUDA-graph capture keeps the programmatic edges.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifndef DPP_PDL_DEFAULT
+#define DPP_PDL_DEFAULT 0
+#endif
+int pdl_mode();     // misc.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int bit, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_mode() & bit) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- BN prologue coefficients ---------------------------------------------------------
 // a = max(x*scale + shift, 0) with scale = gamma*inv_std, shift = beta - mean*scale.
 // mean / inv_std come from fp64 batch sums (train) or stored running stats (test).

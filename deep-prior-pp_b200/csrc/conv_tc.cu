@@ -317,6 +317,9 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     constexpr uint32_t TCOLS = 512;              // 2 accumulators + the A stages; one CTA per SM
     const bool resident = a.kchunks <= RB;       // the whole weight image of this n-tile stays in the ring
 
+    // ---- private set-up: nothing here touches global memory, so under programmatic dependent launch it
+    //      overlaps the tail of the previous kernel of the chain
+    pdl_trigger();
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(bar(s), NPROD_WARPS / 2); mbar_init(bar(NS + s), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NS + i), 1); mbar_init(bar(2 * NS + 2 + i), 4); }
@@ -328,10 +331,13 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (a.has_in_bn)
-        for (int c = tid; c < a.Cin; c += NTHREADS_CONV) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
     for (int c = tid; c < a.kchunks * 2; c += NTHREADS_CONV)
         s_tab[c] = make_int4(a.tab[c >> 1][(c & 1) * 4], a.tab[c >> 1][(c & 1) * 4 + 1], a.tab[c >> 1][(c & 1) * 4 + 2], a.tab[c >> 1][(c & 1) * 4 + 3]);
+    for (int c = tid; c < 8 * 2 * BN; c += NTHREADS_CONV) s_stat[c] = 0.0;
+    // ---- everything below reads what the previous kernels wrote (statistics, activations, weight images)
+    pdl_wait();
+    if (a.has_in_bn)
+        for (int c = tid; c < a.Cin; c += NTHREADS_CONV) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
     for (int c = tid; c < BN; c += NTHREADS_CONV) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
     if (a.has_mask)
         for (int c = tid; c < BN; c += NTHREADS_CONV) {
@@ -341,7 +347,6 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
             s_msc[c] = sc; s_msh[c] = a.mask_bn.beta[cta_n0 + c] - mean * sc;
             s_mmean[c] = mean; s_mistd[c] = istd;
         }
-    for (int c = tid; c < 8 * 2 * BN; c += NTHREADS_CONV) s_stat[c] = 0.0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -558,14 +563,16 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 if (ob[i] >= 0) ob[i] += c4 * 4;
             }
             // side operand: one column batch at a time, issue-all-then-consume (see the producers)
-            float4 sdq[NIT];
+            // two batches in flight (registers): the loads of batch b + 2 are issued as soon as batch b is consumed
+            float4 sdq[2][NIT];
             auto side_round = [&](int b) {
 #pragma unroll
                 for (int i = 0; i < NIT; ++i)
-                    sdq[i] = (side != nullptr && ob[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(side + ob[i] + b * CB))
-                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sdq[b & 1][i] = (side != nullptr && ob[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(side + ob[i] + b * CB))
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             side_round(0);
+            if (NB > 1) side_round(1);
             PROF(30);
             if (lane == 0) mbar_wait_relaxed(bar(2 * NS + acc), aphase);
             __syncwarp();
@@ -607,7 +614,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < NIT; ++i) {
-                    const float4 sd = sdq[i];
+                    const float4 sd = sdq[b & 1][i];
                     float4 y = *reinterpret_cast<const float4 *>(stg + G::addr(i * RPI + rsub, c4));
                     const bool valid = ob[i] >= 0;
                     if (fwd) {
@@ -633,22 +640,27 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                     }
                     if (valid) *reinterpret_cast<float4 *>(a.out + ob[i] + b * CB) = y;
                 }
-                if (b + 1 < NB) side_round(b + 1);     // in flight during the statistics / next TMEM load
+                if (b + 2 < NB) side_round(b + 2);     // in flight during the statistics and the whole next batch
                 PROF(35);
                 if (want_stats) {
-                    // lanes with equal c4 hold partial sums of the same 4 columns over different rows
-#pragma unroll
-                    for (int o = LPR; o < 32; o <<= 1) {
-                        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, o); s0.y += __shfl_xor_sync(0xffffffffu, s0.y, o);
-                        s0.z += __shfl_xor_sync(0xffffffffu, s0.z, o); s0.w += __shfl_xor_sync(0xffffffffu, s0.w, o);
-                        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-                        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-                    }
-                    if (rsub == 0) {                   // one owner lane per (warp, column): plain fp64 read-modify-write
-                        stw[cl] += (double)s0.x; stw[cl + 1] += (double)s0.y; stw[cl + 2] += (double)s0.z; stw[cl + 3] += (double)s0.w;
-                        stw[BN + cl] += (double)s1.x; stw[BN + cl + 1] += (double)s1.y;
-                        stw[BN + cl + 2] += (double)s1.z; stw[BN + cl + 3] += (double)s1.w;
-                    }
+                    // The 8 lanes with equal c4 (rsub = lane / 4) hold partial sums of the same 8 values (4 columns x
+                    // {sum, sum of squares / products}).  Recursive halving: each round a lane keeps half of its values
+                    // and hands the other half to its partner, so 4 + 2 + 1 shuffles leave ONE complete sum per lane
+                    // (instead of 3 x 8 butterfly shuffles) and every lane does one fp64 read-modify-write.
+                    static_assert(LPR == 4, "statistics reduction assumes 4 lanes per row");
+                    const bool h2 = (lane & 4) != 0, h3 = (lane & 8) != 0, h4 = (lane & 16) != 0;
+                    float k0 = h2 ? s1.x : s0.x, k1 = h2 ? s1.y : s0.y, k2 = h2 ? s1.z : s0.z, k3 = h2 ? s1.w : s0.w;
+                    const float g0 = h2 ? s0.x : s1.x, g1 = h2 ? s0.y : s1.y, g2 = h2 ? s0.z : s1.z, g3 = h2 ? s0.w : s1.w;
+                    k0 += __shfl_xor_sync(0xffffffffu, g0, 4); k1 += __shfl_xor_sync(0xffffffffu, g1, 4);
+                    k2 += __shfl_xor_sync(0xffffffffu, g2, 4); k3 += __shfl_xor_sync(0xffffffffu, g3, 4);
+                    float m0 = h3 ? k2 : k0, m1 = h3 ? k3 : k1;
+                    const float n0 = h3 ? k0 : k2, n1 = h3 ? k1 : k3;
+                    m0 += __shfl_xor_sync(0xffffffffu, n0, 8); m1 += __shfl_xor_sync(0xffffffffu, n1, 8);
+                    float t0 = h4 ? m1 : m0;
+                    const float u0 = h4 ? m0 : m1;
+                    t0 += __shfl_xor_sync(0xffffffffu, u0, 16);
+                    // this lane now owns value index (h2, h3, h4) -> kind = h2, column = cl + 2*h3 + h4
+                    stw[(h2 ? BN : 0) + cl + (h3 ? 2 : 0) + (h4 ? 1 : 0)] += (double)t0;
                 }
                 __syncwarp();                          // staging tile is rewritten by the next batch
                 PROF(36);
@@ -999,7 +1011,7 @@ int launch_tc(const TCArgs &a, cudaStream_t st) {
     int ntiles = a.Cn / BN;
     int grid = tiles < 148 ? tiles : 148;
     grid -= grid % ntiles;
-    k_conv_tc<BN, PASSES><<<grid, NTHREADS_CONV, L::TOTAL, st>>>(a);
+    if (launch_pdl(1, k_conv_tc<BN, PASSES>, dim3(grid), dim3(NTHREADS_CONV), L::TOTAL, st, a) != cudaSuccess) return -1;
     return 0;
 }
 

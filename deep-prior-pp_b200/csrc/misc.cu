@@ -1,14 +1,22 @@
 // ABI plumbing: error state, device info, layout conversion, fills.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace dpp {
 thread_local char g_err[512] = "";
+static int g_pdl = -1;
+int pdl_mode() {
+    if (g_pdl < 0) { const char *e = getenv("DPP_PDL"); g_pdl = e ? atoi(e) : DPP_PDL_DEFAULT; }
+    return g_pdl;
+}
 }
 
 using namespace dpp;
 
 extern "C" int dpp_abi_version(void) { return DPP_ABI_VERSION; }
 extern "C" const char *dpp_last_error(void) { return dpp::g_err; }
+extern "C" int dpp_set_pdl(int mode) { dpp::g_pdl = mode < 0 ? -1 : mode; return DPP_OK; }
 
 extern "C" int dpp_device_info(int device, int *cc_out, int *sm_count_out, char *name_out, int name_cap) {
     cudaDeviceProp p;

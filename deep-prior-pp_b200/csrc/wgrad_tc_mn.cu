@@ -147,6 +147,7 @@ k_wgrad_mn(WArgs a) {
     int c_end = c_begin + a.chunks_per_split; if (c_end > total_chunks) c_end = total_chunks;
     const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
 
+    pdl_trigger();      // private set-up first (see common.cuh: programmatic dependent launch)
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NST + s), 1); }
         mbar_init(bar(2 * NST), 1);
@@ -157,10 +158,11 @@ k_wgrad_mn(WArgs a) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (a.has_in_bn)
-        for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
     // zero the MMA stages once: padded dy columns (BN = 16) and rows beyond Kw stay zero
     for (int i = tid; i < NST * L::STAGE_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    pdl_wait();
+    if (a.has_in_bn)
+        for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -350,7 +352,7 @@ int launch(WArgs &a, cudaStream_t st) {
     if (splits > total_chunks) splits = total_chunks;
     a.chunks_per_split = (total_chunks + splits - 1) / splits;
     a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
-    k_wgrad_mn<BN, PASSES><<<tiles * a.splits, NTHREADS, L::TOTAL, st>>>(a);
+    if (launch_pdl(2, k_wgrad_mn<BN, PASSES>, dim3(tiles * a.splits), dim3(NTHREADS), L::TOTAL, st, a) != cudaSuccess) return -1;
     return 0;
 }
 

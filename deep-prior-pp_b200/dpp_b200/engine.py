@@ -108,6 +108,9 @@ class Engine(object):
         # backward-weights kernels run on a second stream (forked/joined inside the step, also under graph
         # capture): their results are only needed by ADAM, so they fill the SMs the dgrad chain leaves idle
         self._wgrad_stream = torch.cuda.Stream(device=self.dev) if os.environ.get('DPP_WGRAD_STREAM', '1') != '0' else None
+        # data-parallel runs: the FC tail's gradients (90 % of the arena, complete when the backward pass has
+        # barely started) are all-reduced on this stream underneath the whole conv backward
+        self._comm_stream = None
         self._lower()
         self._alloc_params()
         self._alloc_activations()
@@ -562,8 +565,29 @@ class Engine(object):
                                  _ptr(self.pview(bn.gamma, G)), _ptr(self.pview(bn.beta, G)), None,
                                  raw.pixels, int(c), st)
 
+        # arena offset where the trailing run of FC parameters starts (the arena is in layer order)
+        early_lo, early_done = None, True
+        if self.allreduce_fn is not None and self.world > 1 and os.environ.get('DPP_EARLY_ALLREDUCE', '1') != '0':
+            tail = []
+            for op in reversed(self.ops):
+                if op['kind'] != 'fc':
+                    break
+                tail.append(op)
+            if tail and len(tail) < len(self.ops):
+                early_lo = min(self.slots[id(v)].offset for op in tail for v in (op['layer'].W, op['layer'].b))
+                early_done = False
+        self._early_lo = None
         for op in reversed(self.ops):
             k = op['kind']
+            if k != 'fc' and not early_done:
+                # the FC backward is complete: start summing [early_lo, end) over the ranks now
+                early_done = True
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(device=self.dev)
+                self._comm_stream.wait_stream(main)
+                with torch.cuda.stream(self._comm_stream):
+                    self.allreduce_fn(G[early_lo:])
+                self._early_lo = early_lo
             if k == 'fc':
                 L = op['layer']
                 src = op['src']
@@ -629,6 +653,8 @@ class Engine(object):
                 raise NotImplementedError(k)
         if forked:
             main.wait_stream(side)                  # join: the gradient arena is complete
+        if self._early_lo is not None:
+            main.wait_stream(self._comm_stream)
 
     # ---------------------------------------------------------------------------------
     # public API
@@ -685,7 +711,8 @@ class Engine(object):
         lib.dpp_loss_sqerr(_ptr(self.t_out.buf), _ptr(self.y_in), _ptr(self.t_out.grad), _ptr(self.cost), self.B, d, st)
         self._run_backward()
         if self.allreduce_fn is not None:
-            self.allreduce_fn(self.G)
+            early = getattr(self, '_early_lo', None)
+            self.allreduce_fn(self.G if early is None else self.G[:early])
         lib.dpp_adam_step(_ptr(self.W), _ptr(self.G), _ptr(self.M), _ptr(self.V), _ptr(self.hyper), self.n_w, st)
         lib.dpp_adam_tick(_ptr(self.hyper), st)
         if self.pack_items is not None:

@@ -46,6 +46,9 @@ const char *dpp_last_error(void);
 /* name of the device the library would run on, compute capability major*10+minor; fails
  * with DPP_ECUDA when no CUDA device is present (the product has no CPU path). */
 int dpp_device_info(int device, int *cc_out, int *sm_count_out, char *name_out, int name_cap);
+/* Programmatic dependent launch of the step's kernel chain (bit 0: main chain, bit 1: backward-weights
+ * kernels); -1 = re-read DPP_PDL from the environment.  Takes effect for launches issued after the call. */
+int dpp_set_pdl(int mode);
 
 /* ---------------------------------------------------------------------------------------
  * BatchNorm reference handed to conv/fc prologues (reference: net/batchnormlayer.py:154-192).
