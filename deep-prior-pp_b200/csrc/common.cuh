@@ -43,7 +43,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 #ifndef DPP_PDL_DEFAULT
-#define DPP_PDL_DEFAULT 0
+#define DPP_PDL_DEFAULT 3
 #endif
 int pdl_mode();     // misc.cu
 

@@ -336,17 +336,50 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     for (int c = tid; c < 8 * 2 * BN; c += NTHREADS_CONV) s_stat[c] = 0.0;
     // ---- everything below reads what the previous kernels wrote (statistics, activations, weight images)
     pdl_wait();
-    if (a.has_in_bn)
-        for (int c = tid; c < a.Cin; c += NTHREADS_CONV) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
-    for (int c = tid; c < BN; c += NTHREADS_CONV) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
-    if (a.has_mask)
-        for (int c = tid; c < BN; c += NTHREADS_CONV) {
-            float mean, istd;
-            bn_mean_istd(a.mask_bn, cta_n0 + c, a.Cn, mean, istd);
-            const float sc = a.mask_bn.gamma[cta_n0 + c] * istd;
-            s_msc[c] = sc; s_msh[c] = a.mask_bn.beta[cta_n0 + c] - mean * sc;
+    // Three independent coefficient jobs on disjoint thread ranges, every job with all its global loads issued
+    // before the fp64 arithmetic: one exposed memory latency instead of a chain of dependent ones.
+    if (tid < 256) {                                   // input-BN scale / shift (Cin <= 256)
+        const int c = tid;
+        if (a.has_in_bn && c < a.Cin) {
+            const bool batch = a.in_bn.sums != nullptr;
+            const double s1 = batch ? a.in_bn.sums[c] : 0.0, s2 = batch ? a.in_bn.sums[a.Cin + c] : 0.0;
+            const float rm = batch ? 0.f : a.in_bn.mean[c], ri = batch ? 0.f : a.in_bn.inv_std[c];
+            const float g = a.in_bn.gamma[c], be = a.in_bn.beta[c];
+            float mean = rm, istd = ri;
+            if (batch) {
+                const double m = s1 / a.in_bn.count;
+                double var = s2 / a.in_bn.count - m * m;
+                if (var < 0.0) var = 0.0;
+                mean = (float)m;
+                istd = (float)(1.0 / sqrt(var + (double)a.in_bn.eps));
+            }
+            const float sc = g * istd;
+            s_scale[c] = sc; s_shift[c] = be - mean * sc;
+        }
+    } else if (tid < 256 + 128) {                      // mask-BN coefficients of this CTA's n-tile (dgrad)
+        const int c = tid - 256;
+        if (a.has_mask && c < BN) {
+            const int cg = cta_n0 + c;
+            const bool batch = a.mask_bn.sums != nullptr;
+            const double s1 = batch ? a.mask_bn.sums[cg] : 0.0, s2 = batch ? a.mask_bn.sums[a.Cn + cg] : 0.0;
+            const float rm = batch ? 0.f : a.mask_bn.mean[cg], ri = batch ? 0.f : a.mask_bn.inv_std[cg];
+            const float g = a.mask_bn.gamma[cg], be = a.mask_bn.beta[cg];
+            float mean = rm, istd = ri;
+            if (batch) {
+                const double m = s1 / a.mask_bn.count;
+                double var = s2 / a.mask_bn.count - m * m;
+                if (var < 0.0) var = 0.0;
+                mean = (float)m;
+                istd = (float)(1.0 / sqrt(var + (double)a.mask_bn.eps));
+            }
+            const float sc = g * istd;
+            s_msc[c] = sc; s_msh[c] = be - mean * sc;
             s_mmean[c] = mean; s_mistd[c] = istd;
         }
+    } else if (tid < 256 + 256) {                      // forward bias of this CTA's n-tile
+        const int c = tid - 384;
+        if (c < BN) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -9,8 +9,14 @@
 // (descriptor: LBO = 4096 B between column blocks, SBO = 1024 B between 8-pixel groups, a_major = b_major =
 // MN in the instruction descriptor).  Producers therefore store whole 16-byte pieces, like the forward kernel.
 //
-// Warp roles / pipeline are those of k_wgrad_tc: warps 0-3 producers (cp.async into private raw slots,
-// BN+ReLU, TF32 hi/lo split), warp 8 lane 0 MMA issuer, warps 4-7 epilogue (TMEM -> red.global.add.v4.f32).
+// Warp roles: warps 0-7 producers (cp.async into private raw slots, BN+ReLU, TF32 hi/lo split), warp 8 MMA
+// issuer; when the pixel loop is done warps 4-7 run the epilogue (TMEM -> red.global.add.v4.f32).
+// Producer mapping (per 32-pixel chunk): warp (q, hf) owns row quarter q and half hf of its 8 row pieces;
+// lane = (pixel sub-row r8 = lane / 4, piece pc = lane % 4).  A thread therefore handles ONE (tap, 4 channels)
+// piece - tap offset and BN coefficients live in registers - for the 4 pixels r8, r8 + 8, r8 + 16, r8 + 24.
+// The 4 lanes of a pixel read 64 contiguous bytes, and a warp's 16-byte stores fall on 8 rows x 4 swizzled
+// columns = all 8 bank groups 4 times: the minimum 4 wavefronts (lane = pixel would take 8).  The dy tile is
+// spread the same way over all 256 threads: thread = (pixel tid / 8, piece tid % 8 of every 32-channel block).
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -101,9 +107,11 @@ struct WArgs {
     const float *x; const float *dy; float *dw; float *db;
     int N, H, W, Cin, Cout, k, stride, pad, Ho, Wo;
     dpp_bn_ref in_bn; int has_in_bn;
-    int mtiles, ntiles, splits, chunks_per_split;
+    int mtiles, ntiles;
+    int splits[8], cps[8];       // per m-tile: pixel splits (CTAs) and 32-pixel chunks per split, sized by the tile's row count
     int lbo16, sbo16, kstep;     // experiment knobs (DPP_MN_LBO / DPP_MN_SBO / DPP_MN_KSTEP), defaults 256 / 32 / 1024
     int knobs;                   // tuning bits (DPP_WG_KNOBS): 1 = L1-allocating activation gathers for k > 1
+    int wsh, hsh;                // log2(Wo), log2(Ho) when both are powers of two, else -1
 };
 
 template <int BN, int PASSES>
@@ -112,9 +120,10 @@ struct Lay {
     static constexpr int A_BYTES = PASSES * 4 * 4096;             // 4 column blocks of 32 (tap,c) rows x 32 pixels
     static constexpr int B_BYTES = PASSES * (BNP / 32) * 4096;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NPB = BN / 16;                           // dy pieces (16 B) per thread per chunk
-    static constexpr int SLOT = (8 + NPB) * 16 + 16;
-    static constexpr int RAW_BYTES = 128 * SLOT;
+    static constexpr int NDY = BNP / 32;                          // dy pieces (16 B) per producer thread per chunk
+    static constexpr int UNITS = (4 + NDY) | 1;                   // 16-byte units per thread slot, odd: conflict-free LDS.128
+    static constexpr int SLOT = UNITS * 16;
+    static constexpr int RAW_BYTES = 256 * SLOT;
     static constexpr int RD = (NST * STAGE_BYTES + 3 * RAW_BYTES + 4096 <= 225 * 1024) ? 3 : 2;
     static constexpr int RAW_OFF = NST * STAGE_BYTES;
     static constexpr int BAR_OFF = RAW_OFF + RD * RAW_BYTES;
@@ -126,7 +135,7 @@ template <int BN, int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_wgrad_mn(WArgs a) {
     using L = Lay<BN, PASSES>;
-    constexpr int RD = L::RD, D = RD - 1, BNP = L::BNP, NPB = L::NPB;
+    constexpr int RD = L::RD, D = RD - 1, BNP = L::BNP, NDY = L::NDY;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
     const uint32_t sbase = smem_u32(smem);
@@ -137,19 +146,20 @@ k_wgrad_mn(WArgs a) {
     float *s_shift = s_scale + 256;
     constexpr uint32_t TCOLS = BNP <= 32 ? 32 : (BNP <= 64 ? 64 : 128);
 
-    const int tile = blockIdx.x % (a.mtiles * a.ntiles), split = blockIdx.x / (a.mtiles * a.ntiles);
-    const int mt = tile / a.ntiles, nt = tile % a.ntiles;
+    const int nt = blockIdx.x % a.ntiles;
+    int split = blockIdx.x / a.ntiles, mt = 0;
+    while (mt + 1 < a.mtiles && split >= a.splits[mt]) { split -= a.splits[mt]; ++mt; }
     const int kd0 = mt * TM, o0 = nt * BN;
     const int Kw = a.k * a.k * a.Cin;
     const int P = a.N * a.Ho * a.Wo;
     const int total_chunks = (P + 31) / 32;
-    const int c_begin = split * a.chunks_per_split;
-    int c_end = c_begin + a.chunks_per_split; if (c_end > total_chunks) c_end = total_chunks;
+    const int c_begin = split * a.cps[mt];
+    int c_end = c_begin + a.cps[mt]; if (c_end > total_chunks) c_end = total_chunks;
     const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
 
     pdl_trigger();      // private set-up first (see common.cuh: programmatic dependent launch)
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NST + s), 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 256); mbar_init(bar(NST + s), 1); }
         mbar_init(bar(2 * NST), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -169,114 +179,139 @@ k_wgrad_mn(WArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // producers: thread = (pixel j of the 32-pixel chunk, column quarter q)
-        const int j = tid & 31, q = tid >> 5;
+    if (warp < 8) {
+        const int q = warp & 3, hf = warp >> 2;
+        const int pc = lane & 3, r8 = lane >> 2;
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
         const bool use_ca = (a.knobs & 1) && a.k > 1;
         const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, Wo = a.Wo, Ho = a.Ho, stride = a.stride;
-        // piece g of this thread covers rows kd0 + q*32 + g*4 .. +3 = one tap, 4 channels
-        int g_dr[8], g_ds[8], g_ch[8];
-        bool g_ok[8];
+        // ---- activation role: piece g of quarter q = rows kd .. kd+3 = one tap, 4 channels
+        const int g = hf * 4 + pc;
+        const int kd = kd0 + q * 32 + g * 4;
+        const bool g_ok = kd < Kw;                   // rows beyond K are never written: the stage stays zero there
+        const int tap = g_ok ? kd / Cin : 0;
+        const int chn = g_ok ? kd - tap * Cin : 0;
+        const int dr = tap / a.k - a.pad, ds = tap % a.k - a.pad;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pro && g_ok) { sc = *reinterpret_cast<const float4 *>(s_scale + chn); sf = *reinterpret_cast<const float4 *>(s_shift + chn); }
+        // byte offset inside a stage of (column block q, pixel row j = i*8 + r8, piece g): the swizzle only looks at j & 3 = r8 & 3
+        const uint32_t a_off = q * 4096 + r8 * 128 + (((uint32_t)g ^ ((uint32_t)(r8 & 3) << 1)) << 4);
+        // ---- dy role: pixel jb of the chunk, piece p8 of every 32-channel block m
+        const int jb = tid >> 3, p8 = tid & 7;
+        const uint32_t b_off = L::A_BYTES + jb * 128 + (((uint32_t)p8 ^ ((uint32_t)(jb & 3) << 1)) << 4);
+        float dbp[NDY * 4];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const int kd = kd0 + q * 32 + g * 4;
-            g_ok[g] = kd < Kw;
-            const int tap = g_ok[g] ? kd / Cin : 0;
-            g_ch[g] = g_ok[g] ? kd - tap * Cin : 0;
-            g_dr[g] = tap / a.k - a.pad; g_ds[g] = tap % a.k - a.pad;
-        }
-        float dbp[NPB * 4];
-#pragma unroll
-        for (int i = 0; i < NPB * 4; ++i) dbp[i] = 0.f;
-        // within-stage byte offset of (block, pixel row j, 16-byte piece c): block*4096 + j*128 + ((c ^ ((j&3)<<1))<<4)
-        const uint32_t rowoff = j * 128;
-        const uint32_t sw = (j & 3) << 1;
-        // pixel cursor of the issue side, advanced by 32 pixels per chunk without divisions
-        int p_i = c_begin * 32 + j;
-        int wo_i = p_i % Wo, ho_i = (p_i / Wo) % Ho, n_i = p_i / (Wo * Ho);
-        uint32_t vbits = 0;       // 8 validity bits per in-flight chunk
+        for (int i = 0; i < NDY * 4; ++i) dbp[i] = 0.f;
+        uint32_t vbits = 0;       // 4 validity bits per in-flight chunk
         for (int ch = -D; ch < nchunks; ++ch) {
             const int ci = ch + D;
             if (ci < nchunks) {
                 const uint32_t slot = sbase + L::RAW_OFF + (ci % RD) * L::RAW_BYTES + tid * L::SLOT;
-                const bool pok = p_i < P;
-                const float *img = a.x + (size_t)n_i * H * W * Cin;
-                const int h0 = ho_i * stride, w0 = wo_i * stride;
+                const int p0 = (c_begin + ci) * 32;
                 uint32_t vm = 0;
+                if (g_ok) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const int hi = h0 + g_dr[g], wi = w0 + g_ds[g];
-                    const bool v = pok && g_ok[g] && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
-                    const float *src = v ? img + ((size_t)hi * W + wi) * Cin + g_ch[g] : a.x;
-                    if (use_ca) cp_async16_ca(slot + g * 16, src, v ? 16u : 0u);
-                    else cp_async16(slot + g * 16, src, v ? 16u : 0u);
-                    vm |= (uint32_t)v << g;
+                    for (int i = 0; i < 4; ++i) {
+                        const int p = p0 + i * 8 + r8;
+                        int wo, ho, n;
+                        if (a.wsh >= 0) { wo = p & (Wo - 1); ho = (p >> a.wsh) & (Ho - 1); n = p >> (a.wsh + a.hsh); }
+                        else { wo = p % Wo; ho = (p / Wo) % Ho; n = p / (Wo * Ho); }
+                        const int hi = ho * stride + dr, wi = wo * stride + ds;
+                        const bool v = p < P && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+                        const float *src = v ? a.x + (((size_t)n * H + hi) * W + wi) * Cin + chn : a.x;
+                        if (use_ca) cp_async16_ca(slot + i * 16, src, v ? 16u : 0u);
+                        else cp_async16(slot + i * 16, src, v ? 16u : 0u);
+                        vm |= (uint32_t)v << i;
+                    }
                 }
+                {
+                    const int pd = p0 + jb;
+                    const bool pok = pd < P;
 #pragma unroll
-                for (int g = 0; g < NPB; ++g)
-                    cp_async16(slot + (8 + g) * 16, pok ? a.dy + (size_t)p_i * Cout + o0 + q * (BN / 4) + g * 4 : a.dy, pok ? 16u : 0u);
-                const uint32_t sh = 8 * (ci % RD);
-                vbits = (vbits & ~(0xFFu << sh)) | (vm << sh);
-                p_i += 32; wo_i += 32;
-                while (wo_i >= Wo) { wo_i -= Wo; if (++ho_i == Ho) { ho_i = 0; ++n_i; } }
+                    for (int m = 0; m < NDY; ++m)
+                        if ((m * 8 + p8) * 4 < BN)
+                            cp_async16(slot + (4 + m) * 16, pok ? a.dy + (size_t)pd * Cout + o0 + (m * 8 + p8) * 4 : a.dy, pok ? 16u : 0u);
+                }
+                const uint32_t sh = 4 * (ci % RD);
+                vbits = (vbits & ~(0xFu << sh)) | (vm << sh);
             }
             cp_async_commit();
             if (ch < 0) continue;
             cp_async_wait<D>();
             const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
             const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
-            const uint32_t vm = (vbits >> (8 * (ch % RD))) & 0xFFu;
+            const uint32_t vm = (vbits >> (4 * (ch % RD))) & 0xFu;
             if (lane == 0) mbar_wait(bar(NST + stage), phase ^ 1);
             __syncwarp();
-            unsigned char *sA = smem + stage * L::STAGE_BYTES + q * 4096 + rowoff;       // column block q
-            unsigned char *sB = smem + stage * L::STAGE_BYTES + L::A_BYTES + rowoff;
+            unsigned char *st = smem + stage * L::STAGE_BYTES;
+            if (g_ok) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                float4 xv = *reinterpret_cast<const float4 *>(slot + g * 16);
-                if (pro) {
-                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + g_ch[g]);
-                    const float4 sf = *reinterpret_cast<const float4 *>(s_shift + g_ch[g]);
-                    xv.x = fmaf(xv.x, sc.x, sf.x); xv.y = fmaf(xv.y, sc.y, sf.y);
-                    xv.z = fmaf(xv.z, sc.z, sf.z); xv.w = fmaf(xv.w, sc.w, sf.w);
-                    if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f); }
-                }
-                if (!((vm >> g) & 1u)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                const uint32_t off = (g ^ sw) << 4;
-                uint4 h;
-                h.x = to_tf32(xv.x); h.y = to_tf32(xv.y); h.z = to_tf32(xv.z); h.w = to_tf32(xv.w);
-                *reinterpret_cast<uint4 *>(sA + off) = h;
-                if (PASSES > 1) {
-                    uint4 l;
-                    l.x = to_tf32(xv.x - __uint_as_float(h.x)); l.y = to_tf32(xv.y - __uint_as_float(h.y));
-                    l.z = to_tf32(xv.z - __uint_as_float(h.z)); l.w = to_tf32(xv.w - __uint_as_float(h.w));
-                    *reinterpret_cast<uint4 *>(sA + 4 * 4096 + off) = l;
+                for (int i = 0; i < 4; ++i) {
+                    float4 xv = *reinterpret_cast<const float4 *>(slot + i * 16);
+                    if (pro) {
+                        xv.x = fmaf(xv.x, sc.x, sf.x); xv.y = fmaf(xv.y, sc.y, sf.y);
+                        xv.z = fmaf(xv.z, sc.z, sf.z); xv.w = fmaf(xv.w, sc.w, sf.w);
+                        if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f); }
+                    }
+                    if (!((vm >> i) & 1u)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned char *dst = st + a_off + i * 1024;
+                    uint4 h;
+                    h.x = to_tf32(xv.x); h.y = to_tf32(xv.y); h.z = to_tf32(xv.z); h.w = to_tf32(xv.w);
+                    *reinterpret_cast<uint4 *>(dst) = h;
+                    if (PASSES > 1) {
+                        uint4 l;
+                        l.x = to_tf32(xv.x - __uint_as_float(h.x)); l.y = to_tf32(xv.y - __uint_as_float(h.y));
+                        l.z = to_tf32(xv.z - __uint_as_float(h.z)); l.w = to_tf32(xv.w - __uint_as_float(h.w));
+                        *reinterpret_cast<uint4 *>(dst + 4 * 4096) = l;
+                    }
                 }
             }
 #pragma unroll
-            for (int g = 0; g < NPB; ++g) {
-                const float4 bv = *reinterpret_cast<const float4 *>(slot + (8 + g) * 16);
-                dbp[g * 4] += bv.x; dbp[g * 4 + 1] += bv.y; dbp[g * 4 + 2] += bv.z; dbp[g * 4 + 3] += bv.w;
-                const int pc = q * NPB + g;                 // piece index along the channel axis (4 channels each)
-                const uint32_t off = (pc >> 3) * 4096 + (((pc & 7) ^ sw) << 4);
+            for (int m = 0; m < NDY; ++m) {
+                if ((m * 8 + p8) * 4 >= BN) continue;
+                const float4 bv = *reinterpret_cast<const float4 *>(slot + (4 + m) * 16);
+                dbp[m * 4] += bv.x; dbp[m * 4 + 1] += bv.y; dbp[m * 4 + 2] += bv.z; dbp[m * 4 + 3] += bv.w;
+                unsigned char *dst = st + b_off + m * 4096;
                 uint4 h;
                 h.x = to_tf32(bv.x); h.y = to_tf32(bv.y); h.z = to_tf32(bv.z); h.w = to_tf32(bv.w);
-                *reinterpret_cast<uint4 *>(sB + off) = h;
+                *reinterpret_cast<uint4 *>(dst) = h;
                 if (PASSES > 1) {
                     uint4 l;
                     l.x = to_tf32(bv.x - __uint_as_float(h.x)); l.y = to_tf32(bv.y - __uint_as_float(h.y));
                     l.z = to_tf32(bv.z - __uint_as_float(h.z)); l.w = to_tf32(bv.w - __uint_as_float(h.w));
-                    *reinterpret_cast<uint4 *>(sB + (BNP / 32) * 4096 + off) = l;
+                    *reinterpret_cast<uint4 *>(dst + NDY * 4096) = l;
                 }
             }
             fence_proxy_async();
             mbar_arrive(bar(stage));
         }
         if (a.db != nullptr && mt == 0) {
+            // lanes l, l+8, l+16, l+24 hold the same dy piece for 4 different pixels
 #pragma unroll
-            for (int i = 0; i < NPB * 4; ++i) {
-                float t = warp_sum(dbp[i]);
-                if (j == 0) atomicAdd(&a.db[o0 + q * (BN / 4) + i], t);
+            for (int i = 0; i < NDY * 4; ++i) {
+                float t = dbp[i];
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                const int m = i >> 2;
+                if (lane < 8 && (m * 8 + p8) * 4 < BN) atomicAdd(&a.db[o0 + (m * 8 + p8) * 4 + (i & 3)], t);
+            }
+        }
+        if (warp >= 4 && nchunks > 0) {
+            // epilogue (warps 4-7: TMEM lane quarter = warp % 4): row = (tap, c) index, columns = output channels
+            const int ew = warp - 4;
+            const int kd = kd0 + ew * 32 + lane;
+            if (lane == 0) mbar_wait(bar(2 * NST), 0);
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll
+            for (int cb = 0; cb < BN; cb += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + cb, v);
+                if (kd < Kw) {
+                    float *dst = a.dw + (size_t)kd * a.Cout + o0 + cb;
+#pragma unroll
+                    for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
+                }
             }
         }
     } else if (warp == 8) {
@@ -309,22 +344,6 @@ k_wgrad_mn(WArgs a) {
                 if (ch == nchunks - 1) mma_commit(bar(2 * NST));
             }
         }
-    } else if (nchunks > 0) {
-        const int ew = warp - 4;
-        const int kd = kd0 + ew * 32 + lane;
-        if (lane == 0) mbar_wait(bar(2 * NST), 0);
-        __syncwarp();
-        tc_fence_after();
-#pragma unroll
-        for (int cb = 0; cb < BN; cb += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + cb, v);
-            if (kd < Kw) {
-                float *dst = a.dw + (size_t)kd * a.Cout + o0 + cb;
-#pragma unroll
-                for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
-            }
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -345,14 +364,38 @@ int launch(WArgs &a, cudaStream_t st) {
     const int Kw = a.k * a.k * a.Cin;
     a.mtiles = (Kw + TM - 1) / TM;
     a.ntiles = a.Cout / BN;
-    const int tiles = a.mtiles * a.ntiles;
+    if (a.mtiles > 8) return -1;
     const int P = a.N * a.Ho * a.Wo;
     const int total_chunks = (P + 31) / 32;
-    int splits = 148 / tiles; if (splits < 1) splits = 1;
-    if (splits > total_chunks) splits = total_chunks;
-    a.chunks_per_split = (total_chunks + splits - 1) / splits;
-    a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
-    if (launch_pdl(2, k_wgrad_mn<BN, PASSES>, dim3(tiles * a.splits), dim3(NTHREADS), L::TOTAL, st, a) != cudaSuccess) return -1;
+    // CTA budget per n-tile, shared between the m-tiles in proportion to their producer work per pixel chunk:
+    // A pieces (valid rows / 4) + dy pieces (BN / 4) + a fixed synchronisation cost.  The last m-tile of a 3x3
+    // layer often holds only a few rows (K = 144 -> 128 + 16) and gets correspondingly fewer CTAs.
+    int cost[8], total_cost = 0, grid = 0;
+    for (int t = 0; t < a.mtiles; ++t) {
+        const int rows = Kw - t * TM < TM ? Kw - t * TM : TM;
+        cost[t] = rows / 4 + BN / 4 + 8;
+        total_cost += cost[t];
+    }
+    int budget = 148 / a.ntiles; if (budget < a.mtiles) budget = a.mtiles;
+    int used = 0;
+    for (int t = 0; t < a.mtiles; ++t) {
+        int sp = budget * cost[t] / total_cost; if (sp < 1) sp = 1;
+        if (sp > total_chunks) sp = total_chunks;
+        a.splits[t] = sp; used += sp;
+    }
+    for (int guard = 0; used < budget && guard < 256; ++guard) {      // hand out the remainder to the most loaded tiles
+        int best = -1;
+        for (int t = 0; t < a.mtiles; ++t)
+            if (a.splits[t] < total_chunks && (best < 0 || (int64_t)cost[t] * a.splits[best] > (int64_t)cost[best] * a.splits[t])) best = t;
+        if (best < 0) break;
+        ++a.splits[best]; ++used;
+    }
+    for (int t = 0; t < a.mtiles; ++t) {
+        a.cps[t] = (total_chunks + a.splits[t] - 1) / a.splits[t];
+        a.splits[t] = (total_chunks + a.cps[t] - 1) / a.cps[t];
+        grid += a.splits[t] * a.ntiles;
+    }
+    if (launch_pdl(2, k_wgrad_mn<BN, PASSES>, dim3(grid), dim3(NTHREADS), L::TOTAL, st, a) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -371,6 +414,11 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
     { const char *e; a.lbo16 = (e = getenv("DPP_MN_LBO")) ? atoi(e) : 256; a.sbo16 = (e = getenv("DPP_MN_SBO")) ? atoi(e) : 32;
       a.kstep = (e = getenv("DPP_MN_KSTEP")) ? atoi(e) : 1024;
       a.knobs = (e = getenv("DPP_WG_KNOBS")) ? atoi(e) : 0; }
+    a.wsh = a.hsh = -1;
+    if ((a.Wo & (a.Wo - 1)) == 0 && (a.Ho & (a.Ho - 1)) == 0) {
+        a.wsh = 0; while ((1 << a.wsh) < a.Wo) ++a.wsh;
+        a.hsh = 0; while ((1 << a.hsh) < a.Ho) ++a.hsh;
+    }
     const int bn = d->Cout > 128 ? 128 : d->Cout;
     const bool p3 = d->precision == 1;
     int rc = -1;

@@ -120,6 +120,15 @@ def main():
             db = torch.zeros(Cout, device='cuda')
 
             def graph_time(fn):
+                if os.environ.get('PROBE_EAGER', '0') == '1':       # profiler runs: no graph replays
+                    for _ in range(3):
+                        fn(None)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(20):
+                        fn(None)
+                    e1.record(); torch.cuda.synchronize()
+                    return e0.elapsed_time(e1) / 20 * 1e3
                 with torch.cuda.stream(side):
                     fn(sp)
                 torch.cuda.synchronize()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`) per kernel.
 
-usage: python tools/launch_summary.py launches.csv [--steps N] [--md]
+usage: python tools/launch_summary.py launches.csv [--steps N] [--step n] [--md]
 Prints, per kernel name (template arguments kept, parameter list dropped): launches, total us, average us,
 share of the summed GPU time.  With --steps the totals are divided by the number of profiled steps.
 """
@@ -31,13 +31,18 @@ def load(path):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    args = [a for a in sys.argv[1:] if not a.startswith('--') and not a.isdigit()]
     steps = 1
     if '--steps' in sys.argv:
         steps = int(sys.argv[sys.argv.index('--steps') + 1])
         args = [a for a in args if a != str(steps)]
     md = '--md' in sys.argv
     L = load(args[0])
+    if '--step' in sys.argv:
+        # one steady-state step: the launches between the n-th and (n+1)-th k_adam_tick (a rotation of one step)
+        n = int(sys.argv[sys.argv.index('--step') + 1])
+        ticks = [i for i, l in enumerate(L) if l[0].startswith('k_adam_tick')]
+        L = L[ticks[n] + 1:ticks[n + 1] + 1]
     agg = collections.OrderedDict()
     for name, v, g, b in L:
         a = agg.setdefault(name, [0, 0.0])
