@@ -166,7 +166,7 @@ struct TCArgs {
     int wmode;            // 0 forward, 1 dgrad
     int kchunks;          // ceil(k*k*Cin / 32)
     int wsh, hsh;         // log2(Wg), log2(Hg) when both are powers of two, else -1 (generic division)
-    int knobs;            // tuning bits (DPP_TC_KNOBS): 1 = L1-allocating gathers for k > 1
+    int knobs;            // tuning bits (DPP_TC_KNOBS): 1 = L1-allocating gathers for k > 1, 2 = lane-per-row gather (old mapping)
     dpp_bn_ref in_bn; int has_in_bn;
     const float *bias; const float *residual; double *out_stats;
     int accumulate; dpp_bn_ref mask_bn; int has_mask; const float *x_pre; double *dz_stats;
@@ -405,6 +405,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
         const float *const gin = a.in;
         const bool use_ca = (a.knobs & 1) && a.k > 1;
+        const bool coalesced = !(a.knobs & 2);
         // raw slot layout: [8 pieces][128 rows][16 B] -> conflict-free for cp.async writes and LDS.128 reads
         const uint32_t raw_u32 = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
         const unsigned char *raw_ptr = smem + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
@@ -432,15 +433,35 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 const float *p0 = gin + (v0 ? r_off + e0.z : 0), *p1 = gin + (v1 ? r_off + e1.z : 0);
                 const uint32_t dst = raw_u32 + islot * (TM * 128);
                 const uint32_t z0 = v0 ? 16u : 0u, z1 = v1 ? 16u : 0u;
+                if (coalesced) {
+                    // The warp's 32 rows x 8 pieces are fetched with lane = (row t*4 + lane/8, piece lane%8): the 8 lanes
+                    // of a row read its two 64-byte tap segments, so one instruction touches 8 lines instead of 32
+                    // (the L1 tag stage handles one line per cycle and was the serial resource of the gather).
+                    // Row geometry comes from the owning lane by shuffle; the slot is [row][piece ^ (row & 7)].
+                    const int pcs = lane & 7;
+                    const int4 e = pcs < 4 ? e0 : e1;
+                    const uint32_t sbuf = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + islot * (TM * 128) + q * 32 * 128;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (DBG(1)) break;
-                    if (use_ca) {
-                        cp_async16_ca(dst + j * 2048, p0 + j * 4, z0);
-                        cp_async16_ca(dst + (j + 4) * 2048, p1 + j * 4, z1);
-                    } else {
-                        cp_async16(dst + j * 2048, p0 + j * 4, z0);
-                        cp_async16(dst + (j + 4) * 2048, p1 + j * 4, z1);
+                    for (int t = 0; t < 8; ++t) {
+                        const int lrow = t * 4 + (lane >> 3);
+                        const int o_off = __shfl_sync(0xffffffffu, r_off, lrow);
+                        const int o_h0 = __shfl_sync(0xffffffffu, r_h0, lrow);
+                        const int o_w0 = __shfl_sync(0xffffffffu, r_w0, lrow);
+                        const bool v = o_off >= 0 && (unsigned)(o_h0 + e.x) < (unsigned)Hin && (unsigned)(o_w0 + e.y) < (unsigned)Win;
+                        const float *src = gin + (v ? o_off + e.z + (pcs & 3) * 4 : 0);
+                        cp_async16(sbuf + lrow * 128 + ((pcs ^ (lrow & 7)) << 4), src, v ? 16u : 0u);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (DBG(1)) break;
+                        if (use_ca) {
+                            cp_async16_ca(dst + j * 2048, p0 + j * 4, z0);
+                            cp_async16_ca(dst + (j + 4) * 2048, p1 + j * 4, z1);
+                        } else {
+                            cp_async16(dst + j * 2048, p0 + j * 4, z0);
+                            cp_async16(dst + (j + 4) * 2048, p1 + j * 4, z1);
+                        }
                     }
                 }
                 const uint32_t sh2 = 2 * islot, sh8 = 8 * islot;
@@ -459,6 +480,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
             const uint32_t vb = (vring >> (2 * pslot)) & 3u;
             const int kc = (int)((cring >> (8 * pslot)) & 0xffu);
             const unsigned char *rp = raw_ptr + pslot * (TM * 128);
+            const unsigned char *rpc = smem + L::RAW_OFF + grp * RDG * (TM * 128) + pslot * (TM * 128) + row * 128;   // [row][piece ^ (row & 7)]
             if (++pslot == RDG) pslot = 0;
             const int4 e0 = s_tab[kc * 2], e1 = s_tab[kc * 2 + 1];
             PROF(11);
@@ -474,7 +496,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int pj = hh * 2 + j;         // piece 0-3: tap A, 4-7: tap B
-                    float4 x = *reinterpret_cast<const float4 *>(rp + pj * 2048);
+                    float4 x = *reinterpret_cast<const float4 *>(coalesced ? rpc + ((pj ^ (lane & 7)) << 4) : rp + pj * 2048);
                     if (pro) {
                         const int chan = (pj < 4 ? e0.w : e1.w) + (pj & 3) * 4;
                         const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);

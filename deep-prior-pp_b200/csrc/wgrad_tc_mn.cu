@@ -124,7 +124,10 @@ struct Lay {
     static constexpr int UNITS = (4 + NDY) | 1;                   // 16-byte units per thread slot, odd: conflict-free LDS.128
     static constexpr int SLOT = UNITS * 16;
     static constexpr int RAW_BYTES = 256 * SLOT;
-    static constexpr int RD = (NST * STAGE_BYTES + 3 * RAW_BYTES + 4096 <= 225 * 1024) ? 3 : 2;
+    // raw landing slots = prefetch distance + 1: as many as fit next to the two MMA stages (the loop is bound by
+    // the memory latency divided by this distance, not by the producer arithmetic), at most 6
+    static constexpr int RD_FIT = (220 * 1024 - NST * STAGE_BYTES) / RAW_BYTES;
+    static constexpr int RD = RD_FIT > 6 ? 6 : (RD_FIT < 2 ? 2 : RD_FIT);
     static constexpr int RAW_OFF = NST * STAGE_BYTES;
     static constexpr int BAR_OFF = RAW_OFF + RD * RAW_BYTES;
     static constexpr int COEF_OFF = BAR_OFF + 256;
@@ -373,7 +376,7 @@ int launch(WArgs &a, cudaStream_t st) {
     int cost[8], total_cost = 0, grid = 0;
     for (int t = 0; t < a.mtiles; ++t) {
         const int rows = Kw - t * TM < TM ? Kw - t * TM : TM;
-        cost[t] = rows / 4 + BN / 4 + 8;
+        cost[t] = rows / 4 + BN / 4 + 64;       // the fixed term is the per-chunk pipeline latency, which dominates
         total_cost += cost[t];
     }
     int budget = 148 / a.ntiles; if (budget < a.mtiles) budget = a.mtiles;
