@@ -162,7 +162,7 @@ k_wgrad_mn(WArgs a) {
 
     pdl_trigger();      // private set-up first (see common.cuh: programmatic dependent launch)
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 256); mbar_init(bar(NST + s), 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 8); mbar_init(bar(NST + s), 1); }   // full: one arrival per producer warp
         mbar_init(bar(2 * NST), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -285,8 +285,9 @@ k_wgrad_mn(WArgs a) {
                     *reinterpret_cast<uint4 *>(dst + NDY * 4096) = l;
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(bar(stage));
+            fence_proxy_async();                 // every writer orders its own stores towards the async proxy ...
+            __syncwarp();                        // ... the warp agrees, and one lane publishes the warp's share
+            if (lane == 0) mbar_arrive(bar(stage));
         }
         if (a.db != nullptr && mt == 0) {
             // lanes l, l+8, l+16, l+24 hold the same dy piece for 4 different pixels
