@@ -26,7 +26,6 @@ namespace {
 
 constexpr int TM = 128;
 constexpr int NTHREADS = 288;
-constexpr int NST = 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -114,7 +113,7 @@ struct WArgs {
     int wsh, hsh;                // log2(Wo), log2(Ho) when both are powers of two, else -1
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int NST>
 struct Lay {
     static constexpr int BNP = BN < 32 ? 32 : BN;                 // MMA N (padded to one 32-channel block)
     static constexpr int A_BYTES = PASSES * 4 * 4096;             // 4 column blocks of 32 (tap,c) rows x 32 pixels
@@ -134,10 +133,10 @@ struct Lay {
     static constexpr int TOTAL = COEF_OFF + 2 * 256 * 4 + 1024;
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int NST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_wgrad_mn(WArgs a) {
-    using L = Lay<BN, PASSES>;
+    using L = Lay<BN, PASSES, NST>;
     constexpr int RD = L::RD, D = RD - 1, BNP = L::BNP, NDY = L::NDY;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
@@ -357,12 +356,12 @@ k_wgrad_mn(WArgs a) {
     }
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int NST>
 int launch(WArgs &a, cudaStream_t st) {
-    using L = Lay<BN, PASSES>;
+    using L = Lay<BN, PASSES, NST>;
     static bool done = false;
     if (!done) {
-        if (cudaFuncSetAttribute(k_wgrad_mn<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(k_wgrad_mn<BN, PASSES, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return -1;
         done = true;
     }
     const int Kw = a.k * a.k * a.Cin;
@@ -399,7 +398,7 @@ int launch(WArgs &a, cudaStream_t st) {
         a.splits[t] = (total_chunks + a.cps[t] - 1) / a.cps[t];
         grid += a.splits[t] * a.ntiles;
     }
-    if (launch_pdl(2, k_wgrad_mn<BN, PASSES>, dim3(grid), dim3(NTHREADS), L::TOTAL, st, a) != cudaSuccess) return -1;
+    if (launch_pdl(2, k_wgrad_mn<BN, PASSES, NST>, dim3(grid), dim3(NTHREADS), L::TOTAL, st, a) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -425,11 +424,18 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
     }
     const int bn = d->Cout > 128 ? 128 : d->Cout;
     const bool p3 = d->precision == 1;
+    // MMA stages: the tcgen05.commit -> mbarrier -> producer round trip is long compared with a 32-pixel chunk, so
+    // three stages where shared memory allows (BN <= 64); DPP_WG_NST=2 selects the two-stage build for comparison
+    static int nst_env = -1;
+    if (nst_env < 0) { const char *e = getenv("DPP_WG_NST"); nst_env = e ? atoi(e) : 3; }
+    const bool three = nst_env >= 3 && bn <= 64;
     int rc = -1;
-    if (bn == 16) rc = p3 ? launch<16, 2>(a, S(stream)) : launch<16, 1>(a, S(stream));
-    else if (bn == 32) rc = p3 ? launch<32, 2>(a, S(stream)) : launch<32, 1>(a, S(stream));
-    else if (bn == 64) rc = p3 ? launch<64, 2>(a, S(stream)) : launch<64, 1>(a, S(stream));
-    else if (bn == 128) rc = p3 ? launch<128, 2>(a, S(stream)) : launch<128, 1>(a, S(stream));
+#define DPP_WG_CASE(B_)                                                                                   \
+    if (bn == B_) rc = p3 ? (three ? launch<B_, 2, 3>(a, S(stream)) : launch<B_, 2, 2>(a, S(stream)))      \
+                          : (three ? launch<B_, 1, 3>(a, S(stream)) : launch<B_, 1, 2>(a, S(stream)));
+    DPP_WG_CASE(16) DPP_WG_CASE(32) DPP_WG_CASE(64)
+#undef DPP_WG_CASE
+    if (bn == 128) rc = p3 ? launch<128, 2, 2>(a, S(stream)) : launch<128, 1, 2>(a, S(stream));
     if (rc != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
     DPP_LAUNCH_CHECK();
     return DPP_OK;
