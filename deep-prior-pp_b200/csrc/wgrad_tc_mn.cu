@@ -46,6 +46,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// polling variant: mbarrier.test_wait returns at once, so the hand-off latency is one poll period
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -186,6 +199,7 @@ k_wgrad_mn(WArgs a) {
         const int pc = lane & 3, r8 = lane >> 2;
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
         const bool use_ca = (a.knobs & 1) && a.k > 1;
+        const bool kspin = (a.knobs & 2) != 0, kskip_p = (a.knobs & 8) != 0;     // experiment knobs (timing ablations)
         const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, Wo = a.Wo, Ho = a.Ho, stride = a.stride;
         // ---- activation role: piece g of quarter q = rows kd .. kd+3 = one tap, 4 channels
         const int g = hf * 4 + pc;
@@ -243,10 +257,10 @@ k_wgrad_mn(WArgs a) {
             const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
             const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
             const uint32_t vm = (vbits >> (4 * (ch % RD))) & 0xFu;
-            if (lane == 0) mbar_wait(bar(NST + stage), phase ^ 1);
+            if (lane == 0) { if (kspin) mbar_spin(bar(NST + stage), phase ^ 1); else mbar_wait(bar(NST + stage), phase ^ 1); }
             __syncwarp();
             unsigned char *st = smem + stage * L::STAGE_BYTES;
-            if (g_ok) {
+            if (g_ok && !kskip_p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float4 xv = *reinterpret_cast<const float4 *>(slot + i * 16);
@@ -270,7 +284,7 @@ k_wgrad_mn(WArgs a) {
             }
 #pragma unroll
             for (int m = 0; m < NDY; ++m) {
-                if ((m * 8 + p8) * 4 >= BN) continue;
+                if ((m * 8 + p8) * 4 >= BN || kskip_p) continue;
                 const float4 bv = *reinterpret_cast<const float4 *>(slot + (4 + m) * 16);
                 dbp[m * 4] += bv.x; dbp[m * 4 + 1] += bv.y; dbp[m * 4 + 2] += bv.z; dbp[m * 4 + 3] += bv.w;
                 unsigned char *dst = st + b_off + m * 4096;
@@ -324,13 +338,13 @@ k_wgrad_mn(WArgs a) {
                                        ((uint32_t)(BNP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int ch = 0; ch < nchunks; ++ch) {
                 const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
-                mbar_wait(bar(stage), phase);
+                if (a.knobs & 2) mbar_spin(bar(stage), phase); else mbar_wait(bar(stage), phase);
                 __syncwarp();
                 tc_fence_after();
                 const uint32_t sa = sbase + stage * L::STAGE_BYTES;
                 const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {            // 4 groups of 8 pixels
+                for (int ks = 0; ks < ((a.knobs & 4) ? 1 : 4); ++ks) {            // 4 groups of 8 pixels (knob 4: timing ablation)
                     const uint64_t ah = make_desc_mn(sa + ks * a.kstep, a.lbo16, a.sbo16), bh = make_desc_mn(sb + ks * a.kstep, a.lbo16, a.sbo16);
                     const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
                     if (PASSES > 1) {
@@ -424,10 +438,10 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
     }
     const int bn = d->Cout > 128 ? 128 : d->Cout;
     const bool p3 = d->precision == 1;
-    // MMA stages: the tcgen05.commit -> mbarrier -> producer round trip is long compared with a 32-pixel chunk, so
-    // three stages where shared memory allows (BN <= 64); DPP_WG_NST=2 selects the two-stage build for comparison
+    // MMA stages: two by default.  A third stage (DPP_WG_NST=3, BN <= 64) was measured on B200 and changes nothing
+    // (A 76.9 vs 76.5 us, B 56.6 vs 56.2 us): the loop is not bound by the stage hand-off but by the load path.
     static int nst_env = -1;
-    if (nst_env < 0) { const char *e = getenv("DPP_WG_NST"); nst_env = e ? atoi(e) : 3; }
+    if (nst_env < 0) { const char *e = getenv("DPP_WG_NST"); nst_env = e ? atoi(e) : 2; }
     const bool three = nst_env >= 3 && bn <= 64;
     int rc = -1;
 #define DPP_WG_CASE(B_)                                                                                   \
