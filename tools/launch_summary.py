@@ -11,14 +11,15 @@ import re
 import sys
 
 
-def load(path):
+def load(path, metric='gpu__time_duration.sum'):
     rows = list(csv.reader(open(path, errors='replace')))
     h = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
     H = rows[h]
     ki, vi, gi, bi = H.index('Kernel Name'), H.index('Metric Value'), H.index('Grid Size'), H.index('Block Size')
+    mi = H.index('Metric Name')
     out = []
     for r in rows[h + 1:]:
-        if len(r) <= vi:
+        if len(r) <= vi or r[mi] != metric:
             continue
         try:
             v = float(r[vi].replace(',', ''))
