@@ -199,6 +199,40 @@ def test_type1_with_pca_tail_forward():
     assert _rel(out, oout.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+def test_mean_joint_error_mm_matches_oracle(precision):
+    """north_star: mean 3D joint error within 0.1 mm of the reference on the same synthetic batch.
+    Synthetic NYU crops (data/synthetic.py), type-1 ResNet with the PCA prior layer (30 -> 14*3), deterministic
+    forward as handpose_evaluation does: joints_mm = out * cube_z / 2; error = mean_j ||pred_j - gt_j||."""
+    from data import synthetic
+    B, J = 8, 14
+    ds = synthetic.generate('NYU', B, seed=23455)
+    comp, mean = synthetic.random_orthonormal_pca(30, 3 * J, seed=1)
+    net, onet, eng = _build(1, B, J, 3, precision=precision)
+    # install the PCA prior in the last layer of both nets (main_nyu_posereg_embedding.py:148-158)
+    net.layers[-1].W.set_value(comp.astype(np.float32))
+    net.layers[-1].b.set_value(mean.astype(np.float32))
+    with torch.no_grad():
+        onet.layers[-1].params[0].copy_(torch.from_numpy(comp.astype(np.float32)))
+        onet.layers[-1].params[1].copy_(torch.from_numpy(mean.astype(np.float32)))
+    x = ds['x'].astype(np.float32)
+    out = net.computeOutput(x)
+    with torch.no_grad():
+        oout, _ = onet.forward(torch.from_numpy(x), deterministic=True)
+    oout = oout.numpy()
+    half = (ds['cube'][:, 2] / 2.0).reshape(B, 1, 1)
+    gt = ds['gt3Dcrop'].reshape(B, J, 3)
+    pred = out.reshape(B, J, 3) * half
+    opred = oout.reshape(B, J, 3) * half
+    err = np.linalg.norm(pred - gt, axis=2).mean()
+    oerr = np.linalg.norm(opred - gt, axis=2).mean()
+    dmax = np.abs(pred - opred).max()
+    print("mean joint error: engine %.4f mm, oracle %.4f mm, max joint coordinate difference %.2e mm" % (err, oerr, dmax))
+    assert abs(err - oerr) < 0.1
+    assert dmax < 0.1
+    assert _rel(out, oout) < 1e-4
+
+
 def test_block0_backward_matches_torch_gpu_autograd_and_oracle():
     """Isolates the stem: (a) engine dW0 vs torch autograd on the engine's own dy_stem, (b) the
     engine's dy_stem vs the oracle's gradient at the stem output."""
