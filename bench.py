@@ -92,6 +92,27 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def shutdown_distributed(dist, eng=None):
+    """Leave a multi-rank run promptly.  Destroying the NCCL communicator while captured graphs that contain its
+    collectives are alive can block for minutes at interpreter exit (seen on 2 x B200: JSON printed at once, the
+    ranks exited only when the launcher's timeout fired).  Drop the graphs first, synchronise, and arm a watchdog
+    that ends the process if the tear-down still stalls - the measurement is complete and printed by then."""
+    import torch
+    sys.stdout.flush()
+    timer = threading.Timer(60.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    try:
+        if eng is not None:
+            eng._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    timer.cancel()
+
+
 def make_workload(seed=23455):
     """synthetic NYU set + PCA stand-in + per-sample augmentation records for many steps"""
     from data import synthetic
@@ -305,7 +326,7 @@ def run_b200(args):
 
     if rank != 0:
         if dist is not None:
-            dist.destroy_process_group()
+            shutdown_distributed(dist, eng)
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -335,7 +356,7 @@ def run_b200(args):
     }
     print(json.dumps(out))
     if dist is not None:
-        dist.destroy_process_group()
+        shutdown_distributed(dist, eng)
 
 
 def count_launches(eng):

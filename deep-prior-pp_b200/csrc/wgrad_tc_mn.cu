@@ -24,6 +24,21 @@ using namespace dpp;
 
 namespace {
 
+#ifdef DPP_PROFILE
+// Debug timeline (tools/conv_probe.py): CTA 0 appends (tag, clock64) pairs per role into a global buffer.
+__device__ long long *g_prof_wg = nullptr;
+#define PROF_DECL(base_) int prof_n_ = (base_); long long *const prof_p_ = blockIdx.x == 0 ? g_prof_wg : nullptr
+#define PROF(tag_)                                                                   \
+    do {                                                                             \
+        if (prof_p_ != nullptr && prof_n_ % 1000 < 990) {                            \
+            prof_p_[prof_n_] = (tag_); prof_p_[prof_n_ + 1] = clock64(); prof_n_ += 2; \
+        }                                                                            \
+    } while (0)
+#else
+#define PROF_DECL(base_)
+#define PROF(tag_)
+#endif
+
 constexpr int TM = 128;
 constexpr int NTHREADS = 288;
 
@@ -155,6 +170,8 @@ k_wgrad_mn(WArgs a) {
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    PROF_DECL(lane == 0 ? (warp == 0 ? 0 : warp == 8 ? 1000 : warp == 4 ? 2000 : warp == 7 ? 3000 : 4000) : 4000);
+    PROF(1);
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };      // full[s]=s, empty[s]=NST+s, done=2*NST
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
     float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);
@@ -193,6 +210,7 @@ k_wgrad_mn(WArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    PROF(2);
 
     if (warp < 8) {
         const int q = warp & 3, hf = warp >> 2;
@@ -253,12 +271,15 @@ k_wgrad_mn(WArgs a) {
             }
             cp_async_commit();
             if (ch < 0) continue;
+            PROF(10);
             cp_async_wait<D>();
+            PROF(11);
             const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
             const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
             const uint32_t vm = (vbits >> (4 * (ch % RD))) & 0xFu;
             if (lane == 0) { if (kspin) mbar_spin(bar(NST + stage), phase ^ 1); else mbar_wait(bar(NST + stage), phase ^ 1); }
             __syncwarp();
+            PROF(12);
             unsigned char *st = smem + stage * L::STAGE_BYTES;
             if (g_ok && !kskip_p) {
 #pragma unroll
@@ -298,10 +319,13 @@ k_wgrad_mn(WArgs a) {
                     *reinterpret_cast<uint4 *>(dst + NDY * 4096) = l;
                 }
             }
+            PROF(14);
             fence_proxy_async();                 // every writer orders its own stores towards the async proxy ...
             __syncwarp();                        // ... the warp agrees, and one lane publishes the warp's share
             if (lane == 0) mbar_arrive(bar(stage));
+            PROF(13);
         }
+        PROF(3);
         if (a.db != nullptr && mt == 0) {
             // lanes l, l+8, l+16, l+24 hold the same dy piece for 4 different pixels
 #pragma unroll
@@ -320,6 +344,7 @@ k_wgrad_mn(WArgs a) {
             if (lane == 0) mbar_wait(bar(2 * NST), 0);
             __syncwarp();
             tc_fence_after();
+            PROF(31);
 #pragma unroll
             for (int cb = 0; cb < BN; cb += 16) {
                 float v[16];
@@ -341,6 +366,7 @@ k_wgrad_mn(WArgs a) {
                 if (a.knobs & 2) mbar_spin(bar(stage), phase); else mbar_wait(bar(stage), phase);
                 __syncwarp();
                 tc_fence_after();
+                PROF(22);
                 const uint32_t sa = sbase + stage * L::STAGE_BYTES;
                 const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
@@ -359,11 +385,14 @@ k_wgrad_mn(WArgs a) {
                 }
                 mma_commit(bar(NST + stage));
                 if (ch == nchunks - 1) mma_commit(bar(2 * NST));
+                PROF(23);
             }
         }
     }
+    PROF(32);
     tc_fence_before();
     __syncthreads();
+    PROF(4);
     if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
@@ -454,3 +483,11 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }
+
+#ifdef DPP_PROFILE
+extern "C" int dpp_debug_set_prof_wg(void *buf) {
+    long long *p = reinterpret_cast<long long *>(buf);
+    DPP_CUDA(cudaMemcpyToSymbol(g_prof_wg, &p, sizeof(p)));
+    return DPP_OK;
+}
+#endif

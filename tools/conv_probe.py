@@ -27,7 +27,7 @@ SHAPES = {  # N, H, Cin, Cout, k, stride, residual
     'Z_tiny': (1, 8, 64, 64, 1, 1, 0),
 }
 TAGS = {1: 'entry', 2: 'setup done', 3: 'role done', 4: 'exit', 10: 'P round start', 11: 'P chunk: loads->wait stage',
-        12: 'P stage free', 13: 'P arrived', 20: 'M acc free', 21: 'M B ready', 22: 'M A ready', 23: 'M committed',
+        12: 'P stage free', 13: 'P arrived', 10: 'P issued', 11: 'P data landed', 20: 'M acc free', 21: 'M B ready', 22: 'M A ready', 23: 'M committed',
         30: 'E side issued', 31: 'E acc ready', 32: 'E tile done',
         14: 'P stored', 15: 'P fenced', 33: 'E tmem loaded', 34: 'E staged', 35: 'E batch stored', 36: 'E batch stats done'}
 
@@ -143,6 +143,20 @@ def main():
             t_wg = graph_time(lambda stp: lib.dpp_conv2d_wgrad(C.byref(d), P(x), C.byref(bn), P(dy), P(dw), P(db), stp))
             bd = 4.0 * (dy.numel() + 2 * x.numel())
             bw = 4.0 * (dy.numel() + x.numel())
+            if os.environ.get('PROBE_WG_TIMELINE', '0') == '1':
+                try:
+                    setw = lib.raw('dpp_debug_set_prof_wg')
+                    setw.restype = C.c_int
+                    setw.argtypes = [C.c_void_p]
+                    prof = torch.zeros(5000, dtype=torch.int64, device='cuda')
+                    setw(prof.data_ptr())
+                    lib.dpp_conv2d_wgrad(C.byref(d), P(x), C.byref(bn), P(dy), P(dw), P(db), None)
+                    torch.cuda.synchronize()
+                    setw(None)
+                    print("  wgrad timeline (CTA 0; P = producer warp 0, M = MMA warp, E = warp 4, L = warp 7)")
+                    timeline(prof.cpu().numpy(), int(os.environ.get('PROBE_EVENTS', '90')))
+                except AttributeError:
+                    print("  (no dpp_debug_set_prof_wg in this build)")
             print("%-22s dgrad graph %7.1f us (%5.0f GB/s)   wgrad graph %7.1f us (%5.0f GB/s)" % (
                 name, t_dg, bd / t_dg / 1e3, t_wg, bw / t_wg / 1e3))
         if has_prof:
