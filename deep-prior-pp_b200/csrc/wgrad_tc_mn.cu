@@ -9,14 +9,17 @@
 // (descriptor: LBO = 4096 B between column blocks, SBO = 1024 B between 8-pixel groups, a_major = b_major =
 // MN in the instruction descriptor).  Producers therefore store whole 16-byte pieces, like the forward kernel.
 //
-// Warp roles: warps 0-7 producers (cp.async into private raw slots, BN+ReLU, TF32 hi/lo split), warp 8 MMA
+// Warp roles: warps 0-15 producers (cp.async into private raw slots, BN+ReLU, TF32 hi/lo split), warp 16 MMA
 // issuer; when the pixel loop is done warps 4-7 run the epilogue (TMEM -> red.global.add.v4.f32).
-// Producer mapping (per 32-pixel chunk): warp (q, hf) owns row quarter q and half hf of its 8 row pieces;
-// lane = (pixel sub-row r8 = lane / 4, piece pc = lane % 4).  A thread therefore handles ONE (tap, 4 channels)
-// piece - tap offset and BN coefficients live in registers - for the 4 pixels r8, r8 + 8, r8 + 16, r8 + 24.
-// The 4 lanes of a pixel read 64 contiguous bytes, and a warp's 16-byte stores fall on 8 rows x 4 swizzled
-// columns = all 8 bank groups 4 times: the minimum 4 wavefronts (lane = pixel would take 8).  The dy tile is
-// spread the same way over all 256 threads: thread = (pixel tid / 8, piece tid % 8 of every 32-channel block).
+// The pixel loop is bound by the instruction latency of the producer warps (in-kernel timeline, gpu call 10:
+// address generation 1300 + transform 850 of a 2650-cycle chunk period with 8 warps), hence 16 warps with a
+// mapping that gives every thread ONE pixel per chunk:
+//   activations: thread = (pixel j = (t/4) % 32, piece gq = t%4 + 4*(t/128)) and handles pieces gq and gq + 16 of
+//     the tile's 32 (tap, 4-channel) pieces: one pixel decode per chunk, tap offsets / BN coefficients in
+//     registers; the 4 lanes of a pixel read 64 contiguous bytes; a warp's 16-byte stores cover 8 rows x 4
+//     swizzled columns = every bank group 4 times, the minimum 4 wavefronts.  Pieces beyond K are skipped, so a
+//     layer with few rows (1x1 16->64: 4 pieces) spreads them over 4 warps instead of loading one warp.
+//   dy: thread = (pixel t/16, piece t%16 (+16 for 128 channels)).
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -40,7 +43,9 @@ __device__ long long *g_prof_wg = nullptr;
 #endif
 
 constexpr int TM = 128;
-constexpr int NTHREADS = 288;
+constexpr int NPROD = 16;                   // producer warps
+constexpr int W_MMA = NPROD;                // MMA issuer warp
+constexpr int NTHREADS = 32 * (NPROD + 1);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -147,14 +152,15 @@ struct Lay {
     static constexpr int A_BYTES = PASSES * 4 * 4096;             // 4 column blocks of 32 (tap,c) rows x 32 pixels
     static constexpr int B_BYTES = PASSES * (BNP / 32) * 4096;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NDY = BNP / 32;                          // dy pieces (16 B) per producer thread per chunk
-    static constexpr int UNITS = (4 + NDY) | 1;                   // 16-byte units per thread slot, odd: conflict-free LDS.128
+    static constexpr int NDY = BNP / 32;                          // 32-channel column blocks of the dy tile
+    static constexpr int NDYH = BNP >= 64 ? BNP / 64 : 1;         // dy pieces (16 B) per producer thread per chunk
+    static constexpr int UNITS = (2 + NDYH) | 1;                  // 16-byte units per thread slot, odd: conflict-free LDS.128
     static constexpr int SLOT = UNITS * 16;
-    static constexpr int RAW_BYTES = 256 * SLOT;
+    static constexpr int RAW_BYTES = 32 * NPROD * SLOT;
     // raw landing slots = prefetch distance + 1: as many as fit next to the two MMA stages (the loop is bound by
     // the memory latency divided by this distance, not by the producer arithmetic), at most 6
     static constexpr int RD_FIT = (220 * 1024 - NST * STAGE_BYTES) / RAW_BYTES;
-    static constexpr int RD = RD_FIT > 6 ? 6 : (RD_FIT < 2 ? 2 : RD_FIT);
+    static constexpr int RD = RD_FIT > 8 ? 8 : (RD_FIT < 2 ? 2 : RD_FIT);
     static constexpr int RAW_OFF = NST * STAGE_BYTES;
     static constexpr int BAR_OFF = RAW_OFF + RD * RAW_BYTES;
     static constexpr int COEF_OFF = BAR_OFF + 256;
@@ -165,12 +171,12 @@ template <int BN, int PASSES, int NST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_wgrad_mn(WArgs a) {
     using L = Lay<BN, PASSES, NST>;
-    constexpr int RD = L::RD, D = RD - 1, BNP = L::BNP, NDY = L::NDY;
+    constexpr int RD = L::RD, D = RD - 1, BNP = L::BNP, NDY = L::NDY, NDYH = L::NDYH;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    PROF_DECL(lane == 0 ? (warp == 0 ? 0 : warp == 8 ? 1000 : warp == 4 ? 2000 : warp == 7 ? 3000 : 4000) : 4000);
+    PROF_DECL(lane == 0 ? (warp == 0 ? 0 : warp == W_MMA ? 1000 : warp == 4 ? 2000 : warp == 7 ? 3000 : 4000) : 4000);
     PROF(1);
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };      // full[s]=s, empty[s]=NST+s, done=2*NST
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
@@ -191,11 +197,11 @@ k_wgrad_mn(WArgs a) {
 
     pdl_trigger();      // private set-up first (see common.cuh: programmatic dependent launch)
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 8); mbar_init(bar(NST + s), 1); }   // full: one arrival per producer warp
+        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), NPROD); mbar_init(bar(NST + s), 1); }   // full: one arrival per producer warp
         mbar_init(bar(2 * NST), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -212,62 +218,73 @@ k_wgrad_mn(WArgs a) {
     const uint32_t tmem_base = *tmem_slot;
     PROF(2);
 
-    if (warp < 8) {
-        const int q = warp & 3, hf = warp >> 2;
-        const int pc = lane & 3, r8 = lane >> 2;
+    if (warp < NPROD) {
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
         const bool use_ca = (a.knobs & 1) && a.k > 1;
         const bool kspin = (a.knobs & 2) != 0, kskip_p = (a.knobs & 8) != 0;     // experiment knobs (timing ablations)
         const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, Wo = a.Wo, Ho = a.Ho, stride = a.stride;
-        // ---- activation role: piece g of quarter q = rows kd .. kd+3 = one tap, 4 channels
-        const int g = hf * 4 + pc;
-        const int kd = kd0 + q * 32 + g * 4;
-        const bool g_ok = kd < Kw;                   // rows beyond K are never written: the stage stays zero there
-        const int tap = g_ok ? kd / Cin : 0;
-        const int chn = g_ok ? kd - tap * Cin : 0;
-        const int dr = tap / a.k - a.pad, ds = tap % a.k - a.pad;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pro && g_ok) { sc = *reinterpret_cast<const float4 *>(s_scale + chn); sf = *reinterpret_cast<const float4 *>(s_shift + chn); }
-        // byte offset inside a stage of (column block q, pixel row j = i*8 + r8, piece g): the swizzle only looks at j & 3 = r8 & 3
-        const uint32_t a_off = q * 4096 + r8 * 128 + (((uint32_t)g ^ ((uint32_t)(r8 & 3) << 1)) << 4);
-        // ---- dy role: pixel jb of the chunk, piece p8 of every 32-channel block m
-        const int jb = tid >> 3, p8 = tid & 7;
-        const uint32_t b_off = L::A_BYTES + jb * 128 + (((uint32_t)p8 ^ ((uint32_t)(jb & 3) << 1)) << 4);
-        float dbp[NDY * 4];
+        // ---- activation role: pixel j of the chunk, pieces gq and gq + 16 (rows kd0 + piece*4 .. +3 = one tap, 4 channels)
+        const int j = (tid >> 2) & 31;
+        const int gq = (tid & 3) + 4 * (tid >> 7);
+        const uint32_t a_sw = (uint32_t)(j & 3) << 1;
+        bool g_ok[2];
+        int g_dr[2], g_ds[2], g_ch[2];
+        uint32_t a_off[2];
+        float4 sc[2], sf[2];
 #pragma unroll
-        for (int i = 0; i < NDY * 4; ++i) dbp[i] = 0.f;
-        uint32_t vbits = 0;       // 4 validity bits per in-flight chunk
+        for (int k = 0; k < 2; ++k) {
+            const int piece = gq + 16 * k;
+            const int kd = kd0 + piece * 4;
+            g_ok[k] = kd < Kw;                       // rows beyond K are never written: the stage stays zero there
+            const int tap = g_ok[k] ? kd / Cin : 0;
+            g_ch[k] = g_ok[k] ? kd - tap * Cin : 0;
+            g_dr[k] = tap / a.k - a.pad; g_ds[k] = tap % a.k - a.pad;
+            a_off[k] = (uint32_t)(piece >> 3) * 4096 + j * 128 + ((((uint32_t)piece & 7) ^ a_sw) << 4);
+            sc[k] = make_float4(1.f, 1.f, 1.f, 1.f); sf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pro && g_ok[k]) { sc[k] = *reinterpret_cast<const float4 *>(s_scale + g_ch[k]); sf[k] = *reinterpret_cast<const float4 *>(s_shift + g_ch[k]); }
+        }
+        const bool any_a = g_ok[0];                  // piece gq + 16 is valid only if piece gq is
+        // ---- dy role: pixel jb of the chunk, piece p16 (+ 16 m) along the channel axis
+        const int jb = tid >> 4, p16 = tid & 15;
+        const uint32_t b_sw = (uint32_t)(jb & 3) << 1;
+        float dbp[NDYH * 4];
+#pragma unroll
+        for (int i = 0; i < NDYH * 4; ++i) dbp[i] = 0.f;
+        uint32_t vbits = 0;       // 2 validity bits per in-flight chunk
         for (int ch = -D; ch < nchunks; ++ch) {
             const int ci = ch + D;
             if (ci < nchunks) {
                 const uint32_t slot = sbase + L::RAW_OFF + (ci % RD) * L::RAW_BYTES + tid * L::SLOT;
                 const int p0 = (c_begin + ci) * 32;
                 uint32_t vm = 0;
-                if (g_ok) {
+                if (any_a) {
+                    const int p = p0 + j;
+                    int wo, ho, n;
+                    if (a.wsh >= 0) { wo = p & (Wo - 1); ho = (p >> a.wsh) & (Ho - 1); n = p >> (a.wsh + a.hsh); }
+                    else { wo = p % Wo; ho = (p / Wo) % Ho; n = p / (Wo * Ho); }
+                    const float *img = a.x + (size_t)n * H * W * Cin;
+                    const int h0 = ho * stride, w0 = wo * stride;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int p = p0 + i * 8 + r8;
-                        int wo, ho, n;
-                        if (a.wsh >= 0) { wo = p & (Wo - 1); ho = (p >> a.wsh) & (Ho - 1); n = p >> (a.wsh + a.hsh); }
-                        else { wo = p % Wo; ho = (p / Wo) % Ho; n = p / (Wo * Ho); }
-                        const int hi = ho * stride + dr, wi = wo * stride + ds;
+                    for (int k = 0; k < 2; ++k) {
+                        if (!g_ok[k]) continue;
+                        const int hi = h0 + g_dr[k], wi = w0 + g_ds[k];
                         const bool v = p < P && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
-                        const float *src = v ? a.x + (((size_t)n * H + hi) * W + wi) * Cin + chn : a.x;
-                        if (use_ca) cp_async16_ca(slot + i * 16, src, v ? 16u : 0u);
-                        else cp_async16(slot + i * 16, src, v ? 16u : 0u);
-                        vm |= (uint32_t)v << i;
+                        const float *src = v ? img + (hi * W + wi) * Cin + g_ch[k] : a.x;
+                        if (use_ca) cp_async16_ca(slot + k * 16, src, v ? 16u : 0u);
+                        else cp_async16(slot + k * 16, src, v ? 16u : 0u);
+                        vm |= (uint32_t)v << k;
                     }
                 }
                 {
                     const int pd = p0 + jb;
                     const bool pok = pd < P;
 #pragma unroll
-                    for (int m = 0; m < NDY; ++m)
-                        if ((m * 8 + p8) * 4 < BN)
-                            cp_async16(slot + (4 + m) * 16, pok ? a.dy + (size_t)pd * Cout + o0 + (m * 8 + p8) * 4 : a.dy, pok ? 16u : 0u);
+                    for (int m = 0; m < NDYH; ++m)
+                        if ((p16 + 16 * m) * 4 < BN)
+                            cp_async16(slot + (2 + m) * 16, pok ? a.dy + (size_t)pd * Cout + o0 + (p16 + 16 * m) * 4 : a.dy, pok ? 16u : 0u);
                 }
-                const uint32_t sh = 4 * (ci % RD);
-                vbits = (vbits & ~(0xFu << sh)) | (vm << sh);
+                const uint32_t sh = 2 * (ci % RD);
+                vbits = (vbits & ~(3u << sh)) | (vm << sh);
             }
             cp_async_commit();
             if (ch < 0) continue;
@@ -276,22 +293,23 @@ k_wgrad_mn(WArgs a) {
             PROF(11);
             const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
             const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
-            const uint32_t vm = (vbits >> (4 * (ch % RD))) & 0xFu;
+            const uint32_t vm = (vbits >> (2 * (ch % RD))) & 3u;
             if (lane == 0) { if (kspin) mbar_spin(bar(NST + stage), phase ^ 1); else mbar_wait(bar(NST + stage), phase ^ 1); }
             __syncwarp();
             PROF(12);
             unsigned char *st = smem + stage * L::STAGE_BYTES;
-            if (g_ok && !kskip_p) {
+            if (any_a && !kskip_p) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 xv = *reinterpret_cast<const float4 *>(slot + i * 16);
+                for (int k = 0; k < 2; ++k) {
+                    if (!g_ok[k]) continue;
+                    float4 xv = *reinterpret_cast<const float4 *>(slot + k * 16);
                     if (pro) {
-                        xv.x = fmaf(xv.x, sc.x, sf.x); xv.y = fmaf(xv.y, sc.y, sf.y);
-                        xv.z = fmaf(xv.z, sc.z, sf.z); xv.w = fmaf(xv.w, sc.w, sf.w);
+                        xv.x = fmaf(xv.x, sc[k].x, sf[k].x); xv.y = fmaf(xv.y, sc[k].y, sf[k].y);
+                        xv.z = fmaf(xv.z, sc[k].z, sf[k].z); xv.w = fmaf(xv.w, sc[k].w, sf[k].w);
                         if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f); }
                     }
-                    if (!((vm >> i) & 1u)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    unsigned char *dst = st + a_off + i * 1024;
+                    if (!((vm >> k) & 1u)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned char *dst = st + a_off[k];
                     uint4 h;
                     h.x = to_tf32(xv.x); h.y = to_tf32(xv.y); h.z = to_tf32(xv.z); h.w = to_tf32(xv.w);
                     *reinterpret_cast<uint4 *>(dst) = h;
@@ -304,11 +322,12 @@ k_wgrad_mn(WArgs a) {
                 }
             }
 #pragma unroll
-            for (int m = 0; m < NDY; ++m) {
-                if ((m * 8 + p8) * 4 >= BN || kskip_p) continue;
-                const float4 bv = *reinterpret_cast<const float4 *>(slot + (4 + m) * 16);
+            for (int m = 0; m < NDYH; ++m) {
+                const int pcm = p16 + 16 * m;
+                if (pcm * 4 >= BN || kskip_p) continue;
+                const float4 bv = *reinterpret_cast<const float4 *>(slot + (2 + m) * 16);
                 dbp[m * 4] += bv.x; dbp[m * 4 + 1] += bv.y; dbp[m * 4 + 2] += bv.z; dbp[m * 4 + 3] += bv.w;
-                unsigned char *dst = st + b_off + m * 4096;
+                unsigned char *dst = st + L::A_BYTES + (pcm >> 3) * 4096 + jb * 128 + ((((uint32_t)pcm & 7) ^ b_sw) << 4);
                 uint4 h;
                 h.x = to_tf32(bv.x); h.y = to_tf32(bv.y); h.z = to_tf32(bv.z); h.w = to_tf32(bv.w);
                 *reinterpret_cast<uint4 *>(dst) = h;
@@ -327,17 +346,16 @@ k_wgrad_mn(WArgs a) {
         }
         PROF(3);
         if (a.db != nullptr && mt == 0) {
-            // lanes l, l+8, l+16, l+24 hold the same dy piece for 4 different pixels
+            // lanes l and l + 16 hold the same dy piece for the warp's 2 pixels
 #pragma unroll
-            for (int i = 0; i < NDY * 4; ++i) {
+            for (int i = 0; i < NDYH * 4; ++i) {
                 float t = dbp[i];
-                t += __shfl_xor_sync(0xffffffffu, t, 8);
                 t += __shfl_xor_sync(0xffffffffu, t, 16);
-                const int m = i >> 2;
-                if (lane < 8 && (m * 8 + p8) * 4 < BN) atomicAdd(&a.db[o0 + (m * 8 + p8) * 4 + (i & 3)], t);
+                const int pcm = p16 + 16 * (i >> 2);
+                if (lane < 16 && pcm * 4 < BN) atomicAdd(&a.db[o0 + pcm * 4 + (i & 3)], t);
             }
         }
-        if (warp >= 4 && nchunks > 0) {
+        if (warp >= 4 && warp < 8 && nchunks > 0) {
             // epilogue (warps 4-7: TMEM lane quarter = warp % 4): row = (tap, c) index, columns = output channels
             const int ew = warp - 4;
             const int kd = kd0 + ew * 32 + lane;
@@ -356,7 +374,7 @@ k_wgrad_mn(WArgs a) {
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == W_MMA) {
         if (nchunks > 0) {      // converged warp, elected issue
             // c_format F32, a/b TF32, a_major = b_major = MN (bits 15, 16), N = BNP, M = 128
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
@@ -393,7 +411,7 @@ k_wgrad_mn(WArgs a) {
     tc_fence_before();
     __syncthreads();
     PROF(4);
-    if (warp == 8) {
+    if (warp == W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
