@@ -732,7 +732,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
 #pragma unroll
                 for (int w = 0; w < 8; ++w) tsum += s_stat[w * 2 * BN + idx];
                 const int kind = idx / BN, col = idx - kind * BN;
-                atomicAdd(&st[kind * a.Cn + cta_n0 + col], tsum);
+                if (!(a.knobs & 4)) atomicAdd(&st[kind * a.Cn + cta_n0 + col], tsum);     // knob 4: timing ablation (wrong statistics)
             }
         }
     }

@@ -43,6 +43,8 @@ __device__ long long *g_prof_wg = nullptr;
 #endif
 
 constexpr int TM = 128;
+constexpr int WS_R = 16;                    // replicas of the split reduction (see WArgs::ws)
+constexpr size_t WS_TILE_FLOATS = (size_t)WS_R * 16 * 128 * 128;   // [16 tiles][R][128 rows][<= 128 columns]
 constexpr int NPROD = 16;                   // producer warps
 constexpr int W_MMA = NPROD;                // MMA issuer warp
 constexpr int NTHREADS = 32 * (NPROD + 1);
@@ -144,6 +146,9 @@ struct WArgs {
     int lbo16, sbo16, kstep;     // experiment knobs (DPP_MN_LBO / DPP_MN_SBO / DPP_MN_KSTEP), defaults 256 / 32 / 1024
     int knobs;                   // tuning bits (DPP_WG_KNOBS): 1 = L1-allocating activation gathers for k > 1
     int wsh, hsh;                // log2(Wo), log2(Ho) when both are powers of two, else -1
+    // Split-pixel reduction without a 148-way atomic pile-up: a CTA adds its tile into replica (split % R) of the
+    // library workspace, the last CTA of a tile (arrival counter) folds the R replicas into dW and re-zeroes them.
+    float *ws; int *ctr; int R;
 };
 
 template <int BN, int PASSES, int NST>
@@ -195,6 +200,9 @@ k_wgrad_mn(WArgs a) {
     int c_end = c_begin + a.cps[mt]; if (c_end > total_chunks) c_end = total_chunks;
     const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
 
+    __shared__ float s_db[128];      // this CTA's bias-gradient partial (m-tile 0 only)
+    __shared__ int s_last;
+    if (tid < 128) s_db[tid] = 0.f;
     pdl_trigger();      // private set-up first (see common.cuh: programmatic dependent launch)
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(bar(s), NPROD); mbar_init(bar(NST + s), 1); }   // full: one arrival per producer warp
@@ -352,7 +360,7 @@ k_wgrad_mn(WArgs a) {
                 float t = dbp[i];
                 t += __shfl_xor_sync(0xffffffffu, t, 16);
                 const int pcm = p16 + 16 * (i >> 2);
-                if (lane < 16 && pcm * 4 < BN) atomicAdd(&a.db[o0 + pcm * 4 + (i & 3)], t);
+                if (lane < 16 && pcm * 4 < BN) atomicAdd(&s_db[pcm * 4 + (i & 3)], t);     // shared-memory atomic: 16 warps
             }
         }
         if (warp >= 4 && warp < 8 && nchunks > 0) {
@@ -368,7 +376,7 @@ k_wgrad_mn(WArgs a) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + cb, v);
                 if (kd < Kw) {
-                    float *dst = a.dw + (size_t)kd * a.Cout + o0 + cb;
+                    float *dst = a.ws + ((size_t)((mt * a.ntiles + nt) * a.R + split % a.R) * TM + ew * 32 + lane) * BN + cb;
 #pragma unroll
                     for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
                 }
@@ -415,6 +423,56 @@ k_wgrad_mn(WArgs a) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
+    // ---- last CTA of this (m-tile, n-tile): fold the replicas into dW (and db)
+    const int tile_id = mt * a.ntiles + nt;
+    const bool has_db = a.db != nullptr && mt == 0;
+    float *const wdb = a.ws + WS_TILE_FLOATS + (size_t)(nt * a.R) * 128;     // [R][128] bias-gradient replicas of n-tile nt
+    if (has_db && tid < BN) atomicAdd(wdb + (split % a.R) * 128 + tid, s_db[tid]);   // s_db is complete: __syncthreads above
+    __threadfence();                                  // this CTA's reductions are ordered before its arrival
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&a.ctr[tile_id], 1) == a.splits[mt] - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const int rows = Kw - kd0 < TM ? Kw - kd0 : TM;
+        float *base = a.ws + (size_t)tile_id * a.R * TM * BN;
+        for (int e = tid; e < rows * (BN / 4); e += NTHREADS) {
+            const int row = e / (BN / 4), c4 = e - row * (BN / 4);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < a.R; ++r) {
+                float4 *p = reinterpret_cast<float4 *>(base + ((size_t)r * TM + row) * BN) + c4;
+                const float4 v = __ldcg(p);           // written by other SMs' L2 reductions
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                __stcg(p, make_float4(0.f, 0.f, 0.f, 0.f));   // leave the workspace clean for the next launch
+            }
+            float4 *d = reinterpret_cast<float4 *>(a.dw + (size_t)(kd0 + row) * a.Cout + o0) + c4;
+            float4 o = *d;
+            o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+            *d = o;
+        }
+        if (has_db && tid < BN) {
+            float acc = 0.f;
+            for (int r = 0; r < a.R; ++r) { acc += __ldcg(wdb + r * 128 + tid); __stcg(wdb + r * 128 + tid, 0.f); }
+            a.db[o0 + tid] += acc;
+        }
+        if (tid == 0) a.ctr[tile_id] = 0;
+    }
+}
+
+// library-owned workspace of the split reduction (16 replicas x up to 16 tiles of 128 x 128 floats) + arrival counters
+constexpr size_t WS_FLOATS = WS_TILE_FLOATS + (size_t)2 * WS_R * 128;
+float *g_ws = nullptr;
+int *g_ctr = nullptr;
+
+int ws_init() {
+    if (g_ws != nullptr) return 0;
+    float *w = nullptr; int *c = nullptr;
+    if (cudaMalloc(&w, WS_FLOATS * sizeof(float)) != cudaSuccess) return -1;
+    if (cudaMalloc(&c, 64 * sizeof(int)) != cudaSuccess) { cudaFree(w); return -1; }
+    if (cudaMemset(w, 0, WS_FLOATS * sizeof(float)) != cudaSuccess || cudaMemset(c, 0, 64 * sizeof(int)) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) { cudaFree(w); cudaFree(c); return -1; }
+    g_ws = w; g_ctr = c;
+    return 0;
 }
 
 template <int BN, int PASSES, int NST>
@@ -459,6 +517,11 @@ int launch(WArgs &a, cudaStream_t st) {
         a.splits[t] = (total_chunks + a.cps[t] - 1) / a.cps[t];
         grid += a.splits[t] * a.ntiles;
     }
+    if (ws_init() != 0 || a.mtiles * a.ntiles > 16) return -1;
+    a.ws = g_ws; a.ctr = g_ctr;
+    int smin = a.splits[0];
+    for (int t = 1; t < a.mtiles; ++t) if (a.splits[t] < smin) smin = a.splits[t];
+    a.R = smin < WS_R ? smin : WS_R;
     if (launch_pdl(2, k_wgrad_mn<BN, PASSES, NST>, dim3(grid), dim3(NTHREADS), L::TOTAL, st, a) != cudaSuccess) return -1;
     return 0;
 }
@@ -509,3 +572,10 @@ extern "C" int dpp_debug_set_prof_wg(void *buf) {
     return DPP_OK;
 }
 #endif
+
+// Allocates the library-owned workspace of the backward-weights split reduction (idempotent).  Must be called
+// outside CUDA-graph capture (Engine does it at construction); dpp_conv2d_wgrad allocates lazily otherwise.
+extern "C" int dpp_wgrad_workspace_init(void) {
+    if (ws_init() != 0) return dpp::fail(DPP_ECUDA, "%s: workspace allocation failed", __func__);
+    return DPP_OK;
+}

@@ -93,6 +93,7 @@ class Engine(object):
         if not torch.cuda.is_available():
             raise DppError("dpp_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         lib.load()
+        lib.dpp_wgrad_workspace_init()     # library-owned scratch: allocated here, never inside a graph capture
         self.torch = torch
         self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         self.net = net

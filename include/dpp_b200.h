@@ -49,6 +49,9 @@ int dpp_device_info(int device, int *cc_out, int *sm_count_out, char *name_out, 
 /* Programmatic dependent launch of the step's kernel chain (bit 0: main chain, bit 1: backward-weights
  * kernels); -1 = re-read DPP_PDL from the environment.  Takes effect for launches issued after the call. */
 int dpp_set_pdl(int mode);
+/* Allocates the library-owned workspace of the backward-weights split reduction (16 MB, idempotent).  Call once
+ * outside CUDA-graph capture; dpp_conv2d_wgrad allocates it lazily otherwise. */
+int dpp_wgrad_workspace_init(void);
 
 /* ---------------------------------------------------------------------------------------
  * BatchNorm reference handed to conv/fc prologues (reference: net/batchnormlayer.py:154-192).
