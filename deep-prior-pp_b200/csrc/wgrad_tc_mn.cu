@@ -376,7 +376,8 @@ k_wgrad_mn(WArgs a) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + cb, v);
                 if (kd < Kw) {
-                    float *dst = a.ws + ((size_t)((mt * a.ntiles + nt) * a.R + split % a.R) * TM + ew * 32 + lane) * BN + cb;
+                    float *dst = a.splits[mt] == 1 ? a.dw + (size_t)kd * a.Cout + o0 + cb      // sole contributor: straight into dW
+                                                   : a.ws + ((size_t)((mt * a.ntiles + nt) * a.R + split % a.R) * TM + ew * 32 + lane) * BN + cb;
 #pragma unroll
                     for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
                 }
@@ -427,6 +428,10 @@ k_wgrad_mn(WArgs a) {
     const int tile_id = mt * a.ntiles + nt;
     const bool has_db = a.db != nullptr && mt == 0;
     float *const wdb = a.ws + WS_TILE_FLOATS + (size_t)(nt * a.R) * 128;     // [R][128] bias-gradient replicas of n-tile nt
+    if (a.splits[mt] == 1) {                          // unsplit tile: nothing to fold
+        if (has_db && tid < BN) a.db[o0 + tid] += s_db[tid];
+        return;
+    }
     if (has_db && tid < BN) atomicAdd(wdb + (split % a.R) * 128 + tid, s_db[tid]);   // s_db is complete: __syncthreads above
     __threadfence();                                  // this CTA's reductions are ordered before its arrival
     __syncthreads();
@@ -519,9 +524,13 @@ int launch(WArgs &a, cudaStream_t st) {
     }
     if (ws_init() != 0 || a.mtiles * a.ntiles > 16) return -1;
     a.ws = g_ws; a.ctr = g_ctr;
-    int smin = a.splits[0];
-    for (int t = 1; t < a.mtiles; ++t) if (a.splits[t] < smin) smin = a.splits[t];
-    a.R = smin < WS_R ? smin : WS_R;
+    // replicas: enough to keep the same-address reduction chain at ~8 CTAs, no more (the last CTA folds R tiles)
+    int smin = a.splits[0], smax = a.splits[0];
+    for (int t = 1; t < a.mtiles; ++t) { if (a.splits[t] < smin) smin = a.splits[t]; if (a.splits[t] > smax) smax = a.splits[t]; }
+    a.R = (smax + 7) / 8;
+    if (a.R > WS_R) a.R = WS_R;
+    if (a.R > smin) a.R = smin;
+    if (a.R < 1) a.R = 1;
     if (launch_pdl(2, k_wgrad_mn<BN, PASSES, NST>, dim3(grid), dim3(NTHREADS), L::TOTAL, st, a) != cudaSuccess) return -1;
     return 0;
 }
