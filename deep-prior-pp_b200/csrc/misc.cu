@@ -105,3 +105,13 @@ extern "C" int dpp_fill_f64(double *p, double value, int64_t n, void *stream) {
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }
+
+// Strided device-to-device copy (rows x width bytes): concatenation of flattened tower outputs into the first
+// hidden layer's input (reference: net/scalenet.py:174-178, T.concatenate(..., axis=1)).
+extern "C" int dpp_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width, int64_t rows,
+                          void *stream) {
+    DPP_CHECK_ARG(dst && src && width > 0 && rows > 0 && dst_pitch >= width && src_pitch >= width);
+    DPP_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)rows,
+                               cudaMemcpyDeviceToDevice, S(stream)));
+    return DPP_OK;
+}

@@ -64,6 +64,7 @@ class Slot(object):
         self.shape = tuple(var.shape)
         self.size = int(np.prod(self.shape)) if len(self.shape) else 1
         self.chw = None             # FC rows permuted from (c,h,w) to (h,w,c)
+        self.segments = None        # ... per concatenated tower: [(first row, (c,h,w)), ...]
 
     # reference layout <-> device layout
     def to_device_layout(self, v):
@@ -74,6 +75,12 @@ class Slot(object):
         if self.var.kind == 'fcW' and self.chw is not None:
             c, h, w = self.chw
             return np.ascontiguousarray(v.reshape(c, h, w, -1).transpose(1, 2, 0, 3)).reshape(-1)
+        if self.var.kind == 'fcW' and self.segments is not None:
+            out = np.array(v, np.float32, copy=True)
+            for r0, (c, h, w) in self.segments:
+                n = c * h * w
+                out[r0:r0 + n] = v[r0:r0 + n].reshape(c, h, w, -1).transpose(1, 2, 0, 3).reshape(n, -1)
+            return out.reshape(-1)
         return np.ascontiguousarray(v).reshape(-1)
 
     def from_device_layout(self, flat):
@@ -84,6 +91,13 @@ class Slot(object):
         if self.var.kind == 'fcW' and self.chw is not None:
             c, h, w = self.chw
             return np.ascontiguousarray(flat.reshape(h, w, c, -1).transpose(2, 0, 1, 3)).reshape(self.shape)
+        if self.var.kind == 'fcW' and self.segments is not None:
+            v = flat.reshape(self.shape)
+            out = v.copy()
+            for r0, (c, h, w) in self.segments:
+                n = c * h * w
+                out[r0:r0 + n] = v[r0:r0 + n].reshape(h, w, c, -1).transpose(2, 0, 1, 3).reshape(n, -1)
+            return out
         return flat.reshape(self.shape).copy()
 
 
@@ -155,13 +169,22 @@ class Engine(object):
         val = {}                      # id(sym) -> Tensor
         virt = {}                     # id(relu sym) -> (bn layer, raw Tensor) not materialised
         inputs = [s for s in order if s.op == 'input']
-        if len(inputs) != 1:
-            raise NotImplementedError("engine handles single-input graphs (ScaleNet towers are run per tower)")
-        tin = Tensor('input', self.net.cfgParams.inputDim)
-        tin.is_input = True
-        self.tensors.append(tin)
-        self.t_in = tin
-        val[id(inputs[0])] = tin
+        if isinstance(self.net.inputVar, (list, tuple)):
+            # multi-input net (ScaleNet): inputs in the order of net.inputVar, dims from cfgParams.inputDim[k]
+            inputs = [v for v in self.net.inputVar if id(v) in seen]
+            dims = list(self.net.cfgParams.inputDim)
+        else:
+            if len(inputs) != 1:
+                raise NotImplementedError("a single-input net with %d graph inputs" % len(inputs))
+            dims = [self.net.cfgParams.inputDim]
+        self.t_ins = []
+        for k, (sym_in, dim) in enumerate(zip(inputs, dims)):
+            tin = Tensor('input' if k == 0 else 'input%d' % k, dim)
+            tin.is_input = True
+            self.tensors.append(tin)
+            self.t_ins.append(tin)
+            val[id(sym_in)] = tin
+        self.t_in = self.t_ins[0]
 
         def new_tensor(name, shape):
             t = Tensor(name, shape)
@@ -198,6 +221,19 @@ class Engine(object):
                 t2.alias = t4
                 t2.chw = t4.shape[1:]
                 val[id(s)] = t2
+                continue
+            if s.op == 'concat':
+                srcs = [val[id(i)] for i in s.inputs]
+                if not all(isinstance(t, Tensor) and len(t.shape) == 2 for t in srcs):
+                    raise NotImplementedError("concat of non-flattened tensors")
+                cat = new_tensor('concat', (srcs[0].shape[0], int(sum(t.shape[1] for t in srcs))))
+                cat.segments, off = [], 0
+                for t in srcs:
+                    if t.chw is not None:
+                        cat.segments.append((off, tuple(t.chw)))
+                    off += t.shape[1]
+                self.ops.append(dict(kind='concat', srcs=srcs, dst=cat))
+                val[id(s)] = cat
                 continue
             if s.op == 'reshape':
                 raise NotImplementedError("reshape hidden->conv is unused on the hot path")
@@ -305,6 +341,8 @@ class Engine(object):
         for op in self.ops:
             if op['kind'] == 'fc' and getattr(op['src'], 'chw', None) is not None:
                 self.slots[id(op['layer'].W)].chw = tuple(op['src'].chw)
+            if op['kind'] == 'fc' and getattr(op['src'], 'segments', None):
+                self.slots[id(op['layer'].W)].segments = list(op['src'].segments)
         self.W = torch.zeros(self.n_w, dtype=torch.float32, device=self.dev)
         self.R = torch.zeros(self.n_r, dtype=torch.float32, device=self.dev)
         self.G = self.M = self.V = None
@@ -408,7 +446,8 @@ class Engine(object):
         for op in self.ops:
             if op['kind'] == 'convpool':
                 op['argmax'] = torch.zeros(self._nhwc_shape(op['dst']), dtype=torch.uint8, device=self.dev)
-        self.x_nchw = torch.zeros(self.t_in.shape, dtype=torch.float32, device=self.dev)
+        self.x_nchw_all = [torch.zeros(t.shape, dtype=torch.float32, device=self.dev) for t in self.t_ins]
+        self.x_nchw = self.x_nchw_all[0]
         self.cost = torch.zeros(1, dtype=torch.float32, device=self.dev)
 
     def _alloc_training(self):
@@ -517,6 +556,15 @@ class Engine(object):
                                    _ptr(self.pview(L.W)), _ptr(self.pview(L.b)),
                                    _ptr(op['residual'].buf) if op['residual'] is not None else None,
                                    _ptr(op['dst'].buf), stats, st)
+            elif k == 'concat':
+                dst = op['dst'].buf
+                off = 0
+                for t in op['srcs']:
+                    buf = t.alias.buf if hasattr(t, 'alias') else t.buf
+                    n = int(t.shape[1])
+                    lib.dpp_copy2d(C.c_void_p(dst.data_ptr() + 4 * off), 4 * int(dst.shape[1]), _ptr(buf), 4 * n, 4 * n,
+                                   self.B, st)
+                    off += n
             elif k == 'bn_apply':
                 bnref = self._bnref(op['bn'], op['src'], train, relu=op['relu'])
                 c = op['src'].shape[1]
@@ -600,6 +648,9 @@ class Engine(object):
                 lib.dpp_fc_bwd(_ptr(base.buf), _ptr(self.pview(L.W)), _ptr(op['dst'].buf), _ptr(op['dst'].grad),
                                _ptr(self.pview(L.W, G)), _ptr(self.pview(L.b, G)), _ptr(dx), _ptr(op['scratch']),
                                self.B, n_in, n_out, relu, _ptr(mask), 1.0, self.precision, st)
+            elif k == 'concat':
+                raise NotImplementedError("backward through a tower concatenation: ScaleNet training is out of scope "
+                                          "(DESIGN.md section 8)")
             elif k == 'bn_apply':
                 bn, raw = op['bn'], op['src']
                 bnref = self._bnref(bn, raw, True, relu=op['relu'])
@@ -671,17 +722,21 @@ class Engine(object):
         self._run_forward(train=not deterministic)
         return self.t_out.buf
 
-    def set_input_nchw(self, x_host_or_dev):
+    def set_input_nchw(self, x_host_or_dev, which=0):
         torch = self.torch
         if isinstance(x_host_or_dev, np.ndarray):
             x_host_or_dev = torch.from_numpy(np.ascontiguousarray(x_host_or_dev, np.float32))
-        self.x_nchw.copy_(x_host_or_dev.reshape(self.x_nchw.shape), non_blocking=True)
-        n, c, h, w = self.t_in.shape
-        lib.dpp_nchw_to_nhwc(_ptr(self.x_nchw), _ptr(self.t_in.buf), n, c, h, w, self._stream())
+        stage, tin = self.x_nchw_all[which], self.t_ins[which]
+        stage.copy_(x_host_or_dev.reshape(stage.shape), non_blocking=True)
+        n, c, h, w = tin.shape
+        lib.dpp_nchw_to_nhwc(_ptr(stage), _ptr(tin.buf), n, c, h, w, self._stream())
 
     def forward_host(self, batch_list, deterministic=True):
-        """computeOutput's inner step: numpy NCHW batch in, numpy output out."""
-        self.set_input_nchw(batch_list[0])
+        """computeOutput's inner step: numpy NCHW batch(es) in, numpy output out."""
+        if len(batch_list) != len(self.t_ins):
+            raise DppError("network takes %d input(s), got %d" % (len(self.t_ins), len(batch_list)))
+        for k, b in enumerate(batch_list):
+            self.set_input_nchw(b, which=k)
         out = self.forward_device(deterministic=deterministic)
         return out.cpu().numpy()
 

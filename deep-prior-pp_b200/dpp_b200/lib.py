@@ -78,6 +78,7 @@ _SIGS = {
     'dpp_adam_tick': (C.c_int, [P, P]),
     'dpp_set_pdl': (C.c_int, [C.c_int]),
     'dpp_wgrad_workspace_init': (C.c_int, []),
+    'dpp_copy2d': (C.c_int, [P, C.c_int64, P, C.c_int64, C.c_int64, C.c_int64, P]),
     'dpp_fill_f32': (C.c_int, [P, C.c_float, C.c_int64, P]),
     'dpp_fill_f64': (C.c_int, [P, C.c_double, C.c_int64, P]),
 }

@@ -59,7 +59,7 @@ def shared(value, name=None, borrow=False, kind='plain'):
 
 
 class Sym(object):
-    """Node of the recorded graph.  op in {'input','layer','relu','add','flatten','reshape'}."""
+    """Node of the recorded graph.  op in {'input','layer','relu','add','flatten','reshape','concat'}."""
 
     def __init__(self, op, inputs=(), layer=None, shape=None, name=None):
         self.op = op
@@ -89,6 +89,15 @@ class Sym(object):
 
 def tensor4(name=None):
     return Sym('input', name=name)
+
+
+def concatenate(tensor_list, axis=1):
+    """T.concatenate of flattened (B, n_i) tensors along the feature axis (scalenet.py:174-178)."""
+    assert axis == 1
+    shp = None
+    if all(t.shape is not None for t in tensor_list):
+        shp = (tensor_list[0].shape[0], int(sum(t.shape[1] for t in tensor_list)))
+    return Sym('concat', tuple(tensor_list), shape=shp)
 
 
 def matrix(name=None):

@@ -227,6 +227,10 @@ int dpp_adam_step(float *w, const float *g, float *m, float *v, const float *hyp
 int dpp_adam_tick(float *hyper, void *stream); /* t += 1 after all dpp_adam_step calls    */
 
 /* fill helpers (capturable) */
+/* Strided device-to-device copy of `rows` rows of `width` bytes (pitches in bytes): concatenation of the
+ * flattened ScaleNet tower outputs (reference: net/scalenet.py:174-178). */
+int dpp_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width, int64_t rows,
+               void *stream);
 int dpp_fill_f32(float *p, float value, int64_t n, void *stream);
 int dpp_fill_f64(double *p, double value, int64_t n, void *stream);
 

@@ -162,6 +162,11 @@ class OracleNet(object):
         self.program.append(('flatten', src, dst))
         return dst
 
+    def add_concat(self, srcs):
+        dst = self._newv()
+        self.program.append(('concat', list(srcs), dst))
+        return dst
+
     # -- parameter views ----------------------------------------------------------
     @property
     def params(self):
@@ -347,6 +352,34 @@ def build_poseregnet(rng, type=0, nChan=1, wIn=128, hIn=128, batchSize=128, numJ
         v = net.add_fc(v, 30, numJoints * nDims, 'None')
     else:
         raise NotImplementedError()
+    net.out_vid = v
+    return net
+
+
+def build_scalenet(rng, type=1, nChan=1, wIn=128, hIn=128, batchSize=128, numJoints=1, nDims=3, resizeFactor=2):
+    """scalenet.py:49-193 (type 1): three towers of three 'valid' ConvPool layers on inputs -1, -2, -3 (the crop
+    and its centre crops), flatten + concatenate, FC1024 - dropout - FC1024 - dropout - FC(J*D)."""
+    if type != 1:
+        raise NotImplementedError()
+    net = OracleNet(rng, (batchSize, nChan, hIn, wIn))
+    f = resizeFactor
+    net.multi_inputs = [(batchSize, nChan, hIn, wIn), (batchSize, nChan, hIn // f, wIn // f),
+                        (batchSize, nChan, hIn // f ** 2, wIn // f ** 2)]
+    towers = [[(5, 4), (5, 2), (3, 1)], [(5, 2), (5, 2), (3, 1)], [(5, 2), (5, 1), (3, 1)]]
+    flats, nfeat = [], 0
+    for t, spec in enumerate(towers):
+        v, c, hw = -(t + 1), nChan, net.multi_inputs[t][2:]
+        for k, pool in spec:
+            v, c, hw = net.add_convpool(v, c, hw, 8, k, pool, 'valid', 'ReLU', None)
+        flats.append((v, c * hw[0] * hw[1]))
+        nfeat += c * hw[0] * hw[1]
+    # the reference flattens when the first hidden layer is wired, after all ConvPool layers exist
+    v = net.add_concat([net.add_flatten(fv) for fv, _ in flats])
+    v = net.add_fc(v, nfeat, 1024, 'ReLU')
+    v = net.add_dropout(v)
+    v = net.add_fc(v, 1024, 1024, 'ReLU')
+    v = net.add_dropout(v)
+    v = net.add_fc(v, 1024, numJoints * nDims, 'None')
     net.out_vid = v
     return net
 

@@ -48,9 +48,26 @@ def resnet_case():
                 fc2_grad=grads[-2].numpy(), out_after_step=out2.numpy())
 
 
+def scalenet_case():
+    """ScaleNet type 1 (scalenet.py:49-193), deterministic forward on a synthetic crop and its centre crops."""
+    import torch
+    from oracle import nets as O
+    from data import synthetic
+    B = 2
+    ds = synthetic.generate('NYU', B, seed=31)
+    x0 = ds['x'].astype(np.float32)
+    x1 = np.ascontiguousarray(x0[:, :, 32:96, 32:96])
+    x2 = np.ascontiguousarray(x0[:, :, 48:80, 48:80])
+    net = O.build_scalenet(np.random.RandomState(23455), type=1, batchSize=B, numJoints=1, nDims=3)
+    with torch.no_grad():
+        out, _ = net.forward([torch.from_numpy(x0), torch.from_numpy(x1), torch.from_numpy(x2)], deterministic=True)
+    return dict(x0=x0, out_det=out.numpy())
+
+
 if __name__ == '__main__':
     np.savez_compressed(os.path.join(HERE, 'augment_nyu.npz'), **augment_case('NYU', 'NYU_CAM', ['com', 'rot', 'none'], 8, 11))
     np.savez_compressed(os.path.join(HERE, 'augment_msra.npz'),
                         **augment_case('MSRA15', 'MSRA_CAM', ['com', 'rot', 'sc', 'none'], 8, 13))
     np.savez_compressed(os.path.join(HERE, 'resnet_b2.npz'), **resnet_case())
+    np.savez_compressed(os.path.join(HERE, 'scalenet_b2.npz'), **scalenet_case())
     print("golden vectors written to", HERE)
