@@ -66,3 +66,48 @@ def random_orthonormal_pca(n_components, dim, seed=0):
     rng = np.random.RandomState(seed)
     q, _ = np.linalg.qr(rng.randn(dim, dim))
     return q[:n_components].astype(f64), (rng.randn(dim) * 0.05).astype(f64)
+
+
+def generate_frames(name, n, seed=23455, cube=None, edge_fraction=0.25, nd=0.):
+    """Synthetic full depth frames for the inference cascade (BASELINE config 5; the reference's FileDevice feeds
+    NYU test frames, src/test_realtimepipeline.py:66-73): ``importer.depth_map_size`` frames in integer mm with
+    undefined depth ``nd``, a hand-like union of ellipses inside the cube around a random CoM, background clutter
+    behind the cube, and - for ``edge_fraction`` of the frames - a CoM so close to the border that the crop window
+    leaves the frame (getCrop's zero padding).  Returns dict(frames (n,H,W) f32, com3D (n,3) f32 true CoMs,
+    lastcom (n,3) f64 the perturbed CoMs a detector / previous frame would hand over, cube, importer)."""
+    rng = np.random.RandomState(seed)
+    di = make_importer(name)
+    cube = tuple(cube if cube is not None else DATASETS[name][1])
+    Wf, Hf = di.depth_map_size
+    frames = np.full((n, Hf, Wf), nd, f32)
+    com3D = np.zeros((n, 3), f32)
+    lastcom = np.zeros((n, 3), f64)
+    yy, xx = np.mgrid[0:Hf, 0:Wf]
+    for i in range(n):
+        z = rng.uniform(450, 900)
+        r_px = 0.5 * cube[0] / z * di.fx                     # half the window edge in pixels
+        if rng.rand() < edge_fraction:
+            u = rng.choice([rng.uniform(0.3 * r_px, 0.9 * r_px), Wf - rng.uniform(0.3 * r_px, 0.9 * r_px)])
+            v = rng.uniform(r_px, Hf - r_px)
+            if rng.rand() < 0.5:
+                v = rng.choice([rng.uniform(0.3 * r_px, 0.9 * r_px), Hf - rng.uniform(0.3 * r_px, 0.9 * r_px)])
+        else:
+            u = rng.uniform(1.1 * r_px, Wf - 1.1 * r_px)
+            v = rng.uniform(1.1 * r_px, Hf - 1.1 * r_px)
+        com = np.array([u, v, z], f64)
+        d = frames[i]
+        # clutter behind the hand (cut by the z-threshold) and a near occluder in one corner of some frames
+        m = (yy > v + 0.5 * r_px) & (np.abs(xx - u) < 0.4 * r_px)
+        d[m] = np.rint(z + cube[2] * rng.uniform(0.6, 1.5))
+        if rng.rand() < 0.3:
+            m = (xx < u - 0.7 * r_px) & (yy < v - 0.7 * r_px)
+            d[m] = np.rint(z - cube[2] * rng.uniform(0.55, 0.8))
+        for _ in range(6):
+            cx, cy = u + rng.uniform(-0.6, 0.6, 2) * r_px
+            ax, ay = rng.uniform(0.06, 0.35, 2) * r_px
+            depth = np.rint(z + rng.uniform(-0.4, 0.4) * cube[2] / 2.)
+            m = ((xx - cx) / ax) ** 2 + ((yy - cy) / ay) ** 2 <= 1.0
+            d[m] = depth
+        com3D[i] = di.jointImgTo3D(com)
+        lastcom[i] = com + np.array([rng.uniform(-6, 6), rng.uniform(-6, 6), rng.uniform(-15, 15)])
+    return dict(frames=frames, com3D=com3D, lastcom=lastcom, cube=cube, importer=di, nd=f32(nd))

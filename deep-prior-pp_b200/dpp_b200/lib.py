@@ -29,6 +29,14 @@ class AugRec(C.Structure):
                 ('half_new', C.c_float), ('m', C.c_double * 9)]
 
 
+class CropRec(C.Structure):
+    _fields_ = [('src_index', C.c_int32), ('xstart', C.c_int32), ('ystart', C.c_int32), ('wb', C.c_int32),
+                ('hb', C.c_int32), ('rw', C.c_int32), ('rh', C.c_int32), ('px', C.c_int32), ('py', C.c_int32),
+                ('flags', C.c_int32), ('zstart', C.c_float), ('zend', C.c_float), ('fill', C.c_float),
+                ('hi', C.c_float), ('lo', C.c_float), ('comz', C.c_float), ('half', C.c_float),
+                ('reserved', C.c_float), ('ifx', C.c_double), ('ify', C.c_double)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
                 ('Cout', C.c_int), ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int),
@@ -51,6 +59,13 @@ AUG_REC_DTYPE = [('src_index', '<i4'), ('mode', '<i4'), ('half_old', '<f4'), ('c
                  ('zstart', '<f4'), ('zend', '<f4'), ('bg', '<f4'), ('lo', '<f4'),
                  ('comz_new', '<f4'), ('half_new', '<f4'), ('m', '<f8', (9,))]
 
+# numpy dtype mirroring dpp_crop_rec
+CROP_REC_DTYPE = [('src_index', '<i4'), ('xstart', '<i4'), ('ystart', '<i4'), ('wb', '<i4'), ('hb', '<i4'),
+                  ('rw', '<i4'), ('rh', '<i4'), ('px', '<i4'), ('py', '<i4'), ('flags', '<i4'), ('zstart', '<f4'),
+                  ('zend', '<f4'), ('fill', '<f4'), ('hi', '<f4'), ('lo', '<f4'), ('comz', '<f4'), ('half', '<f4'),
+                  ('reserved', '<f4'), ('ifx', '<f8'), ('ify', '<f8')]
+CROP_NORMALISE, CROP_CLAMP, CROP_MIRROR = 1, 2, 4
+
 P = C.c_void_p
 _SIGS = {
     'dpp_abi_version': (C.c_int, []),
@@ -59,6 +74,8 @@ _SIGS = {
     'dpp_nchw_to_nhwc': (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int, P]),
     'dpp_nhwc_to_nchw': (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int, P]),
     'dpp_augment_fwd': (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, P]),
+    'dpp_recrop_fwd': (C.c_int, [P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P]),
+    'dpp_joint_errors': (C.c_int, [P, P, P, P, P, C.c_int, C.c_int, P]),
     'dpp_convpool_fwd': (C.c_int, [P, P, P, P, P, P] + [C.c_int] * 9 + [P]),
     'dpp_convpool_bwd': (C.c_int, [P, P, P, P, P, P, P, P] + [C.c_int] * 9 + [P]),
     'dpp_conv_pack_size': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -1,12 +1,14 @@
-"""HandDetector - the augmentation subset (reference: src/util/handdetector.py: comToBounds
-:204-226, comToTransform :228-258, moveCoM :678-710, rotateHand :712-747, scaleHand :750-780,
-recropHand :782-803).  The geometry (3x3 matrices, crop bounds, label transforms) stays on the
-host in fp64 exactly as the reference computes it; every pixel operation - the cv2.warpAffine /
-cv2.warpPerspective nearest-neighbour gathers, the z-thresholds and the CoM normalisation - runs
-in ``dpp_augment_fwd`` (csrc/augment.cu).  ``aug_record`` turns one sample's draw into the
-``dpp_aug_rec`` the kernel consumes; ``NetTrainer`` batches those records per macro batch.
+"""HandDetector - the augmentation and cascade subset (reference: src/util/handdetector.py: comToBounds
+:204-226, comToTransform :228-258, getCrop :260-296, resizeCrop :336-351, cropArea3D :382-490, track :511-533,
+refineCoM :634-676, moveCoM :678-710, rotateHand :712-747, scaleHand :750-780, recropHand :782-803).  The geometry
+(3x3 matrices, crop bounds, label transforms) stays on the host in fp64 exactly as the reference computes it; every
+pixel operation runs on the device: the cv2.warpAffine / cv2.warpPerspective nearest-neighbour gathers, the
+z-thresholds and the CoM normalisation of the augmentation in ``dpp_augment_fwd`` (csrc/augment.cu), the window /
+padding / cv2.resize-NN / paste / normalisation of the cascade's crops in ``dpp_recrop_fwd`` (csrc/recrop.cu).
+``aug_record`` turns one sample's draw into the ``dpp_aug_rec`` the augmentation kernel consumes (``NetTrainer``
+batches those per macro batch); ``dpp_b200.cascade`` builds ``dpp_crop_rec`` batches for the cascade.
 
-Hand detection (detect/track/cropArea3D/...) is out of scope (CPU, serial)."""
+Contour-based hand detection (detect / estimateHandsize / calculateCoM) is out of scope (CPU, serial)."""
 import math
 import numpy as np
 
@@ -81,11 +83,16 @@ class HandDetector(object):
             zstart = self.minDepth
             zend = self.maxDepth
         else:
-            c2 = f64(f32(com[2]))
+            if np.asarray(com).dtype == f32:     # com out of joint3DToImg: the products are float32
+                c2 = f64(f32(com[2]))
+                p0 = f64(f32(com[0]) * f32(com[2]))
+                p1 = f64(f32(com[1]) * f32(com[2]))
+            else:                                # com out of detect() / a python tuple: float64 throughout
+                c2 = f64(com[2])
+                p0 = f64(com[0]) * c2
+                p1 = f64(com[1]) * c2
             zstart = c2 - f64(size[2]) / 2.
             zend = c2 + f64(size[2]) / 2.
-            p0 = f64(f32(com[0]) * f32(com[2]))
-            p1 = f64(f32(com[1]) * f32(com[2]))
             xstart = int(np.floor((p0 / self.fx - f64(size[0]) / 2.) / c2 * self.fx + 0.5))
             xend = int(np.floor((p0 / self.fx + f64(size[0]) / 2.) / c2 * self.fx + 0.5))
             ystart = int(np.floor((p1 / self.fy - f64(size[1]) / 2.) / c2 * self.fy + 0.5))
@@ -208,3 +215,87 @@ class HandDetector(object):
         rec, _, new_cube, _, Mnew = self.aug_record(0, 'sc', np.zeros(3), 0., sc, com, cube, M, joints3D, raw=True)
         new_dpt = self._warp_raw(dpt, rec) if (int(rec['mode']) & 15) == 2 else dpt
         return new_dpt, joints3D, list(new_cube), Mnew
+
+    # -- cascade: crop around a CoM (single-frame, reference-signature methods; one launch per call) ------------
+    def getNDValue(self):
+        """handdetector.py:122-130: mode of the undefined-depth pixels of ``self.dpt``."""
+        from dpp_b200.cascade import nd_value
+        return nd_value(self.dpt)
+
+    def _frame_dev(self):
+        import torch
+        from dpp_b200.lib import DppError
+        if not torch.cuda.is_available():
+            raise DppError("HandDetector crops run in dpp_recrop_fwd; there is no CPU fallback")
+        if getattr(self, '_dpt_dev', None) is None:
+            self._dpt_dev = torch.from_numpy(np.ascontiguousarray(self.dpt, f32)[None]).cuda()
+        return self._dpt_dev
+
+    def cropArea3D(self, com=None, size=(250, 250, 250), dsize=(128, 128), docom=False):
+        """handdetector.py:382-490 for a given CoM (``docom=False``, as the realtime pipeline calls it): returns
+        (crop float32 dsize, M 3x3, com).  ``com=None`` / ``docom=True`` need calculateCoM (out of scope)."""
+        import torch
+        from dpp_b200.cascade import pose_records, run_crop_records
+        if len(size) != 3 or len(dsize) != 2:
+            raise ValueError("Size must be 3D and dsize 2D bounding box")
+        if com is None or docom is True:
+            raise NotImplementedError("CoM estimation from the depth map is outside the B200 path")
+        if self.importer is None:
+            raise ValueError("cropArea3D needs the importer's camera model")
+        coms = np.asarray(com)[None]
+        rec, M, _ = pose_records(coms, size, self.fx, self.fy, self.importer, self.dpt.shape, self.getNDValue(), dsize)
+        rec['flags'] = 0                                     # raw crop in mm: the caller normalises
+        frames = self._frame_dev()
+        out = torch.empty((1, dsize[1], dsize[0]), dtype=torch.float32, device=frames.device)
+        run_crop_records(frames, rec, out)
+        return out[0].cpu().numpy(), M[0], com
+
+    def refineCoM(self, cropped, size, com):
+        """handdetector.py:634-676: normalise the dsize crop, take its 1/2 and 1/4 centre crops, run the
+        refinement net; returns the 3D offset in mm."""
+        import torch
+        from dpp_b200.cascade import run_crop_records
+        from dpp_b200.lib import CROP_REC_DTYPE, CROP_NORMALISE, CROP_CLAMP
+        if self.refineNet.cfgParams.numInputs != 3:
+            raise NotImplementedError("Number of inputs is {}".format(self.refineNet.cfgParams.numInputs))
+        cropped = np.ascontiguousarray(cropped, f32)
+        h, w = cropped.shape
+        rec = np.zeros(1, dtype=CROP_REC_DTYPE)              # identity window over the given crop
+        rec['wb'], rec['hb'], rec['rw'], rec['rh'] = w, h, w, h
+        rec['flags'] = CROP_NORMALISE | CROP_CLAMP
+        rec['zstart'], rec['zend'] = -np.inf, np.inf
+        rec['hi'] = f32(f64(com[2]) + f64(size[2]) / 2.)
+        rec['lo'] = f32(f64(com[2]) - f64(size[2]) / 2.)
+        rec['comz'] = f32(com[2])
+        rec['half'] = f32(f64(size[2]) / 2.)
+        rec['ifx'] = rec['ify'] = 1.
+        dev = torch.from_numpy(cropped[None]).cuda()
+        x0 = torch.empty((1, h, w), dtype=torch.float32, device=dev.device)
+        x1 = torch.empty((1, h // 2, w // 2), dtype=torch.float32, device=dev.device)
+        x2 = torch.empty((1, h // 4, w // 4), dtype=torch.float32, device=dev.device)
+        run_crop_records(dev, rec, x0, x1, x2)
+        jts = self.refineNet.computeOutput([t.cpu().numpy()[:, None] for t in (x0, x1, x2)])
+        return jts[0] * f32(f64(size[2]) / 2.)
+
+    def track(self, com, size=(250, 250, 250), dsize=(128, 128), doHandSize=True):
+        """handdetector.py:511-533: refine the CoM with the refinement net.  Hand-size estimation from contours
+        (``doHandSize=True``) is CPU contour work outside the B200 path."""
+        import torch
+        from dpp_b200.cascade import refine_records, run_crop_records
+        if doHandSize is True:
+            raise NotImplementedError("hand-size estimation (cv2 contours) is outside the B200 path")
+        if self.refineNet is None or self.importer is None:
+            raise RuntimeError("Need refineNet for this")
+        rec = refine_records(np.asarray(com)[None], size, self.fx, self.fy, self.dpt.shape, dsize)
+        rec['flags'] = 0                                     # raw window stretched to dsize, in mm
+        frames = self._frame_dev()
+        rz = torch.empty((1, dsize[1], dsize[0]), dtype=torch.float32, device=frames.device)
+        run_crop_records(frames, rec, rz)
+        newCom3D = (self.refineCoM(rz[0].cpu().numpy(), size, com) + self.importer.jointImgTo3D(com)).astype(f32)
+        com = self.importer.joint3DToImg(newCom3D)
+        if np.allclose(com, 0.):
+            x0, y0, wb, hb = int(rec['xstart'][0]), int(rec['ystart'][0]), int(rec['wb'][0]), int(rec['hb'][0])
+            yy, xx = y0 + hb // 2, x0 + wb // 2
+            inside = 0 <= yy < self.dpt.shape[0] and 0 <= xx < self.dpt.shape[1]
+            com[2] = self.dpt[yy, xx] if inside else 0.
+        return com, size

@@ -101,6 +101,43 @@ typedef struct dpp_aug_rec {
 int dpp_augment_fwd(const float *crops, const dpp_aug_rec *recs, float *out, int n_out,
                     int H, int W, void *stream);
 
+/* ---- hand crop of the inference cascade -------------------------------------------------
+ * Replaces, per frame, HandDetector.getCrop (util/handdetector.py:260-296: window + zero padding +
+ * z-threshold), resizeCrop = cv2.resize INTER_NEAREST (:336-351), cropArea3D's centred paste on a
+ * getNDValue() canvas (:467-476), the normalisation of refineCoM (:640-647) or of
+ * RealtimeHandposePipeline.detect (util/realtimehandposepipeline.py:327-332), refineCoM's 1/2 and 1/4
+ * centre crops (:656-667) and estimatePose's mirroring (:346-349).  One record per output crop; the
+ * window geometry (comToBounds, :204-226) is computed on the host in fp64 as the reference does.
+ * flags: bit 0 = normalise (v == 0 -> hi; (v - comz) / half), bit 1 = also clamp to [lo, hi]
+ * (refineCoM; the pipeline's own clip() result is discarded by the reference), bit 2 = mirror x.
+ * Bit-exact against oracle/cascade.py (cv2 4.13.0 resizeNN index rule).                          */
+typedef struct dpp_crop_rec {
+    int32_t src_index;      /* frame of `frames` to read                                          */
+    int32_t xstart, ystart; /* top-left of the window in the frame (may be negative)              */
+    int32_t wb, hb;         /* window size (xend - xstart, yend - ystart)                         */
+    int32_t rw, rh;         /* cv2.resize target size                                             */
+    int32_t px, py;         /* where the resized patch is pasted in the H x W output              */
+    int32_t flags;
+    float zstart, zend;     /* f32 z-thresholds of getCrop                                        */
+    float fill;             /* canvas value outside the patch (getNDValue)                        */
+    float hi, lo;           /* f32(com_z + cube_z/2), f32(com_z - cube_z/2)                       */
+    float comz, half;       /* f32 com_z, f32(cube_z/2)                                           */
+    float reserved;
+    double ifx, ify;        /* 1. / (rw / wb), 1. / (rh / hb) in fp64 (cv2's inverse scale)       */
+} dpp_crop_rec;
+
+/* frames [n_frames, Hf, Wf] fp32 (mm); out0 [n_out, H, W]; out1 [n_out, H/2, W/2] and
+ * out2 [n_out, H/4, W/4] (centre crops of out0, may be NULL).  W % 32 == 0, H % 8 == 0.          */
+int dpp_recrop_fwd(const float *frames, const dpp_crop_rec *recs, float *out0, float *out1, float *out2,
+                   int n_out, int Hf, int Wf, int H, int W, void *stream);
+
+/* ---- pose error metrics (util/handpose_evaluation.py:92-181; trainer/poseregnettrainer.py:123-125)
+ * pred, gt [n_frames, J, 3] (mm).  err [n_frames, J] = sqrt(sum((gt - pred)^2)) per joint,
+ * frame_mean / frame_max [n_frames] = nan-mean / nan-max over the joints of a frame; any output may
+ * be NULL.  getMeanError = mean(frame_mean), getMaxError = max(frame_max).                      */
+int dpp_joint_errors(const float *pred, const float *gt, float *err, float *frame_mean, float *frame_max,
+                     int n_frames, int J, void *stream);
+
 /* ---- ConvPoolLayer (net/convpoollayer.py:251-282): conv -> maxpool -> +bias -> act ----
  * x [N,H,W,Cin] NHWC, w KC [(k*k*Cin)][Cout], y [N,Hp,Wp,Cout]; pad = k/2 ('half') or 0
  * ('valid'); pool >= 1 (floor, ignore_border).  argmax (uint8, same shape as y, may be

@@ -64,10 +64,36 @@ def scalenet_case():
     return dict(x0=x0, out_det=out.numpy())
 
 
+def cascade_case():
+    """Inference cascade (track -> cropArea3D -> normalise -> pose; oracle/cascade.py) on synthetic NYU frames with
+    cv2.resize as the executable ground truth and two tiny linear maps standing in for the nets (the nets have their
+    own vectors); odd frames are treated as right hands (mirrored)."""
+    from oracle import cascade as OC, augment as OA
+    from data import synthetic
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_oracle_cascade import _tiny_fns, FX, FY
+    n, fn_seed = 6, 77
+    fr = synthetic.generate_frames('NYU', n, seed=21, edge_fraction=0.5)
+    # the golden file stores the windows only (a 640x480 frame is 1.2 MB): keep frames small by cropping the
+    # frame to uint16-representable integer mm and letting npz compress it
+    refine_fn, pose_fn = _tiny_fns(fn_seed)
+    ocam = OA.Camera(**OA.NYU_CAM)
+    res = [OC.cascade_frame(fr['frames'][i], fr['lastcom'][i], fr['cube'], ocam, FX, FY, refine_fn, pose_fn,
+                            right_hand=bool(i % 2), use_cv2=True) for i in range(n)]
+    return dict(frames=fr['frames'], lastcom=fr['lastcom'], cube=np.array(fr['cube']), fn_seed=np.int64(fn_seed),
+                com=np.stack([r['com'] for r in res]), crop=np.stack([r['crop'] for r in res]),
+                com3D=np.stack([r['com3D'] for r in res]), M=np.stack([r['M'] for r in res]),
+                pose=np.stack([r['pose'] for r in res]))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'cascade':      # add the cascade vector without touching the others
+        np.savez_compressed(os.path.join(HERE, 'cascade_nyu.npz'), **cascade_case())
+        sys.exit(0)
     np.savez_compressed(os.path.join(HERE, 'augment_nyu.npz'), **augment_case('NYU', 'NYU_CAM', ['com', 'rot', 'none'], 8, 11))
     np.savez_compressed(os.path.join(HERE, 'augment_msra.npz'),
                         **augment_case('MSRA15', 'MSRA_CAM', ['com', 'rot', 'sc', 'none'], 8, 13))
     np.savez_compressed(os.path.join(HERE, 'resnet_b2.npz'), **resnet_case())
     np.savez_compressed(os.path.join(HERE, 'scalenet_b2.npz'), **scalenet_case())
+    np.savez_compressed(os.path.join(HERE, 'cascade_nyu.npz'), **cascade_case())
     print("golden vectors written to", HERE)
