@@ -447,7 +447,14 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true', help='skip the live kernel timing (profiler runs)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiler runs)')
-    args = ap.parse_args()
+    ap.add_argument('--workload', default='train', choices=['train', 'cascade'],
+                    help="train = BASELINE configs[1] (the headline); cascade = configs[4], tools/bench_cascade.py")
+    args, rest = ap.parse_known_args()
+    if args.workload == 'cascade':
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import bench_cascade
+        return bench_cascade.main(['--steps', str(args.steps), '--warmup', str(args.warmup)] + rest
+                                  + (['--no-cpu-baseline'] if args.no_cpu_baseline else []))
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -187,7 +187,9 @@ def run_crop_records(frames_dev, recs_np, out0, out1=None, out2=None):
             raise ValueError("output tensor has the wrong size / layout")
     if not frames_dev.is_contiguous() or frames_dev.dtype != torch.float32:
         raise ValueError("frames must be contiguous float32")
-    rec_dev = torch.from_numpy(recs_np.view(np.uint8).reshape(n, -1)).to(frames_dev.device, non_blocking=False)
+    if n == 0:
+        return out0
+    rec_dev = torch.from_numpy(recs_np.view(np.uint8).reshape(n, recs_np.dtype.itemsize)).to(frames_dev.device)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     lib.dpp_recrop_fwd(C.c_void_p(frames_dev.data_ptr()), C.c_void_p(rec_dev.data_ptr()), C.c_void_p(out0.data_ptr()),
                        C.c_void_p(out1.data_ptr()) if out1 is not None else None,
