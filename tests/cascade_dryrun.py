@@ -109,4 +109,5 @@ import test_gpu_cascade as T
 for name in ['NYU', 'ICVL', 'MSRA15']:
     T.test_recrop_kernel_bit_exact(name); print('recrop', name, 'ok')
 T.test_joint_errors_match_reference_formulas(); print('joint errors ok')
+T.test_handpose_evaluation_metrics(); print('evaluation ok')
 T.test_cascade_matches_oracle(); print('cascade ok')

@@ -162,3 +162,41 @@ def test_joint_errors_match_reference_formulas():
     gt = np.full((2, 3, 3), np.nan, f32)
     _, fmean, fmax = [t.cpu().numpy() for t in joint_errors(np.zeros((2, 3, 3), f32), gt)]
     assert np.isnan(fmean).all() and np.isnan(fmax).all()
+
+
+def test_handpose_evaluation_metrics():
+    """util/handpose_evaluation.py surface (reference src/util/handpose_evaluation.py:92-228) against the reference's
+    NumPy one-liners; float32 on the device vs float64-accumulating NumPy -> 1e-5 relative."""
+    import scipy.stats  # noqa: F401
+    from util.handpose_evaluation import HandposeEvaluation
+    rng = np.random.RandomState(11)
+    n, J = 40, 14
+    gt = (rng.randn(n, J, 3) * 40).astype(f32)
+    pr = (gt + rng.randn(n, J, 3) * 9).astype(f32)
+    gt[3, 2] = np.nan
+    gt[7] = np.nan                                          # a frame without annotation
+    ev = HandposeEvaluation(list(gt), list(pr))
+    e = np.sqrt(np.square(gt - pr).sum(axis=2))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        tol = dict(rtol=1e-5)
+        assert np.isclose(ev.getMeanError(), np.nanmean(np.nanmean(e, axis=1)), **tol)
+        assert np.isclose(ev.getStdError(), np.nanmean(np.nanstd(e, axis=1)), **tol)
+        np.testing.assert_allclose(ev.getMeanErrorOverSeq(), np.nanmean(e, axis=1), **tol)
+        assert np.isclose(ev.getMedianError(), np.nanmedian(e), **tol)
+        assert np.isclose(ev.getMaxError(), np.nanmax(e), **tol)
+        np.testing.assert_allclose(ev.getMaxErrorOverSeq(), np.nanmax(e, axis=1), **tol)
+        for j in (0, 2, 13):
+            assert np.isclose(ev.getJointMeanError(j), np.nanmean(e[:, j]), **tol)
+            assert np.isclose(ev.getJointStdError(j), np.nanstd(e[:, j]), **tol)
+            assert np.isclose(ev.getJointMaxError(j), np.nanmax(e[:, j]), **tol)
+            np.testing.assert_allclose(ev.getJointErrorOverSeq(j), e[:, j], rtol=1e-6)
+            assert np.array_equal(ev.getJointDiffOverSeq(j), (gt - pr)[:, j], equal_nan=True)
+        for dist in (10., 20., 40.):
+            assert ev.getNumFramesWithinMaxDist(dist) == (np.nanmax(e, axis=1) <= dist).sum()
+            assert ev.getNumFramesWithinMeanDist(dist) == (np.nanmean(e, axis=1) <= dist).sum()
+            assert ev.getNumFramesWithinMedianDist(dist) == (np.median(e, axis=1) <= dist).sum()
+            assert ev.getJointNumFramesWithinMaxDist(dist, 5) == (e[:, 5] <= dist).sum()
+    with pytest.raises(ValueError):
+        HandposeEvaluation(list(gt), list(pr[:-1]))
