@@ -8,9 +8,17 @@ loss, backward, ADAM.  Every function cites the reference file:line it follows.
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import it.  The product package never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
-(SURVEY.md section 4), and its own implementation (Theano 0.9 / Python 2.7) cannot be
-executed in this environment.  The pins are (a) cv2 4.13.0 as installed here for the warp
-index rules (``oracle/augment.py`` checks its NumPy index model against cv2 itself) and
-(b) the committed vectors under ``tests/golden/`` produced by ``tests/golden/make_golden.py``.
+PARITY STATUS
+* Augmentation, crop geometry, projections, cascade crops, sampleRandomPoses (oracle/augment.py, oracle/cascade.py):
+  PINNED AGAINST THE REFERENCE'S OWN CODE.  oracle/ref_harness.py executes the reference's Python sources from
+  /root/reference (py2 -> py3 pass in memory: print statements, classic integer division, xrange; nothing copied) in
+  the build container; tests/golden/make_reference_vectors.py stored its outputs in tests/golden/reference_pins.npz and
+  tests/test_reference_pins.py compares the oracle with them (and, where /root/reference exists, live on fresh
+  seeds): every index / integer result bit-exact, float results within a few float32 ulps (the fixture ran under
+  NumPy 2, the oracle restates the reference-era NumPy 1.x promotion rules).  The pixel rules of the
+  warps are additionally pinned to cv2 4.13.0 itself (tests/test_oracle_warp.py, tests/test_oracle_cascade.py).
+* Networks, cost, gradients, ADAM (oracle/nets.py): PARITY UNPINNED - those are Theano 0.9 graphs in the reference;
+  Theano cannot be installed or run here (Python 3.12, no network) and the reference ships no tests or fixtures
+  (SURVEY.md section 4).  The restatement follows the cited layer files line by line; the committed vectors
+  tests/golden/{resnet_b2,scalenet_b2}.npz pin it against drift only.
 """

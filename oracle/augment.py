@@ -1,8 +1,9 @@
 """CPU oracle: restatement of the reference's depth-crop augmentation (NumPy + cv2).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED by the reference (no
-tests/fixtures); pinned here against cv2 4.13.0 itself (``*_cv2`` variants) and the
-committed golden vectors.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PINNED against the reference's own code
+executed in the build container (oracle/ref_harness.py -> tests/golden/reference_pins.npz,
+tests/test_reference_pins.py: warp indices bit-exact, floats within a few float32 ulps), against
+cv2 4.13.0 itself (``*_cv2`` variants) and the committed golden vectors.
 
 Reference code restated (all under /root/reference/src):
   trainer/nettrainer.py:919-997      NetTrainer.augmentCrop
@@ -11,6 +12,7 @@ Reference code restated (all under /root/reference/src):
       :712-747 rotateHand, :750-780 scaleHand, :782-803 recropHand
   data/transformations.py:71-88 rotatePoint2D
   data/importers.py:80-119 (ICVL/base), :756-793 (MSRA15), :1187-1224 (NYU) projections
+  util/handdetector.py:805-909 sampleRandomPoses (rot3D=False), data/transformations.py:91-103 rotatePoints2D
 
 Dtype discipline: the reference ran on NumPy 1.x value-based casting.
 Every scalar expression below is written with the dtype NumPy 1.x would have produced:
@@ -420,3 +422,105 @@ def augment_poses(xDB, comDB, cubeDB, MDB, gt3DcropDB, idxs, draws, aug_modes, c
         else:
             ys.append(lab.reshape(-1).astype(f32))
     return np.stack(xs).astype(f32), np.stack(ys).astype(f32)
+
+
+# --------------------------------------------------------------------------------------
+# sampleRandomPoses, handdetector.py:805-909  (rot3D=False; the mains never set it,
+# main_nyu_posereg_embedding.py:87-88, and rot3D needs the absent transforms3d package)
+# --------------------------------------------------------------------------------------
+POSE_MODES = ['none', 'rot', 'sc', 'com', 'rot+com', 'com+rot', 'rot+com+sc', 'rot+sc+com', 'sc+rot+com',
+              'sc+com+rot', 'com+sc+rot', 'com+rot+sc']
+
+
+def draw_pose_params(rng, n_modes, n_base, num_poses, sigma_com=5., sigma_sc=0.02, rot_range=180.):
+    """handdetector.py:837-841: five array draws, in this order."""
+    n = int(num_poses)
+    modes = rng.randint(0, n_modes, n)
+    ridxs = rng.randint(0, n_base, n)
+    off = rng.randn(n, 3) * sigma_com
+    sc = np.fabs(rng.randn(n) * sigma_sc + 1.)
+    rot = rng.uniform(-rot_range, rot_range, size=(n, 3))
+    return modes, ridxs, off, sc, rot
+
+
+def _rotate_points_2d(cam, pts3d, center2d, angle):
+    """importer.joints3DToImg -> transformations.py:91-103 rotatePoints2D -> importer.jointsImgTo3D."""
+    joint_2D = cam.joints3DToImg(pts3d.astype(f32))
+    alpha = f64(angle) * np.pi / 180.
+    ca, sa = np.cos(alpha), np.sin(alpha)
+    data_2D = np.zeros_like(joint_2D)
+    for k in range(joint_2D.shape[0]):
+        pp = joint_2D[k].copy()
+        pp[0:2] -= center2d[0:2]                   # f32
+        pr = np.zeros_like(pp)
+        pr[0] = f64(pp[0]) * ca - f64(pp[1]) * sa  # f32 scalar * f64 scalar -> f64, store f32
+        pr[1] = f64(pp[0]) * sa + f64(pp[1]) * ca
+        pr[2] = pp[2]
+        pr[0:2] += center2d[0:2]
+        data_2D[k] = pr
+    return cam.jointsImgTo3D(data_2D)
+
+
+def sample_random_poses(cam, rng, base_poses, base_com, base_cube, num_poses, aug_modes, retall=False,
+                        sigma_com=None, sigma_sc=None, rot_range=None):
+    """handdetector.py:805-909 with rot3D=False.  base_* are float32 arrays (the mains pass float32)."""
+    sigma_com = 5. if sigma_com is None else sigma_com
+    sigma_sc = 0.02 if sigma_sc is None else sigma_sc
+    rot_range = 180. if rot_range is None else rot_range
+    assert all(m in POSE_MODES for m in aug_modes)
+    n = int(num_poses)
+    new_poses = np.zeros((n, base_poses.shape[1], base_poses.shape[2]), dtype=base_poses.dtype)
+    new_com = np.zeros((n, 3), dtype=base_poses.dtype)
+    new_cube = np.zeros((n, 3), dtype=base_poses.dtype)
+    modes, ridxs, off, sc, rot = draw_pose_params(rng, len(aug_modes), base_poses.shape[0], n, sigma_com, sigma_sc,
+                                                  rot_range)
+    if aug_modes == ['none']:
+        half = (base_cube[:, 2] / f32(2.))                         # f32 array / python float stays f32
+        if retall is True:
+            return base_poses / half[:, None, None], base_com, base_cube
+        return base_poses / half[:, None, None]
+    for i in range(n):
+        name = aug_modes[modes[i]]
+        cube = base_cube[ridxs[i]]
+        com3D = base_com[ridxs[i]]
+        pose = base_poses[ridxs[i]]
+
+        def half():                                   # new_cube[i][2]/2.: f32 scalar / python float -> f64 -> the
+            return f32(f64(new_cube[i][2]) / 2.)      # f32 array is divided by it in f32
+        if name == 'com':
+            new_com[i] = com3D.astype(f64) + off[i]
+            new_cube[i] = cube
+            new_poses[i] = (pose + com3D - new_com[i]) / half()
+        elif name == 'rot':
+            new_com[i] = com3D
+            new_cube[i] = cube
+            data3D = _rotate_points_2d(cam, pose + new_com[i], cam.joint3DToImg(com3D), rot[i, 0])
+            new_poses[i] = (data3D - new_com[i]) / half()
+        elif name == 'sc':
+            new_com[i] = com3D
+            new_cube[i] = cube * f32(sc[i])           # f32 array * f64 scalar: the scalar is cast to f32
+            new_poses[i] = pose / half()
+        elif name == 'none':
+            new_com[i] = com3D
+            new_cube[i] = cube
+            new_poses[i] = pose / half()
+        elif name in ('rot+com', 'com+rot'):
+            new_com[i] = com3D.astype(f64) + off[i]
+            new_cube[i] = cube
+            p = (pose + com3D - new_com[i])
+            data3D = _rotate_points_2d(cam, p + com3D, cam.joint3DToImg(new_com[i]), rot[i, 0])
+            new_poses[i] = (data3D - com3D) / half()
+        elif name in ('rot+com+sc', 'rot+sc+com'):
+            # the other four orderings compare the LIST aug_modes with a string in the reference (:893) and
+            # therefore fall through to NotImplementedError
+            new_com[i] = com3D.astype(f64) + off[i]
+            new_cube[i] = cube
+            p = (pose + com3D - new_com[i])
+            p = p * f32(sc[i])
+            data3D = _rotate_points_2d(cam, p + com3D, cam.joint3DToImg(new_com[i]), rot[i, 0])
+            new_poses[i] = (data3D - com3D) / half()
+        else:
+            raise NotImplementedError()
+    if retall is True:
+        return new_poses, new_com, new_cube, rot
+    return new_poses

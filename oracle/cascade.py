@@ -1,7 +1,9 @@
 """CPU oracle: restatement of the reference's inference cascade (CoM refinement -> re-crop -> pose regression).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED by the reference (no tests / fixtures);
-the nearest-neighbour resize rule is pinned against cv2 4.13.0 itself (``resize_nn_cv2`` vs ``resize_nn``,
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PINNED against the reference's own HandDetector.track /
+refineCoM / cropArea3D executed in the build container (oracle/ref_harness.py -> tests/golden/reference_pins.npz,
+tests/test_reference_pins.py: the refinement net's inputs and the pose net's crop bit-exact); the nearest-neighbour
+resize rule is also pinned against cv2 4.13.0 itself (``resize_nn_cv2`` vs ``resize_nn``,
 tests/test_oracle_cascade.py) and the whole cascade by the committed vector tests/golden/cascade_nyu.npz.
 
 Reference code restated (all under /root/reference/src):

@@ -1,0 +1,151 @@
+"""Executes the reference's OWN Python sources from /root/reference in this (Python 3.12 / NumPy 2 / cv2 4.13)
+container, to pin the oracle and to generate golden vectors.  TEST INFRASTRUCTURE ONLY; build-container only
+(/root/reference does not exist on the GPU box - nothing under tests/ -m gpu, smoke() or bench.py imports this).
+
+The reference is Python 2.7.  Nothing is copied into the repository: the sources are read where they lie, given a
+mechanical py2 -> py3 pass IN MEMORY and exec'd:
+  * ``print x`` statements -> ``print(x)`` (regex on the statement lines),
+  * every ``a / b`` is rewritten (AST) to ``_py2div(a, b)``: floor division when both operands are integers
+    (Python / NumPy ints), true division otherwise - Python 2's classic division, which is load-bearing in
+    comToTransform / cropArea3D (``hb * dsize[0] / wb``, SURVEY 8a "py2 hazards"),
+  * ``xrange`` -> ``range``; modules that are absent here and unused by the functions we call (progressbar, cPickle,
+    sharedmem, theano, matplotlib ...) are stubbed; ``numpy.float`` (removed alias of ``float``) and the array-returning
+    ``scipy.stats.mode`` of older SciPy are shimmed.
+What this cannot emulate: NumPy 1.x value-based casting.  Under NumPy 2 (NEP 50) ``float32_scalar * python_float``
+stays float32 where the reference-era NumPy promoted to float64, so on float32 CoMs the reference-as-run-here can
+differ from the reference-as-published in the last bit of a bound; tests/test_reference_pins.py therefore pins the
+oracle on float64 CoMs (both NumPy generations agree there) bit-exactly and reports the float32 cases separately."""
+import ast
+import builtins
+import os
+import re
+import sys
+import types
+
+REF_SRC = os.environ.get('DPP_REFERENCE_SRC', '/root/reference/src')
+
+
+def available():
+    return os.path.isdir(REF_SRC)
+
+
+def _py2div(a, b):
+    import numpy as np
+    ints = (int, np.integer)
+    if isinstance(a, ints) and isinstance(b, ints) and not isinstance(a, bool) and not isinstance(b, bool):
+        return a // b
+    if isinstance(a, np.ndarray) and isinstance(b, (np.ndarray,) + ints) and a.dtype.kind in 'iu' and \
+            (not isinstance(b, np.ndarray) or b.dtype.kind in 'iu'):
+        return a // b
+    return a / b
+
+
+class _Div(ast.NodeTransformer):
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Div):
+            return ast.copy_location(ast.Call(func=ast.Name(id='_py2div', ctx=ast.Load()), args=[node.left, node.right],
+                                              keywords=[]), node)
+        return node
+
+    def visit_AugAssign(self, node):
+        self.generic_visit(node)
+        return node      # ``x /= y`` on arrays is in-place true division in both Pythons for float arrays
+
+
+_PRINT = re.compile(r'^(\s*)print (?!\()(.*)$', re.M)
+
+
+def py3_source(path):
+    src = open(path).read()
+    src = _PRINT.sub(lambda m: '%sprint(%s)' % (m.group(1), m.group(2)), src)
+    src = re.sub(r'^(\s*)print$', r'\1print()', src, flags=re.M)
+    return src
+
+
+def load_module(modname, relpath, extra_globals=None):
+    """exec one reference source file as module ``modname`` (registered in sys.modules)."""
+    path = os.path.join(REF_SRC, relpath)
+    tree = ast.parse(py3_source(path), filename=path)
+    tree = ast.fix_missing_locations(_Div().visit(tree))
+    mod = types.ModuleType(modname)
+    mod.__file__ = path
+    mod.__dict__['_py2div'] = _py2div
+    mod.__dict__['xrange'] = range
+    if extra_globals:
+        mod.__dict__.update(extra_globals)
+    sys.modules[modname] = mod
+    exec(compile(tree, path, 'exec'), mod.__dict__)
+    return mod
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_loaded = {}
+
+
+def reference_modules():
+    """Returns dict(transformations, handdetector, importers, basetypes) - the reference's modules, exec'd."""
+    if _loaded:
+        return _loaded
+    if not available():
+        raise RuntimeError("reference sources not found at %s" % REF_SRC)
+    import numpy
+    if not hasattr(numpy, 'float'):
+        numpy.float = float                      # removed alias the reference uses (numpy.float == float)
+    saved = {k: sys.modules.get(k) for k in ('data', 'data.transformations', 'data.basetypes', 'data.importers', 'util',
+                                             'util.handdetector', 'progressbar', 'cPickle', 'net', 'trainer')}
+    try:
+        import pickle
+        _stub('progressbar')
+        _stub('cPickle', **pickle.__dict__)
+        pkg_d, pkg_u = types.ModuleType('data'), types.ModuleType('util')
+        pkg_d.__path__, pkg_u.__path__ = [], []
+        sys.modules['data'], sys.modules['util'] = pkg_d, pkg_u
+        _loaded['transformations'] = load_module('data.transformations', 'data/transformations.py')
+        _loaded['basetypes'] = load_module('data.basetypes', 'data/basetypes.py')
+        _loaded['handdetector'] = load_module('util.handdetector', 'util/handdetector.py')
+        _loaded['importers'] = load_module('data.importers', 'data/importers.py')
+        # scipy < 1.11 returned arrays from stats.mode (the reference indexes [0][0], handdetector.py:128-130)
+        import scipy.stats
+        _loaded['handdetector'].stats = types.SimpleNamespace(mode=lambda a: scipy.stats.mode(a, keepdims=True))
+    finally:
+        for k, v in saved.items():               # give the product's own ``data`` / ``util`` packages back
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return _loaded
+
+
+def _extract_def(src, name):
+    """Source text of ``def name(`` (first occurrence) up to the next line that is not indented deeper."""
+    lines = src.split('\n')
+    start = next(i for i, l in enumerate(lines) if re.match(r'\s*def %s\(' % re.escape(name), l))
+    indent = len(lines[start]) - len(lines[start].lstrip())
+    end = start + 1
+    while end < len(lines):
+        l = lines[end]
+        if l.strip() and (len(l) - len(l.lstrip())) <= indent:
+            break
+        end += 1
+    import textwrap
+    return textwrap.dedent('\n'.join(lines[start:end]))
+
+
+def reference_function(relpath, name, globs):
+    """Extract ONE function / method (e.g. 'augmentCrop' of NetTrainer) from a reference file whose module-level
+    imports cannot be satisfied here (theano) and which has multi-line py2 print statements elsewhere; exec it
+    stand-alone with ``globs`` as its globals."""
+    path = os.path.join(REF_SRC, relpath)
+    text = _PRINT.sub(lambda m: '%sprint(%s)' % (m.group(1), m.group(2)), _extract_def(open(path).read(), name))
+    tree = ast.fix_missing_locations(_Div().visit(ast.parse(text, filename=path)))
+    g = dict(globs)
+    g.update(_py2div=_py2div, xrange=range, __builtins__=builtins)
+    exec(compile(tree, path, 'exec'), g)
+    return g[name]

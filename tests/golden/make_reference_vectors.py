@@ -1,0 +1,147 @@
+"""Generates tests/golden/reference_pins.npz by EXECUTING THE REFERENCE'S OWN SOURCES (oracle/ref_harness.py: read from
+/root/reference, py2 -> py3 pass in memory, nothing copied) in the build container: Python 3.12, NumPy 2.3, cv2 4.13.
+Run: ``python tests/golden/make_reference_vectors.py``.  tests/test_reference_pins.py checks the oracle against it.
+
+Functions executed (reference file:line):
+  trainer/nettrainer.py:919-997        NetTrainer.augmentCrop  (with HandDetector.moveCoM / rotateHand / scaleHand /
+                                       recropHand / comToTransform / comToBounds, util/handdetector.py:204-258,678-803)
+  util/handdetector.py:511-533,634-676 track (doHandSize=False) + refineCoM with a recording stub net
+  util/handdetector.py:382-490         cropArea3D (docom=False) [+ realtimehandposepipeline.py:327-332 restated inline]
+  util/handdetector.py:805-909         sampleRandomPoses
+  data/importers.py                    NYU / ICVL / MSRA15 jointImgTo3D, joint3DToImg
+NumPy-generation caveat: see oracle/ref_harness.py - float32-scalar arithmetic is float32 under NumPy 2 where the
+reference-era NumPy 1.x used float64, so float outputs can differ from the oracle (which restates NumPy 1.x) in the
+last bits; every integer / index result is expected to agree exactly."""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, 'deep-prior-pp_b200'), os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+DATASETS = {'NYU': ('NYUImporter', 'NYU_CAM', 588., 587.), 'ICVL': ('ICVLImporter', 'ICVL_CAM', 241.42, 241.42),
+            'MSRA15': ('MSRA15Importer', 'MSRA_CAM', 241.42, 241.42)}
+AUG_MODES = ['com', 'rot', 'sc', 'none']
+POSE_MODES = ['com', 'rot', 'sc', 'none', 'rot+com', 'rot+com+sc']
+
+
+class _Cfg(object):
+    numInputs = 3
+
+
+class RecordingNet(object):
+    """stands in for the refinement net: records what refineCoM feeds it, answers with a fixed linear map"""
+    cfgParams = _Cfg()
+
+    def __init__(self, fn):
+        self.fn, self.seen = fn, None
+
+    def computeOutput(self, xs):
+        self.seen = [np.array(x, copy=True) for x in xs]
+        return self.fn(xs)
+
+
+def augment_vectors(ref, name, n, seed):
+    from oracle import ref_harness as RH, augment as OA
+    from data import synthetic
+    cls, camname, _, _ = DATASETS[name]
+    rdi = getattr(ref['importers'], cls)('/nonexistent/')
+    cam = OA.Camera(**getattr(OA, camname))
+    augmentCrop = RH.reference_function('trainer/nettrainer.py', 'augmentCrop', {'numpy': np})
+    ds = synthetic.generate(name, n, seed=seed)
+    rhd = ref['handdetector'].HandDetector(np.zeros((128, 128), np.float32) + 1., abs(rdi.fx), abs(rdi.fy), importer=rdi)
+
+    class Self(object):
+        rng = np.random.RandomState(seed + 1)
+    out = dict(x=ds['x'][:, 0], gt3Dcrop=ds['gt3Dcrop'], cube=ds['cube'], M=ds['M'], rng_seed=np.int64(seed + 1))
+    coms, res = [], []
+    for i in range(n):
+        com = cam.joint3DToImg(ds['com3D'][i])       # NumPy-1.x value (the reference under NumPy 2 is 1-2 ulp off)
+        coms.append(com)
+        res.append(augmentCrop(Self, ds['x'][i, 0].copy(), ds['gt3Dcrop'][i].copy(), com.copy(), ds['cube'][i].copy(),
+                               ds['M'][i].copy(), AUG_MODES, rhd))
+    out.update(com=np.stack(coms), out_img=np.stack([r[0] for r in res]), out_label=np.stack([r[2] for r in res]),
+               out_cube=np.stack([np.asarray(r[3], np.float64) for r in res]), out_com=np.stack([r[4] for r in res]),
+               out_M=np.stack([np.asarray(r[5], np.float64) for r in res]), out_rot=np.array([r[6] for r in res]))
+    return {'augment_%s_%s' % (name, k): v for k, v in out.items()}
+
+
+def cascade_vectors(ref, name, n, seed):
+    from data import synthetic
+    from test_oracle_cascade import _tiny_fns
+    cls, _, fx, fy = DATASETS[name]
+    rdi = getattr(ref['importers'], cls)('/nonexistent/')
+    fr = synthetic.generate_frames(name, n, seed=seed, edge_fraction=0.5)
+    cube = fr['cube']
+    lastcom = fr['lastcom'].astype(np.float32).astype(np.float64)    # float64 dtype, float32-representable values:
+    refine_fn, _ = _tiny_fns(77)                                     # both NumPy generations then agree bit for bit
+    keys = ('x0', 'x1', 'x2', 'loc', 'crop_raw', 'crop', 'M', 'com3D')
+    acc = {k: [] for k in keys}
+    for i in range(n):
+        net = RecordingNet(refine_fn)
+        hd = ref['handdetector'].HandDetector(fr['frames'][i], fx, fy, importer=rdi, refineNet=net)
+        loc, _ = hd.track(lastcom[i].copy(), cube, doHandSize=False)
+        crop, M, com = hd.cropArea3D(com=loc, size=cube, dsize=(128, 128))
+        raw = crop.copy()
+        com3D = rdi.jointImgTo3D(com)
+        sc = (cube[2] / 2.)                          # realtimehandposepipeline.py:327-332
+        crop[crop == 0] = com3D[2] + sc
+        crop.clip(com3D[2] - sc, com3D[2] + sc)
+        crop -= com3D[2]
+        crop /= sc
+        for k, v in zip(keys, (net.seen[0][0, 0], net.seen[1][0, 0], net.seen[2][0, 0], loc, raw, crop, M, com3D)):
+            acc[k].append(np.array(v, copy=True))
+    out = dict(frames=fr['frames'], lastcom=lastcom, cube=np.array(cube), fxfy=np.array([fx, fy]), fn_seed=np.int64(77))
+    out.update({k: np.stack(v) for k, v in acc.items()})
+    return {'cascade_%s_%s' % (name, k): v for k, v in out.items()}
+
+
+def pose_vectors(ref, name, n, seed):
+    from data import synthetic
+    cls = DATASETS[name][0]
+    rdi = getattr(ref['importers'], cls)('/nonexistent/')
+    ds = synthetic.generate(name, 8, seed=seed)
+    r = ref['handdetector'].HandDetector.sampleRandomPoses(rdi, np.random.RandomState(seed + 1), ds['gt3Dcrop'],
+                                                           ds['com3D'], ds['cube'], n, POSE_MODES, retall=True)
+    out = dict(base_poses=ds['gt3Dcrop'], base_com=ds['com3D'], base_cube=ds['cube'], rng_seed=np.int64(seed + 1),
+               out_poses=r[0], out_com=r[1], out_cube=r[2], out_rot=r[3])
+    return {'poses_%s_%s' % (name, k): v for k, v in out.items()}
+
+
+def geometry_vectors(ref, name, n, seed):
+    cls, _, fx, fy = DATASETS[name]
+    rdi = getattr(ref['importers'], cls)('/nonexistent/')
+    rng = np.random.RandomState(seed)
+    W, H = rdi.depth_map_size
+    coms = np.stack([rng.uniform(20, W - 20, n), rng.uniform(20, H - 20, n), rng.uniform(350, 950, n)], axis=1)
+    hd = ref['handdetector'].HandDetector(np.zeros((H, W), np.float32) + 1., fx, fy, importer=rdi)
+    cube = (250, 250, 250)
+    bounds = np.array([hd.comToBounds(c, cube) for c in coms], np.float64)
+    trans = np.stack([hd.comToTransform(c, cube, (128, 128)) for c in coms])
+    p3 = np.stack([rdi.jointImgTo3D(c) for c in coms])
+    pts = np.stack([rng.uniform(-200, 200, n), rng.uniform(-200, 200, n), rng.uniform(350, 950, n)], axis=1)
+    p2 = np.stack([rdi.joint3DToImg(p) for p in pts])
+    out = dict(coms=coms, cube=np.array(cube), bounds=bounds, transform=trans, img_to_3d=p3, pts=pts, to_img=p2)
+    return {'geometry_%s_%s' % (name, k): v for k, v in out.items()}
+
+
+def main():
+    from oracle import ref_harness as RH
+    ref = RH.reference_modules()
+    out = {}
+    for name in ('NYU', 'ICVL', 'MSRA15'):
+        out.update(augment_vectors(ref, name, 16, 300))
+        out.update(pose_vectors(ref, name, 96, 310))
+        out.update(geometry_vectors(ref, name, 64, 320))
+    for name in ('NYU', 'ICVL'):
+        out.update(cascade_vectors(ref, name, 5, 330))
+    path = os.path.join(HERE, 'reference_pins.npz')
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
+
+
+if __name__ == '__main__':
+    main()
