@@ -75,6 +75,7 @@ _SIGS = {
     'dpp_nhwc_to_nchw': (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int, P]),
     'dpp_augment_fwd': (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_int, P]),
     'dpp_recrop_fwd': (C.c_int, [P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P]),
+    'dpp_sample_poses': (C.c_int, [P] * 8 + [C.c_double] * 4 + [C.c_int, P, P, P, C.c_int, C.c_int, P]),
     'dpp_joint_errors': (C.c_int, [P, P, P, P, P, C.c_int, C.c_int, P]),
     'dpp_convpool_fwd': (C.c_int, [P, P, P, P, P, P] + [C.c_int] * 9 + [P]),
     'dpp_convpool_bwd': (C.c_int, [P, P, P, P, P, P, P, P] + [C.c_int] * 9 + [P]),

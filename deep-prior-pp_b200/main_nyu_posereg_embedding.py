@@ -44,11 +44,11 @@ if __name__ == '__main__':
     nChannels = train_data.shape[1]
 
     ####################################
-    # convert data to embedding (the reference fits on 1e6 sampled poses, handdetector.py:805-909;
-    # here: on the training labels plus the label noise the augmentation produces)
+    # convert data to embedding (main_nyu_posereg_embedding.py:85-92: PCA on 1e6 sampled poses)
     pca = PCA(n_components=30)
-    pca.fit(numpy.concatenate([train_gt3D, train_gt3D + rng.randn(*train_gt3D.shape).astype('float32') * 0.03]).reshape(
-        (-1, train_gt3D.shape[1] * 3)))
+    pca.fit(HandDetector.sampleRandomPoses(di, rng, train_gt3Dcrop, train_data_com, train_data_cube,
+                                           float(os.environ.get('DPP_POSES', '1e6')),
+                                           aug_modes).reshape((-1, train_gt3D.shape[1] * 3)))
     train_gt3D_embed = pca.transform(train_gt3D.reshape((train_gt3D.shape[0], train_gt3D.shape[1] * 3)))
     val_gt3D_embed = pca.transform(val_gt3D.reshape((val_gt3D.shape[0], val_gt3D.shape[1] * 3)))
 

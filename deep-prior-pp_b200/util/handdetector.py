@@ -299,3 +299,69 @@ class HandDetector(object):
             inside = 0 <= yy < self.dpt.shape[0] and 0 <= xx < self.dpt.shape[1]
             com[2] = self.dpt[yy, xx] if inside else 0.
         return com, size
+
+    # -- pose sampling for the PCA prior ----------------------------------------------------------------------------
+    POSE_MODE_CODES = {'none': 0, 'rot': 1, 'sc': 2, 'com': 3, 'rot+com': 4, 'com+rot': 4, 'rot+com+sc': 5,
+                       'rot+sc+com': 5}
+
+    @staticmethod
+    def sampleRandomPoses(importer, rng, base_poses, base_com, base_cube, num_poses, aug_modes, retall=False,
+                          rot3D=False, sigma_com=None, sigma_sc=None, rot_range=None):
+        """handdetector.py:805-909.  The five random arrays are drawn on the host from ``rng`` in the reference's
+        order (:837-841, so the stream stays compatible); the per-pose arithmetic runs in ``dpp_sample_poses``
+        (csrc/poses.cu).  ``rot3D=True`` needs the transforms3d package and is never used by the entry scripts."""
+        import ctypes as C
+        import torch
+        from dpp_b200.lib import lib, DppError
+        if rot3D is not False:
+            raise NotImplementedError("rot3D (transforms3d euler2mat) is not part of the B200 path")
+        sigma_com = 5. if sigma_com is None else sigma_com
+        sigma_sc = 0.02 if sigma_sc is None else sigma_sc
+        rot_range = 180. if rot_range is None else rot_range
+        all_modes = ['none', 'rot', 'sc', 'com', 'rot+com', 'com+rot', 'rot+com+sc', 'rot+sc+com', 'sc+rot+com',
+                     'sc+com+rot', 'com+sc+rot', 'com+rot+sc']
+        assert all([aug_modes[i] in all_modes for i in range(len(aug_modes))])
+        n = int(num_poses)
+        modes = rng.randint(0, len(aug_modes), n)
+        ridxs = rng.randint(0, base_poses.shape[0], n)
+        off = rng.randn(n, 3) * sigma_com
+        sc = np.fabs(rng.randn(n) * sigma_sc + 1.)
+        rot = rng.uniform(-rot_range, rot_range, size=(n, 3))
+        if not torch.cuda.is_available():
+            raise DppError("sampleRandomPoses runs in dpp_sample_poses; there is no CPU fallback")
+        only_none = (aug_modes == ['none'])
+        if only_none:                                  # :843-847: the base poses themselves, normalised
+            n = base_poses.shape[0]
+            codes, ridxs = np.zeros(n, np.int32), np.arange(n, dtype=np.int32)
+            off, sc, rot = np.zeros((n, 3)), np.ones(n), np.zeros((n, 3))
+        else:
+            # the four orderings the reference compares as list == str (:893) end in NotImplementedError there too
+            names = [aug_modes[m] for m in np.unique(modes)]
+            bad = [m for m in names if m not in HandDetector.POSE_MODE_CODES]
+            if bad:
+                raise NotImplementedError(bad[0])
+            table = np.array([HandDetector.POSE_MODE_CODES.get(m, -1) for m in aug_modes], np.int32)
+            codes = table[modes]
+        alpha = rot[:, 0] * np.pi / 180.
+        cos_sin = np.stack([np.cos(alpha), np.sin(alpha)], axis=1)
+        dev = torch.device('cuda', torch.cuda.current_device())
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        J = int(base_poses.shape[1])
+        t_in = [up(base_poses, f32), up(base_com, f32), up(base_cube, f32), up(codes, np.int32), up(ridxs, np.int32),
+                up(off, f64), up(sc, f64), up(cos_sin, f64)]
+        new_poses = torch.empty((n, J, 3), dtype=torch.float32, device=dev)
+        new_com = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        new_cube = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        lib.dpp_sample_poses(*[C.c_void_p(t.data_ptr()) for t in t_in], float(importer.fx), float(importer.fy),
+                             float(importer.ux), float(importer.uy), 1 if getattr(importer, 'flip_y', False) else 0,
+                             C.c_void_p(new_poses.data_ptr()), C.c_void_p(new_com.data_ptr()),
+                             C.c_void_p(new_cube.data_ptr()), n, J, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        poses = new_poses.cpu().numpy().astype(base_poses.dtype, copy=False)
+        if only_none:
+            return (poses, base_com, base_cube) if retall is True else poses
+        if retall is True:
+            return poses, new_com.cpu().numpy().astype(base_poses.dtype, copy=False), \
+                new_cube.cpu().numpy().astype(base_poses.dtype, copy=False), rot
+        return poses

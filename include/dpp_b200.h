@@ -131,6 +131,20 @@ typedef struct dpp_crop_rec {
 int dpp_recrop_fwd(const float *frames, const dpp_crop_rec *recs, float *out0, float *out1, float *out2,
                    int n_out, int Hf, int Wf, int H, int W, void *stream);
 
+/* ---- random pose sampling for the PCA prior --------------------------------------------
+ * HandDetector.sampleRandomPoses (util/handdetector.py:805-909, rot3D = False) for n poses: the host
+ * draws the random parameters with the reference's NumPy stream in the reference's order (:837-841)
+ * and passes them in.  mode[i]: 0 none, 1 rot, 2 sc, 3 com, 4 rot+com (= com+rot), 5 rot+com+sc
+ * (= rot+sc+com); ridx[i]: row of the base arrays; off [n,3] mm (fp64); sc [n] (fp64);
+ * cos_sin [n,2] = cos / sin of rot[i,0] * pi / 180 (fp64, computed by the host's libm so the result
+ * is bit-identical to NumPy's).  Camera = the importer's pin-hole model (data/importers.py:80-119,
+ * :756-793, :1187-1224; flip_y for NYU / MSRA15).  Outputs: new_poses [n,J,3] normalised by
+ * new_cube_z / 2, new_com [n,3], new_cube [n,3].                                                  */
+int dpp_sample_poses(const float *base_poses, const float *base_com, const float *base_cube,
+                     const int32_t *mode, const int32_t *ridx, const double *off, const double *sc,
+                     const double *cos_sin, double fx, double fy, double ux, double uy, int flip_y,
+                     float *new_poses, float *new_com, float *new_cube, int n, int J, void *stream);
+
 /* ---- pose error metrics (util/handpose_evaluation.py:92-181; trainer/poseregnettrainer.py:123-125)
  * pred, gt [n_frames, J, 3] (mm).  err [n_frames, J] = sqrt(sum((gt - pred)^2)) per joint,
  * frame_mean / frame_max [n_frames] = nan-mean / nan-max over the joints of a frame; any output may

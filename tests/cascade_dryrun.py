@@ -4,8 +4,8 @@ TEST INFRASTRUCTURE ONLY.  It checks the Python plumbing of the product path - d
 the last batch, pointer hand-off to the C ABI), util/realtimehandposepipeline.py and the single-frame HandDetector
 methods - by running tests/test_gpu_cascade.py's test bodies with
   * torch.cuda faked (tensors stay on the CPU),
-  * dpp_recrop_fwd / dpp_joint_errors emulated from the raw pointers by tests/recrop_model.py (a NumPy transcription of
-    k_recrop) and NumPy,
+  * dpp_recrop_fwd / dpp_joint_errors / dpp_sample_poses emulated from the raw pointers by tests/recrop_model.py (a NumPy transcription of
+    k_recrop), tests/poses_model.py (k_sample_poses) and NumPy,
   * the device engines replaced by the oracle nets.
 Nothing here is reachable from the product: the real entry points raise DppError without CUDA.  The kernels themselves
 are only ever validated on the GPU (pytest -m gpu)."""
@@ -35,10 +35,11 @@ def _nodev(f):
         k.pop('device', None); return f(*a, **k)
     return g
 torch.full, torch.empty = _nodev(_full), _nodev(_empty)
+_DevT0 = torch.device
 _from = torch.Tensor.to
 def _to(self, *a, **k):
     k.pop('non_blocking', None)
-    a = tuple(x for x in a if not isinstance(x, (torch.device, str)))
+    a = tuple(x for x in a if not isinstance(x, (_DevT0, str)))
     return _from(self, *a, **k) if (a or k) else self
 torch.Tensor.to = _to
 
@@ -69,7 +70,29 @@ class FakeLib:
             _arr(fm, (n,), np.float32)[...] = np.nanmean(e, axis=1)
             _arr(fx, (n,), np.float32)[...] = np.nanmax(e, axis=1)
         return 0
+    def dpp_sample_poses(self, bp, bc, bcu, mode, ridx, off, sc, cs, fx, fy, ux, uy, flip, o_p, o_c, o_cu, n, J, st):
+        import poses_model
+        md, ri = _arr(mode, (n,), np.int32), _arr(ridx, (n,), np.int32)
+        nb = int(ri.max()) + 1
+        res = poses_model.run(_arr(bp, (nb, J, 3), np.float32), _arr(bc, (nb, 3), np.float32), _arr(bcu, (nb, 3), np.float32),
+                              md, ri, _arr(off, (n, 3), np.float64), _arr(sc, (n,), np.float64),
+                              _arr(cs, (n, 2), np.float64), (fx, fy, ux, uy, flip))
+        _arr(o_p, (n, J, 3), np.float32)[...] = res[0]
+        _arr(o_c, (n, 3), np.float32)[...] = res[1]
+        _arr(o_cu, (n, 3), np.float32)[...] = res[2]
+        return 0
 PC.lib = FakeLib()
+sys.modules['dpp_b200.lib'].lib = PC.lib
+torch.cuda.current_device = lambda: 0
+_DevT = torch.device
+
+
+class _CpuDevice(object):          # torch.device('cuda', 0) -> the CPU device; isinstance checks keep working
+    def __new__(cls, *a, **k):
+        return _DevT('cpu')
+
+
+torch.device = _CpuDevice
 
 # ---- fake engines: oracle nets
 from oracle import nets as ON
@@ -111,3 +134,7 @@ for name in ['NYU', 'ICVL', 'MSRA15']:
 T.test_joint_errors_match_reference_formulas(); print('joint errors ok')
 T.test_handpose_evaluation_metrics(); print('evaluation ok')
 T.test_cascade_matches_oracle(); print('cascade ok')
+import test_gpu_poses as TP
+for name in ['NYU', 'ICVL', 'MSRA15']:
+    TP.test_sample_random_poses_matches_oracle(name); TP.test_sample_random_poses_matches_reference_fixture(name)
+print('poses ok')

@@ -2,7 +2,7 @@
 # Cascade (f1) + metrics (f4) on the B200: parity tests, config-5 bench line, launch list with DRAM bytes.
 mkdir -p gpurun_out
 export PYTHONPATH=deep-prior-pp_b200:tests:$PYTHONPATH
-timeout 200 python -m pytest tests/test_gpu_cascade.py tests/test_gpu_scalenet.py -m gpu -q -s > gpurun_out/gpu_tests19.log 2>&1
+timeout 200 python -m pytest tests/test_gpu_cascade.py tests/test_gpu_poses.py tests/test_gpu_scalenet.py -m gpu -q -s > gpurun_out/gpu_tests19.log 2>&1
 echo "pytest exit $?" >> gpurun_out/gpu_tests19.log
 tail -25 gpurun_out/gpu_tests19.log
 timeout 150 python tools/bench_cascade.py --batch 1024 --steps 10 --warmup 3 > gpurun_out/cascade_bench_b1024.json 2> gpurun_out/cascade_bench_b1024.err
