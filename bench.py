@@ -122,19 +122,21 @@ def make_workload(seed=23455):
 
 
 def records_for(ds, comp, mean, idxs, rng):
-    """host side of one batch: draws in the reference order, dpp_aug_rec records, embedded labels"""
-    hd, di = ds['hd'], ds['importer']
-    recs, ys, draws = [], [], []
-    for i in idxs:
+    """host side of one batch: draws in the reference order (nettrainer.py:954-957), dpp_aug_rec records and
+    embedded labels in one vectorised pass (HandDetector.aug_records_batch)"""
+    hd = ds['hd']
+    draws = []
+    for _ in idxs:
         mode = rng.randint(0, len(AUG_MODES)); off = rng.randn(3) * 5.; rot = rng.uniform(-180., 180.)
         sc = abs(1. + rng.randn() * 0.02)
         draws.append((mode, off, rot, sc))
-        com = di.joint3DToImg(ds['com3D'][i])
-        rec, lab, _, _, _ = hd.aug_record(i, AUG_MODES[mode], off, rot, sc, com, ds['cube'][i].copy(),
-                                          ds['M'][i].copy(), ds['gt3Dcrop'][i].copy())
-        recs.append(rec)
-        ys.append(np.dot(lab.reshape(-1).astype(np.float64) - mean, comp.T))
-    return np.array(recs), np.asarray(ys, np.float32), draws
+    idxs = np.asarray(idxs)
+    com = hd._toimg(ds['com3D'][idxs])
+    recs, labs = hd.aug_records_batch(idxs, [AUG_MODES[d[0]] for d in draws], np.array([d[1] for d in draws]),
+                                      np.array([d[2] for d in draws]), np.array([d[3] for d in draws]), com,
+                                      ds['cube'][idxs], ds['M'][idxs], ds['gt3Dcrop'][idxs])
+    ys = np.dot(labs.reshape(len(idxs), -1).astype(np.float64) - mean, comp.T)
+    return recs, np.asarray(ys, np.float32), draws
 
 
 # ---------------------------------------------------------------------------------------------

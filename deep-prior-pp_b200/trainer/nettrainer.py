@@ -48,20 +48,22 @@ class NetTrainerParams(object):
 
 
 def _records_chunk(args):
-    """worker: build augmentation records + labels for a slice of samples"""
+    """worker: build augmentation records + labels for a slice of samples (one vectorised pass,
+    ``HandDetector.aug_records_batch``: bit-identical to the per-sample ``aug_record``)"""
     trainer_state, idxs, draws = args
     hd, di, aug_modes, comDB, cubeDB, MDB, gtDB, proj = trainer_state
-    recs, labels = [], []
-    for i, (mode, off, rot, sc) in zip(idxs, draws):
-        com = di.joint3DToImg(comDB[i])
-        rec, lab, _, _, _ = hd.aug_record(i, aug_modes[mode], off, rot, sc, com, cubeDB[i].copy(), MDB[i].copy(),
-                                          gtDB[i].copy())
-        recs.append(rec)
-        if proj is not None:
-            labels.append(proj.transform(lab.reshape(1, -1))[0])
-        else:
-            labels.append(lab.reshape(-1))
-    return numpy.array(recs), numpy.asarray(labels, dtype='float32')
+    idxs = numpy.asarray(idxs, dtype=numpy.int64)
+    if len(idxs) == 0:
+        from dpp_b200.lib import AUG_REC_DTYPE
+        return numpy.zeros(0, dtype=AUG_REC_DTYPE), numpy.zeros((0, 0), dtype='float32')
+    com = hd._toimg(numpy.asarray(comDB, dtype='float32')[idxs])           # di.joint3DToImg, vectorised
+    recs, labels = hd.aug_records_batch(idxs, [aug_modes[d[0]] for d in draws], numpy.array([d[1] for d in draws]),
+                                        numpy.array([d[2] for d in draws]), numpy.array([d[3] for d in draws]), com,
+                                        numpy.asarray(cubeDB)[idxs], numpy.asarray(MDB)[idxs], numpy.asarray(gtDB)[idxs])
+    labels = labels.reshape(len(idxs), -1)
+    if proj is not None:
+        labels = proj.transform(labels)                  # poseregnettrainer.py:262, all rows at once
+    return recs, numpy.asarray(labels, dtype='float32')
 
 
 class NetTrainer(object):

@@ -365,3 +365,170 @@ class HandDetector(object):
             return poses, new_com.cpu().numpy().astype(base_poses.dtype, copy=False), \
                 new_cube.cpu().numpy().astype(base_poses.dtype, copy=False), rot
         return poses
+
+    # -- a whole batch of augmentation records at once -------------------------------------------------------------
+    def _bounds_batch(self, com, size):
+        """comToBounds for float32 CoMs (n,3) and per-sample sizes (n,3); non-degenerate depths only."""
+        com = np.asarray(com, f32)
+        c2 = com[:, 2].astype(f64)
+        p0 = (com[:, 0] * com[:, 2]).astype(f64)               # float32 products
+        p1 = (com[:, 1] * com[:, 2]).astype(f64)
+        s = np.asarray(size).astype(f64) / 2.
+        zstart, zend = c2 - s[:, 2], c2 + s[:, 2]
+        xstart = np.floor((p0 / self.fx - s[:, 0]) / c2 * self.fx + 0.5).astype(np.int64)
+        xend = np.floor((p0 / self.fx + s[:, 0]) / c2 * self.fx + 0.5).astype(np.int64)
+        ystart = np.floor((p1 / self.fy - s[:, 1]) / c2 * self.fy + 0.5).astype(np.int64)
+        yend = np.floor((p1 / self.fy + s[:, 1]) / c2 * self.fy + 0.5).astype(np.int64)
+        return xstart, xend, ystart, yend, zstart, zend
+
+    def _transform_batch(self, com, size, dsize=(128, 128)):
+        """comToTransform for n samples: (n,3,3) float64."""
+        xstart, xend, ystart, yend, _, _ = self._bounds_batch(com, size)
+        wb, hb = xend - xstart, yend - ystart
+        wide = wb > hb
+        s = np.where(wide, dsize[0] / wb.astype(f64), dsize[1] / hb.astype(f64))
+        sz0 = np.where(wide, dsize[0], wb * dsize[1] // hb)
+        sz1 = np.where(wide, hb * dsize[0] // wb, dsize[1])
+        xs = np.floor(dsize[0] / 2. - sz1 / 2.)                # the reference's sz[1] / sz[0] swap
+        ys = np.floor(dsize[1] / 2. - sz0 / 2.)
+        Mt = np.zeros((len(wb), 3, 3), f64)
+        Mt[:, 0, 0] = s
+        Mt[:, 1, 1] = s
+        Mt[:, 2, 2] = 1.
+        Mt[:, 0, 2] = s * (-xstart) + xs
+        Mt[:, 1, 2] = s * (-ystart) + ys
+        return Mt
+
+    @staticmethod
+    def _invert3x3_cv_batch(S):
+        d = S[:, 0, 0] * (S[:, 1, 1] * S[:, 2, 2] - S[:, 1, 2] * S[:, 2, 1]) \
+            - S[:, 0, 1] * (S[:, 1, 0] * S[:, 2, 2] - S[:, 1, 2] * S[:, 2, 0]) \
+            + S[:, 0, 2] * (S[:, 1, 0] * S[:, 2, 1] - S[:, 1, 1] * S[:, 2, 0])
+        d = 1. / d
+        t = np.empty((S.shape[0], 9), f64)
+        t[:, 0] = (S[:, 1, 1] * S[:, 2, 2] - S[:, 1, 2] * S[:, 2, 1]) * d
+        t[:, 1] = (S[:, 0, 2] * S[:, 2, 1] - S[:, 0, 1] * S[:, 2, 2]) * d
+        t[:, 2] = (S[:, 0, 1] * S[:, 1, 2] - S[:, 0, 2] * S[:, 1, 1]) * d
+        t[:, 3] = (S[:, 1, 2] * S[:, 2, 0] - S[:, 1, 0] * S[:, 2, 2]) * d
+        t[:, 4] = (S[:, 0, 0] * S[:, 2, 2] - S[:, 0, 2] * S[:, 2, 0]) * d
+        t[:, 5] = (S[:, 0, 2] * S[:, 1, 0] - S[:, 0, 0] * S[:, 1, 2]) * d
+        t[:, 6] = (S[:, 1, 0] * S[:, 2, 1] - S[:, 1, 1] * S[:, 2, 0]) * d
+        t[:, 7] = (S[:, 0, 1] * S[:, 2, 0] - S[:, 0, 0] * S[:, 2, 1]) * d
+        t[:, 8] = (S[:, 0, 0] * S[:, 1, 1] - S[:, 0, 1] * S[:, 1, 0]) * d
+        return t
+
+    def _to3d(self, pts):
+        """importer.jointImgTo3D on (..., 3): float64 expression, float32 store."""
+        di = self.importer
+        p = np.asarray(pts)
+        c = p.astype(f64)
+        ret = np.zeros(p.shape, f32)
+        ret[..., 0] = (c[..., 0] - di.ux) * c[..., 2] / di.fx
+        if di.flip_y:
+            ret[..., 1] = (di.uy - c[..., 1]) * c[..., 2] / di.fy
+        else:
+            ret[..., 1] = (c[..., 1] - di.uy) * c[..., 2] / di.fy
+        ret[..., 2] = p[..., 2]
+        return ret
+
+    def _toimg(self, pts):
+        """importer.joint3DToImg on (..., 3): the quotient in the sample's own dtype, then float64, float32 store."""
+        di = self.importer
+        p = np.asarray(pts)
+        nz = p[..., 2] != 0.
+        z = np.where(nz, p[..., 2], p.dtype.type(1.))
+        q0 = (p[..., 0] / z).astype(f64)
+        q1 = (p[..., 1] / z).astype(f64)
+        ret = np.zeros(p.shape, f32)
+        ret[..., 0] = np.where(nz, q0 * di.fx + di.ux, di.ux)
+        ret[..., 1] = np.where(nz, (di.uy - q1 * di.fy) if di.flip_y else (q1 * di.fy + di.uy), di.uy)
+        ret[..., 2] = np.where(nz, p[..., 2], 0.)
+        return ret
+
+    def aug_records_batch(self, src_index, mode_names, off, rot, sc, com, cube, M, gt3Dcrop):
+        """``aug_record`` for n samples at once - same results bit for bit (tests/test_host_logic.py), ~25x faster than
+        the per-sample loop, which matters because one B200 consumes > 25 000 records per second.  mode_names: n
+        strings; off (n,3), rot (n,), sc (n,) float64 draws; com (n,3) float32 image coordinates; cube (n,3) float32;
+        M (n,3,3) float32; gt3Dcrop (n,J,3) float32.  Returns (records (n,), curLabel (n,J,3) float32).
+        Everything elementwise is vectorised; the few operations whose result bits depend on the library routine
+        (3x3 ``numpy.dot`` / ``numpy.linalg.inv``, ``math.cos`` / ``numpy.cos`` on scalars) stay per-sample calls."""
+        n = len(src_index)
+        com = np.asarray(com, f32)
+        cube = np.asarray(cube, f32)
+        M = np.asarray(M, f32)
+        gt = np.asarray(gt3Dcrop, f32)
+        off = np.asarray(off, f64).reshape(n, 3)
+        rot = np.asarray(rot, f64).reshape(n)
+        sc = np.asarray(sc, f64).reshape(n)
+        names = np.asarray(mode_names)
+        for m in np.unique(names):
+            if m not in ('com', 'rot', 'sc', 'none'):
+                raise NotImplementedError()
+        if np.isclose(com[:, 2], 0.).any():                   # ill-defined CoMs take the per-sample path
+            out = [self.aug_record(src_index[i], names[i], off[i], rot[i], sc[i], com[i], cube[i], M[i], gt[i])
+                   for i in range(n)]
+            return np.array([o[0] for o in out]), np.stack([o[1] for o in out])
+        rec = np.zeros(n, dtype=AUG_REC_DTYPE)
+        rec['src_index'] = src_index
+        rec['half_old'] = (cube[:, 2].astype(f64) / 2.).astype(f32)
+        rec['comz_old'] = com[:, 2]
+        new_com = com.copy()
+        new_cube = cube.astype(f64)
+        joints = gt.copy()
+        mode = np.zeros(n, np.int32)
+
+        def homography(idx, Mnew):
+            for k, i in enumerate(idx):
+                H = np.dot(Mnew[k], np.linalg.inv(M[i]))
+                rec['m'][i] = invert3x3_cv(H)
+
+        is_com = (names == 'com') & ~np.isclose(off, 0.).all(axis=1)
+        if is_com.any():
+            idx = np.nonzero(is_com)[0]
+            c3 = self._to3d(com[idx])
+            nc = self._toimg(c3.astype(f64) + off[idx])
+            new_com[idx] = nc
+            ok = ~np.isclose(nc[:, 2], 0.)
+            if ok.any():
+                j = idx[ok]
+                homography(j, self._transform_batch(nc[ok], cube[j]))
+                _, _, _, _, zs, ze = self._bounds_batch(nc[ok], cube[j])
+                rec['zstart'][j], rec['zend'][j] = zs.astype(f32), ze.astype(f32)
+                mode[j] = 2
+            joints[idx] = ((gt[idx] + c3[:, None, :]) - self._to3d(nc)[:, None, :]).astype(f32)
+        is_rot = (names == 'rot') & ~np.isclose(rot, 0.)
+        if is_rot.any():
+            idx = np.nonzero(is_rot)[0]
+            r = np.mod(rot[idx], 360)
+            for k, i in enumerate(idx):
+                rec['m'][i] = rotation_inverse_affine((64, 64), -r[k])
+            mode[idx] = 1
+            c3 = self._to3d(com[idx])
+            j2d = self._toimg((gt[idx] + c3[:, None, :]).astype(f32))
+            alpha = r * np.pi / 180.
+            ca = np.array([np.cos(a) for a in alpha])[:, None]
+            sa = np.array([np.sin(a) for a in alpha])[:, None]
+            pp0 = j2d[..., 0] - com[idx, 0][:, None]            # float32
+            pp1 = j2d[..., 1] - com[idx, 1][:, None]
+            d2 = np.zeros_like(j2d)
+            d2[..., 0] = pp0.astype(f64) * ca - pp1.astype(f64) * sa
+            d2[..., 1] = pp0.astype(f64) * sa + pp1.astype(f64) * ca
+            d2[..., 2] = j2d[..., 2]
+            d2[..., 0] += com[idx, 0][:, None]
+            d2[..., 1] += com[idx, 1][:, None]
+            joints[idx] = (self._to3d(d2) - c3[:, None, :]).astype(f32)
+        is_sc = (names == 'sc') & ~np.isclose(sc, 1.)
+        if is_sc.any():
+            idx = np.nonzero(is_sc)[0]
+            new_cube[idx] = cube[idx].astype(f64) * sc[idx][:, None]
+            homography(idx, self._transform_batch(com[idx], new_cube[idx]))
+            _, _, _, _, zs, ze = self._bounds_batch(com[idx], cube[idx])      # z-threshold with the OLD cube
+            rec['zstart'][idx], rec['zend'][idx] = zs.astype(f32), ze.astype(f32)
+            mode[idx] = 2
+        rec['mode'] = mode
+        half_new = (new_cube[:, 2] / 2.).astype(f32)
+        rec['bg'] = (new_com[:, 2].astype(f64) + new_cube[:, 2] / 2.).astype(f32)
+        rec['lo'] = (new_com[:, 2].astype(f64) - new_cube[:, 2] / 2.).astype(f32)
+        rec['comz_new'] = new_com[:, 2]
+        rec['half_new'] = half_new
+        return rec, (joints / half_new[:, None, None]).astype(f32)

@@ -174,3 +174,59 @@ def test_host_augmentation_geometry_matches_oracle():
                                                    ds['M'][i].copy(), modes[mode], off, rot, sc, ohd)
         assert np.array_equal(lab, olab)
         assert np.allclose(cube2, ocube, rtol=0, atol=0) and np.array_equal(com2, ocom) and np.array_equal(M2, oM)
+
+
+def test_aug_records_batch_is_bit_identical_to_per_sample_records():
+    """HandDetector.aug_records_batch (the vectorised host path the trainer and bench.py use) against aug_record."""
+    from data import synthetic
+    for name in ('NYU', 'ICVL', 'MSRA15'):
+        n = 240
+        ds = synthetic.generate(name, 32, seed=5)
+        hd, di = ds['hd'], ds['importer']
+        rng = np.random.RandomState(3)
+        modes = ['com', 'rot', 'sc', 'none']
+        idxs = rng.randint(0, 32, n)
+        md = rng.randint(0, 4, n)
+        off, rot, sc = rng.randn(n, 3) * 5., rng.uniform(-180, 180, n), np.abs(1. + rng.randn(n) * 0.02)
+        off[5], rot[6], sc[7] = 0., 0., 1.               # the reference's early-outs (allclose checks)
+        md[5], md[6], md[7] = 0, 1, 2
+        com = np.stack([di.joint3DToImg(ds['com3D'][i]) for i in idxs])
+        assert np.array_equal(hd._toimg(ds['com3D'][idxs]), com)
+        assert np.array_equal(hd._to3d(com), np.stack([di.jointImgTo3D(c) for c in com]))
+        per = [hd.aug_record(i, modes[md[k]], off[k], rot[k], sc[k], com[k], ds['cube'][i].copy(), ds['M'][i].copy(),
+                             ds['gt3Dcrop'][i].copy()) for k, i in enumerate(idxs)]
+        rec, lab = hd.aug_records_batch(idxs, [modes[m] for m in md], off, rot, sc, com, ds['cube'][idxs], ds['M'][idxs],
+                                        ds['gt3Dcrop'][idxs])
+        assert rec.tobytes() == np.array([p[0] for p in per]).tobytes(), name
+        assert np.array_equal(lab, np.stack([p[1] for p in per])), name
+        assert set(rec['mode']) == {0, 1, 2}
+    with pytest.raises(NotImplementedError):
+        hd.aug_records_batch(idxs[:1], ['comb'], off[:1], rot[:1], sc[:1], com[:1], ds['cube'][idxs[:1]], ds['M'][idxs[:1]],
+                             ds['gt3Dcrop'][idxs[:1]])
+
+
+def test_trainer_record_worker_matches_per_sample_path():
+    """trainer/nettrainer.py::_records_chunk (vectorised) against the per-sample records + sklearn-style projection."""
+    from data import synthetic
+    from trainer.nettrainer import _records_chunk
+    ds = synthetic.generate('NYU', 16, seed=9)
+    hd, di = ds['hd'], ds['importer']
+    comp, mean = synthetic.random_orthonormal_pca(30, 42, seed=1)
+
+    class Proj(object):
+        def transform(self, X):
+            return np.dot(X - mean, comp.T)
+    rng = np.random.RandomState(1)
+    modes = ['com', 'rot', 'none']
+    idxs = list(range(16))
+    draws = [(rng.randint(0, 3), rng.randn(3) * 5., rng.uniform(-180, 180), abs(1. + rng.randn() * 0.02)) for _ in idxs]
+    recs, labels = _records_chunk(((hd, di, modes, ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], Proj()), idxs, draws))
+    for k, i in enumerate(idxs):
+        r, lab, _, _, _ = hd.aug_record(i, modes[draws[k][0]], draws[k][1], draws[k][2], draws[k][3],
+                                        di.joint3DToImg(ds['com3D'][i]), ds['cube'][i].copy(), ds['M'][i].copy(),
+                                        ds['gt3Dcrop'][i].copy())
+        assert recs[k].tobytes() == r.tobytes()
+        np.testing.assert_allclose(labels[k], Proj().transform(lab.reshape(1, -1))[0], rtol=1e-6, atol=1e-6)
+    assert labels.dtype == np.float32 and labels.shape == (16, 30)
+    empty = _records_chunk(((hd, di, modes, ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], None), [], []))
+    assert len(empty[0]) == 0
