@@ -17,7 +17,13 @@ PARITY STATUS
   seeds): every index / integer result bit-exact, float results within a few float32 ulps (the fixture ran under
   NumPy 2, the oracle restates the reference-era NumPy 1.x promotion rules).  The pixel rules of the
   warps are additionally pinned to cv2 4.13.0 itself (tests/test_oracle_warp.py, tests/test_oracle_cascade.py).
-* Networks, cost, gradients, ADAM (oracle/nets.py): PARITY UNPINNED - those are Theano 0.9 graphs in the reference;
+* Network STRUCTURE and INITIALISATION (oracle/nets.py builders and the product's net classes): PINNED against the
+  reference's own constructors - oracle/ref_harness.py::describe_reference_net runs net/resnet.py, net/poseregnet.py,
+  net/scalenet.py and every layer class with an inert stand-in for theano (the numeric work - wiring, layer numbers,
+  dimension arithmetic, weight initialisation, order of random draws, parameter order - runs for real);
+  tests/golden/reference_nets.json holds the result, tests/test_reference_pins.py checks layer lists, dimensions,
+  parameter names / order and the sha1 of every initial weight tensor: bit-identical.
+* Network ARITHMETIC - forward ops, cost, gradients, ADAM (oracle/nets.py): PARITY UNPINNED - those are Theano 0.9 graphs in the reference;
   Theano cannot be installed or run here (Python 3.12, no network) and the reference ships no tests or fixtures
   (SURVEY.md section 4).  The restatement follows the cited layer files line by line; the committed vectors
   tests/golden/{resnet_b2,scalenet_b2}.npz pin it against drift only.

@@ -1,9 +1,12 @@
 """CPU oracle: torch-CPU restatement of the reference networks, cost, gradients and ADAM
 (reference semantics are float32; working precision float64 by default, see DTYPE below).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED: Theano cannot run
-here; the semantics below follow the reference sources line by line plus SURVEY.md
-Appendix A for the Theano op semantics.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Structure and initial weights are PINNED
+against the reference's own constructors (oracle/ref_harness.py::describe_reference_net ->
+tests/golden/reference_nets.json, tests/test_reference_pins.py: layer lists, dimensions,
+parameter order, bit-identical initial weights).  The ARITHMETIC (forward ops, cost,
+gradients, ADAM) is PARITY UNPINNED: Theano cannot run here; the semantics below follow the
+reference sources line by line plus SURVEY.md Appendix A for the Theano op semantics.
 
 Reference files restated (all under /root/reference/src):
   net/resnet.py:45-346 (ResNetParams/ResNet types 0-4), :349-414 (res_block)

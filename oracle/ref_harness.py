@@ -149,3 +149,109 @@ def reference_function(relpath, name, globs):
     g.update(_py2div=_py2div, xrange=range, __builtins__=builtins)
     exec(compile(tree, path, 'exec'), g)
     return g[name]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference's network classes under a stand-in ``theano``
+# ------------------------------------------------------------------------------------------------------------
+class _Shared(object):
+    """theano.shared stand-in: keeps the value; every symbolic use yields an inert placeholder."""
+    _count = 0
+
+    def __init__(self, value=None, name=None, borrow=False, **kw):
+        import numpy as np
+        self.value = np.asarray(value)
+        self.name = name
+        self.auto_name = 'auto_%d' % _Shared._count
+        _Shared._count += 1
+        self.broadcastable = (False,) * self.value.ndim
+
+    def get_value(self, borrow=False):
+        return self.value
+
+    def set_value(self, v, borrow=False):
+        import numpy as np
+        self.value = np.asarray(v)
+
+    def __getattr__(self, k):
+        if k.startswith('__'):
+            raise AttributeError(k)
+        from unittest import mock
+        return mock.MagicMock()
+
+    def _sym(self, *a, **k):
+        from unittest import mock
+        return mock.MagicMock()
+    __add__ = __radd__ = __mul__ = __rmul__ = __sub__ = __rsub__ = __truediv__ = __rtruediv__ = __pow__ = __neg__ = _sym
+
+
+def describe_reference_net(kind, **cfg):
+    """Builds one of the reference's networks (``kind`` in 'ResNet', 'PoseRegNet', 'ScaleNet') by running the
+    reference's own constructors (net/*.py) with rng = RandomState(23455).  Theano is replaced by an inert stand-in:
+    the constructors' NUMERIC work - layer wiring and numbering, dimension arithmetic, weight initialisation and the
+    order of the random draws (net/layer.py:60-118) - runs for real, the symbolic graph calls return placeholders.
+    Returns a JSON-able description: per layer class, layerNum, inputDim, outputDim and per parameter name, shape,
+    sha1 of the float32 bytes, sum and first values; plus the order of ``net.params``."""
+    import hashlib
+    import inspect
+    import pickle
+    from unittest import mock
+    import numpy as np
+    if not available():
+        raise RuntimeError("reference sources not found at %s" % REF_SRC)
+    theano = mock.MagicMock()
+    theano.shared = lambda value=None, name=None, borrow=False, **kw: _Shared(value, name, borrow)
+    theano.config.floatX = 'float32'
+    fake = {'theano': theano, 'theano.tensor': theano.tensor, 'theano.tensor.nnet': theano.tensor.nnet,
+            'theano.tensor.signal': theano.tensor.signal, 'theano.tensor.signal.pool': theano.tensor.signal.pool,
+            'theano.ifelse': theano.ifelse, 'theano.sandbox': theano.sandbox,
+            'theano.sandbox.rng_mrg': theano.sandbox.rng_mrg, 'theano.sandbox.neighbours': theano.sandbox.neighbours,
+            'cPickle': pickle}
+    order = ['util/theano_helpers.py', 'net/layerparams.py', 'net/layer.py', 'net/convlayer.py', 'net/convpoollayer.py',
+             'net/hiddenlayer.py', 'net/poollayer.py', 'net/dropoutlayer.py', 'net/batchnormlayer.py',
+             'net/nonlinearitylayer.py', 'net/netbase.py', 'net/resnet.py', 'net/poseregnet.py', 'net/scalenet.py']
+    names = [r[:-3].replace('/', '.') for r in order]
+    saved = {k: sys.modules.get(k) for k in list(fake) + names + ['net', 'util']}
+
+    class _Cast(dict):                            # numpy.cast[dtype](value), removed in NumPy 2
+        def __missing__(self, k):
+            return lambda v: np.asarray(v, dtype=k)[()]
+    had_cast = 'cast' in np.__dict__
+    old_getargspec = getattr(inspect, 'getargspec', None)
+    try:
+        sys.modules.update(fake)
+        np.cast = _Cast()
+        inspect.getargspec = inspect.getfullargspec            # removed in Python 3.11
+        for pkg in ('net', 'util'):
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+        mods = {n: load_module(n, r) for n, r in zip(names, order)}
+        mod = mods['net.' + kind.lower()]
+        params = getattr(mod, kind + 'Params')(**cfg)
+        net = getattr(mod, kind)(np.random.RandomState(23455), cfgParams=params)
+
+        def pdesc(p):
+            v = np.ascontiguousarray(p.get_value(), dtype=np.float32)
+            return dict(name=p.name, shape=list(v.shape), sha1=hashlib.sha1(v.tobytes()).hexdigest(),
+                        sum=float(v.astype(np.float64).sum()), head=[float(x) for x in v.ravel()[:4]])
+        layers = []
+        for l in net.layers:
+            layers.append(dict(cls=type(l).__name__, layerNum=int(l.layerNum),
+                               inputDim=[int(x) for x in l.cfgParams.inputDim],
+                               outputDim=[int(x) for x in l.cfgParams.outputDim],
+                               params=[pdesc(p) for p in l.params],
+                               params_nontrained=[pdesc(p) for p in getattr(l, 'params_nontrained', [])],
+                               weights=[p.name for p in l.weights]))
+        return dict(kind=kind, cfg=cfg, layers=layers, net_params=[p.name for p in net.params],
+                    outputDim=[int(x) for x in params.outputDim])
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        if not had_cast:
+            del np.cast
+        if old_getargspec is None:
+            del inspect.getargspec

@@ -9,6 +9,7 @@ Functions executed (reference file:line):
   util/handdetector.py:382-490         cropArea3D (docom=False) [+ realtimehandposepipeline.py:327-332 restated inline]
   util/handdetector.py:805-909         sampleRandomPoses
   data/importers.py                    NYU / ICVL / MSRA15 jointImgTo3D, joint3DToImg
+  net/*.py                             ResNet / PoseRegNet / ScaleNet constructors -> tests/golden/reference_nets.json
 NumPy-generation caveat: see oracle/ref_harness.py - float32-scalar arithmetic is float32 under NumPy 2 where the
 reference-era NumPy 1.x used float64, so float outputs can differ from the oracle (which restates NumPy 1.x) in the
 last bits; every integer / index result is expected to agree exactly."""
@@ -128,8 +129,30 @@ def geometry_vectors(ref, name, n, seed):
     return {'geometry_%s_%s' % (name, k): v for k, v in out.items()}
 
 
+NET_CASES = [
+    ('ResNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30)),
+    ('ResNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=14, nDims=3)),
+    ('ResNet', dict(type=4, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=14, nDims=3)),
+    ('PoseRegNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30)),
+    ('ScaleNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, resizeFactor=2, numJoints=1, nDims=3)),
+]
+
+
+def net_descriptions():
+    """net/resnet.py, net/poseregnet.py, net/scalenet.py constructors (and every layer class under net/) executed with
+    an inert theano stand-in: layer lists, dimensions, parameter names / order and the initial weights' sha1."""
+    import json
+    from oracle import ref_harness as RH
+    out = [RH.describe_reference_net(kind, **cfg) for kind, cfg in NET_CASES]
+    path = os.path.join(HERE, 'reference_nets.json')
+    with open(path, 'w') as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     from oracle import ref_harness as RH
+    net_descriptions()
     ref = RH.reference_modules()
     out = {}
     for name in ('NYU', 'ICVL', 'MSRA15'):

@@ -158,3 +158,77 @@ def test_live_reference_cascade():
     out = MK.cascade_vectors(RH.reference_modules(), 'NYU', 12, 977)
     ref = {k: out['cascade_NYU_' + k] for k in ('x0', 'x1', 'x2', 'loc', 'crop_raw', 'crop', 'M', 'com3D')}
     _check_cascade('NYU', out['cascade_NYU_frames'], out['cascade_NYU_lastcom'], tuple(out['cascade_NYU_cube']), 588., 587., ref)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# network classes: layer lists, dimensions, parameter order and INITIAL WEIGHTS against the reference's constructors
+# ------------------------------------------------------------------------------------------------------------
+import hashlib   # noqa: E402
+import json      # noqa: E402
+
+NETS = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_nets.json')))
+
+
+def _product_net(kind, cfg):
+    if kind == 'ResNet':
+        from net.resnet import ResNet as N, ResNetParams as P
+    elif kind == 'PoseRegNet':
+        from net.poseregnet import PoseRegNet as N, PoseRegNetParams as P
+    else:
+        from net.scalenet import ScaleNet as N, ScaleNetParams as P
+    return N(np.random.RandomState(23455), cfgParams=P(**cfg))
+
+
+def _oracle_net(kind, cfg):
+    from oracle import nets as ON
+    cfg = dict(cfg)
+    build = {'ResNet': ON.build_resnet, 'PoseRegNet': ON.build_poseregnet, 'ScaleNet': ON.build_scalenet}[kind]
+    return build(np.random.RandomState(23455), **cfg)
+
+
+def _sha(v):
+    return hashlib.sha1(np.ascontiguousarray(v, dtype=f32).tobytes()).hexdigest()
+
+
+def _check_net_against(desc):
+    kind, cfg = desc['kind'], desc['cfg']
+    net = _product_net(kind, cfg)
+    assert len(net.layers) == len(desc['layers'])
+    for l, rl in zip(net.layers, desc['layers']):
+        where = (kind, cfg['type'], rl['layerNum'], rl['cls'])
+        assert type(l).__name__ == rl['cls'] and l.layerNum == rl['layerNum'], where
+        assert list(l.cfgParams.inputDim) == rl['inputDim'] and list(l.cfgParams.outputDim) == rl['outputDim'], where
+        mine = list(l.params) + list(l.params_nontrained)
+        ref = rl['params'] + rl['params_nontrained']
+        assert [p.name for p in mine] == [p['name'] for p in ref], where
+        for p, rp in zip(mine, ref):
+            v = p.get_value()
+            assert list(v.shape) == rp['shape'] and _sha(v) == rp['sha1'], where + (p.name,)
+        assert [p.name for p in l.weights] == rl['weights'], where
+    assert [p.name for p in net.params] == desc['net_params']
+    assert list(net.cfgParams.outputDim) == desc['outputDim']
+    # the oracle the GPU parity tests compare against starts from the same weights (same draws, same order):
+    # its trainable parameters, in order, are the reference's net.params values
+    onet = _oracle_net(kind, cfg)
+    ref_by_name = {p['name']: p for rl in desc['layers'] for p in rl['params']}
+    ovals = [p.detach().numpy() for p in onet.params]
+    assert len(ovals) == len(desc['net_params'])
+    for name, ov in zip(desc['net_params'], ovals):
+        rp = ref_by_name[name]
+        if name.startswith('conv') and name[4] == 'W':
+            assert list(ov.shape) == rp['shape']
+        assert ov.size == int(np.prod(rp['shape'])) and np.isclose(float(ov.astype(f64).sum()), rp['sum'], rtol=1e-6, atol=1e-5), name
+        assert _sha(ov.reshape(rp['shape'])) == rp['sha1'], (kind, cfg['type'], name)
+
+
+@pytest.mark.parametrize('idx', range(len(NETS)))
+def test_network_classes_against_reference_fixture(idx):
+    _check_net_against(NETS[idx])
+
+
+@live
+def test_live_reference_network_constructor():
+    desc = RH.describe_reference_net('ResNet', type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30)
+    _check_net_against(desc)
+    desc = RH.describe_reference_net('PoseRegNet', type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30)
+    _check_net_against(desc)
