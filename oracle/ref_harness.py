@@ -185,6 +185,57 @@ class _Shared(object):
     __add__ = __radd__ = __mul__ = __rmul__ = __sub__ = __rsub__ = __truediv__ = __rtruediv__ = __pow__ = __neg__ = _sym
 
 
+_NET_FILES = ['util/theano_helpers.py', 'net/layerparams.py', 'net/layer.py', 'net/convlayer.py', 'net/convpoollayer.py',
+              'net/hiddenlayer.py', 'net/poollayer.py', 'net/dropoutlayer.py', 'net/batchnormlayer.py',
+              'net/nonlinearitylayer.py', 'net/netbase.py', 'net/resnet.py', 'net/poseregnet.py', 'net/scalenet.py']
+
+
+class _reference_net_modules(object):
+    """Context manager: the reference's net/*.py exec'd with ``theano_modules`` (name -> module) standing in for
+    Theano; restores sys.modules (the product's own ``net`` / ``util`` packages) and the NumPy / inspect shims."""
+
+    def __init__(self, theano_modules):
+        self.fake = dict(theano_modules)
+
+    def __enter__(self):
+        import inspect
+        import pickle
+        import numpy as np
+        if not available():
+            raise RuntimeError("reference sources not found at %s" % REF_SRC)
+        self.fake['cPickle'] = pickle
+        names = [r[:-3].replace('/', '.') for r in _NET_FILES]
+        self.saved = {k: sys.modules.get(k) for k in list(self.fake) + names + ['net', 'util']}
+
+        class _Cast(dict):                            # numpy.cast[dtype](value), removed in NumPy 2
+            def __missing__(self, k):
+                return lambda v: np.asarray(v, dtype=k)[()]
+        self.had_cast = 'cast' in np.__dict__
+        self.old_getargspec = getattr(inspect, 'getargspec', None)
+        sys.modules.update(self.fake)
+        np.cast = _Cast()
+        inspect.getargspec = inspect.getfullargspec            # removed in Python 3.11
+        for pkg in ('net', 'util'):
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+        return {n: load_module(n, r) for n, r in zip(names, _NET_FILES)}
+
+    def __exit__(self, *exc):
+        import inspect
+        import numpy as np
+        for k, v in self.saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        if not self.had_cast:
+            del np.cast
+        if self.old_getargspec is None:
+            del inspect.getargspec
+        return False
+
+
 def describe_reference_net(kind, **cfg):
     """Builds one of the reference's networks (``kind`` in 'ResNet', 'PoseRegNet', 'ScaleNet') by running the
     reference's own constructors (net/*.py) with rng = RandomState(23455).  Theano is replaced by an inert stand-in:
@@ -193,40 +244,16 @@ def describe_reference_net(kind, **cfg):
     Returns a JSON-able description: per layer class, layerNum, inputDim, outputDim and per parameter name, shape,
     sha1 of the float32 bytes, sum and first values; plus the order of ``net.params``."""
     import hashlib
-    import inspect
-    import pickle
     from unittest import mock
     import numpy as np
-    if not available():
-        raise RuntimeError("reference sources not found at %s" % REF_SRC)
     theano = mock.MagicMock()
     theano.shared = lambda value=None, name=None, borrow=False, **kw: _Shared(value, name, borrow)
     theano.config.floatX = 'float32'
     fake = {'theano': theano, 'theano.tensor': theano.tensor, 'theano.tensor.nnet': theano.tensor.nnet,
             'theano.tensor.signal': theano.tensor.signal, 'theano.tensor.signal.pool': theano.tensor.signal.pool,
             'theano.ifelse': theano.ifelse, 'theano.sandbox': theano.sandbox,
-            'theano.sandbox.rng_mrg': theano.sandbox.rng_mrg, 'theano.sandbox.neighbours': theano.sandbox.neighbours,
-            'cPickle': pickle}
-    order = ['util/theano_helpers.py', 'net/layerparams.py', 'net/layer.py', 'net/convlayer.py', 'net/convpoollayer.py',
-             'net/hiddenlayer.py', 'net/poollayer.py', 'net/dropoutlayer.py', 'net/batchnormlayer.py',
-             'net/nonlinearitylayer.py', 'net/netbase.py', 'net/resnet.py', 'net/poseregnet.py', 'net/scalenet.py']
-    names = [r[:-3].replace('/', '.') for r in order]
-    saved = {k: sys.modules.get(k) for k in list(fake) + names + ['net', 'util']}
-
-    class _Cast(dict):                            # numpy.cast[dtype](value), removed in NumPy 2
-        def __missing__(self, k):
-            return lambda v: np.asarray(v, dtype=k)[()]
-    had_cast = 'cast' in np.__dict__
-    old_getargspec = getattr(inspect, 'getargspec', None)
-    try:
-        sys.modules.update(fake)
-        np.cast = _Cast()
-        inspect.getargspec = inspect.getfullargspec            # removed in Python 3.11
-        for pkg in ('net', 'util'):
-            m = types.ModuleType(pkg)
-            m.__path__ = []
-            sys.modules[pkg] = m
-        mods = {n: load_module(n, r) for n, r in zip(names, order)}
+            'theano.sandbox.rng_mrg': theano.sandbox.rng_mrg, 'theano.sandbox.neighbours': theano.sandbox.neighbours}
+    with _reference_net_modules(fake) as mods:
         mod = mods['net.' + kind.lower()]
         params = getattr(mod, kind + 'Params')(**cfg)
         net = getattr(mod, kind)(np.random.RandomState(23455), cfgParams=params)
@@ -245,13 +272,78 @@ def describe_reference_net(kind, **cfg):
                                weights=[p.name for p in l.weights]))
         return dict(kind=kind, cfg=cfg, layers=layers, net_params=[p.name for p in net.params],
                     outputDim=[int(x) for x in params.outputDim])
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
-        if not had_cast:
-            del np.cast
-        if old_getargspec is None:
-            del inspect.getargspec
+
+
+def run_reference_net(kind, cfg, inputs, deterministic=True, y=None, learning_rate=None, weightreg_factor=0.0,
+                      bn_state=None):
+    """EVALUATES the reference's own network code on concrete inputs with oracle/eager_theano.py standing in for
+    Theano (read that module's header for what this does and does not prove).
+
+    inputs: list of float arrays (one per network input, NCHW); deterministic: the value every ``flag_on`` switch
+    (BatchNormLayer, DropoutLayer) is created with - False = training graph (batch statistics, dropout masks).
+    bn_state: optional {param name: array} written into the shared variables before the forward pass is built is not
+    possible in an eager run, so non-default running statistics are given here and installed at construction.
+    With ``y`` (targets) the reference's cost and gradients are evaluated too (trainer/poseregnettrainer.py:70-111,
+    ``setupFunctions``), and with ``learning_rate`` one ADAM step (trainer/optimizer.py:58-90).
+    Returns dict(out, layer_out {layerNum: array}, masks [dropout masks], bn_updates [(name, new value)],
+    cost, grads {param name: array}, new_params {param name: array})."""
+    import numpy as np
+    from oracle import eager_theano as E
+    fake = E.build_modules()
+    theano, T = fake['theano'], fake['theano.tensor']
+    clones = []
+    flag = 0.0 if deterministic else 1.0
+    state = dict(bn_state or {})
+
+    def shared(value=None, name=None, borrow=False, **kw):
+        if name == 'flag_on':
+            value = np.float32(flag)
+        if name in state:
+            value = np.asarray(state[name], dtype=np.asarray(value).dtype)
+        return E.Shared(value, name, borrow)
+
+    def clone(x, share_inputs=True, **kw):
+        c = E.ET(x.t, getattr(x, 'name', None))
+        clones.append(c)
+        return c
+    theano.shared, theano.clone = shared, clone
+    E.FEED.clear()
+    names = ['x'] if len(inputs) == 1 else ['x%d' % i for i in range(len(inputs))]
+    for n, a in zip(names, inputs):
+        E.FEED[n] = np.asarray(a, np.float64)
+    res = {}
+    with _reference_net_modules(fake) as mods:
+        mod = mods['net.' + kind.lower()]
+        params = getattr(mod, kind + 'Params')(**cfg)
+        net = getattr(mod, kind)(np.random.RandomState(23455), cfgParams=params)
+        res['out'] = net.output.eval().copy()
+        res['layer_out'] = {int(l.layerNum): l.output.eval().copy() for l in net.layers}
+        res['masks'] = [l.mask.eval().copy() for l in net.layers if type(l).__name__ == 'DropoutLayer']
+        res['bn_updates'] = [(c.name, c.default_update.eval().copy()) for c in clones if c.default_update is not None]
+        if y is not None:
+            nj = 14                                   # the evaluation-only expressions (:113-125) need some values
+            E.FEED['y'] = [np.asarray(y, np.float64), np.zeros((params.batch_size, nj, 3))]
+            E.FEED['pca'] = np.zeros((int(np.prod(np.shape(y)[1:])), nj * 3))
+            E.FEED['mean'] = np.zeros(nj * 3)
+            E.FEED['learning_rate'] = np.float64(learning_rate if learning_rate is not None else 0.0)
+            E.FEED['momentum'] = np.float64(0.0)
+            E.FEED[None] = np.float64(0.0)
+            setup = reference_function('trainer/poseregnettrainer.py', 'setupFunctions', {'theano': theano, 'T': T})
+
+            class _Cfg(object):
+                pass
+            tr = types.SimpleNamespace(poseNet=net, cfgParams=_Cfg())
+            tr.cfgParams.batch_size = params.batch_size
+            tr.cfgParams.weightreg_factor = weightreg_factor
+            setup(tr)
+            res['cost'] = float(tr.cost.eval())
+            res['param_order'] = [p.name for p in tr.params]
+            res['grads'] = {p.name: g.eval().copy() for p, g in zip(tr.params, tr.grads)}
+            if learning_rate is not None:
+                adam = reference_function('trainer/optimizer.py', 'ADAM', {'theano': theano, 'T': T, 'numpy': np})
+                opt = types.SimpleNamespace(params=tr.params, grads=tr.grads, updates=[], shared=[])
+                updates = adam(opt, tr.learning_rate)
+                by_id = {id(p): p.name for p in tr.params}
+                res['new_params'] = {by_id[id(s)]: v.eval().copy() for s, v in updates if id(s) in by_id}
+                res['adam_t_next'] = float(updates[-1][1].eval())
+    return res

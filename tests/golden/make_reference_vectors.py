@@ -10,6 +10,8 @@ Functions executed (reference file:line):
   util/handdetector.py:805-909         sampleRandomPoses
   data/importers.py                    NYU / ICVL / MSRA15 jointImgTo3D, joint3DToImg
   net/*.py                             ResNet / PoseRegNet / ScaleNet constructors -> tests/golden/reference_nets.json
+  net/*.py, trainer/poseregnettrainer.py:70-111 (cost, T.grad), trainer/optimizer.py:58-90 (ADAM) EVALUATED with
+                                       oracle/eager_theano.py in place of Theano -> tests/golden/reference_net_eval.npz
 NumPy-generation caveat: see oracle/ref_harness.py - float32-scalar arithmetic is float32 under NumPy 2 where the
 reference-era NumPy 1.x used float64, so float outputs can differ from the oracle (which restates NumPy 1.x) in the
 last bits; every integer / index result is expected to agree exactly."""
@@ -150,9 +152,72 @@ def net_descriptions():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def _stats(a):
+    a = np.asarray(a, np.float64)
+    return np.array([a.sum(), np.abs(a).sum(), np.abs(a).max(), float(a.ravel()[0]), float(a.ravel()[-1])])
+
+
+def net_eval_inputs(kind, cfg, seed, train):
+    """the inputs of one case, regenerated from the seed by the tests (not stored)"""
+    B = cfg['batchSize']
+    rng = np.random.RandomState(seed)
+    x0 = rng.uniform(-1, 1, (B, 1, 128, 128)).astype(np.float32)
+    xs = [x0] if kind != 'ScaleNet' else [x0, np.ascontiguousarray(x0[:, :, 32:96, 32:96]),
+                                           np.ascontiguousarray(x0[:, :, 48:80, 48:80])]
+    y = rng.randn(B, cfg['numJoints'] * cfg['nDims']).astype(np.float32) if train else None
+    return xs, y
+
+
+def net_eval_case(kind, cfg, seed, train):
+    """One evaluation of the reference's own network / trainer code (oracle/eager_theano.py stands in for Theano):
+    inputs, output, per-layer output statistics and - for ``train`` - cost, gradient statistics (full tensors for
+    everything up to 1024 elements), parameters after one ADAM step, BatchNorm running-stat updates, dropout masks."""
+    from oracle import ref_harness as RH
+    xs, y = net_eval_inputs(kind, cfg, seed, train)
+    r = RH.run_reference_net(kind, cfg, xs, deterministic=not train, y=y, learning_rate=1e-3 if train else None)
+    out = dict(out=r['out'], layer_nums=np.array(sorted(r['layer_out'])),
+               layer_stats=np.stack([_stats(r['layer_out'][k]) for k in sorted(r['layer_out'])]))
+    if train:
+        names = r['param_order']
+        out.update(cost=np.float64(r['cost']), param_order=np.array(names),
+                   grad_stats=np.stack([_stats(r['grads'][n]) for n in names]),
+                   newp_stats=np.stack([_stats(r['new_params'][n]) for n in names]),
+                   adam_t_next=np.float64(r['adam_t_next']))
+        for n in names:
+            if r['grads'][n].size <= 1024:
+                out['grad__' + n] = r['grads'][n]
+                out['newp__' + n] = r['new_params'][n]
+        for i, m in enumerate(r['masks']):
+            out['mask%d' % i] = m.astype(np.float32)
+        out['bn_names'] = np.array([n for n, _ in r['bn_updates']])
+        for i, (n, v) in enumerate(r['bn_updates']):
+            out['bn%d' % i] = v
+    return out
+
+
+NET_EVAL_CASES = [
+    ('resnet0_train', 'ResNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30), 11, True),
+    ('resnet1_det', 'ResNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=14, nDims=3), 12, False),
+    ('poseregnet0_train', 'PoseRegNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30), 13, True),
+    ('poseregnet0_det', 'PoseRegNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30), 14, False),
+    ('scalenet1_det', 'ScaleNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, resizeFactor=2, numJoints=1, nDims=3), 15, False),
+]
+
+
+def net_evaluations():
+    out = {}
+    for tag, kind, cfg, seed, train in NET_EVAL_CASES:
+        for k, v in net_eval_case(kind, cfg, seed, train).items():
+            out['%s__%s' % (tag, k)] = v
+    path = os.path.join(HERE, 'reference_net_eval.npz')
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
+
+
 def main():
     from oracle import ref_harness as RH
     net_descriptions()
+    net_evaluations()
     ref = RH.reference_modules()
     out = {}
     for name in ('NYU', 'ICVL', 'MSRA15'):

@@ -232,3 +232,99 @@ def test_live_reference_network_constructor():
     _check_net_against(desc)
     desc = RH.describe_reference_net('PoseRegNet', type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30)
     _check_net_against(desc)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# network ARITHMETIC: the reference's own layer / cost / T.grad / ADAM code, evaluated with oracle/eager_theano.py in
+# place of Theano (tests/golden/reference_net_eval.npz), against the oracle.  Covers everything the reference
+# writes in Python around Theano's primitives; the primitives themselves follow their documented semantics.
+# ------------------------------------------------------------------------------------------------------------
+import sys as _sys   # noqa: E402
+_sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+import make_reference_vectors as MK   # noqa: E402
+
+NE = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_net_eval.npz'))
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, f64), np.asarray(b, f64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+def _stats(a):
+    return MK._stats(a)
+
+
+def _check_net_eval(kind, cfg, seed, train, ref):
+    """ref: dict with the keys of make_reference_vectors.net_eval_case"""
+    import torch
+    from oracle import nets as ON
+    xs, y = MK.net_eval_inputs(kind, cfg, seed, train)
+    onet = _oracle_net(kind, cfg)
+    tx = [torch.from_numpy(x) for x in xs]
+    tin = tx if len(tx) > 1 else tx[0]
+    collect = {}
+    if not train:
+        with torch.no_grad():
+            out, _ = onet.forward(tin, deterministic=True, collect=collect)
+    else:
+        masks = [torch.from_numpy(np.asarray(ref['mask%d' % i])) for i in range(8) if ('mask%d' % i) in ref] or None
+        with torch.no_grad():
+            fwd, _ = onet.forward(tin, deterministic=False, masks=masks, collect=collect)
+        adam = ON.Adam(onet.params)
+        before = [p.detach().numpy().copy() for p in onet.params]
+        cost, out, grads = ON.train_step(onet, adam, tin, torch.from_numpy(y), 1e-3, cfg['numJoints'], cfg['nDims'],
+                                         masks=masks)
+        assert abs(cost - float(ref['cost'])) <= 1e-10 * abs(float(ref['cost']))
+        names = [str(n) for n in ref['param_order']]
+        assert len(names) == len(grads)
+        for i, n in enumerate(names):
+            g = grads[i].numpy()
+            rs = ref['grad_stats'][i]
+            scale = max(rs[2], 1e-30)
+            if rs[2] > 1e-10:                       # conv biases in front of a BatchNorm have an exactly-zero gradient
+                assert np.abs(_stats(g) - rs)[[0, 1, 2]].max() <= 1e-7 * max(rs[1], scale), n
+            else:
+                assert np.abs(g).max() <= 1e-10, n
+            if ('grad__' + n) in ref and rs[2] > 1e-10:
+                assert _rel(g.reshape(ref['grad__' + n].shape), ref['grad__' + n]) <= 1e-8, n
+            # one ADAM step (the oracle folds the constants in float32 like Theano's floatX graph: 1e-6 relative)
+            p_new = onet.params[i].detach().numpy()
+            if rs[2] > 1e-10 and ('newp__' + n) in ref:
+                want = ref['newp__' + n]
+                assert np.abs(p_new.reshape(want.shape) - want).max() <= 2e-6 * max(np.abs(want).max(), 1e-3), n
+                assert np.abs(p_new - before[i]).max() > 0          # the step moved the parameter
+        assert float(ref['adam_t_next']) == 2.0 and float(adam.t) == 2.0
+        # BatchNorm running statistics after the step (EMA of mean AND inv_std, batchnormlayer.py:164-172)
+        bn_layers = [l for l in onet.layers if l.kind == 'bn']
+        assert len(ref['bn_names']) == 2 * len(bn_layers)
+        for i, l in enumerate(bn_layers):
+            for k in (0, 1):
+                v = l.nontrained[k]
+                v = v.numpy() if hasattr(v, 'numpy') else np.asarray(v)
+                assert _rel(v, ref['bn%d' % (2 * i + k)]) <= 1e-6, (i, k)
+    out = out.numpy() if hasattr(out, 'numpy') else out
+    assert _rel(out, ref['out']) <= 1e-10
+    # every layer's output (statistics): the wiring, not just the end result
+    nums = [int(n) for n in ref['layer_nums']]
+    seen = 0
+    for row, ln in enumerate(nums):
+        if ln in collect:
+            s = _stats(collect[ln].detach().numpy())
+            rs = ref['layer_stats'][row]
+            assert np.abs(s - rs)[[0, 1, 2]].max() <= 1e-8 * max(rs[1], 1e-30), (kind, ln)
+            seen += 1
+    assert seen >= 0.9 * len(nums)
+
+
+@pytest.mark.parametrize('case', range(len(MK.NET_EVAL_CASES)))
+def test_network_arithmetic_against_reference_fixture(case):
+    tag, kind, cfg, seed, train = MK.NET_EVAL_CASES[case]
+    ref = {k[len(tag) + 2:]: NE[k] for k in NE.files if k.startswith(tag + '__')}
+    _check_net_eval(kind, cfg, seed, train, ref)
+
+
+@live
+def test_live_reference_train_step():
+    kind, cfg = 'ResNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30)
+    _check_net_eval(kind, cfg, 901, True, MK.net_eval_case(kind, cfg, 901, True))
