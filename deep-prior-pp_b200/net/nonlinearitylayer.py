@@ -35,5 +35,5 @@ class NonlinearityLayer(Layer):
         self.weights = []
 
     def __str__(self):
-        return "inputDim {}, outputDim {}, activiation {}".format(self.cfgParams.inputDim, self.cfgParams.outputDim,
+        return "inputDim {}, outputDim {}, activation {}".format(self.cfgParams.inputDim, self.cfgParams.outputDim,
                                                                   self.cfgParams.activation_str)

@@ -176,6 +176,10 @@ class NetTrainer(object):
     def getSizeMiniBatch(self):
         return self.cfgParams.batch_size * self.sampleSize
 
+    def getSizeMacroBatch(self):
+        """size of a macro batch in MB as the reference defines it (nettrainer.py:422-427)"""
+        return self.getNumMacroBatches() * self.getSizeMiniBatch()
+
     def getNumFullMiniBatches(self):
         return self.getNumMiniBatches()
 

@@ -347,3 +347,32 @@ def run_reference_net(kind, cfg, inputs, deterministic=True, y=None, learning_ra
                 res['new_params'] = {by_id[id(s)]: v.eval().copy() for s, v in updates if id(s) in by_id}
                 res['adam_t_next'] = float(updates[-1][1].eval())
     return res
+
+
+def reference_checkpoint_roundtrip(kind, cfg, save_path=None, load_path=None, seed=23455):
+    """Checkpoint compatibility against the reference's own NetBase.save / NetBase.load (net/netbase.py:405-477), run
+    on a reference network built with the inert theano stand-in.  ``save_path``: the reference net (weights from
+    RandomState(seed)) writes its pickle there.  ``load_path``: a pickle written by the product is loaded by the
+    reference code; returns {param name: value} of the reference net after loading (and its own description string)."""
+    from unittest import mock
+    import numpy as np
+    theano = mock.MagicMock()
+    theano.shared = lambda value=None, name=None, borrow=False, **kw: _Shared(value, name, borrow)
+    theano.config.floatX = 'float32'
+    fake = {'theano': theano, 'theano.tensor': theano.tensor, 'theano.tensor.nnet': theano.tensor.nnet,
+            'theano.tensor.signal': theano.tensor.signal, 'theano.tensor.signal.pool': theano.tensor.signal.pool,
+            'theano.ifelse': theano.ifelse, 'theano.sandbox': theano.sandbox,
+            'theano.sandbox.rng_mrg': theano.sandbox.rng_mrg, 'theano.sandbox.neighbours': theano.sandbox.neighbours}
+    with _reference_net_modules(fake) as mods:
+        mod = mods['net.' + kind.lower()]
+        params = getattr(mod, kind + 'Params')(**cfg)
+        net = getattr(mod, kind)(np.random.RandomState(seed), cfgParams=params)
+        if save_path is not None:
+            net.save(save_path)
+        if load_path is not None:
+            net.load(load_path)
+        vals = {}
+        for l in net.layers:
+            for p in list(l.params) + list(getattr(l, 'params_nontrained', [])):
+                vals[p.name] = np.array(p.get_value(), copy=True)
+        return dict(values=vals, network=str(net))
