@@ -21,11 +21,37 @@ def make_importer(name):
     return getattr(importers, DATASETS[name][0])(None)
 
 
+def _samples(name, n, seed, cube, size):
+    """the synthetic recipe: yields per sample (com3D f32, com f32 image coords, M f64, crop in mm, gt3Dcrop f32)"""
+    from util.handdetector import HandDetector
+    rng = np.random.RandomState(seed)
+    di = make_importer(name)
+    hd = HandDetector(np.zeros((size, size), f32) + 1., abs(di.fx), abs(di.fy), importer=di)
+    J = DATASETS[name][2]
+    yy, xx = np.mgrid[0:size, 0:size]
+    half = cube[2] / 2.
+    cube32 = np.asarray(cube, f32)
+    for i in range(n):
+        c3 = np.array([rng.uniform(-150, 150), rng.uniform(-150, 150), rng.uniform(400, 900)], f32)
+        com = di.joint3DToImg(c3)
+        M = hd.comToTransform(com, cube32, (size, size))
+        d = np.zeros((size, size), f32)
+        for _ in range(6):
+            cx, cy = rng.uniform(16, size - 16, 2)
+            ax, ay = rng.uniform(4, 22, 2)
+            depth = np.rint(f64(com[2]) + rng.uniform(-0.4, 0.4) * half)
+            m = ((xx - cx) / ax) ** 2 + ((yy - cy) / ay) ** 2 <= 1.0
+            m &= (xx >= 16) & (xx < size - 16) & (yy >= 16) & (yy < size - 16)
+            d[m] = depth
+        gt = np.clip(rng.randn(J, 3) * 35., -half, half).astype(f32)
+        yield c3, com, M, d, gt
+    return
+
+
 def generate(name, n, seed=23455, cube=None, size=128):
     """Returns dict(x (n,1,S,S) f32 in [-1,1], gt3D (n,J,3) f32 = gt3Dcrop/(cube_z/2), cube (n,3),
     com3D (n,3), M (n,3,3), gt3Dcrop (n,J,3)) all float32."""
     from util.handdetector import HandDetector
-    rng = np.random.RandomState(seed)
     di = make_importer(name)
     cube = tuple(cube if cube is not None else DATASETS[name][1])
     J = DATASETS[name][2]
@@ -35,30 +61,37 @@ def generate(name, n, seed=23455, cube=None, size=128):
     com3D = np.zeros((n, 3), f32)
     Ms = np.zeros((n, 3, 3), f32)
     gt3Dcrop = np.zeros((n, J, 3), f32)
-    yy, xx = np.mgrid[0:size, 0:size]
     half = cube[2] / 2.
-    for i in range(n):
-        c3 = np.array([rng.uniform(-150, 150), rng.uniform(-150, 150), rng.uniform(400, 900)], f32)
-        com = di.joint3DToImg(c3)
+    for i, (c3, com, M, d, gt) in enumerate(_samples(name, n, seed, cube, size)):
         com3D[i] = c3
-        Ms[i] = hd.comToTransform(com, cubes[i], (size, size)).astype(f32)
-        d = np.zeros((size, size), f32)
-        for _ in range(6):
-            cx, cy = rng.uniform(16, size - 16, 2)
-            ax, ay = rng.uniform(4, 22, 2)
-            depth = np.rint(f64(com[2]) + rng.uniform(-0.4, 0.4) * half)
-            m = ((xx - cx) / ax) ** 2 + ((yy - cy) / ay) ** 2 <= 1.0
-            m &= (xx >= 16) & (xx < size - 16) & (yy >= 16) & (yy < size - 16)
-            d[m] = depth
+        Ms[i] = M.astype(f32)
         # dataset.py:99-103 (normZeroOne False)
         imgD = d.copy()
         imgD[imgD == 0] = f32(f64(com[2]) + half)
         imgD -= com[2]
         imgD /= f32(half)
         x[i, 0] = imgD
-        gt3Dcrop[i] = np.clip(rng.randn(J, 3) * 35., -half, half).astype(f32)
+        gt3Dcrop[i] = gt
     gt3D = gt3Dcrop / f32(half)
     return dict(x=x, gt3D=gt3D.astype(f32), cube=cubes, com3D=com3D, M=Ms, gt3Dcrop=gt3Dcrop, importer=di, hd=hd)
+
+
+def generate_sequence(name, n, seed=23455, cube=None, size=128, seq_name='train'):
+    """The same samples as ``generate`` packed the way the importers' ``loadSequence`` returns them (reference
+    src/data/importers.py:1068-1075 for NYU): a ``NamedImgSequence`` of ``DepthFrame``s with the crop in mm
+    (background 0), the crop transform ``T``, ``gt3Dcrop`` and the 3-D crop centre in ``com`` - the input of
+    ``data.dataset.Dataset.imgStackDepthOnly`` and of the entry scripts' side arrays."""
+    from data.basetypes import DepthFrame, NamedImgSequence
+    from data.transformations import transformPoints2D
+    cube = tuple(cube if cube is not None else DATASETS[name][1])
+    di = make_importer(name)
+    frames = []
+    for c3, com, M, d, gt in _samples(name, n, seed, cube, size):
+        gt3Dorig = (gt + c3).astype(f32)
+        gtorig = di.joints3DToImg(gt3Dorig)                        # joints in the original image (u, v, d)
+        gtcrop = transformPoints2D(gtorig, M)                      # ... and in the crop
+        frames.append(DepthFrame(d, gtorig, gtcrop, M.astype(f32), gt3Dorig, gt, c3, '', '', 'left', {}))
+    return NamedImgSequence(seq_name, frames, {'cube': cube})
 
 
 def random_orthonormal_pca(n_components, dim, seed=0):

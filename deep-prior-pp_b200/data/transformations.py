@@ -28,3 +28,11 @@ def rotatePoint2D(p1, center, angle):
     ps = pr
     ps[0:2] += center[0:2]
     return ps
+
+
+def rotatePoints2D(pts, center, angle):
+    """Rotate every (u,v,d) row of ``pts`` about ``center`` by ``angle`` degrees (transformations.py:91-103)."""
+    ret = pts.copy()
+    for i in range(pts.shape[0]):
+        ret[i] = rotatePoint2D(pts[i], center, angle)
+    return ret

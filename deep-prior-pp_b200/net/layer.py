@@ -13,6 +13,14 @@ class Layer(object):
         self.params_nontrained = []
         self.rng = rng
 
+    def orthogonalize(self, init_vals):
+        """layer.py:49-55: replace the filters by an orthonormal set - the leading left singular vectors of the
+        (fan_in x n_filters) matrix of the drawn values."""
+        flat = numpy.reshape(init_vals, (init_vals.shape[0], -1))
+        left = numpy.linalg.svd(flat.T)[0]
+        basis = left.T[0:init_vals.shape[0]].T
+        return numpy.reshape(basis.swapaxes(0, 1), init_vals.shape)
+
     def getOptimalInitMethod(self, act_str):
         # layer.py:58-70
         if act_str == 'ReLU':
@@ -68,5 +76,5 @@ class Layer(object):
         else:
             raise NotImplementedError("Unknown method!")
         if orthogonal:
-            raise NotImplementedError("orthogonal init is unused on the hot path")
+            init_vals = self.orthogonalize(init_vals)
         return init_vals

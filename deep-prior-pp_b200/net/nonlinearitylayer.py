@@ -19,6 +19,9 @@ class NonlinearityLayerParams(LayerParams):
     def activation(self, value):
         self._activation = value
 
+    def getMemoryRequirement(self):
+        return 0                      # no weights (nonlinearitylayer.py:68-73)
+
 
 class NonlinearityLayer(Layer):
     def __init__(self, rng, inputVar, cfgParams, copyLayer=None, layerNum=None):

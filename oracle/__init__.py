@@ -23,8 +23,11 @@ PARITY STATUS
   dimension arithmetic, weight initialisation, order of random draws, parameter order - runs for real);
   tests/golden/reference_nets.json holds the result, tests/test_reference_pins.py checks layer lists, dimensions,
   parameter names / order and the sha1 of every initial weight tensor: bit-identical.
-* Network ARITHMETIC - forward ops, cost, gradients, ADAM (oracle/nets.py): PARITY UNPINNED - those are Theano 0.9 graphs in the reference;
-  Theano cannot be installed or run here (Python 3.12, no network) and the reference ships no tests or fixtures
-  (SURVEY.md section 4).  The restatement follows the cited layer files line by line; the committed vectors
-  tests/golden/{resnet_b2,scalenet_b2}.npz pin it against drift only.
+* Network ARITHMETIC - forward ops, cost, gradients, ADAM (oracle/nets.py): pinned against the reference's own
+  Python code EVALUATED EAGERLY (oracle/eager_theano.py: a stand-in for Theano whose calls compute, torch-CPU float64
+  + autograd; oracle/ref_harness.py::run_reference_net runs net/*.py, PoseRegNetTrainer.setupFunctions and
+  Optimizer.ADAM through it) -> tests/golden/reference_net_eval.npz, tests/test_reference_pins.py: outputs, every
+  layer's output, cost, all gradients, BatchNorm EMA, one ADAM step.  Theano's PRIMITIVES (conv2d, pool_2d, var, ...)
+  are NOT pinned: Theano 0.9 cannot be installed or run here (Python 3.12, no network) and the reference ships no
+  tests or fixtures; stand-in and oracle both follow the documented semantics.
 """

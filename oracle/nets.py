@@ -4,9 +4,11 @@
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Structure and initial weights are PINNED
 against the reference's own constructors (oracle/ref_harness.py::describe_reference_net ->
 tests/golden/reference_nets.json, tests/test_reference_pins.py: layer lists, dimensions,
-parameter order, bit-identical initial weights).  The ARITHMETIC (forward ops, cost,
-gradients, ADAM) is PARITY UNPINNED: Theano cannot run here; the semantics below follow the
-reference sources line by line plus SURVEY.md Appendix A for the Theano op semantics.
+parameter order, bit-identical initial weights).  The ARITHMETIC is pinned against the
+reference's own layer / cost / T.grad / ADAM code evaluated eagerly with oracle/eager_theano.py
+in place of Theano (tests/golden/reference_net_eval.npz: outputs, per-layer outputs, cost, all
+gradients, BatchNorm EMA, one ADAM step).  Theano's primitive ops themselves stay UNPINNED
+(Theano cannot run here): they follow SURVEY.md Appendix A in both places.
 
 Reference files restated (all under /root/reference/src):
   net/resnet.py:45-346 (ResNetParams/ResNet types 0-4), :349-414 (res_block)

@@ -98,7 +98,7 @@ def reference_modules():
     import numpy
     if not hasattr(numpy, 'float'):
         numpy.float = float                      # removed alias the reference uses (numpy.float == float)
-    saved = {k: sys.modules.get(k) for k in ('data', 'data.transformations', 'data.basetypes', 'data.importers', 'util',
+    saved = {k: sys.modules.get(k) for k in ('data', 'data.transformations', 'data.basetypes', 'data.importers', 'data.dataset', 'util',
                                              'util.handdetector', 'progressbar', 'cPickle', 'net', 'trainer')}
     try:
         import pickle
@@ -111,6 +111,7 @@ def reference_modules():
         _loaded['basetypes'] = load_module('data.basetypes', 'data/basetypes.py')
         _loaded['handdetector'] = load_module('util.handdetector', 'util/handdetector.py')
         _loaded['importers'] = load_module('data.importers', 'data/importers.py')
+        _loaded['dataset'] = load_module('data.dataset', 'data/dataset.py')
         # scipy < 1.11 returned arrays from stats.mode (the reference indexes [0][0], handdetector.py:128-130)
         import scipy.stats
         _loaded['handdetector'].stats = types.SimpleNamespace(mode=lambda a: scipy.stats.mode(a, keepdims=True))

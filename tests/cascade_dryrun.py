@@ -133,6 +133,9 @@ for name in ['NYU', 'ICVL', 'MSRA15']:
     T.test_recrop_kernel_bit_exact(name); print('recrop', name, 'ok')
 T.test_joint_errors_match_reference_formulas(); print('joint errors ok')
 T.test_handpose_evaluation_metrics(); print('evaluation ok')
+for name in ['NYU', 'MSRA15']:
+    T.test_dataset_stack_on_device(name)
+print('dataset ok')
 T.test_cascade_matches_oracle(); print('cascade ok')
 import test_gpu_poses as TP
 for name in ['NYU', 'ICVL', 'MSRA15']:

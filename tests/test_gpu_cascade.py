@@ -200,3 +200,23 @@ def test_handpose_evaluation_metrics():
             assert ev.getJointNumFramesWithinMaxDist(dist, 5) == (e[:, 5] <= dist).sum()
     with pytest.raises(ValueError):
         HandposeEvaluation(list(gt), list(pr[:-1]))
+
+
+@pytest.mark.parametrize('name', ['NYU', 'MSRA15'])
+def test_dataset_stack_on_device(name):
+    """data.dataset.Dataset.imgStackDepthOnly (reference src/data/dataset.py:75-111) through dpp_recrop_fwd: the
+    stack equals the host restatement in data.synthetic.generate - itself pinned to the reference's Dataset code,
+    tests/test_reference_pins.py - bit for bit."""
+    from data import synthetic
+    from data import dataset as D
+    seq = synthetic.generate_sequence(name, 9, seed=43)
+    ds = synthetic.generate(name, 9, seed=43)
+    cls = {'NYU': D.NYUDataset, 'MSRA15': D.MSRA15Dataset}[name]
+    dset = cls([seq])
+    img, lab = dset.imgStackDepthOnly('train')
+    assert img.shape == (9, 1, 128, 128) and img.dtype == np.float32
+    assert np.array_equal(img, ds['x']) and np.array_equal(lab, ds['gt3D'])
+    assert dset.imgStackDepthOnly('train')[0] is img              # localCache
+    assert dset.imgStackDepthOnly('nope') == [] and dset.imgSeq('train') is seq
+    with pytest.raises(NotImplementedError):
+        D.Dataset([seq], localCache=False).imgStackDepthOnly('train', normZeroOne=True)

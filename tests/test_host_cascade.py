@@ -13,4 +13,4 @@ def test_cascade_host_plumbing_dry_run():
                        timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert 'cascade ok' in r.stdout and 'joint errors ok' in r.stdout and 'recrop MSRA15 ok' in r.stdout
-    assert 'evaluation ok' in r.stdout and 'poses ok' in r.stdout
+    assert 'evaluation ok' in r.stdout and 'poses ok' in r.stdout and 'dataset ok' in r.stdout

@@ -410,3 +410,41 @@ def test_live_checkpoints_interoperate_with_reference_netbase(kind, cfg, tmp_pat
     for l in net.layers:
         for p in list(l.params) + list(l.params_nontrained):
             assert np.array_equal(p.get_value(), back['values'][p.name]), p.name
+
+
+@live
+def test_live_reference_layer_init_values():
+    """net/layer.py getInitVals (all methods / modes, orthogonal included) and orthogonalize, reference vs product."""
+    from unittest import mock
+    from net.layer import Layer
+    theano = mock.MagicMock()
+    theano.config.floatX = 'float32'
+    fake = {'theano': theano, 'theano.tensor': theano.tensor}
+    with RH._reference_net_modules(fake) as mods:
+        RL = mods['net.layer'].Layer
+        for seed, (shape, mode) in enumerate([((8, 1, 5, 5), 'conv'), ((16, 8, 3, 3), 'conv'), ((200, 30), 'fc')]):
+            for method, act in (('He', None), ('Xavier', None), ('sigmoid', None), ('tanh', None), (None, 'ReLU'),
+                                (None, 'None')):
+                for orth in (False, True) if mode == 'conv' else (False,):
+                    a = RL(np.random.RandomState(seed)).getInitVals(shape, mode, act_fn=act, method=method, orthogonal=orth)
+                    b = Layer(np.random.RandomState(seed)).getInitVals(shape, mode, act_fn=act, method=method, orthogonal=orth)
+                    assert a.dtype == b.dtype and np.array_equal(a, b), (shape, mode, method, act, orth)
+
+
+@live
+@pytest.mark.parametrize('name', ['NYU', 'ICVL'])
+def test_live_reference_dataset_stack(name):
+    """The reference's own Dataset.imgStackDepthOnly (data/dataset.py:75-111) on a synthetic NamedImgSequence yields
+    exactly the crops / labels data.synthetic.generate hands to the tests and the bench (its normalisation restates
+    dataset.py:99-103); the product's data.dataset.Dataset produces the same stack on the device (GPU test)."""
+    from data import synthetic
+    ref = RH.reference_modules()
+    seq = synthetic.generate_sequence(name, 6, seed=41)
+    RSeq = ref['basetypes'].NamedImgSequence(seq.name, [ref['basetypes'].DepthFrame(*f) for f in seq.data], seq.config)
+    img, lab = ref['dataset'].Dataset([RSeq]).imgStackDepthOnly('train')
+    ds = synthetic.generate(name, 6, seed=41)
+    assert img.dtype == np.float32 and np.array_equal(img, ds['x'])
+    assert np.array_equal(lab, ds['gt3D'])
+    assert np.array_equal(np.stack([f.com for f in seq.data]), ds['com3D'])
+    assert np.array_equal(np.stack([f.T for f in seq.data]), ds['M'])
+    assert np.array_equal(np.stack([f.gt3Dcrop for f in seq.data]), ds['gt3Dcrop'])
