@@ -1,100 +1,50 @@
 """ConvLayer (reference: src/net/convlayer.py:39-266): conv2d(border 'half'|'valid', stride) + bias.
 Arithmetic: dpp_conv2d_fwd/dgrad/wgrad in libdpp_b200.so (include/dpp_b200.h)."""
 import numpy
-from net.layerparams import LayerParams
+from net.layerparams import LayerParams, tracked
 from net.layer import Layer
 from net.sym import Sym, shared
 
 
+def _border(mode):
+    return 'half' if mode == 'same' else mode          # the entry code says 'same', theano's conv2d 'half'
+
+
 class ConvLayerParams(LayerParams):
+    """convlayer.py:39-170.  Reassigning a tracked attribute recomputes filter / image / output shapes."""
+    stride = tracked('stride')
+    border_mode = tracked('border_mode', convert=_border)
+    nFilters = tracked('nFilters')
+    filterDim = tracked('filterDim')
+    activation = tracked('activation', refresh=False)
+    hasBias = tracked('hasbias', refresh=False)
+    filter_shape = property(lambda self: self._filter_shape)
+    image_shape = property(lambda self: self._image_shape)
+
     def __init__(self, inputDim=None, nFilters=None, filterDim=None, activation=None, hasBias=True,
                  filter_shape=None, image_shape=None, outputDim=None, stride=(1, 1), border_mode='valid',
                  init_method=None):
         super(ConvLayerParams, self).__init__(inputDim, outputDim)
-        self._nFilters = nFilters
-        self._filterDim = filterDim
-        self._filter_shape = filter_shape
-        self._image_shape = image_shape
-        self._activation = activation
-        self._hasbias = hasBias
-        self._stride = stride
-        self._border_mode = 'half' if border_mode == 'same' else border_mode
+        self._nFilters, self._filterDim = nFilters, filterDim
+        self._filter_shape, self._image_shape = filter_shape, image_shape
+        self._activation, self._hasbias = activation, hasBias
+        self._stride, self._border_mode = stride, _border(border_mode)
         self._init_method = init_method
         self.update()
 
-    filter_shape = property(lambda self: self._filter_shape)
-    image_shape = property(lambda self: self._image_shape)
-
-    @property
-    def stride(self):
-        return self._stride
-
-    @stride.setter
-    def stride(self, value):
-        self._stride = value
-        self.update()
-
-    @property
-    def border_mode(self):
-        return self._border_mode
-
-    @border_mode.setter
-    def border_mode(self, value):
-        self._border_mode = 'half' if value == 'same' else value
-        self.update()
-
-    @property
-    def nFilters(self):
-        return self._nFilters
-
-    @nFilters.setter
-    def nFilters(self, value):
-        self._nFilters = value
-        self.update()
-
-    @property
-    def filterDim(self):
-        return self._filterDim
-
-    @filterDim.setter
-    def filterDim(self, value):
-        self._filterDim = value
-        self.update()
-
-    @property
-    def activation(self):
-        return self._activation
-
-    @activation.setter
-    def activation(self, value):
-        self._activation = value
-
-    @property
-    def hasBias(self):
-        return self._hasbias
-
-    @hasBias.setter
-    def hasBias(self, value):
-        self._hasbias = value
-
     def _conv_dims(self):
-        # convlayer.py:133-163
-        self._filter_shape = (self._nFilters, self._inputDim[1], self._filterDim[0], self._filterDim[1])
+        """convlayer.py:133-163: [N, nFilters, ceil(H' / stride), ceil(W' / stride)] with H' by border mode; also
+        refreshes filter_shape / image_shape"""
+        n, cin, h, w = self._inputDim
+        kh, kw = self._filterDim
+        self._filter_shape = (self._nFilters, cin, kh, kw)
         self._image_shape = self._inputDim
-        if self._border_mode == 'valid':
-            o = (self._inputDim[0], self._nFilters, self._inputDim[2] - self._filterDim[0] + 1,
-                 self._inputDim[3] - self._filterDim[1] + 1)
-        elif self._border_mode == 'full':
-            o = (self._inputDim[0], self._nFilters, self._inputDim[2] + self._filterDim[0] - 1,
-                 self._inputDim[3] + self._filterDim[1] - 1)
-        elif self._border_mode == 'half':
-            o = (self._inputDim[0], self._nFilters, self._inputDim[2], self._inputDim[3])
-        else:
+        grow = {'valid': (1 - kh, 1 - kw), 'full': (kh - 1, kw - 1), 'half': (0, 0)}
+        if self._border_mode not in grow:
             raise ValueError("Unknown border mode")
-        o = list(o)
-        o[2] = int(numpy.ceil(o[2] / float(self._stride[0])))
-        o[3] = int(numpy.ceil(o[3] / float(self._stride[1])))
-        return o
+        dh, dw = grow[self._border_mode]
+        return [n, self._nFilters, int(numpy.ceil((h + dh) / float(self._stride[0]))),
+                int(numpy.ceil((w + dw) / float(self._stride[1])))]
 
     def update(self):
         self._outputDim = tuple(self._conv_dims())

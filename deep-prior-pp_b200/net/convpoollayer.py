@@ -2,6 +2,7 @@
 ignore_border) -> +bias -> activation.  Arithmetic: dpp_convpool_fwd/bwd in libdpp_b200.so."""
 import numpy
 from net.convlayer import ConvLayerParams
+from net.layerparams import tracked
 from net.layer import Layer
 from net.sym import Sym, shared
 
@@ -17,26 +18,16 @@ class ConvPoolLayerParams(ConvLayerParams):
                                                   image_shape=image_shape, outputDim=outputDim, stride=stride,
                                                   border_mode=border_mode, init_method=init_method)
 
-    @property
-    def poolsize(self):
-        return self._poolsize
-
-    @poolsize.setter
-    def poolsize(self, value):
-        self._poolsize = value
-        self.update()
-
-    @property
-    def poolType(self):
-        return self._poolType
+    poolsize = tracked('poolsize')
+    poolType = property(lambda self: self._poolType)
 
     def update(self):
-        # convpoollayer.py:110-146: conv dims, then // poolsize
-        o = self._conv_dims()
-        o[2] = o[2] // self._poolsize[0]
-        o[3] = o[3] // self._poolsize[1]
-        self._outputDim = tuple(o)
-        if self._poolsize[0] == 1 and self._poolsize[1] == 1:
+        """convpoollayer.py:110-146: the convolution's dimensions, floor-divided by the pooling window (theano's
+        pool_2d with ignore_border=True); a 1x1 window means 'no pooling' (poolType -1)"""
+        n, c, h, w = self._conv_dims()
+        ph, pw = self._poolsize
+        self._outputDim = (n, c, h // ph, w // pw)
+        if (ph, pw) == (1, 1):
             self._poolType = -1
 
 

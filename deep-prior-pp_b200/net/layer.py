@@ -34,47 +34,35 @@ class Layer(object):
         raise NotImplementedError("Unknown activation function: {}".format(act_str))
 
     def getInitVals(self, shape, mode, act_fn=None, method=None, orthogonal=False):
-        # layer.py:72-124
+        """layer.py:72-124: initial weights for a 'conv' (O, I, kh, kw) or 'fc' (n_in, n_out) tensor.  One draw from
+        ``self.rng`` per tensor - normal for 'He', uniform otherwise - so a net built from the same seed reproduces the
+        reference's weights bit for bit (tests/test_reference_pins.py)."""
         if act_fn is None and method is None:
             raise UserWarning("act_fn and method not defined! At least one must be specified.")
-        if act_fn is not None and method is None:
+        if method is None and act_fn is not None:
             method = self.getOptimalInitMethod(act_fn)
+        if mode not in ('conv', 'fc'):
+            raise NotImplementedError()
+        conv = (mode == 'conv')
+        fan_in = numpy.prod(shape[1:]) if conv else None
+        fan_both = (fan_in + shape[0] * numpy.prod(shape[2:])) if conv else None      # fan-in + fan-out of a filter bank
+        glorot_fc = None if conv else numpy.sqrt(6. / numpy.sum(shape))
+        gain = 1.
         if method == 'He':
-            if mode == 'conv':
-                W_bound = numpy.sqrt(2. / numpy.prod(shape[1:]))
-                init_vals = numpy.asarray(self.rng.normal(loc=0.0, scale=W_bound, size=shape), dtype=floatX)
-            elif mode == 'fc':
-                init_vals = numpy.asarray(self.rng.normal(loc=0.0, scale=0.01, size=shape), dtype=floatX)
-            else:
-                raise NotImplementedError()
-        elif method == 'Xavier':
-            if mode == 'conv':
-                W_bound = numpy.sqrt(3. / numpy.prod(shape[1:]))
-            elif mode == 'fc':
-                W_bound = numpy.sqrt(1. / shape[0])
-            else:
-                raise NotImplementedError()
-            init_vals = numpy.asarray(self.rng.uniform(low=-W_bound, high=W_bound, size=shape), dtype=floatX)
-        elif method == 'sigmoid':
-            if mode == 'conv':
-                W_bound = 4. * numpy.sqrt(6. / (numpy.prod(shape[1:]) + (shape[0] * numpy.prod(shape[2:]))))
-                init_vals = numpy.asarray(self.rng.uniform(low=-W_bound, high=W_bound, size=shape), dtype=floatX)
-            elif mode == 'fc':
-                b = numpy.sqrt(6. / numpy.sum(shape))
-                init_vals = 4. * numpy.asarray(self.rng.uniform(low=-b, high=b, size=shape), dtype=floatX)
-            else:
-                raise NotImplementedError()
-        elif method == 'tanh' or method is None:
-            if mode == 'conv':
-                W_bound = 1. / (numpy.prod(shape[1:]) + (shape[0] * numpy.prod(shape[2:])))
-                init_vals = numpy.asarray(self.rng.uniform(low=-W_bound, high=W_bound, size=shape), dtype=floatX)
-            elif mode == 'fc':
-                b = numpy.sqrt(6. / numpy.sum(shape))
-                init_vals = numpy.asarray(self.rng.uniform(low=-b, high=b, size=shape), dtype=floatX)
-            else:
-                raise NotImplementedError()
+            sigma = numpy.sqrt(2. / fan_in) if conv else 0.01
+            draw = self.rng.normal(loc=0.0, scale=sigma, size=shape)
         else:
-            raise NotImplementedError("Unknown method!")
-        if orthogonal:
-            init_vals = self.orthogonalize(init_vals)
-        return init_vals
+            if method == 'Xavier':
+                bound = numpy.sqrt(3. / fan_in) if conv else numpy.sqrt(1. / shape[0])
+            elif method == 'sigmoid':
+                bound = 4. * numpy.sqrt(6. / fan_both) if conv else glorot_fc
+                gain = 1. if conv else 4.             # fully connected: the drawn values are scaled, not the bound
+            elif method == 'tanh' or method is None:
+                bound = 1. / fan_both if conv else glorot_fc
+            else:
+                raise NotImplementedError("Unknown method!")
+            draw = self.rng.uniform(low=-bound, high=bound, size=shape)
+        init_vals = numpy.asarray(draw, dtype=floatX)
+        if gain != 1.:
+            init_vals = gain * init_vals
+        return self.orthogonalize(init_vals) if orthogonal else init_vals

@@ -1,56 +1,53 @@
-"""LayerParams base (reference: src/net/layerparams.py:35-104)."""
+"""LayerParams base (reference: src/net/layerparams.py:35-104): input / output dimensions that re-derive dependent
+shapes when reassigned, a printable activation name, the activation's output range.
+
+The reference writes one property + setter pair per attribute; here ``tracked`` generates them."""
 import inspect
 import numpy
 
 
+def tracked(attr, refresh=True, convert=None):
+    """Property stored in ``_<attr>``.  Assigning it re-derives the dependent dimensions through ``update()`` (the
+    entry scripts poke e.g. ``cfgParams.outputDim`` after construction, main_nyu_posereg_embedding.py:160-162)."""
+    slot = '_' + attr
+
+    def fget(self):
+        return getattr(self, slot)
+
+    def fset(self, value):
+        setattr(self, slot, convert(value) if convert is not None else value)
+        if refresh:
+            self.update()
+    return property(fget, fset)
+
+
+_RANGES = {'tanh': [-1, 1], 'sigmoid': [0, 1], 'ReLU': [0, numpy.inf]}
+
+
 class LayerParams(object):
+    inputDim = tracked('inputDim')
+    outputDim = tracked('outputDim')
+
     def __init__(self, inputDim, outputDim):
-        self._inputDim = inputDim
-        self._outputDim = outputDim
-
-    @property
-    def outputDim(self):
-        return self._outputDim
-
-    @outputDim.setter
-    def outputDim(self, value):
-        self._outputDim = value
-        self.update()
-
-    @property
-    def inputDim(self):
-        return self._inputDim
-
-    @inputDim.setter
-    def inputDim(self, value):
-        self._inputDim = value
-        self.update()
+        self._inputDim, self._outputDim = inputDim, outputDim
 
     def update(self):
-        pass
+        """derived parameter classes recompute their shapes here"""
 
     @property
     def activation_str(self):
-        # layerparams.py:69-83
-        if hasattr(self, 'activation'):
-            if self.activation is None:
-                return str(None)
-            elif inspect.isclass(self.activation):
-                return self.activation.__class__.__name__
-            elif inspect.isfunction(self.activation):
-                return self.activation.__name__
-            else:
-                return str(self.activation)
-        return ''
+        """name the layer descriptions and the initialisation lookup use (layerparams.py:69-83)"""
+        if not hasattr(self, 'activation'):
+            return ''
+        act = self.activation
+        if act is None:
+            return 'None'
+        if inspect.isclass(act):
+            return act.__class__.__name__          # (sic) the reference names the metaclass for classes
+        return act.__name__ if inspect.isfunction(act) else str(act)
 
     def getOutputRange(self):
+        unbounded = [-numpy.inf, numpy.inf]
         if not hasattr(self, 'activation'):
-            return [-numpy.inf, numpy.inf]
-        s = self.activation_str
-        if s == 'tanh':
-            return [-1, 1]
-        if s == 'sigmoid':
-            return [0, 1]
-        if s == 'ReLU':
-            return [0, numpy.inf]
-        return [-numpy.inf, numpy.inf]
+            return unbounded
+        return list(_RANGES.get(self.activation_str, unbounded))
