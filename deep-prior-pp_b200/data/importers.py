@@ -85,6 +85,7 @@ class ICVLImporter(DepthImporter):
         self.crop_joint_idx = 0
         self.refineNet = refineNet
         self.default_cubes = {'train': (250, 250, 250), 'test_seq_1': (250, 250, 250), 'test_seq_2': (250, 250, 250)}
+        self.sides = {'train': 'right', 'test_seq1': 'right', 'test_seq_2': 'right'}       # (sic) importers.py:211
 
 
 class MSRA15Importer(DepthImporter):
@@ -100,6 +101,7 @@ class MSRA15Importer(DepthImporter):
         self.default_cubes = {'P0': (200, 200, 200), 'P1': (200, 200, 200), 'P2': (200, 200, 200),
                               'P3': (180, 180, 180), 'P4': (180, 180, 180), 'P5': (180, 180, 180),
                               'P6': (170, 170, 170), 'P7': (160, 160, 160), 'P8': (150, 150, 150)}
+        self.sides = dict((k, 'right') for k in self.default_cubes)
 
 
 class NYUImporter(DepthImporter):
@@ -112,6 +114,9 @@ class NYUImporter(DepthImporter):
         self.numJoints = 36
         self.crop_joint_idx = 32 if allJoints else 13
         self.default_cubes = {'train': (300, 300, 300), 'test_1': (300, 300, 300), 'test_2': (250, 250, 250),
-                              'test': (300, 300, 300)}
+                              'test': (300, 300, 300), 'train_synth': (300, 300, 300),
+                              'test_synth_1': (300, 300, 300), 'test_synth_2': (250, 250, 250),
+                              'test_synth': (300, 300, 300)}
+        self.sides = dict((k, 'right') for k in self.default_cubes)
         self.restrictedJointsEval = [0, 3, 6, 9, 12, 15, 18, 21, 24, 25, 27, 30, 31, 32]
         self.refineNet = refineNet

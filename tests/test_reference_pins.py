@@ -448,3 +448,71 @@ def test_live_reference_dataset_stack(name):
     assert np.array_equal(np.stack([f.com for f in seq.data]), ds['com3D'])
     assert np.array_equal(np.stack([f.T for f in seq.data]), ds['M'])
     assert np.array_equal(np.stack([f.gt3Dcrop for f in seq.data]), ds['gt3Dcrop'])
+
+
+@live
+def test_live_reference_augment_poses_driver():
+    """PoseRegNetTrainer.augment_poses (trainer/poseregnettrainer.py:221-264) executed from the reference - with the
+    reference's augmentCrop, HandDetector, importer and a PCA projection - against oracle.augment_poses on the same
+    random stream: crops bit-exact for com / rot / none, embedded labels to float32 rounding."""
+    import types
+    from data import synthetic
+    ref = RH.reference_modules()
+    name, n = 'NYU', 40
+    ds = synthetic.generate(name, n, seed=77)
+    comp, mean = synthetic.random_orthonormal_pca(30, ds['gt3Dcrop'].shape[1] * 3, seed=2)
+
+    class Proj(object):                                   # sklearn's PCA.transform
+        def transform(self, X):
+            return np.dot(X - mean, comp.T)
+    rdi = ref['importers'].NYUImporter('/nonexistent/')
+    rhd = ref['handdetector'].HandDetector(np.zeros((128, 128), f32) + 1., abs(rdi.fx), abs(rdi.fy), importer=rdi)
+    cam = OA.Camera(**CAMS[name])
+    modes = ['com', 'rot', 'none']
+    tr = types.SimpleNamespace(train_data_xDB=ds['x'], train_data_comDB=ds['com3D'], train_data_cubeDB=ds['cube'],
+                               train_data_MDB=ds['M'], train_gt3DcropDB=ds['gt3Dcrop'], rng=np.random.RandomState(3),
+                               getNumMacroBatches=lambda: 1)
+    tr.augmentCrop = types.MethodType(RH.reference_function('trainer/nettrainer.py', 'augmentCrop', {'numpy': np}), tr)
+    augment_poses = RH.reference_function('trainer/poseregnettrainer.py', 'augment_poses', {'numpy': np})
+
+    class OracleProjectionImporter(object):     # 'di': joint3DToImg with NumPy-1.x rounding (float32 input: the
+                                                # reference-as-run-here is 1-2 ulp off, see oracle/ref_harness.py)
+        joint3DToImg = staticmethod(cam.joint3DToImg)
+        jointImgTo3D = staticmethod(rdi.jointImgTo3D)
+        joints3DToImg = staticmethod(rdi.joints3DToImg)
+        jointsImgTo3D = staticmethod(rdi.jointsImgTo3D)
+    rhd.importer = rdi
+    params = {'fun': 'augment_poses', 'args': {'normZeroOne': False, 'di': OracleProjectionImporter, 'aug_modes': modes,
+                                               'hd': rhd, 'proj': Proj()}}
+    new_data = {'train_data_x': np.zeros((n, 1, 128, 128), f32), 'train_data_y': np.zeros((n, 30), f32)}
+    augment_poses(tr, params, 0, False, list(range(n)), list(range(n)), new_data)
+    rng = np.random.RandomState(3)
+    draws = [OA.draw_aug_params(rng, len(modes)) for _ in range(n)]
+    ox, oy = OA.augment_poses(ds['x'], ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], list(range(n)), draws, modes,
+                              cam, OA.Hand(cam, use_cv2=True), pca_mean=mean, pca_components=comp)
+    assert np.array_equal(new_data['train_data_x'], ox)
+    assert np.abs(new_data['train_data_y'] - oy).max() <= 64 * ULP
+    assert {modes[d[0]] for d in draws} == set(modes)
+
+
+@live
+def test_live_reference_importer_constants():
+    """Camera models and per-dataset constants of the product's data/importers.py against the reference's importers
+    (data/importers.py:186-210, 536-570, 880-920): intrinsics, joint counts, crop joints, default cubes, projections."""
+    from data import importers as P
+    ref = RH.reference_modules()['importers']
+    rng = np.random.RandomState(0)
+    for cls in ('ICVLImporter', 'MSRA15Importer', 'NYUImporter'):
+        r, p = getattr(ref, cls)('/nonexistent/'), getattr(P, cls)(None)
+        for k in ('fx', 'fy', 'ux', 'uy', 'numJoints', 'crop_joint_idx', 'depth_map_size', 'default_cubes', 'sides'):
+            assert getattr(r, k) == getattr(p, k), (cls, k)
+        if hasattr(r, 'restrictedJointsEval'):
+            assert list(r.restrictedJointsEval) == list(p.restrictedJointsEval)
+        assert np.array_equal(r.getCameraProjection(), p.getCameraProjection())
+        pts = np.stack([rng.uniform(-200, 200, 50), rng.uniform(-200, 200, 50), rng.uniform(300, 1000, 50)], axis=1)
+        for q in pts:                                      # float64 points: identical in both NumPy generations
+            assert np.array_equal(r.joint3DToImg(q), p.joint3DToImg(q))
+            uvd = np.asarray(p.joint3DToImg(q), np.float64)
+            assert np.array_equal(r.jointImgTo3D(uvd), p.jointImgTo3D(uvd))
+        assert np.array_equal(r.joints3DToImg(pts), p.joints3DToImg(pts))
+        assert np.array_equal(r.jointsImgTo3D(pts), p.jointsImgTo3D(pts))
