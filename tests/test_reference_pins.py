@@ -227,11 +227,14 @@ def test_network_classes_against_reference_fixture(idx):
 
 
 @live
-def test_live_reference_network_constructor():
-    desc = RH.describe_reference_net('ResNet', type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30)
-    _check_net_against(desc)
-    desc = RH.describe_reference_net('PoseRegNet', type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30)
-    _check_net_against(desc)
+@pytest.mark.parametrize('kind,types', [('ResNet', (0, 1, 2, 3, 4)), ('PoseRegNet', (0, 11)), ('ScaleNet', (1,))])
+def test_live_reference_network_constructor(kind, types):
+    """every network type the reference can build (its other type numbers raise NotImplementedError there too)"""
+    for t in types:
+        cfg = dict(type=t, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30)
+        if kind == 'ScaleNet':
+            cfg.update(resizeFactor=2, nDims=3)
+        _check_net_against(RH.describe_reference_net(kind, **cfg))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -516,3 +519,13 @@ def test_live_reference_importer_constants():
             assert np.array_equal(r.jointImgTo3D(uvd), p.jointImgTo3D(uvd))
         assert np.array_equal(r.joints3DToImg(pts), p.joints3DToImg(pts))
         assert np.array_equal(r.jointsImgTo3D(pts), p.jointsImgTo3D(pts))
+
+
+@live
+@pytest.mark.parametrize('kind,cfg,train', [
+    ('ResNet', dict(type=4, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30), True),      # dropout + 30-D bottleneck
+    ('ResNet', dict(type=2, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30), False),
+    ('PoseRegNet', dict(type=11, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30), True),
+    ('ScaleNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, resizeFactor=2, numJoints=1, nDims=3), True)])
+def test_live_reference_arithmetic_other_types(kind, cfg, train):
+    _check_net_eval(kind, cfg, 555, train, MK.net_eval_case(kind, cfg, 555, train))
