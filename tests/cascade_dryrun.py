@@ -108,6 +108,9 @@ class FakeEngine:
         self.output_sym = net.output
         if len(dims) == 3:
             self.onet = ON.build_scalenet(np.random.RandomState(23455), type=1, batchSize=self.B, numJoints=1, nDims=3)
+        elif type(net).__name__ == 'PoseRegNet':
+            self.onet = ON.build_poseregnet(np.random.RandomState(23455), type=0, batchSize=self.B,
+                                            numJoints=cfg.numJoints, nDims=cfg.nDims)
         else:
             self.onet = ON.build_resnet(np.random.RandomState(23455), type=1, batchSize=self.B, numJoints=cfg.numJoints, nDims=3)
     def _x(self): return [t.buf.permute(0, 3, 1, 2).contiguous() for t in self.t_ins]

@@ -196,9 +196,9 @@ def net_eval_case(kind, cfg, seed, train):
 
 
 NET_EVAL_CASES = [
-    ('resnet0_train', 'ResNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30), 11, True),
+    ('resnet0_train', 'ResNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=4, numJoints=1, nDims=30), 11, True),
     ('resnet1_det', 'ResNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=14, nDims=3), 12, False),
-    ('poseregnet0_train', 'PoseRegNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=3, numJoints=1, nDims=30), 13, True),
+    ('poseregnet0_train', 'PoseRegNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=4, numJoints=1, nDims=30), 13, True),
     ('poseregnet0_det', 'PoseRegNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30), 14, False),
     ('scalenet1_det', 'ScaleNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, resizeFactor=2, numJoints=1, nDims=3), 15, False),
 ]
