@@ -1,0 +1,59 @@
+"""GPU parity DIRECTLY against the reference's own code (not only through the oracle): see the test's docstring.
+Sorted last on purpose (pytest -x): it is the newest test of round 1."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_engine_against_reference_code_fixture():
+    """The CUDA path directly against the REFERENCE'S OWN CODE: tests/golden/reference_net_eval.npz holds what the
+    reference's layer constructors, cost expression and T.grad produce when evaluated eagerly (oracle/eager_theano.py
+    stands in for Theano's primitives; made by tests/golden/make_reference_vectors.py in the build container).
+    Same seeds -> same initial weights (pinned bit for bit in tests/test_reference_pins.py), same inputs; outputs and
+    cost within north_star's 1e-4 relative."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_reference_vectors as MK
+    from net.resnet import ResNet, ResNetParams
+    from net.poseregnet import PoseRegNet, PoseRegNetParams
+    from net.scalenet import ScaleNet, ScaleNetParams
+    from dpp_b200.engine import Engine
+    NE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_net_eval.npz'))
+    cases = {c[0]: c for c in MK.NET_EVAL_CASES}
+    # deterministic forward passes through the reference call surface
+    for tag, N, P in (('resnet1_det', ResNet, ResNetParams), ('poseregnet0_det', PoseRegNet, PoseRegNetParams),
+                      ('scalenet1_det', ScaleNet, ScaleNetParams)):
+        _, kind, cfg, seed, train = cases[tag]
+        xs, _ = MK.net_eval_inputs(kind, cfg, seed, train)
+        net = N(np.random.RandomState(23455), cfgParams=P(**cfg))
+        net.setDeterministic()
+        out = net.computeOutput(xs if len(xs) > 1 else xs[0])
+        r = _rel(out, NE[tag + '__out'])
+        print(tag, "vs reference code: rel err", r)
+        assert out.shape == NE[tag + '__out'].shape and r < 1e-4
+    # training graph: batch statistics forward, cost
+    _, kind, cfg, seed, train = cases['resnet0_train']
+    xs, y = MK.net_eval_inputs(kind, cfg, seed, train)
+    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(**cfg))
+    eng = Engine(net, precision=1)
+    net._eng = eng
+    eng.set_input_nchw(xs[0])
+    out = eng.forward_device(deterministic=False).cpu().numpy()
+    r = _rel(out, NE['resnet0_train__out'])
+    print("resnet0_train forward vs reference code: rel err", r)
+    assert r < 1e-4
+    eng._alloc_training()
+    eng.y_in.copy_(torch.from_numpy(y))
+    cost = float(eng.train_step(1e-3, use_graph=False).cpu()[0])
+    ref_cost = float(NE['resnet0_train__cost'])
+    print("resnet0_train cost", cost, "reference code", ref_cost)
+    assert abs(cost - ref_cost) <= 1e-4 * abs(ref_cost)
