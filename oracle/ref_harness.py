@@ -377,3 +377,60 @@ def reference_checkpoint_roundtrip(kind, cfg, save_path=None, load_path=None, se
             for p in list(l.params) + list(getattr(l, 'params_nontrained', [])):
                 vals[p.name] = np.array(p.get_value(), copy=True)
         return dict(values=vals, network=str(net))
+
+
+def run_reference_adam(param_values, grads_per_step, learning_rates):
+    """The reference's Optimizer.ADAM (trainer/optimizer.py:58-90) evaluated with oracle/eager_theano.py over several
+    steps.  An eager graph is one-shot, so every step rebuilds the update expressions with the optimiser state of the
+    previous step (t, first / second moments) installed into the shared variables ADAM() creates, in creation
+    order.  Returns the parameter values after every step (list of lists, float64)."""
+    import numpy as np
+    from oracle import eager_theano as E
+    fake = E.build_modules()
+    theano, T = fake['theano'], fake['theano.tensor']
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    if not hasattr(np, 'cast'):
+        class _Cast(dict):
+            def __missing__(self, k):
+                return lambda v: np.asarray(v, dtype=k)[()]
+        np.cast = _Cast()
+        added_cast = True
+    else:
+        added_cast = False
+    try:
+        adam = reference_function('trainer/optimizer.py', 'ADAM', {'theano': theano, 'T': T, 'numpy': np})
+        values = [np.asarray(p, np.float64).copy() for p in param_values]
+        state = None                                       # (t, [m0, v0, m1, v1, ...])
+        history = []
+        for grads, lr in zip(grads_per_step, learning_rates):
+            created = []
+
+            def shared(value=None, name=None, borrow=False, **kw):
+                k = len(created)
+                if state is not None:
+                    value = np.asarray(state[0] if k == 0 else state[1][k - 1], dtype=np.asarray(value).dtype)
+                s = E.Shared(value, name, borrow)
+                created.append(s)
+                return s
+            theano.shared = shared
+            params = [E.Shared(v.astype(np.float32), 'p%d' % i) for i, v in enumerate(values)]
+            for p, v in zip(params, values):                   # keep float64 state between the rebuilt steps
+                p.set_value(v)
+            created.clear()
+            opt = types.SimpleNamespace(params=params, grads=[E.ET(np.asarray(g, np.float64)) for g in grads],
+                                        updates=[], shared=[])
+            updates = adam(opt, E.ET(np.float64(lr)))
+            new = {id(s): v.eval().copy() for s, v in updates}
+            values = [new[id(p)] for p in params]
+            state = (new[id(created[0])], [new[id(s)] for s in created[1:]])
+            history.append([v.copy() for v in values])
+        return history
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        if added_cast:
+            del np.cast

@@ -529,3 +529,28 @@ def test_live_reference_importer_constants():
     ('ScaleNet', dict(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, resizeFactor=2, numJoints=1, nDims=3), True)])
 def test_live_reference_arithmetic_other_types(kind, cfg, train):
     _check_net_eval(kind, cfg, 555, train, MK.net_eval_case(kind, cfg, 555, train))
+
+
+@live
+def test_live_reference_adam_over_several_steps():
+    """Optimizer.ADAM (trainer/optimizer.py:58-90) evaluated from the reference source for 5 consecutive steps (state
+    carried between the rebuilt graphs) against oracle.Adam - the timestep-dependent parts (bias corrections
+    1 - beta^t, beta1 * gamma^(t-1), t += 1) are what a single step cannot show.  The reference evaluation is float64,
+    the oracle folds constants in float32 like a floatX graph: 1e-5 of the accumulated update."""
+    import torch
+    from oracle import nets as ON
+    rng = np.random.RandomState(12)
+    shapes = [(7, 5), (11,)]
+    p0 = [rng.randn(*s).astype(f32) for s in shapes]
+    grads = [[(rng.randn(*s) * (10. ** rng.uniform(-3, 1))).astype(f32) for s in shapes] for _ in range(5)]
+    lrs = [1e-3, 1e-3, 3e-4, 3e-4, 1e-4]
+    hist = RH.run_reference_adam(p0, grads, lrs)
+    ps = [torch.tensor(p.copy()) for p in p0]
+    adam = ON.Adam(ps)
+    for step in range(5):
+        adam.step([torch.from_numpy(g) for g in grads[step]], lrs[step])
+        for p, want, start in zip(ps, hist[step], p0):
+            moved = np.abs(want - start).max()
+            # + a few float32 ulps of the parameter itself (the oracle stores float32, the eager run float64)
+            assert np.abs(p.numpy() - want).max() <= 1e-5 * moved + 4 * ULP * np.abs(want).max(), step
+    assert float(adam.t) == 6.0
