@@ -240,10 +240,12 @@ class HandDetector(object):
             raise ValueError("Size must be 3D and dsize 2D bounding box")
         if com is None or docom is True:
             raise NotImplementedError("CoM estimation from the depth map is outside the B200 path")
-        if self.importer is None:
-            raise ValueError("cropArea3D needs the importer's camera model")
+        di = self.importer
+        if di is None:        # the raw crop does not depend on the camera model (only the caller's normalisation does)
+            import types
+            di = types.SimpleNamespace(ux=0., uy=0., fx=1., fy=1., flip_y=False)
         coms = np.asarray(com)[None]
-        rec, M, _ = pose_records(coms, size, self.fx, self.fy, self.importer, self.dpt.shape, self.getNDValue(), dsize)
+        rec, M, _ = pose_records(coms, size, self.fx, self.fy, di, self.dpt.shape, self.getNDValue(), dsize)
         rec['flags'] = 0                                     # raw crop in mm: the caller normalises
         frames = self._frame_dev()
         out = torch.empty((1, dsize[1], dsize[0]), dtype=torch.float32, device=frames.device)
