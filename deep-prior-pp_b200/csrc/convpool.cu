@@ -374,10 +374,18 @@ int make_dims(CPDims &d, int N, int H, int W, int Cin, int Cout, int k, int pad,
 
 }  // namespace
 
+// convpool8.cu: opt-in specialised kernels for the 8-filter 'valid' towers (DPP_CONVPOOL_FAST=1)
+int dpp_convpool8_try(const float *x, const float *w, const float *bias, float *y, uint8_t *argmax, double *stats, int N,
+                      int H, int W, int Cin, int Cout, int k, int pad, int pool, int relu, void *stream);
+
 extern "C" int dpp_convpool_fwd(const float *x, const float *w, const float *bias, float *y, uint8_t *argmax,
                                 double *stats, int N, int H, int W, int Cin, int Cout, int k, int pad, int pool,
                                 int relu, void *stream) {
     DPP_CHECK_ARG(x && w && bias && y && N > 0 && Cin > 0 && Cout > 0 && k > 0 && pool >= 1 && pool <= 8);
+    {
+        const int rc8 = dpp_convpool8_try(x, w, bias, y, argmax, stats, N, H, W, Cin, Cout, k, pad, pool, relu, stream);
+        if (rc8 != DPP_ENOTSUP) return rc8;
+    }
     CPDims d;
     DPP_CHECK_ARG(make_dims(d, N, H, W, Cin, Cout, k, pad, pool) == 0);
     size_t smem = sizeof(float) * ((size_t)k * k * Cin * Cout + (size_t)d.patch * d.patch * Cin + 2 * Cout);
