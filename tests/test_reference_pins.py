@@ -554,3 +554,87 @@ def test_live_reference_adam_over_several_steps():
             # + a few float32 ulps of the parameter itself (the oracle stores float32, the eager run float64)
             assert np.abs(p.numpy() - want).max() <= 1e-5 * moved + 4 * ULP * np.abs(want).max(), step
     assert float(adam.t) == 6.0
+
+
+@live
+def test_live_reference_layer_params_classes():
+    """Every *LayerParams class on the path: derived dimensions, memory requirement, activation name and output range
+    after construction and after reassigning inputDim / filters / stride / pool size, reference vs product."""
+    from unittest import mock
+    import importlib
+    theano = mock.MagicMock()
+    theano.config.floatX = 'float32'
+    fake = {'theano': theano, 'theano.tensor': theano.tensor}
+
+    def snapshot(p):
+        out = {}
+        for k in ('inputDim', 'outputDim', 'activation_str', 'filter_shape', 'image_shape', 'stride', 'border_mode',
+                  'nFilters', 'filterDim', 'poolsize', 'poolType', 'hasBias'):
+            if hasattr(p, k):
+                v = getattr(p, k)
+                out[k] = tuple(int(x) for x in v) if isinstance(v, (tuple, list)) else v
+        out['mem'] = int(p.getMemoryRequirement()) if hasattr(p, 'getMemoryRequirement') else None
+        out['range'] = [float(x) for x in p.getOutputRange()]
+        return out
+
+    def relu_like(mods):
+        return mods['util.theano_helpers'].ReLU
+
+    with RH._reference_net_modules(fake) as mods:
+        ref_cases = []
+        R = mods
+        act = relu_like(mods)
+        cp = R['net.convpoollayer'].ConvPoolLayerParams(inputDim=(4, 1, 128, 128), nFilters=8, filterDim=(5, 5),
+                                                        poolsize=(4, 4), activation=act)
+        ref_cases.append(('cp', snapshot(cp)))
+        cp.inputDim = (4, 1, 64, 64)
+        cp.poolsize = (2, 2)
+        ref_cases.append(('cp2', snapshot(cp)))
+        cv = R['net.convlayer'].ConvLayerParams(inputDim=(4, 32, 64, 64), nFilters=16, filterDim=(1, 1), stride=(2, 2),
+                                                border_mode='same', activation=None, init_method='He')
+        ref_cases.append(('cv', snapshot(cv)))
+        cv.filterDim = (3, 3)
+        cv.stride = (1, 1)
+        cv.nFilters = 64
+        ref_cases.append(('cv2', snapshot(cv)))
+        cv.border_mode = 'valid'
+        ref_cases.append(('cv3', snapshot(cv)))
+        hl = R['net.hiddenlayer'].HiddenLayerParams(inputDim=(4, 16384), outputDim=(4, 1024), activation=act)
+        ref_cases.append(('hl', snapshot(hl)))
+        hn = R['net.hiddenlayer'].HiddenLayerParams(inputDim=(4, 30), outputDim=(4, 42), activation=None)
+        ref_cases.append(('hn', snapshot(hn)))
+        bn = R['net.batchnormlayer'].BatchNormLayerParams(inputDim=(4, 64, 8, 8))
+        ref_cases.append(('bn', snapshot(bn)))
+        nl = R['net.nonlinearitylayer'].NonlinearityLayerParams(inputDim=(4, 64, 8, 8), activation=act)
+        ref_cases.append(('nl', snapshot(nl)))
+        dr = R['net.dropoutlayer'].DropoutLayerParams(inputDim=(4, 1024), outputDim=(4, 1024))
+        ref_cases.append(('dr', snapshot(dr)))
+    from util.theano_helpers import ReLU
+    from net.convpoollayer import ConvPoolLayerParams
+    from net.convlayer import ConvLayerParams
+    from net.hiddenlayer import HiddenLayerParams
+    from net.batchnormlayer import BatchNormLayerParams
+    from net.nonlinearitylayer import NonlinearityLayerParams
+    from net.dropoutlayer import DropoutLayerParams
+    mine = []
+    cp = ConvPoolLayerParams(inputDim=(4, 1, 128, 128), nFilters=8, filterDim=(5, 5), poolsize=(4, 4), activation=ReLU)
+    mine.append(('cp', snapshot(cp)))
+    cp.inputDim = (4, 1, 64, 64)
+    cp.poolsize = (2, 2)
+    mine.append(('cp2', snapshot(cp)))
+    cv = ConvLayerParams(inputDim=(4, 32, 64, 64), nFilters=16, filterDim=(1, 1), stride=(2, 2), border_mode='same',
+                         activation=None, init_method='He')
+    mine.append(('cv', snapshot(cv)))
+    cv.filterDim = (3, 3)
+    cv.stride = (1, 1)
+    cv.nFilters = 64
+    mine.append(('cv2', snapshot(cv)))
+    cv.border_mode = 'valid'
+    mine.append(('cv3', snapshot(cv)))
+    mine.append(('hl', snapshot(HiddenLayerParams(inputDim=(4, 16384), outputDim=(4, 1024), activation=ReLU))))
+    mine.append(('hn', snapshot(HiddenLayerParams(inputDim=(4, 30), outputDim=(4, 42), activation=None))))
+    mine.append(('bn', snapshot(BatchNormLayerParams(inputDim=(4, 64, 8, 8)))))
+    mine.append(('nl', snapshot(NonlinearityLayerParams(inputDim=(4, 64, 8, 8), activation=ReLU))))
+    mine.append(('dr', snapshot(DropoutLayerParams(inputDim=(4, 1024), outputDim=(4, 1024)))))
+    for (tag, r), (_, m) in zip(ref_cases, mine):
+        assert r == m, (tag, r, m)
