@@ -1,8 +1,9 @@
 """Camera models of the dataset importers (reference: src/data/importers.py: DepthImporter
 :51-150, ICVLImporter :186-210, MSRA15Importer :536-570 + :756-793, NYUImporter :880-920 +
 :1187-1224).  Only the pin-hole projections and per-dataset constants are on the hot path
-(augmentation label math); the file readers are out of scope (datasets are absent - synthetic
-inputs come from ``data.synthetic``).
+(augmentation label math); the file readers are out of scope (datasets are absent):
+``loadSequence`` keeps its signature and returns a deterministic synthetic ``NamedImgSequence``
+(``data.synthetic``) so that the entry scripts' data preparation runs unchanged.
 
 dtype discipline: the reference ran on NumPy 1.x value-based casting, where
 ``np.float32 scalar (op) python float`` is computed in float64 and only the store into the
@@ -65,6 +66,35 @@ class DepthImporter(object):
         ret[2] = sample[2]
         return ret
 
+    # -- sequences ----------------------------------------------------------------------------------------------
+    _dataset_name = None            # key of data.synthetic.DATASETS; set by the dataset importers
+
+    def _synthetic_sequence(self, seqName, Nmax, shuffle, rng, cube):
+        """``loadSequence`` without dataset files.  The readers of the reference (importers.py:233-372, :597-735,
+        :943-1087: PNG / binary depth maps, annotation files, hand detection, pickle cache) are out of scope and the
+        datasets are absent; what the rest of the pipeline consumes is the returned ``NamedImgSequence`` of
+        ``DepthFrame``s, which ``data.synthetic.generate_sequence`` builds with the same fields, dtypes and value
+        ranges.  The sequence is deterministic per (dataset, sequence name); count: ``Nmax`` or DPP_SYNTH_FRAMES."""
+        import os
+        import zlib
+        from data import synthetic
+        from data.basetypes import NamedImgSequence
+        if cube is None:
+            cube = self.default_cubes[seqName]
+        else:
+            assert isinstance(cube, tuple)
+            assert len(cube) == 3
+        n = int(os.environ.get('DPP_SYNTH_FRAMES', '256'))
+        if Nmax != float('inf'):
+            n = min(n, int(Nmax))
+        seed = zlib.crc32(('%s/%s' % (self._dataset_name, seqName)).encode()) % (2 ** 31)
+        seq = synthetic.generate_sequence(self._dataset_name, n, seed=seed, cube=cube, seq_name=seqName)
+        data = list(seq.data)
+        if shuffle and rng is not None:
+            print("Shuffling")
+            rng.shuffle(data)                           # importers.py:368-370
+        return NamedImgSequence(seqName, data, {'cube': cube})
+
     def getCameraProjection(self):
         ret = np.zeros((4, 4), np.float32)
         ret[0, 0] = self.fx
@@ -86,6 +116,12 @@ class ICVLImporter(DepthImporter):
         self.refineNet = refineNet
         self.default_cubes = {'train': (250, 250, 250), 'test_seq_1': (250, 250, 250), 'test_seq_2': (250, 250, 250)}
         self.sides = {'train': 'right', 'test_seq1': 'right', 'test_seq_2': 'right'}       # (sic) importers.py:211
+        self._dataset_name = 'ICVL'
+
+    def loadSequence(self, seqName, subSeq=None, Nmax=float('inf'), shuffle=False, rng=None, docom=False, cube=None):
+        if (subSeq is not None) and (not isinstance(subSeq, list)):
+            raise TypeError("subSeq must be None or list")
+        return self._synthetic_sequence(seqName, Nmax, shuffle, rng, cube)
 
 
 class MSRA15Importer(DepthImporter):
@@ -102,6 +138,12 @@ class MSRA15Importer(DepthImporter):
                               'P3': (180, 180, 180), 'P4': (180, 180, 180), 'P5': (180, 180, 180),
                               'P6': (170, 170, 170), 'P7': (160, 160, 160), 'P8': (150, 150, 150)}
         self.sides = dict((k, 'right') for k in self.default_cubes)
+        self._dataset_name = 'MSRA15'
+
+    def loadSequence(self, seqName, subSeq=None, Nmax=float('inf'), shuffle=False, rng=None, docom=False, cube=None):
+        if (subSeq is not None) and (not isinstance(subSeq, list)):
+            raise TypeError("subSeq must be None or list")
+        return self._synthetic_sequence(seqName, Nmax, shuffle, rng, cube)
 
 
 class NYUImporter(DepthImporter):
@@ -120,3 +162,7 @@ class NYUImporter(DepthImporter):
         self.sides = dict((k, 'right') for k in self.default_cubes)
         self.restrictedJointsEval = [0, 3, 6, 9, 12, 15, 18, 21, 24, 25, 27, 30, 31, 32]
         self.refineNet = refineNet
+        self._dataset_name = 'NYU'
+
+    def loadSequence(self, seqName, Nmax=float('inf'), shuffle=False, rng=None, docom=False, cube=None):
+        return self._synthetic_sequence(seqName, Nmax, shuffle, rng, cube)

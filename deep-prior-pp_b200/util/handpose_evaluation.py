@@ -99,3 +99,42 @@ class HandposeEvaluation(object):
 
     def getJointNumFramesWithinMaxDist(self, dist, jointID):
         return int((self._errors()[0][:, jointID] <= dist).sum())
+
+    # -- plots (matplotlib / vtk): out of scope ------------------------------------------------------------------
+    def plotEvaluation(self, basename, methodName='Our method', baseline=None):
+        raise NotImplementedError("evaluation plots (matplotlib) are outside the B200 path; the metrics are available "
+                                  "through the get* methods")
+
+    plotResult = plotJoints = plotResult3D = plotEvaluation
+
+
+class ICVLHandposeEvaluation(HandposeEvaluation):
+    """handpose_evaluation.py:684-737 without the plot styling: 16 joints (C, T1-3, I1-3, M1-3, R1-3, P1-3)."""
+
+    def __init__(self, gt, joints, dolegend=True, linewidth=1):
+        super(ICVLHandposeEvaluation, self).__init__(gt, joints, dolegend, linewidth)
+        self.jointNames = ['C'] + ['%s%d' % (f, k) for f in 'TIMRP' for k in (1, 2, 3)]
+        self.plotMaxJointDist = 80
+        self.fps = 10.0
+
+
+class NYUHandposeEvaluation(HandposeEvaluation):
+    """handpose_evaluation.py:740-850 without the plot styling; ``joints`` selects the 14 evaluation joints
+    ('eval', the entry scripts' setting) or all 36."""
+
+    def __init__(self, gt, joint, joints='eval', dolegend=True, linewidth=1):
+        super(NYUHandposeEvaluation, self).__init__(gt, joint, dolegend, linewidth)
+        if joints not in ('eval', 'all'):
+            raise ValueError("Unknown joint parameter")
+        self.plotMaxJointDist = 80
+        self.fps = 25.0
+
+
+class MSRAHandposeEvaluation(HandposeEvaluation):
+    """handpose_evaluation.py:853-910 without the plot styling: 21 joints (wrist + 4 per finger)."""
+
+    def __init__(self, gt, joints, dolegend=True, linewidth=1):
+        super(MSRAHandposeEvaluation, self).__init__(gt, joints, dolegend, linewidth)
+        self.jointNames = ['C'] + ['%s%d' % (f, k) for f in 'TIMRP' for k in (1, 2, 3, 4)]
+        self.plotMaxJointDist = 80
+        self.fps = 20.0

@@ -99,6 +99,9 @@ from oracle import nets as ON
 class FakeT:
     def __init__(self, shape): self.shape = tuple(shape); self.buf = torch.zeros((shape[0], shape[2], shape[3], shape[1]))
 class FakeEngine:
+    """forward-only stand-in for dpp_b200.engine.Engine: the oracle net of the same architecture, carrying the PRODUCT
+    net's current parameter values (and its appended PCA prior layer, main_nyu_posereg_embedding.py:148-158)"""
+
     def __init__(self, net):
         cfg = net.cfgParams
         self.dev = torch.device('cpu')
@@ -106,23 +109,58 @@ class FakeEngine:
         dims = cfg.inputDim if isinstance(cfg.inputDim, list) else [cfg.inputDim]
         self.t_ins = [FakeT(d) for d in dims]
         self.output_sym = net.output
-        if len(dims) == 3:
-            self.onet = ON.build_scalenet(np.random.RandomState(23455), type=1, batchSize=self.B, numJoints=1, nDims=3)
-        elif type(net).__name__ == 'PoseRegNet':
-            self.onet = ON.build_poseregnet(np.random.RandomState(23455), type=0, batchSize=self.B,
-                                            numJoints=cfg.numJoints, nDims=cfg.nDims)
+        self.ops = [dict(kind="conv"), dict(kind="fc"), dict(kind="concat", srcs=[1, 2, 3])]
+        kind = type(net).__name__
+        nd = net.layers[-1].cfgParams.outputDim[1]
+        n_own = len(cfg.layers) if getattr(cfg, 'layers', None) else None      # layers the net class itself built
+        extra = [] if n_own is None else net.layers[n_own:]
+        if kind == 'ScaleNet':
+            self.onet = ON.build_scalenet(np.random.RandomState(23455), type=cfg_type(net), batchSize=self.B, numJoints=1, nDims=3)
+        elif kind == 'PoseRegNet':
+            base_out = net.layers[n_own - 1].cfgParams.outputDim[1] if extra else nd
+            self.onet = ON.build_poseregnet(np.random.RandomState(23455), type=cfg_type(net), batchSize=self.B,
+                                            numJoints=1, nDims=base_out)
         else:
-            self.onet = ON.build_resnet(np.random.RandomState(23455), type=1, batchSize=self.B, numJoints=cfg.numJoints, nDims=3)
-    def _x(self): return [t.buf.permute(0, 3, 1, 2).contiguous() for t in self.t_ins]
+            extra = []
+            self.onet = ON.build_resnet(np.random.RandomState(23455), type=cfg_type(net), batchSize=self.B,
+                                        numJoints=1, nDims=nd)
+        own_params = [p for l in (net.layers[:n_own] if n_own else net.layers) for p in l.params]
+        assert len(own_params) == len(self.onet.params)
+        with torch.no_grad():
+            for po, pp in zip(self.onet.params, own_params):
+                po.copy_(torch.from_numpy(np.asarray(pp.get_value(), np.float64)).to(po.dtype).reshape(po.shape))
+        for l in extra:                                  # the PCA prior layer(s) appended by the entry script
+            ON.append_pca_layer(self.onet, l.W.get_value(), l.b.get_value())
+
+    def _x(self):
+        return [t.buf.permute(0, 3, 1, 2).contiguous() for t in self.t_ins]
+
     def forward_device(self, deterministic=True):
         with torch.no_grad():
             xs = self._x()
             o, _ = self.onet.forward(xs if len(xs) > 1 else xs[0], deterministic=True)
         return o
+
     def forward_host(self, batch, deterministic=True):
-        for t, b in zip(self.t_ins, batch): t.buf.copy_(torch.from_numpy(b).permute(0, 2, 3, 1))
+        for t, b in zip(self.t_ins, batch):
+            t.buf.copy_(torch.from_numpy(b).permute(0, 2, 3, 1))
         return self.forward_device().numpy()
-    def release(self): pass
+
+    def release(self):
+        pass
+
+
+def cfg_type(net):
+    """ResNetParams keeps its type; the PoseRegNet / ScaleNet parameter classes do not (like the reference's):
+    type 0 of PoseRegNet has 8 layers, type 11 has 9 (tests/golden/reference_nets.json); ScaleNet is type 1 only."""
+    kind = type(net).__name__
+    if kind == 'ResNet':
+        return net.cfgParams.type
+    if kind == 'ScaleNet':
+        return 1
+    return 0 if len(net.cfgParams.layers) == 8 else 11
+
+
 from net import netbase
 def _engine(self):
     eng = getattr(self, '_eng', None)
@@ -144,3 +182,78 @@ import test_gpu_poses as TP
 for name in ['NYU', 'ICVL', 'MSRA15']:
     TP.test_sample_random_poses_matches_oracle(name); TP.test_sample_random_poses_matches_reference_fixture(name)
 print('poses ok')
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's OWN entry scripts against the product package (build container only: needs /root/reference)
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference_entry_script(script, workdir):
+    """Executes /root/reference/src/<script> - py2 -> py3 pass in memory (oracle/ref_harness.py), nothing else changed -
+    with ``deep-prior-pp_b200/`` as its ``src/``.  Everything the script does on the host runs for real: sequences from
+    the importers (synthetic backend), Dataset stacks, side arrays, HandDetector.sampleRandomPoses + PCA, network and
+    trainer construction, setData / addStaticData / addManagedData / compileFunctions, later save(), the PCA prior
+    layer, computeOutput() and the HandposeEvaluation metrics.  Replaced: the device (see the top of this file),
+    ``train()`` itself (returns made-up costs: the training loop is a GPU test, tests/test_gpu_trainer.py) and
+    matplotlib.  The run ends where the script asks for other methods' published result files (``loadBaseline``)."""
+    import ast
+    import pickle
+    import types
+    from unittest import mock
+    from oracle import ref_harness as RH
+    import trainer.poseregnettrainer as TP
+    plt = mock.MagicMock()
+    mpl = types.ModuleType('matplotlib')
+    mpl.use = lambda *a, **k: None
+    mpl.pyplot = plt
+    stubs = {'matplotlib': mpl, 'matplotlib.pyplot': plt, 'cPickle': pickle}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    calls = []
+
+    def fake_train(self, n_epochs=50, storeFilters=False):
+        calls.append(n_epochs)
+        return [1.0, 0.5], [], [[0.3, 0.2]]
+    real_train, TP.PoseRegNetTrainer.train = TP.PoseRegNetTrainer.train, fake_train
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    os.makedirs('eval', exist_ok=True)
+    text = RH.py3_source(os.path.join(RH.REF_SRC, script))
+    tree = ast.fix_missing_locations(RH._Div().visit(ast.parse(text, filename=script)))
+    g = {'__name__': '__main__', '__file__': script, '_py2div': RH._py2div, 'xrange': range}
+    ended = None
+    try:
+        exec(compile(tree, script, 'exec'), g)
+        ended = 'completed'
+    except AttributeError as e:
+        if 'loadBaseline' not in str(e):
+            raise
+        ended = 'loadBaseline'
+    finally:
+        os.chdir(cwd)
+        TP.PoseRegNetTrainer.train = real_train
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert calls, "the script never reached train()"
+    hpe = g.get('hpe')
+    return ended, calls, g, hpe
+
+
+if __name__ == '__main__' or True:
+    from oracle import ref_harness as _RH
+    if _RH.available():
+        import tempfile
+        os.environ.setdefault('DPP_SYNTH_FRAMES', '40')
+        for script in ('main_nyu_posereg_embedding.py', 'main_icvl_posereg_embedding.py'):
+            with tempfile.TemporaryDirectory() as d:
+                ended, calls, g, hpe = run_reference_entry_script(script, d)
+            joints = g['joints']
+            print(script, 'ran to', ended, '| train(n_epochs=%d)' % calls[0], '| joints', joints.shape,
+                  '| mean error %.1f mm' % hpe.getMeanError())
+            assert ended == 'loadBaseline' and joints.shape[1:] == (g['train_gt3D'].shape[1], 3)
+            assert g['poseNet'].cfgParams.numJoints == g['train_gt3D'].shape[1] and np.isfinite(hpe.getMeanError())
+        print('entry scripts ok')
+    else:
+        print('entry scripts skipped (no /root/reference)')

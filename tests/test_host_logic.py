@@ -230,3 +230,30 @@ def test_trainer_record_worker_matches_per_sample_path():
     assert labels.dtype == np.float32 and labels.shape == (16, 30)
     empty = _records_chunk(((hd, di, modes, ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], None), [], []))
     assert len(empty[0]) == 0
+
+
+def test_importers_load_synthetic_sequences_with_reference_signature():
+    """data/importers.py ``loadSequence`` (reference importers.py:233, :597, :943 signatures) without dataset files."""
+    from data.importers import NYUImporter, ICVLImporter, MSRA15Importer
+    from data.basetypes import NamedImgSequence, DepthFrame
+    rng = np.random.RandomState(23455)
+    di = NYUImporter('../data/NYU/', refineNet=None)
+    s1 = di.loadSequence('train', Nmax=6, shuffle=True, rng=rng, docom=False)
+    s2 = di.loadSequence('test_1', Nmax=4, docom=False)
+    assert isinstance(s1, NamedImgSequence) and s1.name == 'train' and len(s1.data) == 6 and len(s2.data) == 4
+    assert s1.config == {'cube': (300, 300, 300)} and isinstance(s1.data[0], DepthFrame)
+    f = s1.data[0]
+    assert f.dpt.shape == (128, 128) and f.dpt.dtype == np.float32 and f.gt3Dcrop.shape == (14, 3)
+    assert f.T.shape == (3, 3) and f.com.shape == (3,) and f.gtorig.shape == (14, 3) and f.gtcrop.shape == (14, 3)
+    assert np.allclose(f.gt3Dorig, f.gt3Dcrop + f.com)
+    again = NYUImporter(None).loadSequence('train', Nmax=6)           # deterministic per (dataset, sequence)
+    assert sorted(float(x.com[2]) for x in again.data) == sorted(float(x.com[2]) for x in s1.data)
+    assert [float(x.com[2]) for x in again.data] != [float(x.com[2]) for x in s1.data]        # s1 was shuffled
+    assert len(ICVLImporter(None).loadSequence('train', ['0'], Nmax=3, cube=(200, 200, 200)).data) == 3
+    assert ICVLImporter(None).loadSequence('test_seq_1', Nmax=2).data[0].gt3Dcrop.shape == (16, 3)
+    m = MSRA15Importer(None).loadSequence('P3', Nmax=2)
+    assert m.config['cube'] == (180, 180, 180) and m.data[0].gt3Dcrop.shape == (21, 3)
+    with pytest.raises(TypeError):
+        ICVLImporter(None).loadSequence('train', subSeq='0')
+    with pytest.raises(KeyError):
+        NYUImporter(None).loadSequence('no_such_sequence')

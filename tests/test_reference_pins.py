@@ -638,3 +638,53 @@ def test_live_reference_layer_params_classes():
     mine.append(('dr', snapshot(DropoutLayerParams(inputDim=(4, 1024), outputDim=(4, 1024)))))
     for (tag, r), (_, m) in zip(ref_cases, mine):
         assert r == m, (tag, r, m)
+
+
+@live
+def test_live_reference_helpers_and_entry_script_imports():
+    """(1) util/helpers.py against the reference's helpers (shuffle order with the same RandomState, chunks, cartesian,
+    gaussian_kernel).  (2) Every import statement of the reference's entry scripts (main_*_posereg_embedding*.py,
+    test_realtimepipeline.py) resolves against the product package: the scripts' own data preparation / training /
+    evaluation code finds the modules, classes and functions it names.  Stubbed: matplotlib (absent in this image,
+    plots are out of scope), cPickle (= pickle), util.cameradevice (camera capture, out of scope)."""
+    import ast
+    import sys
+    import types
+    import util.helpers as PH
+    RHm = RH.load_module('ref_helpers_tmp', 'util/helpers.py')
+    sys.modules.pop('ref_helpers_tmp', None)
+    a = [np.arange(40).reshape(20, 2).copy(), np.arange(20).copy()]
+    b = [x.copy() for x in a]
+    RHm.shuffle_many_inplace(a, np.random.RandomState(4))
+    PH.shuffle_many_inplace(b, np.random.RandomState(4))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and not np.array_equal(a[1], np.arange(20))
+    assert list(RHm.chunks(list(range(11)), 4)) == list(PH.chunks(list(range(11)), 4))
+    assert np.array_equal(RHm.cartesian(([1, 2, 3], [4, 5], [6, 7])), PH.cartesian(([1, 2, 3], [4, 5], [6, 7])))
+    for k in (3, 5, 8):
+        np.testing.assert_allclose(RHm.gaussian_kernel(k), PH.gaussian_kernel(k), rtol=1e-6)
+    stubs = {'matplotlib': types.ModuleType('matplotlib'), 'matplotlib.pyplot': types.ModuleType('matplotlib.pyplot'),
+             'cPickle': __import__('pickle'), 'util.cameradevice': types.ModuleType('util.cameradevice')}
+    stubs['matplotlib'].use = lambda *a, **k: None
+    stubs['matplotlib'].pyplot = stubs['matplotlib.pyplot']
+    stubs['util.cameradevice'].CreativeCameraDevice = stubs['util.cameradevice'].FileDevice = object
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        for script in ('main_nyu_posereg_embedding.py', 'main_icvl_posereg_embedding.py',
+                       'main_msra15_posereg_embedding_crossval.py', 'test_realtimepipeline.py'):
+            tree = ast.parse(RH.py3_source(os.path.join(RH.REF_SRC, script)))
+            imports = [n for n in ast.walk(tree) if isinstance(n, (ast.Import, ast.ImportFrom))]
+            assert len(imports) >= 8
+            for node in imports:
+                code = compile(ast.Module(body=[node], type_ignores=[]), script, 'exec')
+                try:
+                    exec(code, {})
+                except Exception as e:      # name the statement that does not resolve
+                    raise AssertionError("%s: `%s` does not resolve against the product package: %r"
+                                         % (script, ast.unparse(node), e))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
