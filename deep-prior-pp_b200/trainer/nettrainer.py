@@ -222,9 +222,10 @@ class NetTrainer(object):
         d['train_y'] = f(self.train_data_yDB.reshape(self.train_data_yDB.shape[0], -1))
         nb = self.val_data_xDB.shape[0] // self.cfgParams.batch_size * self.cfgParams.batch_size
         d['val_x'] = f(self.val_data_xDB[:nb].reshape((nb,) + self.val_data_xDB.shape[-2:]))
-        d['val_y'] = f(self.val_data_yDB[:nb].reshape(nb, -1))
+        flat = lambda a: a[:nb].reshape(nb, int(numpy.prod(a.shape[1:])))      # nb may be 0: fewer validation samples than a batch
+        d['val_y'] = f(flat(self.val_data_yDB))
         if hasattr(self, 'val_data_y3DDB'):
-            d['val_y3D'] = f(self.val_data_y3DDB[:nb].reshape(nb, -1))
+            d['val_y3D'] = f(flat(self.val_data_y3DDB))
         self._dev_dirty = False
 
     # -- augmentation pipeline ----------------------------------------------------------------------

@@ -70,6 +70,16 @@ class FakeLib:
             _arr(fm, (n,), np.float32)[...] = np.nanmean(e, axis=1)
             _arr(fx, (n,), np.float32)[...] = np.nanmax(e, axis=1)
         return 0
+    def dpp_augment_fwd(self, crops, recs, out, n_out, H, W, st):
+        import augment_model
+        from dpp_b200.lib import AUG_REC_DTYPE
+        if n_out == 0:
+            return 0
+        rec = _arr(recs, (n_out,), np.dtype(AUG_REC_DTYPE))
+        src = _arr(crops, (int(rec['src_index'].max()) + 1, H, W), np.float32)
+        _arr(out, (n_out, H, W), np.float32)[...] = augment_model.run(src, rec, H, W)
+        return 0
+
     def dpp_sample_poses(self, bp, bc, bcu, mode, ridx, off, sc, cs, fx, fy, ux, uy, flip, o_p, o_c, o_cu, n, J, st):
         import poses_model
         md, ri = _arr(mode, (n,), np.int32), _arr(ridx, (n,), np.int32)
@@ -83,6 +93,8 @@ class FakeLib:
         return 0
 PC.lib = FakeLib()
 sys.modules['dpp_b200.lib'].lib = PC.lib
+import dpp_b200.augment as _AUG
+_AUG.lib = PC.lib
 torch.cuda.current_device = lambda: 0
 _DevT = torch.device
 
@@ -131,6 +143,28 @@ class FakeEngine:
                 po.copy_(torch.from_numpy(np.asarray(pp.get_value(), np.float64)).to(po.dtype).reshape(po.shape))
         for l in extra:                                  # the PCA prior layer(s) appended by the entry script
             ON.append_pca_layer(self.onet, l.W.get_value(), l.b.get_value())
+        self.net, self.own_params = net, own_params
+        self.t_in = self.t_ins[0]
+        self.y_in, self.adam = None, None
+        self.mask_gen = torch.Generator().manual_seed(1)
+
+    def _alloc_training(self):
+        if self.y_in is None:
+            self.y_in = torch.zeros((self.B, int(self.net.layers[-1].cfgParams.outputDim[1])), dtype=torch.float32)
+            self.adam = ON.Adam(self.onet.params)
+
+    def train_step(self, lr=None, use_graph=True):
+        """one oracle train step (batch statistics, dropout masks, ADAM, BN EMA) on the staged batch; the new weights
+        are written back to the product's variables like the device arena would hold them"""
+        self._alloc_training()
+        masks = [(torch.rand((self.B, int(l.cfgParams.outputDim[1])), generator=self.mask_gen) < l.prob_keep).double()
+                 for l in self.net.layers if type(l).__name__ == 'DropoutLayer'] or None
+        cfg = self.net.cfgParams
+        cost, _, _ = ON.train_step(self.onet, self.adam, self._x()[0], self.y_in.clone(), float(lr), cfg.numJoints,
+                                   cfg.nDims, masks=masks)
+        for po, pp in zip(self.onet.params, self.own_params):
+            pp.set_value(po.detach().numpy().astype(np.float32).reshape(pp.get_value().shape))
+        return torch.tensor([cost], dtype=torch.float32)
 
     def _x(self):
         return [t.buf.permute(0, 3, 1, 2).contiguous() for t in self.t_ins]
@@ -138,8 +172,8 @@ class FakeEngine:
     def forward_device(self, deterministic=True):
         with torch.no_grad():
             xs = self._x()
-            o, _ = self.onet.forward(xs if len(xs) > 1 else xs[0], deterministic=True)
-        return o
+            o, _ = self.onet.forward(xs if len(xs) > 1 else xs[0], deterministic=deterministic)
+        return o.float()                                  # the device buffers are float32
 
     def forward_host(self, batch, deterministic=True):
         for t, b in zip(self.t_ins, batch):
@@ -164,7 +198,7 @@ def cfg_type(net):
 from net import netbase
 def _engine(self):
     eng = getattr(self, '_eng', None)
-    if eng is None:
+    if eng is None or eng.output_sym is not self.output:      # rebuilt when layers were appended, like NetBase._engine
         eng = FakeEngine(self); self._eng = eng
     return eng
 netbase.NetBase._engine = _engine
@@ -193,8 +227,9 @@ def run_reference_entry_script(script, workdir):
     the importers (synthetic backend), Dataset stacks, side arrays, HandDetector.sampleRandomPoses + PCA, network and
     trainer construction, setData / addStaticData / addManagedData / compileFunctions, later save(), the PCA prior
     layer, computeOutput() and the HandposeEvaluation metrics.  Replaced: the device (see the top of this file),
-    ``train()`` itself (returns made-up costs: the training loop is a GPU test, tests/test_gpu_trainer.py) and
-    matplotlib.  The run ends where the script asks for other methods' published result files (``loadBaseline``)."""
+    the number of epochs (2 instead of 100; the loop itself - record workers, device augmentation from the
+    original crops, minibatches, validation observers, snapshots, best-parameter restore - runs with the oracle as the
+    arithmetic) and matplotlib.  The run ends where the script asks for other methods' published result files (``loadBaseline``)."""
     import ast
     import pickle
     import types
@@ -210,10 +245,13 @@ def run_reference_entry_script(script, workdir):
     sys.modules.update(stubs)
     calls = []
 
+    real_train = TP.PoseRegNetTrainer.train
+
     def fake_train(self, n_epochs=50, storeFilters=False):
-        calls.append(n_epochs)
-        return [1.0, 0.5], [], [[0.3, 0.2]]
-    real_train, TP.PoseRegNetTrainer.train = TP.PoseRegNetTrainer.train, fake_train
+        calls.append(n_epochs)                   # the scripts ask for 100 epochs; two are enough to walk the loop
+        self.verbose = False
+        return real_train(self, n_epochs=2, storeFilters=storeFilters)
+    TP.PoseRegNetTrainer.train = fake_train
     cwd = os.getcwd()
     os.chdir(workdir)
     os.makedirs('eval', exist_ok=True)
@@ -245,8 +283,10 @@ if __name__ == '__main__' or True:
     from oracle import ref_harness as _RH
     if _RH.available():
         import tempfile
-        os.environ.setdefault('DPP_SYNTH_FRAMES', '40')
-        for script in ('main_nyu_posereg_embedding.py', 'main_icvl_posereg_embedding.py'):
+        # 130 frames: two minibatches (the second padded with random real samples) and one full validation batch;
+        # 40 frames: fewer validation samples than a batch (the observers average over zero batches, like the reference)
+        for script, frames in (('main_nyu_posereg_embedding.py', '130'), ('main_icvl_posereg_embedding.py', '40')):
+            os.environ['DPP_SYNTH_FRAMES'] = frames
             with tempfile.TemporaryDirectory() as d:
                 ended, calls, g, hpe = run_reference_entry_script(script, d)
             joints = g['joints']

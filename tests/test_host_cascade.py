@@ -3,9 +3,9 @@ with the device faked (kernel emulated by tests/recrop_model.py, engines by the 
 it monkey-patches torch.cuda.  It validates records, batch padding, pointer hand-off, the RealtimeHandposePipeline and
 HandDetector surfaces; the CUDA kernels are validated by tests/test_gpu_cascade.py on the GPU.  Where /root/reference
 exists it also EXECUTES THE REFERENCE'S OWN ENTRY SCRIPTS (main_nyu / main_icvl_posereg_embedding.py, py2 -> py3 pass in
-memory) against the product package: data preparation, PCA on 1e6 sampled poses, network / trainer set-up, and - after
-a stubbed train() - save, PCA prior layer, computeOutput and the evaluation metrics all run through the product's
-classes unchanged."""
+memory) against the product package: data preparation, PCA on 1e6 sampled poses, network / trainer set-up, train()
+(two epochs, oracle arithmetic behind the emulated device), save, PCA prior layer, computeOutput and the evaluation
+metrics all run through the product's classes unchanged."""
 import os
 import subprocess
 import sys
