@@ -349,7 +349,10 @@ def run_b200(args):
                    "l2": "inputs (134 MB of crops + 0.9 GB of activations per step) exceed the 126 MB L2",
                    "precision_mode": precision},
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4,
+                "note": "per step: crops + augmentation records + labels copied from pinned host memory, cost read "
+                        "back; the records are built on the host BEFORE the timed region (vectorised, ~2 ms per batch "
+                        "on one thread, i.e. less than a step)"},
         "gpu_launches": n_launch * args.steps,
         "clocks": clk,
         "roofline": roof,
