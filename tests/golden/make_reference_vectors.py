@@ -6,7 +6,7 @@ Functions executed (reference file:line):
   trainer/nettrainer.py:919-997        NetTrainer.augmentCrop  (with HandDetector.moveCoM / rotateHand / scaleHand /
                                        recropHand / comToTransform / comToBounds, util/handdetector.py:204-258,678-803)
   util/handdetector.py:511-533,634-676 track (doHandSize=False) + refineCoM with a recording stub net
-  util/handdetector.py:382-490         cropArea3D (docom=False) [+ realtimehandposepipeline.py:327-332 restated inline]
+  util/realtimehandposepipeline.py:296-368  detect (tracking branch: track + cropArea3D + normalisation), estimatePose
   util/handdetector.py:805-909         sampleRandomPoses
   data/importers.py                    NYU / ICVL / MSRA15 jointImgTo3D, joint3DToImg
   net/*.py                             ResNet / PoseRegNet / ScaleNet constructors -> tests/golden/reference_nets.json
@@ -72,6 +72,42 @@ def augment_vectors(ref, name, n, seed):
     return {'augment_%s_%s' % (name, k): v for k, v in out.items()}
 
 
+class _Val(object):
+    def __init__(self, value):
+        self.value = value
+
+
+def reference_pipeline(ref, rdi, fx, fy, cube, comref_net, pose_net=None, right_hand=False):
+    """A stand-in ``self`` carrying the reference's OWN RealtimeHandposePipeline.detect / estimatePose
+    (util/realtimehandposepipeline.py:296-368, extracted and executed by oracle/ref_harness.py) in the tracking state
+    the realtime loop is in after initialisation."""
+    import types
+    from oracle import ref_harness as RH
+    g = {'numpy': np, 'HandDetector': ref['handdetector'].HandDetector}
+    p = types.SimpleNamespace(STATE_IDLE=0, STATE_INIT=1, STATE_RUN=2, HAND_LEFT=0, HAND_RIGHT=1,
+                              sync={'config': {'fx': fx, 'fy': fy, 'cube': tuple(cube)}}, importer=rdi,
+                              comrefNet=comref_net, poseNet=pose_net, state=_Val(2), tracking=_Val(True),
+                              hand=_Val(1 if right_hand else 0), lastcom=(0, 0, 0), handsizes=[], numinitframes=50,
+                              verbose=False)
+    p.detect = types.MethodType(RH.reference_function('util/realtimehandposepipeline.py', 'detect', g), p)
+    p.estimatePose = types.MethodType(RH.reference_function('util/realtimehandposepipeline.py', 'estimatePose', g), p)
+    return p
+
+
+class _PoseNetStub(object):
+    """what detect() asks the pose net for: its input size"""
+    def __init__(self, fn=None):
+        import types
+        dim = (1, 1, 128, 128)
+        self.cfgParams = types.SimpleNamespace(inputDim=dim)
+        self.layers = [types.SimpleNamespace(cfgParams=types.SimpleNamespace(inputDim=dim))]
+        self.fn, self.seen = fn, None
+
+    def computeOutput(self, x):
+        self.seen = np.array(x, copy=True)
+        return self.fn(x)
+
+
 def cascade_vectors(ref, name, n, seed):
     from data import synthetic
     from test_oracle_cascade import _tiny_fns
@@ -85,16 +121,12 @@ def cascade_vectors(ref, name, n, seed):
     acc = {k: [] for k in keys}
     for i in range(n):
         net = RecordingNet(refine_fn)
-        hd = ref['handdetector'].HandDetector(fr['frames'][i], fx, fy, importer=rdi, refineNet=net)
-        loc, _ = hd.track(lastcom[i].copy(), cube, doHandSize=False)
-        crop, M, com = hd.cropArea3D(com=loc, size=cube, dsize=(128, 128))
-        raw = crop.copy()
-        com3D = rdi.jointImgTo3D(com)
-        sc = (cube[2] / 2.)                          # realtimehandposepipeline.py:327-332
-        crop[crop == 0] = com3D[2] + sc
-        crop.clip(com3D[2] - sc, com3D[2] + sc)
-        crop -= com3D[2]
-        crop /= sc
+        pipe = reference_pipeline(ref, rdi, fx, fy, cube, net, _PoseNetStub())
+        pipe.lastcom = lastcom[i].copy()
+        crop, M, com3D = pipe.detect(fr['frames'][i])                # the reference's own detect(): track + cropArea3D
+        loc = pipe.lastcom                                           # + its normalisation (:327-332)
+        hd = ref['handdetector'].HandDetector(fr['frames'][i], fx, fy, importer=rdi, refineNet=None)
+        raw, _, _ = hd.cropArea3D(com=loc, size=cube, dsize=(128, 128))
         for k, v in zip(keys, (net.seen[0][0, 0], net.seen[1][0, 0], net.seen[2][0, 0], loc, raw, crop, M, com3D)):
             acc[k].append(np.array(v, copy=True))
     out = dict(frames=fr['frames'], lastcom=lastcom, cube=np.array(cube), fxfy=np.array([fx, fy]), fn_seed=np.int64(77))

@@ -688,3 +688,34 @@ def test_live_reference_helpers_and_entry_script_imports():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@live
+def test_live_reference_pipeline_detect_and_estimate_pose():
+    """RealtimeHandposePipeline.detect (tracking branch) and estimatePose (util/realtimehandposepipeline.py:296-368)
+    executed from the reference, for the left and the (mirrored) right hand, against oracle.cascade_frame."""
+    from data import synthetic
+    ref = RH.reference_modules()
+    rdi = ref['importers'].NYUImporter('/nonexistent/')
+    cam = OA.Camera(**CAMS['NYU'])
+    fr = synthetic.generate_frames('NYU', 6, seed=71, edge_fraction=0.5)
+    lastcom = fr['lastcom'].astype(f32).astype(f64)
+    refine_fn, pose_fn = _tiny_fns(77)
+    for right in (False, True):
+        for i in range(6):
+            net, pnet = MK.RecordingNet(refine_fn), MK._PoseNetStub(pose_fn)
+            pipe = MK.reference_pipeline(ref, rdi, 588., 587., fr['cube'], net, pnet, right_hand=right)
+            pipe.lastcom = lastcom[i].copy()
+            crop, M, com3D = pipe.detect(fr['frames'][i])
+            jj = pipe.estimatePose(crop, com3D)
+            pose = jj * fr['cube'][2] / 2. + com3D                      # processVideo, :197-198
+            want = OC.cascade_frame(fr['frames'][i], lastcom[i], fr['cube'], cam, 588., 587., refine_fn, pose_fn,
+                                    right_hand=right)
+            # same refined CoM in (the reference's): crop, mirrored net input and pose agree
+            crop_o, M_o, c3_o = OC.pipeline_detect(fr['frames'][i], pipe.lastcom, fr['cube'], cam, 588., 587.)
+            assert np.array_equal(crop, crop_o) and np.array_equal(M, M_o)
+            assert np.array_equal(pnet.seen[0, 0], crop_o[:, ::-1] if right else crop_o)
+            jo = OC.estimate_pose(crop_o, pose_fn, right)
+            assert np.array_equal(jj, jo)
+            np.testing.assert_allclose(pose, jo * f32(fr['cube'][2] / 2.) + c3_o, rtol=1e-6, atol=1e-4)
+            np.testing.assert_allclose(want['com'], pipe.lastcom, rtol=4 * ULP, atol=2e-4)
