@@ -434,3 +434,45 @@ def run_reference_adam(param_values, grads_per_step, learning_rates):
                 sys.modules[k] = v
         if added_cast:
             del np.cast
+
+
+def reference_netbase_behaviour(kind, cfg):
+    """NetBase's bookkeeping methods on a reference network (inert theano): the deterministic switch, hasDropout, the
+    params / weights views with filters, weightVals round trip.  Returns a plain dict of observations."""
+    from unittest import mock
+    import numpy as np
+    theano = mock.MagicMock()
+    theano.shared = lambda value=None, name=None, borrow=False, **kw: _Shared(value, name, borrow)
+    theano.config.floatX = 'float32'
+    fake = {'theano': theano, 'theano.tensor': theano.tensor, 'theano.tensor.nnet': theano.tensor.nnet,
+            'theano.tensor.signal': theano.tensor.signal, 'theano.tensor.signal.pool': theano.tensor.signal.pool,
+            'theano.ifelse': theano.ifelse, 'theano.sandbox': theano.sandbox,
+            'theano.sandbox.rng_mrg': theano.sandbox.rng_mrg, 'theano.sandbox.neighbours': theano.sandbox.neighbours}
+    with _reference_net_modules(fake) as mods:
+        mod = mods['net.' + kind.lower()]
+        net = getattr(mod, kind)(np.random.RandomState(23455), cfgParams=getattr(mod, kind + 'Params')(**cfg))
+        return observe_netbase(net)
+
+
+def observe_netbase(net):
+    """the observations of ``reference_netbase_behaviour``, for a reference OR a product network"""
+    import numpy as np
+    obs = {'hasDropout': bool(net.hasDropout()), 'det0': bool(net.isDeterministic())}
+    net.setDeterministic()
+    obs['det1'] = bool(net.isDeterministic())
+    net.unsetDeterministic()
+    obs['det2'] = bool(net.isDeterministic())
+    obs['params'] = [p.name for p in net.params]
+    obs['weights'] = [p.name for p in net.weights]
+    obs['all_params'] = [p.name for p in net.all_params]
+    first = list(net.params)[0]            # py2's dict.values() was a list (netbase.py:165)
+    net.params_filter = [first]
+    obs['params_filtered'] = [p.name for p in net.params]
+    net.params_filter = []
+    # (weightVals is not observed: the reference's recGetWeightVals needs Python 2's list-returning dict.values())
+    try:
+        net.params_filter = [object()]
+        obs['bad_filter'] = 'accepted'
+    except Exception as e:
+        obs['bad_filter'] = type(e).__name__
+    return obs

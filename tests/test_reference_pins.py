@@ -719,3 +719,15 @@ def test_live_reference_pipeline_detect_and_estimate_pose():
             assert np.array_equal(jj, jo)
             np.testing.assert_allclose(pose, jo * f32(fr['cube'][2] / 2.) + c3_o, rtol=1e-6, atol=1e-4)
             np.testing.assert_allclose(want['com'], pipe.lastcom, rtol=4 * ULP, atol=2e-4)
+
+
+@live
+@pytest.mark.parametrize('kind,cfg', [
+    ('PoseRegNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30)),
+    ('ResNet', dict(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=30))])
+def test_live_reference_netbase_bookkeeping(kind, cfg):
+    """NetBase (net/netbase.py:141-203, 318-403): deterministic switch, hasDropout, params / weights views and their
+    filters - the same sequence of calls on the reference's net and on the product's."""
+    ref = RH.reference_netbase_behaviour(kind, cfg)
+    mine = RH.observe_netbase(_product_net(kind, cfg))
+    assert ref == mine, {k: (ref[k], mine[k]) for k in ref if ref[k] != mine[k]}
