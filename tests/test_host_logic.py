@@ -257,3 +257,29 @@ def test_importers_load_synthetic_sequences_with_reference_signature():
         ICVLImporter(None).loadSequence('train', subSeq='0')
     with pytest.raises(KeyError):
         NYUImporter(None).loadSequence('no_such_sequence')
+
+
+def test_aug_records_batch_edge_cases_match_per_sample_path():
+    """offsets / angles / scales at the reference's ``allclose`` early-outs (1e-9 offsets, 0 / 360 / 1e-7 degrees, scale
+    1 +- 1e-10), large offsets, both rotation directions: the vectorised path must stay bit-identical."""
+    from data import synthetic
+    modes = ['com', 'rot', 'sc', 'none']
+    for name in ('NYU', 'MSRA15'):
+        ds = synthetic.generate(name, 32, seed=99)
+        hd = ds['hd']
+        rng = np.random.RandomState(17)
+        for rep in range(3):
+            n = 300
+            idxs, md = rng.randint(0, 32, n), rng.randint(0, 4, n)
+            off = rng.randn(n, 3) * rng.choice([1e-9, 0.5, 5., 40.], n)[:, None]
+            rot = rng.uniform(-180, 180, n) * rng.choice([1e-9, 1e-3, 1., 1.], n)
+            rot[rng.rand(n) < 0.05] = rng.choice([0., 360., -360., 180., 90., 1e-7])
+            sc = np.abs(1. + rng.randn(n) * rng.choice([1e-10, 0.02, 0.2], n))
+            sc[rng.rand(n) < 0.05] = 1.0
+            com = hd._toimg(ds['com3D'][idxs])
+            per = [hd.aug_record(i, modes[md[k]], off[k], rot[k], sc[k], com[k], ds['cube'][i].copy(), ds['M'][i].copy(),
+                                 ds['gt3Dcrop'][i].copy()) for k, i in enumerate(idxs)]
+            rec, lab = hd.aug_records_batch(idxs, [modes[m] for m in md], off, rot, sc, com, ds['cube'][idxs],
+                                            ds['M'][idxs], ds['gt3Dcrop'][idxs])
+            assert rec.tobytes() == np.array([p[0] for p in per]).tobytes(), (name, rep)
+            assert np.array_equal(lab, np.stack([p[1] for p in per])), (name, rep)
