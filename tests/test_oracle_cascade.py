@@ -120,3 +120,31 @@ def test_joint_error_reference_formulas():
     gt, pr = rng.randn(5, 14, 3).astype(f32) * 40, rng.randn(5, 14, 3).astype(f32) * 40
     e = np.sqrt(np.square(gt - pr).sum(axis=2))
     assert e.shape == (5, 14) and np.isclose(np.nanmean(np.nanmean(e, axis=1)), e.mean())
+
+
+def test_crop_records_with_anisotropic_cubes_and_textured_frames():
+    """cubes with different x / y extents (non-square windows: aspect-preserving resize + canvas filler on either
+    axis), dense random depth with holes, frames addressed out of order, float64 and float32 CoMs."""
+    from data import synthetic
+    from dpp_b200 import cascade as PC
+    rng = np.random.RandomState(5)
+    di, ocam = synthetic.make_importer('NYU'), OA.Camera(**OA.NYU_CAM)
+    Hf, Wf = 480, 640
+    frames = np.rint(rng.uniform(300, 1200, (4, Hf, Wf))).astype(f32)
+    frames[rng.rand(4, Hf, Wf) < 0.3] = 0
+    for cube in ((300, 240, 300), (200, 260, 250)):
+        c = np.stack([rng.uniform(40, Wf - 40, 12), rng.uniform(40, Hf - 40, 12), rng.uniform(350, 1500, 12)], axis=1)
+        idx = rng.randint(0, 4, 12)
+        for coms in (c, c.astype(f32)):
+            rec, M, c3 = PC.pose_records(coms, cube, FX, FY, di, (Hf, Wf), 0., src_index=idx)
+            out = recrop_model.run(frames, rec)
+            x0 = recrop_model.run(frames, PC.refine_records(coms, cube, FX, FY, (Hf, Wf), src_index=idx))
+            assert (rec['rw'] != rec['rh']).any()
+            for i in range(12):
+                crop, Mo, c3o = OC.pipeline_detect(frames[idx[i]], coms[i], cube, ocam, FX, FY, ndvalue=0., use_cv2=True)
+                b = OC.com_to_bounds(coms[i], cube, FX, FY)
+                t = OC.refine_inputs(OC.resize_nn_cv2(OC.get_crop(frames[idx[i]], *b), (128, 128)), cube, coms[i])
+                assert np.array_equal(crop, out[i]) and np.array_equal(Mo, M[i]) and np.array_equal(c3o, c3[i])
+                assert np.array_equal(t[0][0, 0], x0[i])
+    with pytest.raises(ValueError):                   # a window entirely outside the frame is rejected, not guessed
+        PC.pose_records(np.array([[-400., 100., 600.]]), (300, 300, 300), FX, FY, di, (Hf, Wf), 0.)
