@@ -283,3 +283,41 @@ def test_aug_records_batch_edge_cases_match_per_sample_path():
                                             ds['M'][idxs], ds['gt3Dcrop'][idxs])
             assert rec.tobytes() == np.array([p[0] for p in per]).tobytes(), (name, rep)
             assert np.array_equal(lab, np.stack([p[1] for p in per])), (name, rep)
+
+
+def test_engine_lowering_is_pure_host_logic():
+    """dpp_b200.engine.Engine._lower turns the recorded layer graph into the op list the C ABI executes; it needs no
+    device.  Checks the op inventory of every net on the path and the convolution descriptors against SURVEY 8a's
+    shape table (64 convolutions incl. the stem, 20 of them 3x3, 6 with stride 2 - stage 4 keeps 256 channels, so its
+    blocks are identity blocks and ignore the stride, resnet.py:349-414; 60 BatchNorms in front of convolutions)."""
+    from dpp_b200.engine import Engine
+    from net.scalenet import ScaleNet, ScaleNetParams
+
+    def lower(net):
+        eng = Engine.__new__(Engine)
+        eng.net, eng.output_sym, eng.B, eng.precision = net, net.output, int(net.cfgParams.batch_size), 1
+        eng._lower()
+        return eng
+
+    def kinds(eng):
+        out = {}
+        for op in eng.ops:
+            out[op['kind']] = out.get(op['kind'], 0) + 1
+        return out
+    rng = np.random.RandomState(23455)
+    eng = lower(ResNet(rng, cfgParams=ResNetParams(type=0, batchSize=4, numJoints=1, nDims=30)))
+    assert kinds(eng) == {'convpool': 1, 'conv': 63, 'bn_apply': 1, 'fc': 3} and eng.t_out.shape == (4, 30)
+    descs = [eng._conv_desc(op) for op in eng.ops if op['kind'] == 'conv']
+    assert sum(1 for d in descs if d.k == 3) == 20 and sum(1 for d in descs if d.stride == 2) == 6
+    assert all(d.pad == d.k // 2 and d.N == 4 for d in descs)
+    macs = sum(d.Ho * d.Wo * d.Cout * d.k * d.k * d.Cin for d in descs) + 128 * 128 * 32 * 25
+    assert abs(macs / 1e6 - 107.0) < 0.1                          # SURVEY 8a: 107.0 M conv MACs per frame
+    assert len(set(id(op['in_bn']) for op in eng.ops if op['kind'] == 'conv' and op['in_bn'] is not None)) == 60
+    eng = lower(ResNet(rng, cfgParams=ResNetParams(type=1, batchSize=2, numJoints=14, nDims=3)))
+    assert kinds(eng)['fc'] == 4 and eng.t_out.shape == (2, 42)
+    eng = lower(PoseRegNet(rng, cfgParams=PoseRegNetParams(type=0, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1,
+                                                           nDims=30)))
+    assert kinds(eng) == {'convpool': 3, 'fc': 3}
+    eng = lower(ScaleNet(rng, cfgParams=ScaleNetParams(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=3)))
+    assert kinds(eng) == {'convpool': 9, 'concat': 1, 'fc': 3} and len(eng.t_ins) == 3
+    assert [t.shape for t in eng.t_ins] == [(2, 1, 128, 128), (2, 1, 64, 64), (2, 1, 32, 32)]
