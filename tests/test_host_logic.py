@@ -321,3 +321,38 @@ def test_engine_lowering_is_pure_host_logic():
     eng = lower(ScaleNet(rng, cfgParams=ScaleNetParams(type=1, nChan=1, wIn=128, hIn=128, batchSize=2, numJoints=1, nDims=3)))
     assert kinds(eng) == {'convpool': 9, 'concat': 1, 'fc': 3} and len(eng.t_ins) == 3
     assert [t.shape for t in eng.t_ins] == [(2, 1, 128, 128), (2, 1, 64, 64), (2, 1, 32, 32)]
+
+
+def test_parameter_layout_conversions_between_reference_and_device():
+    """engine.Slot: reference layouts (what get_value / set_value / the pickles carry) <-> device layouts documented in
+    include/dpp_b200.h.  Conv weights: W_kc[(r*kw + s)*Cin + c][o] = W[o][c][kh-1-r][kw-1-s] (true convolution,
+    pre-flipped); FC weights behind a flattened NCHW tensor: rows (c,h,w) -> (h,w,c) because activations are NHWC on the
+    device; ScaleNet's concatenated towers: the same permutation per tower segment.  Round trips are exact."""
+    from dpp_b200.engine import Slot
+    from net.sym import shared
+    rng = np.random.RandomState(3)
+    w = rng.randn(6, 4, 5, 3).astype(np.float32)                       # (O, I, kh, kw)
+    s = Slot(shared(w, kind='convW'), 'w', 0)
+    d = s.to_device_layout(w).reshape(5 * 3 * 4, 6)
+    for (r, t, c, o) in [(0, 0, 0, 0), (4, 2, 3, 5), (1, 2, 0, 3), (3, 0, 2, 1)]:
+        assert d[(r * 3 + t) * 4 + c, o] == w[o, c, 5 - 1 - r, 3 - 1 - t]
+    assert np.array_equal(s.from_device_layout(s.to_device_layout(w)), w)
+    C, H, Wd, n_out = 3, 2, 4, 5
+    f = rng.randn(C * H * Wd, n_out).astype(np.float32)                # rows in the reference's (c,h,w) flatten order
+    s = Slot(shared(f, kind='fcW'), 'w', 0)
+    s.chw = (C, H, Wd)
+    d = s.to_device_layout(f).reshape(H * Wd * C, n_out)
+    for (c, h, x) in [(0, 0, 0), (2, 1, 3), (1, 0, 2)]:
+        assert np.array_equal(d[(h * Wd + x) * C + c], f[(c * H + h) * Wd + x])
+    assert np.array_equal(s.from_device_layout(s.to_device_layout(f)), f)
+    # two towers of (2,1,2) and (1,2,2) features concatenated (ScaleNet, scalenet.py:174-178)
+    g = rng.randn(4 + 4, 3).astype(np.float32)
+    s = Slot(shared(g, kind='fcW'), 'w', 0)
+    s.segments = [(0, (2, 1, 2)), (4, (1, 2, 2))]
+    d = s.to_device_layout(g).reshape(8, 3)
+    assert np.array_equal(d[(0 * 2 + 1) * 2 + 1], g[(1 * 1 + 0) * 2 + 1])          # tower 0: (c=1,h=0,w=1)
+    assert np.array_equal(d[4 + (1 * 2 + 0) * 1 + 0], g[4 + (0 * 2 + 1) * 2 + 0])  # tower 1: (c=0,h=1,w=0)
+    assert np.array_equal(s.from_device_layout(s.to_device_layout(g)), g)
+    b = rng.randn(7).astype(np.float32)
+    s = Slot(shared(b), 'w', 0)
+    assert np.array_equal(s.from_device_layout(s.to_device_layout(b)), b)
