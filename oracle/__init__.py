@@ -3,10 +3,12 @@
 This package restates, on the CPU (NumPy fp64/fp32 + torch-CPU fp32 + cv2), the
 algorithms of the reference (moberweger/deep-prior-pp) for the single hot path this
 repository re-implements in CUDA: depth-crop augmentation -> ResNet/PoseRegNet forward,
-loss, backward, ADAM.  Every function cites the reference file:line it follows.
+loss, backward, ADAM; the inference cascade (CoM refinement -> re-crop -> pose); pose sampling.
+Every function cites the reference file:line it follows.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
-``--impl reference`` legs may import it.  The product package never does.
+``--impl reference`` legs may import it (``__graft_entry__.build()`` additionally checks that
+``ref_harness`` can load the reference sources where they exist).  The product package never does.
 
 PARITY STATUS
 * Augmentation, crop geometry, projections, cascade crops, sampleRandomPoses (oracle/augment.py, oracle/cascade.py):
