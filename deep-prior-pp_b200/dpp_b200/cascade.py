@@ -163,6 +163,9 @@ def nd_value(dpt):
     sel = lo if lo.shape[0] > hi.shape[0] else hi
     if sel.shape[0] == 0:
         raise ValueError("frame has no undefined-depth pixels: pass ndvalue explicitly")
+    first = sel[0]
+    if (sel == first).all():             # the usual case - one marker value (0 or 32001): no sort needed
+        return first
     vals, counts = np.unique(sel, return_counts=True)
     return vals[np.argmax(counts)]
 
