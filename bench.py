@@ -320,9 +320,16 @@ def run_b200(args):
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3)) if not args.no_e2e else float('nan')
     e2e_val = B * world / (ms_e2e / 1000.)
 
-    # ---- the same, with the host-side record preparation INSIDE the timed region (single GPU only: an exception on
-    # one rank must not leave the others waiting in a collective).  Extra evidence, never the headline: any failure
-    # is reported in the key instead of breaking the bench line.
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel class, timed live with CUDA events on this stream
+    roof = measure_dominant_kernel(eng, torch) if not args.no_roofline else None
+    # ---- kernel launches per step (counted from the engine's op list)
+    n_launch = count_launches(eng) + 1
+
+    # ---- e2e again, with the host-side record preparation INSIDE the timed region (single GPU only: an exception on
+    # one rank must not leave the others waiting in a collective).  Extra evidence, never the headline: it runs after
+    # every contract measurement has been taken, and any failure is reported in the key instead of breaking the line.
     e2e_prep = None
     if world == 1 and not args.no_e2e:
         try:
@@ -364,13 +371,6 @@ def run_b200(args):
                                 "computed on one host thread inside the timed region (overlapping the previous step)"}
         except Exception as exc:                 # pragma: no cover
             e2e_prep = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
-    clk = clocks.stop() if rank == 0 else None
-
-    # ---- roofline of the dominant kernel class, timed live with CUDA events on this stream
-    roof = measure_dominant_kernel(eng, torch) if not args.no_roofline else None
-    # ---- kernel launches per step (counted from the engine's op list)
-    n_launch = count_launches(eng) + 1
-
     if rank != 0:
         if dist is not None:
             shutdown_distributed(dist, eng)
