@@ -85,3 +85,9 @@ class _NoClocks(object):
 bench.ClockSampler = _NoClocks
 bench.count_launches = lambda eng: 1
 bench.main()
+
+# ---- the cascade bench (tools/bench_cascade.py, BASELINE config 5) the same way ---------------------------------------
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tools'))
+import bench_cascade                                           # noqa: E402
+
+bench_cascade.main(['--batch', '8', '--steps', '2', '--warmup', '1', '--cpu-frames', '2'])
