@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(BT)
 k_bn_bwd_apply(const float *__restrict__ dz, const float *__restrict__ x, dpp_bn_ref bn,
                const double *__restrict__ dz_stats, const float *__restrict__ skip, float *__restrict__ dx,
                float *__restrict__ dgamma, float *__restrict__ dbeta, double *__restrict__ dbias_stats,
-               int64_t pixels, int C) {
+               int64_t pixels, int C, float pscale) {
     __shared__ float s_k1[256], s_mdz[256], s_mdzx[256], s_mean[256], s_istd[256];
     __shared__ float s_red[BT][4];
     const int tid = threadIdx.x;
@@ -30,8 +30,8 @@ k_bn_bwd_apply(const float *__restrict__ dz, const float *__restrict__ x, dpp_bn
         s_mdz[c] = (float)(dz_stats[c] / bn.count);
         s_mdzx[c] = (float)(dz_stats[C + c] / bn.count);
         if (blockIdx.x == 0) {
-            if (dbeta) dbeta[c] += (float)dz_stats[c];
-            if (dgamma) dgamma[c] += (float)dz_stats[C + c];
+            if (dbeta) dbeta[c] += pscale * (float)dz_stats[c];
+            if (dgamma) dgamma[c] += pscale * (float)dz_stats[C + c];
         }
     }
     __syncthreads();
@@ -163,11 +163,11 @@ int ew_grid(int64_t pixels, int C) {
 
 extern "C" int dpp_bn_bwd_apply(const float *dz, const float *x, const dpp_bn_ref *bn, const double *dz_stats,
                                 const float *skip, float *dx, float *dgamma, float *dbeta, double *dbias_stats,
-                                int64_t pixels, int C, void *stream) {
+                                int64_t pixels, int C, float param_grad_scale, void *stream) {
     DPP_CHECK_ARG(dz && x && bn && dz_stats && dx && pixels > 0);
     DPP_CHECK_ARG(C % 4 == 0 && C <= 256 && 256 % (C / 4) == 0 && bn->sums != nullptr);
     DPP_CUDA(launch_pdl(1, k_bn_bwd_apply, dim3(ew_grid(pixels, C)), dim3(BT), 0, S(stream), dz, x, *bn, dz_stats, skip, dx,
-                        dgamma, dbeta, dbias_stats, pixels, C));
+                        dgamma, dbeta, dbias_stats, pixels, C, param_grad_scale));
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }

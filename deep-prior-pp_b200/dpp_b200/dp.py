@@ -2,7 +2,51 @@
 One process per GPU; the minibatch shards over ranks, each rank holds a full weight replica, and
 the flat gradient arena is summed with one bucketed all-reduce per step; 1/world is folded into
 ADAM (hyper[3]).  torch.distributed is the transport (NCCL on GPUs, gloo in CPU tests)."""
+import os
 import numpy as np
+
+
+def env_world():
+    """(rank, world, local_rank) as torchrun exports them; (0, 1, 0) in a plain process"""
+    return (int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')),
+            int(os.environ.get('LOCAL_RANK', '0')))
+
+
+def init_process_group(backend=None):
+    """Join the job torchrun started (idempotent).  Returns (dist module or None, rank, world).  One process per
+    GPU: the CUDA device is LOCAL_RANK; backend NCCL on GPUs, gloo in the CPU tests."""
+    rank, world, local = env_world()
+    if world <= 1:
+        return None, 0, 1
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend)
+    return dist, dist.get_rank(), dist.get_world_size()
+
+
+def local_batch(batch, world):
+    """samples of one global minibatch that a rank computes (strong scaling: the reference's batch size stays the
+    GLOBAL one, e.g. BASELINE config 3: 512 over 8 GPUs = 64 per GPU)"""
+    if batch % world:
+        raise ValueError("batch size %d does not divide over %d ranks" % (batch, world))
+    return batch // world
+
+
+def local_rows(n_aligned, batch, rank, world):
+    """rows of the (minibatch-aligned) data set that live on this rank: slice [rank*b, (rank+1)*b) of every global
+    minibatch, in minibatch order - local minibatch m is rows [m*b, (m+1)*b) of the result"""
+    if n_aligned % batch:
+        raise ValueError("data set of %d rows is not aligned to the batch size %d" % (n_aligned, batch))
+    b = local_batch(batch, world)
+    m = np.arange(n_aligned // batch, dtype=np.int64)[:, None] * batch
+    return (m + rank * b + np.arange(b, dtype=np.int64)[None, :]).reshape(-1)
 
 
 def shard_range(n_samples, rank, world):

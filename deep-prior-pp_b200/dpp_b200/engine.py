@@ -37,9 +37,11 @@ def _ptr(t):
 class Tensor(object):
     """A materialised activation: NHWC (4-D) or (B, n) (2-D) fp32 device buffer."""
 
-    def __init__(self, name, shape_nchw):
+    def __init__(self, name, shape_nchw, batch=None):
         self.name = name
         self.shape = tuple(int(v) for v in shape_nchw)    # reference (NCHW or (B,n)) shape
+        if batch is not None:
+            self.shape = (int(batch),) + self.shape[1:]   # this device's share of the minibatch
         self.buf = None
         self.grad = None
         self.bn = None              # BatchNormLayer normalising this tensor (if any)
@@ -102,7 +104,9 @@ class Slot(object):
 
 
 class Engine(object):
-    def __init__(self, net, precision=None, device=None):
+    def __init__(self, net, precision=None, device=None, batch=None):
+        """``batch``: samples per step on THIS device.  Defaults to the net's batch size; a data-parallel rank
+        passes its shard of the global minibatch (trainer/nettrainer.py: global batch / world)."""
         torch = _torch()
         if not torch.cuda.is_available():
             raise DppError("dpp_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -112,12 +116,16 @@ class Engine(object):
         self.dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         self.net = net
         self.output_sym = net.output
-        self.B = int(net.cfgParams.batch_size)
+        self.B = int(net.cfgParams.batch_size) if batch is None else int(batch)
+        if self.B < 1:
+            raise DppError("Engine batch must be >= 1")
         if precision is None:
             precision = int(os.environ.get('DPP_PRECISION', '1'))
         self.precision = precision
         self.world = 1
+        self.rank = 0
         self.allreduce_fn = None
+        self.syncbn = False
         self._graphs = {}
         self._masks_injected = None
         # backward-weights kernels run on a second stream (forked/joined inside the step, also under graph
@@ -179,7 +187,7 @@ class Engine(object):
             dims = [self.net.cfgParams.inputDim]
         self.t_ins = []
         for k, (sym_in, dim) in enumerate(zip(inputs, dims)):
-            tin = Tensor('input' if k == 0 else 'input%d' % k, dim)
+            tin = Tensor('input' if k == 0 else 'input%d' % k, dim, self.B)
             tin.is_input = True
             self.tensors.append(tin)
             self.t_ins.append(tin)
@@ -187,7 +195,7 @@ class Engine(object):
         self.t_in = self.t_ins[0]
 
         def new_tensor(name, shape):
-            t = Tensor(name, shape)
+            t = Tensor(name, shape, self.B)
             self.tensors.append(t)
             return t
 
@@ -476,6 +484,18 @@ class Engine(object):
         # hyper: lr, t, -, grad_scale
         self.hyper = torch.tensor([0.0, 1.0, 0.0, 1.0], dtype=torch.float32, device=self.dev)
         self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        if getattr(self.net, 'params_filter', None):
+            raise NotImplementedError("net.params_filter (frozen layers): the ADAM kernel updates the whole arena")
+        alphas = set(float(bn.cfgParams.alpha) for bn in self.bns)
+        if len(alphas) > 1:
+            raise NotImplementedError("BatchNorm layers with different EMA factors: %s" % sorted(alphas))
+        self._build_ema_items()
+        self._train_ready = True
+
+    def _build_ema_items(self):
+        """table of the running-statistics update (one launch for all BNs); the sample count behind the fp64 sums
+        is the global one under SyncBN"""
+        torch = self.torch
         items = (BnEmaItem * max(len(self.bns), 1))()
         for i, bn in enumerate(self.bns):
             f0, _, c = self.bn_stat_off[id(bn)]
@@ -483,12 +503,11 @@ class Engine(object):
             items[i].sums = self.STATS.data_ptr() + 8 * f0
             items[i].mean = self.pview(bn.mean).data_ptr()
             items[i].inv_std = self.pview(bn.inv_std).data_ptr()
-            items[i].count = float(raw.pixels)
+            items[i].count = float(raw.pixels) * (self.world if self.syncbn else 1)
             items[i].C = c
             items[i].eps = float(bn.cfgParams.epsilon)
         raw_bytes = bytes(items)
         self.ema_items = torch.frombuffer(bytearray(raw_bytes), dtype=torch.uint8).to(self.dev)
-        self._train_ready = True
 
     # ---------------------------------------------------------------------------------
     # kernels
@@ -504,7 +523,7 @@ class Engine(object):
         r.inv_std = self.pview(bn.inv_std).data_ptr()
         r.gamma = self.pview(bn.gamma).data_ptr()
         r.beta = self.pview(bn.beta).data_ptr()
-        r.count = float(raw.pixels)
+        r.count = float(raw.pixels) * (self.world if self.syncbn else 1)
         r.eps = float(bn.cfgParams.epsilon)
         r.relu = relu
         return r
@@ -514,7 +533,7 @@ class Engine(object):
         p = L.cfgParams
         n, ci, h, w = p.inputDim
         d = ConvDesc()
-        d.N, d.H, d.W, d.Cin = int(n), int(h), int(w), int(ci)
+        d.N, d.H, d.W, d.Cin = self.B, int(h), int(w), int(ci)
         d.Cout = int(p.nFilters)
         d.k = int(p.filterDim[0])
         d.stride = int(p.stride[0])
@@ -531,6 +550,15 @@ class Engine(object):
         f0, b0, _ = self.bn_stat_off[id(bn)]
         return C.c_void_p(self.STATS.data_ptr() + 8 * (f0 if which == 0 else b0))
 
+    def _sync_stats(self, bn, which):
+        """SyncBN: sum this BN's fp64 statistics ({sum, sumsq} forward / {sum dz, sum dz*xhat} backward) over the
+        data-parallel ranks, in stream order between the kernel that produced them and the one that reads them, so
+        that G ranks x B/G samples normalise exactly like one device with B samples (net/batchnormlayer.py:154-159
+        takes the statistics over the whole minibatch)."""
+        f0, b0, c = self.bn_stat_off[id(bn)]
+        lo = f0 if which == 0 else b0
+        self.stats_allreduce_fn(self.STATS[lo:lo + 2 * c])
+
     def _run_forward(self, train):
         st = self._stream()
         for op in self.ops:
@@ -545,7 +573,7 @@ class Engine(object):
                 relu = 1 if p.activation_str == 'ReLU' else 0
                 stats = self._stats_ptr(op['out_bn']) if (op['out_bn'] is not None and train) else None
                 lib.dpp_convpool_fwd(_ptr(op['src'].buf), _ptr(self.pview(L.W)), _ptr(self.pview(L.b)),
-                                     _ptr(op['dst'].buf), _ptr(op['argmax']), stats, int(n), int(h), int(w), int(ci),
+                                     _ptr(op['dst'].buf), _ptr(op['argmax']), stats, self.B, int(h), int(w), int(ci),
                                      int(p.nFilters), int(p.filterDim[0]), int(pad), int(p.poolsize[0]), relu, st)
             elif k == 'conv':
                 L = op['layer']
@@ -585,6 +613,50 @@ class Engine(object):
                                self.B, n_in, n_out, relu, _ptr(mask), scale, self.precision, st)
             else:
                 raise NotImplementedError(k)
+            if train and self.syncbn and op.get('out_bn') is not None:
+                self._sync_stats(op['out_bn'], 0)       # the consumer's prologue reads the global sums
+
+    def _grad_slots_of(self, op, bn_done):
+        """arena slots whose gradients are issued by the backward kernels of ``op`` (+ the BNs it completes)"""
+        out = []
+        if op['kind'] in ('conv', 'convpool', 'fc'):
+            L = op['layer']
+            out += [self.slots[id(L.W)], self.slots[id(L.b)]]
+        for bn in bn_done:
+            out += [self.slots[id(bn.gamma)], self.slots[id(bn.beta)]]
+        return out
+
+    def _plan_buckets(self, min_elems):
+        """Data-parallel exchange plan: the gradient arena is in layer order and the backward pass completes it from
+        the END (FC tail first, stem last).  Walk the reverse op list, track the longest fully-issued suffix of the
+        arena and cut a bucket [lo, hi) after the op that completes it once it holds >= min_elems parameters - the FC
+        tail (90 % of the bytes) becomes the first bucket as soon as the FC backward is issued, the deep conv stages
+        follow, and only the small remainder (first stage + stem) trails the last backward kernel.
+        Returns {index in reversed(self.ops): (lo, hi)} plus the trailing (lo, hi) or None."""
+        pending = {id(bn): len(self.bn_consumers.get(id(bn), [])) for bn in self.bns}
+        done = set()
+        order = sorted(self.w_slots, key=lambda sl: sl.offset)
+        cuts, hi, k_suffix = {}, self.n_w, len(order)
+        for i, op in enumerate(reversed(self.ops)):
+            finished = []
+            bn = op.get('in_bn') if op['kind'] == 'conv' else (op.get('bn') if op['kind'] == 'bn_apply' else None)
+            if bn is not None:
+                pending[id(bn)] -= 1
+                if pending[id(bn)] == 0:
+                    finished.append(bn)
+            for sl in self._grad_slots_of(op, finished):
+                done.add(id(sl))
+            while k_suffix > 0 and id(order[k_suffix - 1]) in done:
+                k_suffix -= 1
+            lo = order[k_suffix].offset if k_suffix < len(order) else self.n_w
+            if k_suffix == 0:
+                lo = 0
+            is_fc_tail_end = op['kind'] == 'fc' and (i + 1 == len(self.ops) or list(reversed(self.ops))[i + 1]['kind'] != 'fc')
+            if hi - lo >= min_elems or (is_fc_tail_end and hi > lo):
+                if lo > 0:                       # the bucket that reaches offset 0 is the trailing one
+                    cuts[i] = (lo, hi)
+                    hi = lo
+        return cuts, ((0, hi) if hi > 0 else None)
 
     def _run_backward(self):
         """Reverse walk.  t.grad of the output tensor must hold dCost/dOut on entry."""
@@ -603,40 +675,46 @@ class Engine(object):
         for op in self.ops:
             if op['kind'] == 'conv' and op['residual'] is not None:
                 skip_of[id(op['residual'])] = op['dst']
+        # parameter gradients of a BN are the global sums under SyncBN: every rank adds 1/world of them, so that the
+        # SUM all-reduce of the arena (and ADAM's 1/world) yields them exactly once
+        pscale = (1.0 / self.world) if self.syncbn else 1.0
 
         def finish_bn(bn, raw):
             """all consumers contributed dz (+stats): apply the BN backward, producing raw.grad"""
+            if self.syncbn:
+                self._sync_stats(bn, 1)
             bnref = self._bnref(bn, raw, True)
             c = raw.shape[1]
             sk = skip_of.get(id(raw))
             lib.dpp_bn_bwd_apply(_ptr(self.dz[id(bn)]), _ptr(raw.buf), C.byref(bnref), self._stats_ptr(bn, 1),
                                  _ptr(sk.grad) if sk is not None else None, _ptr(raw.grad),
                                  _ptr(self.pview(bn.gamma, G)), _ptr(self.pview(bn.beta, G)), None,
-                                 raw.pixels, int(c), st)
+                                 raw.pixels, int(c), pscale, st)
 
-        # arena offset where the trailing run of FC parameters starts (the arena is in layer order)
-        early_lo, early_done = None, True
-        if self.allreduce_fn is not None and self.world > 1 and os.environ.get('DPP_EARLY_ALLREDUCE', '1') != '0':
-            tail = []
-            for op in reversed(self.ops):
-                if op['kind'] != 'fc':
-                    break
-                tail.append(op)
-            if tail and len(tail) < len(self.ops):
-                early_lo = min(self.slots[id(v)].offset for op in tail for v in (op['layer'].W, op['layer'].b))
-                early_done = False
-        self._early_lo = None
-        for op in reversed(self.ops):
+        # data-parallel exchange: buckets of the gradient arena, all-reduced on the comm stream as soon as the
+        # backward kernels that fill them have been issued (on the main stream and on the backward-weights stream)
+        cuts, trailing = {}, None
+        exchanging = self.allreduce_fn is not None and self.world > 1
+        if exchanging:
+            if os.environ.get('DPP_EARLY_ALLREDUCE', '1') != '0':
+                cuts, trailing = self._bucket_plan
+            else:
+                trailing = (0, self.n_w)
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.dev)
+        self._exchanged = []
+
+        def exchange(lo, hi):
+            comm = self._comm_stream
+            comm.wait_stream(main)
+            if side is not None and forked:
+                comm.wait_stream(side)
+            with torch.cuda.stream(comm):
+                self.allreduce_fn(G[lo:hi])
+            self._exchanged.append((lo, hi))
+
+        for i, op in enumerate(reversed(self.ops)):
             k = op['kind']
-            if k != 'fc' and not early_done:
-                # the FC backward is complete: start summing [early_lo, end) over the ranks now
-                early_done = True
-                if self._comm_stream is None:
-                    self._comm_stream = torch.cuda.Stream(device=self.dev)
-                self._comm_stream.wait_stream(main)
-                with torch.cuda.stream(self._comm_stream):
-                    self.allreduce_fn(G[early_lo:])
-                self._early_lo = early_lo
             if k == 'fc':
                 L = op['layer']
                 src = op['src']
@@ -699,14 +777,18 @@ class Engine(object):
                 dx = None if op['src'].is_input else op['src'].grad
                 lib.dpp_convpool_bwd(_ptr(op['src'].buf), _ptr(self.pview(L.W)), _ptr(op['dst'].buf),
                                      _ptr(op['argmax']), _ptr(op['dst'].grad), _ptr(self.pview(L.W, G)),
-                                     _ptr(self.pview(L.b, G)), _ptr(dx), int(n), int(h), int(w), int(ci),
+                                     _ptr(self.pview(L.b, G)), _ptr(dx), self.B, int(h), int(w), int(ci),
                                      int(p.nFilters), int(p.filterDim[0]), int(pad), int(p.poolsize[0]), relu, st)
             else:
                 raise NotImplementedError(k)
+            if i in cuts:
+                exchange(*cuts[i])
+        if exchanging and trailing is not None:
+            exchange(*trailing)
         if forked:
             main.wait_stream(side)                  # join: the gradient arena is complete
-        if self._early_lo is not None:
-            main.wait_stream(self._comm_stream)
+        if exchanging:
+            main.wait_stream(self._comm_stream)     # ... and summed over the ranks
 
     # ---------------------------------------------------------------------------------
     # public API
@@ -718,6 +800,9 @@ class Engine(object):
         if self._packs_dirty:
             self._repack()
         if not deterministic:
+            if self.dropout_layers:
+                self._alloc_training()          # the masks live with the training buffers
+                self._draw_masks()
             lib.dpp_fill_f64(_ptr(self.STATS), 0.0, self.STATS.numel(), st)
         self._run_forward(train=not deterministic)
         return self.t_out.buf
@@ -766,9 +851,6 @@ class Engine(object):
         d = int(self.y_in.shape[1])
         lib.dpp_loss_sqerr(_ptr(self.t_out.buf), _ptr(self.y_in), _ptr(self.t_out.grad), _ptr(self.cost), self.B, d, st)
         self._run_backward()
-        if self.allreduce_fn is not None:
-            early = getattr(self, '_early_lo', None)
-            self.allreduce_fn(self.G if early is None else self.G[:early])
         lib.dpp_adam_step(_ptr(self.W), _ptr(self.G), _ptr(self.M), _ptr(self.V), _ptr(self.hyper), self.n_w, st)
         lib.dpp_adam_tick(_ptr(self.hyper), st)
         if self.pack_items is not None:
@@ -779,11 +861,27 @@ class Engine(object):
     def set_lr(self, lr):
         self.hyper[0:1].fill_(float(lr))
 
-    def set_world(self, world, allreduce_fn):
-        self._alloc_training()
-        self.world = world
+    def set_world(self, world, allreduce_fn, rank=0, syncbn=False, stats_allreduce_fn=None, bucket_elems=None):
+        """Data-parallel mode (the reference is single-device).  ``allreduce_fn(t)`` sums a float32 slice
+        of the gradient arena over the ranks in place, on the CURRENT stream (torch.distributed.all_reduce).
+        ``syncbn``: also sum every BatchNorm's fp64 statistics (forward and backward) with ``stats_allreduce_fn``
+        (default: the same function), which makes ``world`` ranks x B/world samples compute the single-device
+        function of the global minibatch."""
+        self.world = int(world)
+        self.rank = int(rank)
         self.allreduce_fn = allreduce_fn
-        self.hyper[3:4].fill_(1.0 / world)
+        self.syncbn = bool(syncbn) and self.world > 1
+        self.stats_allreduce_fn = stats_allreduce_fn or allreduce_fn
+        self._graphs = {}
+        self._alloc_training()
+        self._build_ema_items()                      # the counts behind the statistics depend on world / syncbn
+        for op in self.ops:                          # every rank draws its own dropout masks
+            if op['kind'] == 'fc' and op['dropout'] is not None:
+                op['mask_gen'].manual_seed(op['dropout'].mask_seed + self.rank)
+        self.hyper[3:4].fill_(1.0 / self.world)
+        if bucket_elems is None:
+            bucket_elems = int(os.environ.get('DPP_BUCKET_ELEMS', str(256 * 1024)))
+        self._bucket_plan = self._plan_buckets(bucket_elems)
 
     def train_step(self, lr=None, use_graph=True):
         """One ``train_model`` call (poseregnettrainer.py:146-160) on the batch in

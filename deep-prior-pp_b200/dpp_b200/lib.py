@@ -84,7 +84,7 @@ _SIGS = {
     'dpp_conv2d_fwd': (C.c_int, [C.POINTER(ConvDesc), P, C.POINTER(BnRef), P, P, P, P, P, P]),
     'dpp_conv2d_dgrad': (C.c_int, [C.POINTER(ConvDesc), P, P, P, C.c_int, C.POINTER(BnRef), P, P, P]),
     'dpp_conv2d_wgrad': (C.c_int, [C.POINTER(ConvDesc), P, C.POINTER(BnRef), P, P, P, P]),
-    'dpp_bn_bwd_apply': (C.c_int, [P, P, C.POINTER(BnRef), P, P, P, P, P, P, C.c_int64, C.c_int, P]),
+    'dpp_bn_bwd_apply': (C.c_int, [P, P, C.POINTER(BnRef), P, P, P, P, P, P, C.c_int64, C.c_int, C.c_float, P]),
     'dpp_bn_apply': (C.c_int, [P, C.POINTER(BnRef), P, C.c_int64, C.c_int, P]),
     'dpp_bn_relu_bwd_reduce': (C.c_int, [P, P, C.POINTER(BnRef), P, P, C.c_int64, C.c_int, P]),
     'dpp_bn_ema_update': (C.c_int, [P, C.c_int, C.c_float, P]),

@@ -225,10 +225,14 @@ int dpp_conv2d_wgrad(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *i
  * dbeta += sum dz.  `bn` must be in train mode (sums != NULL).  dz and dx may alias.
  * skip (may be NULL) is the gradient arriving over the identity connection.
  * dbias_stats (may be NULL, fp64 [C]) accumulates sum_p dx for the bias gradient of the
- * conv layers that produced x (their db is that sum).                                    */
+ * conv layers that produced x (their db is that sum).
+ * param_grad_scale multiplies the two parameter gradients: 1, or 1/world when dz_stats holds
+ * sums over ALL data-parallel ranks (SyncBN) and the gradient arena is summed over the ranks
+ * afterwards.                                                                              */
 int dpp_bn_bwd_apply(const float *dz, const float *x, const dpp_bn_ref *bn,
                      const double *dz_stats, const float *skip, float *dx, float *dgamma,
-                     float *dbeta, double *dbias_stats, int64_t pixels, int C, void *stream);
+                     float *dbeta, double *dbias_stats, int64_t pixels, int C,
+                     float param_grad_scale, void *stream);
 
 /* materialise a = bn(x) (+relu): used for the last BN+ReLU in front of the FC stack      */
 int dpp_bn_apply(const float *x, const dpp_bn_ref *bn, float *y, int64_t pixels, int C,

@@ -246,7 +246,10 @@ class OracleNet(object):
                 W, b = l.params
                 o = a @ W + b
                 if l.act == 'ReLU':
-                    o = torch.clamp_min(o, 0)
+                    if relu_masks is not None and l.layerNum in relu_masks:
+                        o = o * relu_masks[l.layerNum].to(DTYPE)    # imposed decisions (see 'relu' above)
+                    else:
+                        o = torch.clamp_min(o, 0)
             elif l.kind == 'dropout':
                 if deterministic:
                     o = (1.0 - l.p) * a                     # dropoutlayer.py:104

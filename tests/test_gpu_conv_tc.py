@@ -129,3 +129,122 @@ def test_wgrad_tc_vs_simt(shape, precision, tol, mn, monkeypatch):
     print(shape, precision, "wgrad rel err", err)
     assert err < tol
     assert np.allclose(b1, b0, rtol=1e-4, atol=1e-4 * np.abs(b0).max())
+
+
+# ---------------------------------------------------------------------------------------------------
+# The benchmarked shapes (batch 128 and beyond) against an INDEPENDENT reference: torch float64 on the
+# GPU (no TF32 anywhere).  tiles >> 148, so every persistent CTA walks several tiles: accumulator
+# double-buffer phase flips, both epilogue warpgroups, A-stage ring across tiles, resident weight images
+# (kchunks <= ring) and streamed ones (kchunks > ring), odd and even tiles per CTA, split / replica
+# choices of the backward-weights kernel.  Reference semantics: net/convlayer.py:230-235 (conv2d 'half',
+# subsample), net/batchnormlayer.py:154-159 (batch statistics), nonlinearitylayer.py:119 (ReLU).
+# ---------------------------------------------------------------------------------------------------
+BIG_SHAPES = [  # N, H, Cin, Cout, k, stride           m-tiles x n-tiles (tiles per CTA), weight image
+    (128, 32, 16, 16, 3, 1),      # 1024 (6-7), resident 5 chunks, BN=16
+    (128, 32, 16, 64, 1, 1),      # 1024 (6-7), resident, BN=64, residual epilogue
+    (128, 32, 64, 16, 1, 1),      # 1024, 2 chunks
+    (128, 64, 32, 16, 1, 2),      # 1024, stride 2 gather / strided scatter in dgrad
+    (128, 64, 32, 64, 1, 2),      # projection shortcut
+    (128, 16, 32, 32, 3, 1),      # 256 (1-2), 9 chunks > ring of 6: streamed weights across tiles
+    (128, 16, 32, 128, 1, 1),     # 256, BN=128
+    (128, 16, 128, 32, 1, 1),     # 256, 4 chunks
+    (128, 8, 64, 64, 3, 1),       # 64 tiles, 18 chunks streamed
+    (128, 8, 256, 64, 1, 1),      # 64 tiles, 8 chunks streamed (ring 4)
+    (128, 8, 64, 256, 1, 1),      # 64 x 2 n-tiles
+    (512, 8, 64, 64, 3, 1),       # 256 tiles (1-2), 18 chunks streamed, BN=64
+    (512, 8, 64, 256, 1, 1),      # 512 tiles (3-4), 2 n-tiles
+    (37, 32, 16, 16, 3, 1),       # 296 tiles = exactly 2 per CTA
+    (19, 32, 16, 64, 1, 1),       # 152 tiles: 4 CTAs with 2 tiles, 144 with 1
+]
+
+
+def _ref_ops(N, H, Cin, Cout, k, stride, x, w, bias, gamma, beta, res, dy, dx_prev, dz_kernel=None, eps=1e-4):
+    """float64 torch restatement of the three fused operations (NHWC in / out like the kernels)."""
+    import torch.nn.functional as F
+    xd = x.double().permute(0, 3, 1, 2)
+    m = xd.mean((0, 2, 3), keepdim=True)
+    v = (xd * xd).mean((0, 2, 3), keepdim=True) - m * m
+    istd = 1.0 / torch.sqrt(v.clamp_min(0) + eps)
+    sc = gamma.double().view(1, -1, 1, 1) * istd
+    # the kernels evaluate the prologue in fp32 (x * scale + shift); do the ReLU decision on the same fp32 values
+    scf, shf = sc.float(), (beta.double().view(1, -1, 1, 1) - m * sc).float()
+    pre32 = torch.addcmul(shf, x.permute(0, 3, 1, 2), scf)
+    a = torch.relu(pre32).double().requires_grad_(True)
+    W = w.double().reshape(k, k, Cin, Cout).permute(3, 2, 0, 1).contiguous().requires_grad_(True)
+    y0 = F.conv2d(a, W, None, stride=stride, padding=k // 2)
+    out = {}
+    y = y0 + bias.double().view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res.double().permute(0, 3, 1, 2)
+    out['y'] = y.permute(0, 2, 3, 1).detach()
+    out['stats'] = torch.cat([y.sum((0, 2, 3)), (y * y).sum((0, 2, 3))]).detach()
+    if dy is not None:
+        ga, gW = torch.autograd.grad(y0, (a, W), dy.double().permute(0, 3, 1, 2))
+        da = ga
+        if dx_prev is not None:
+            da = da + dx_prev.double().permute(0, 3, 1, 2)
+        on = pre32 > 0
+        if dz_kernel is not None:
+            # a BN output within fp32 roundoff of 0 may legitimately land on either side (the kernel folds
+            # gamma * inv_std in fp32): for those few elements take the kernel's own on / off decision
+            near = pre32.abs() < 1e-5
+            out['near'] = int(near.sum())
+            on = torch.where(near, dz_kernel.permute(0, 3, 1, 2) != 0, on)
+        dz = torch.where(on, da, torch.zeros_like(da))
+        xhat = (xd - m) * istd
+        out['dz'] = dz.permute(0, 2, 3, 1)
+        out['dzstats'] = torch.cat([dz.sum((0, 2, 3)), (dz * xhat).sum((0, 2, 3))])
+        out['dw'] = gW.permute(2, 3, 1, 0).reshape(k * k * Cin, Cout)
+        out['db'] = dy.double().sum((0, 1, 2))
+    return out
+
+
+def _relmax(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("shape", BIG_SHAPES)
+@pytest.mark.parametrize("precision,tol", [(1, 2e-5), (0, 2e-5)])
+def test_bench_shapes_vs_torch_fp64(shape, precision, tol):
+    """forward (+ residual, statistics), backward-data (accumulate where the layer is stride 1, ReLU mask,
+    BN-backward statistics) and backward-weights of one layer at the benchmarked batch size, each compared
+    with float64 torch.  precision 0 anchors the fp32 SIMT kernels (the other tests' comparison partner) to
+    the same independent reference."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, H, Cin, Cout, k, stride = shape
+    d, x, w, bias, bn, Ho, keep = _setup(N, H, Cin, Cout, k, stride, precision)
+    gamma, beta = keep[-3], keep[-2]
+    g = torch.Generator(device='cuda').manual_seed(21)
+    res = torch.randn(N, Ho, Ho, Cout, device='cuda', generator=g)
+    dy = torch.randn(N, Ho, Ho, Cout, device='cuda', generator=g)
+    acc = stride == 1
+    dx = torch.randn(N, H, H, Cin, device='cuda', generator=g) if acc else torch.zeros(N, H, H, Cin, device='cuda')
+    # forward
+    y = torch.full((N, Ho, Ho, Cout), float('nan'), device='cuda')
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda')
+    lib.dpp_conv2d_fwd(C.byref(d), P(x), C.byref(bn), P(w), P(bias), P(res), P(y), P(stats), None)
+    torch.cuda.synchronize()
+    # backward-data
+    dzs = torch.zeros(2 * Cin, dtype=torch.float64, device='cuda')
+    dxo = dx.clone()
+    lib.dpp_conv2d_dgrad(C.byref(d), P(dy), P(w), P(dxo), 1 if acc else 0, C.byref(bn), P(x), P(dzs), None)
+    torch.cuda.synchronize()
+    ref = _ref_ops(N, H, Cin, Cout, k, stride, x, w, bias, gamma, beta, res, dy, dx if acc else None, dz_kernel=dxo)
+    e_y = _relmax(y, ref['y'])
+    e_s = _relmax(stats, ref['stats'])
+    e_dz = _relmax(dxo, ref['dz'])
+    e_dzs = float((dzs - ref['dzstats']).abs().max() / ref['dzstats'].abs().max())
+    # backward-weights
+    dw = torch.zeros(k * k * Cin, Cout, device='cuda')
+    db = torch.zeros(Cout, device='cuda')
+    lib.dpp_conv2d_wgrad(C.byref(d), P(x), C.byref(bn), P(dy), P(dw), P(db), None)
+    torch.cuda.synchronize()
+    e_dw = _relmax(dw, ref['dw'])
+    e_db = _relmax(db, ref['db'])
+    print(shape, "precision", precision, "fwd %.2e stats %.2e | dgrad %.2e stats %.2e | wgrad %.2e db %.2e"
+          % (e_y, e_s, e_dz, e_dzs, e_dw, e_db))
+    assert not torch.isnan(y).any()
+    assert e_y < tol and e_dz < tol
+    assert e_s < 1e-5 and e_dzs < 1e-4        # fp32 tile partials summed in fp64
+    assert e_dw < 5e-5 and e_db < 1e-5        # reduction over up to 5e5 pixels in fp32 partials

@@ -89,14 +89,21 @@ def _engine_relu_masks(net, onet, eng, w_before):
         lib.dpp_bn_apply(_ptr(raw.buf), C.byref(ref), _ptr(tmp), raw.pixels, int(raw.shape[1]), eng._stream())
         n, c, h, w = raw.shape
         masks[i + 1] = (tmp.reshape(n, h, w, c) > 0).permute(0, 3, 1, 2).contiguous().cpu()
+    # the ReLU inside a HiddenLayer (no dropout behind it): on where the stored output is positive.  One flip among
+    # the 128 x 1024 units of the first FC layer moves every gradient below it by ~1 / sqrt(#units) = 0.3 %.
+    for op in eng.ops:
+        if op['kind'] == 'fc' and op['dropout'] is None and op['layer'].cfgParams.activation_str == 'ReLU':
+            masks[op['layer'].layerNum] = (op['dst'].buf > 0).cpu()
     eng.W.copy_(w_after)
     torch.cuda.synchronize()
     return masks
 
 
-@pytest.mark.parametrize("use_graph,precision", [(False, 0), (True, 0), (True, 1)])
-def test_train_step_matches_oracle(use_graph, precision):
-    """precision 0 = fp32 SIMT kernels, 1 = 3xTF32 tcgen05 kernels (conv fwd/dgrad/wgrad).
+@pytest.mark.parametrize("use_graph,precision,B", [(False, 0, 4), (True, 0, 4), (True, 1, 4), (True, 1, 128)])
+def test_train_step_matches_oracle(use_graph, precision, B):
+    """precision 0 = fp32 SIMT kernels, 1 = 3xTF32 tcgen05 kernels (conv fwd/dgrad/wgrad).  B = 128 is the
+    benchmarked configuration (BASELINE config 2): every persistent conv CTA walks several tiles there, the
+    backward-weights kernels use their batch-128 split / replica choice and the FC GEMMs their split-K.
 
     Gradient parity is taken with the engine's ReLU decisions imposed on the (fp64) oracle: about 1e-6 of
     the ~5e6 BN->ReLU inputs lie within fp32 roundoff of 0 and may legitimately land on either side in two
@@ -105,13 +112,13 @@ def test_train_step_matches_oracle(use_graph, precision):
     decisions pinned, the two backward passes compute the same function and must agree to fp32 accuracy.
     The un-pinned comparison is still made, with the loose bound such flips allow."""
     from oracle import nets as O
-    B, D = 4, 30
+    D = 30
     net, onet, eng = _build(0, B, 1, D, precision=precision)
     x, y = _data(B, D)
     adam = O.Adam(onet.params)
     lr = 1e-3
     lays = [l for l in onet.layers for _ in l.params]
-    for step in range(2):
+    for step in range(2 if B <= 16 else 1):
         eng.set_input_nchw(x)
         eng._alloc_training()
         eng.y_in.copy_(torch.from_numpy(y))
@@ -124,7 +131,7 @@ def test_train_step_matches_oracle(use_graph, precision):
             col = {}
             onet.forward(torch.from_numpy(x), deterministic=False, collect=col)
             for ln, m in masks.items():
-                nflip += int(((col[ln] > 0) != m).sum())
+                nflip += int(((col[ln] > 0) != m).sum())       # (a unit that is exactly 0 counts as off on both sides)
         # un-pinned gradients (no state change: plain autograd on the oracle)
         out_free, _ = onet.forward(torch.from_numpy(x), deterministic=False)
         cost_free = O.cost_fn(onet, out_free, torch.from_numpy(y), B, 1, D, 0.0)
@@ -134,6 +141,7 @@ def test_train_step_matches_oracle(use_graph, precision):
         print("step", step, "cost", cost, ocost, "relu decisions differing from the fp64 oracle:", nflip)
         assert abs(cost - ocost) < 1e-4 * abs(ocost)
         worst, worst2, worst_free = 0.0, 0.0, 0.0
+        table = []
         for p, og, gf, l in zip(net.params, ograds, g_free, lays):
             g = grads[id(p)]
             if l.kind in ('conv', 'convpool') and g.ndim == 1:
@@ -142,13 +150,19 @@ def test_train_step_matches_oracle(use_graph, precision):
             e = float(np.abs(g - og).max() / (np.abs(og).max() + 1e-12))
             e2 = float(np.linalg.norm((g - og).ravel()) / (np.linalg.norm(og.ravel()) + 1e-30))
             worst, worst2 = max(worst, e), max(worst2, e2)
-            assert e < 5e-4 and e2 < 5e-4, (p.name, e, e2)   # fp32 (engine) vs fp64 (oracle) through 189 layers
+            table.append((p.name, l.kind, e, e2))
             if gf is not None:
                 gf = gf.numpy()
                 ef = float(np.linalg.norm((g - gf).ravel()) / (np.linalg.norm(gf.ravel()) + 1e-30))
                 worst_free = max(worst_free, ef)
                 assert ef < 0.25, (p.name, ef)     # loose: a handful of roundoff-level ReLU flips at batch 4 (see docstring)
         print("pinned-ReLU grad err: max-rel %.3g, rel-L2 %.3g; un-pinned rel-L2 %.3g" % (worst, worst2, worst_free))
+        bad = [t for t in table if not (t[2] < 5e-4 and t[3] < 5e-4)]   # fp32 (engine) vs fp64 (oracle) through 189 layers
+        if bad:
+            print("gradient tensors, forward order (name kind max-rel rel-L2):")
+            for t in table:
+                print("   %-12s %-9s %.3g %.3g%s" % (t + (("  <-- " if t in bad else ""),)))
+        assert not bad, bad[:4]
         # parameters after this ADAM step.  The first ADAM step is lr*sign(g): an entry whose gradient is
         # within roundoff of 0 may move the other way (|diff| = 2 lr); such entries must be rare, the rest
         # must agree closely.  Then hand the engine's weights to the oracle so that the next step again
