@@ -1,19 +1,27 @@
 #!/usr/bin/env python
 """bench.py - the driver's measurement contract for the DeepPrior++ hot path on B200.
 
-One "step" = one pass of the hot path over one batch of synthetic NYU crops:
-  dpp_augment_fwd (rot/com/none, from the HBM-resident ORIGINAL crops) -> ResNet (type 0,
-  nDims 30) forward -> cost -> backward -> [NCCL all-reduce] -> ADAM -> BN running-stat EMA.
-Workload = BASELINE.json configs[1]: "NYU posereg_embedding ResNet training, batch 128 synthetic
-depth, 1xB200".  For N > 1 every rank runs the same per-GPU batch (weak scaling, global batch
-128*N) with one gradient all-reduce per step.
+One "step" = one pass of the hot path over one batch of synthetic depth crops:
+  dpp_augment_fwd (from the HBM-resident ORIGINAL crops) -> ResNet (type 0, nDims 30) forward -> cost ->
+  backward -> [NCCL gradient exchange] -> ADAM -> BN running-stat EMA.
+
+Workloads (BASELINE.json configs):
+  train   (default) configs[1]: NYU posereg_embedding ResNet training, batch 128 per GPU, aug com/rot/none.
+          N > 1: every rank runs the same per-GPU batch (weak scaling, global batch 128*N).
+  icvl512 configs[2]: ICVL 16-joint, GLOBAL batch 512 split over the N ranks (strong scaling), gradient exchange in
+          stage-ordered buckets; --syncbn sums the BatchNorm statistics over the ranks as well.
+  msra15  configs[3]: MSRA15 21-joint (y-flipped projection, per-subject cubes), aug com/rot/sc/none, batch 128 per GPU.
+  cascade configs[4]: tools/bench_cascade.py.
 
   value : whole-job frames/s with all inputs resident in HBM when the timed region starts
-  e2e   : the same metric through the reference-facing API with HOST buffers: per step the
-          batch's crops + augmentation records + labels are copied from pinned host memory and
-          the cost is read back (what trainer.train_model() returns to the caller)
-  --impl reference : the CPU oracle restatement (torch-CPU + cv2) of the same step on the host
-          cores (the reference's own Theano path cannot run here: no Theano/Python 2).
+  e2e   : the same metric through HOST buffers: per step the random draws, the augmentation records and the
+          embedded labels are computed on the host INSIDE the timed region, the batch's crops + records + labels are
+          copied from pinned host memory and the cost is read back (what trainer.train_model() returns)
+  trainer_api : frames/s of PoseRegNetTrainer.train() itself (the reference-facing call), epochs of a resident set
+  strong : (default workload, every N) the icvl512 step at this N, so that the driver's 1/2/4/8 runs also hold a
+          strong-scaling curve
+  --impl reference : the CPU oracle restatement (torch-CPU + cv2) of the same step on the host cores (the
+          reference's own Theano path cannot run here: no Theano / Python 2).
 """
 import argparse
 import json
@@ -37,7 +45,20 @@ TRAIN_GFLOP_PER_FRAME = 0.7229     # BASELINE.md section 2 (fwd + dgrad + wgrad,
 B = 128
 E = 30
 N_RESIDENT = 2048                  # crops resident in HBM: 2048 * 64 KiB = 134 MB > 126 MB L2
+STRONG_GLOBAL_B = 512              # BASELINE config 3
 AUG_MODES = ['com', 'rot', 'none']
+
+WORKLOADS = {
+    # name: (dataset, aug modes, per-GPU batch ('B' = bench.B) or None = global batch / N, global batch, description)
+    'train': ('NYU', ['com', 'rot', 'none'], 'B', None,
+              "NYU posereg_embedding ResNet(type 0, 30-D embedding) training, batch 128/GPU, aug rot/com/none"),
+    'icvl512': ('ICVL', ['com', 'rot', 'none'], None, 'STRONG',
+                "ICVL 16-joint posereg_embedding ResNet(type 0, 30-D embedding) training, GLOBAL batch 512 split over "
+                "the ranks, aug rot/com/none"),
+    'msra15': ('MSRA15', ['com', 'rot', 'sc', 'none'], 'B', None,
+               "MSRA15 21-joint crossval config, ResNet(type 0, 30-D embedding) training, batch 128/GPU, "
+               "aug rot/scale/com/none on the device"),
+}
 
 
 def peaks():
@@ -92,7 +113,7 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def shutdown_distributed(dist, eng=None):
+def shutdown_distributed(dist, engs=()):
     """Leave a multi-rank run promptly.  Destroying the NCCL communicator while captured graphs that contain its
     collectives are alive can block for minutes at interpreter exit (seen on 2 x B200: JSON printed at once, the
     ranks exited only when the launcher's timeout fired).  Drop the graphs first, synchronise, and arm a watchdog
@@ -103,8 +124,9 @@ def shutdown_distributed(dist, eng=None):
     timer.daemon = True
     timer.start()
     try:
-        if eng is not None:
-            eng._graphs.clear()
+        for eng in engs:
+            if eng is not None:
+                eng._graphs.clear()
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
@@ -113,82 +135,129 @@ def shutdown_distributed(dist, eng=None):
     timer.cancel()
 
 
-def make_workload(seed=23455):
-    """synthetic NYU set + PCA stand-in + per-sample augmentation records for many steps"""
+def make_workload(seed=23455, dataset='NYU', n=None):
+    """synthetic set + PCA stand-in"""
     from data import synthetic
-    ds = synthetic.generate('NYU', N_RESIDENT, seed=seed)
+    ds = synthetic.generate(dataset, N_RESIDENT if n is None else n, seed=seed)
     comp, mean = synthetic.random_orthonormal_pca(E, ds['gt3D'].shape[1] * 3, seed=1)
     return ds, comp, mean
 
 
-def records_for(ds, comp, mean, idxs, rng):
+def records_for(ds, comp, mean, idxs, rng, aug_modes=None):
     """host side of one batch: draws in the reference order (nettrainer.py:954-957), dpp_aug_rec records and
     embedded labels in one vectorised pass (HandDetector.aug_records_batch)"""
+    aug_modes = AUG_MODES if aug_modes is None else aug_modes
     hd = ds['hd']
     draws = []
     for _ in idxs:
-        mode = rng.randint(0, len(AUG_MODES)); off = rng.randn(3) * 5.; rot = rng.uniform(-180., 180.)
+        mode = rng.randint(0, len(aug_modes)); off = rng.randn(3) * 5.; rot = rng.uniform(-180., 180.)
         sc = abs(1. + rng.randn() * 0.02)
         draws.append((mode, off, rot, sc))
     idxs = np.asarray(idxs)
     com = hd._toimg(ds['com3D'][idxs])
-    recs, labs = hd.aug_records_batch(idxs, [AUG_MODES[d[0]] for d in draws], np.array([d[1] for d in draws]),
+    recs, labs = hd.aug_records_batch(idxs, [aug_modes[d[0]] for d in draws], np.array([d[1] for d in draws]),
                                       np.array([d[2] for d in draws]), np.array([d[3] for d in draws]), com,
                                       ds['cube'][idxs], ds['M'][idxs], ds['gt3Dcrop'][idxs])
     ys = np.dot(labs.reshape(len(idxs), -1).astype(np.float64) - mean, comp.T)
     return recs, np.asarray(ys, np.float32), draws
 
 
+def first_batch(ds, comp, mean, nb, seed=1234):
+    """the batch the cost check runs on: same recipe in bench.py (device) and tests/golden/make_bench_golden.py (oracle)"""
+    rng = np.random.RandomState(seed)
+    idxs = rng.randint(0, ds['x'].shape[0], nb)
+    r, y, draws = records_for(ds, comp, mean, idxs, rng)
+    return idxs, r, y, draws
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU arm: oracle restatement (reference-equivalent CPU path)
 # ---------------------------------------------------------------------------------------------
 def cpu_threads():
-    # torch-CPU convolutions on 8x8..64x64 maps stop scaling (and regress) beyond ~16 threads
-    return min(os.cpu_count() or 1, int(os.environ.get('DPP_CPU_THREADS', '16')))
+    """all host cores the process may use (DPP_CPU_THREADS overrides)"""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    return int(os.environ.get('DPP_CPU_THREADS', str(avail)))
 
 
-def cpu_step_time(ds, comp, mean, steps, threads):
+_AUG_STATE = None
+
+
+def _aug_worker(job):
+    """one of the para_num_proc = 8 augmentation workers of the reference (trainer/nettrainer.py:59,666-689)"""
+    from oracle import augment as OA
+    ds, comp, mean = _AUG_STATE
+    idxs, draws = job
+    cam = OA.Camera(**OA.NYU_CAM)
+    ohd = OA.Hand(cam, use_cv2=True)
+    return OA.augment_poses(ds['x'], ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], list(idxs), draws,
+                            AUG_MODES, cam, ohd, pca_mean=mean, pca_components=comp)
+
+
+def cpu_step_time(ds, comp, mean, steps, threads, workers=8):
+    import multiprocessing
     import torch
     from oracle import nets as ON, augment as OA
+    global _AUG_STATE
+    _AUG_STATE = (ds, comp, mean)
+    pool = multiprocessing.get_context('fork').Pool(workers) if workers > 1 else None     # forked before torch threads spin up
     torch.set_num_threads(threads)
     ON.set_dtype(torch.float32)          # the timed CPU arm runs in the reference's precision
     onet = ON.build_resnet(np.random.RandomState(23455), type=0, batchSize=B, numJoints=1, nDims=E)
     adam = ON.Adam(onet.params)
-    cam = OA.Camera(**OA.NYU_CAM)
-    ohd = OA.Hand(cam, use_cv2=True)
     rng = np.random.RandomState(99)
     times = []
-    for s in range(steps):
-        idxs = rng.randint(0, N_RESIDENT, B)
-        draws = [OA.draw_aug_params(rng, len(AUG_MODES)) for _ in idxs]
-        t0 = time.time()
-        x, y = OA.augment_poses(ds['x'], ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], list(idxs), draws,
-                                AUG_MODES, cam, ohd, pca_mean=mean, pca_components=comp)
-        ON.train_step(onet, adam, torch.from_numpy(x), torch.from_numpy(y), 1e-4, 1, E)
-        times.append(time.time() - t0)
+    try:
+        for s in range(steps):
+            idxs = rng.randint(0, ds['x'].shape[0], B)
+            draws = [OA.draw_aug_params(rng, len(AUG_MODES)) for _ in idxs]
+            t0 = time.time()
+            if pool is not None:
+                per = (B + workers - 1) // workers
+                parts = pool.map(_aug_worker, [(idxs[i:i + per], draws[i:i + per]) for i in range(0, B, per)])
+                x = np.concatenate([p[0] for p in parts]); y = np.concatenate([p[1] for p in parts])
+            else:
+                x, y = _aug_worker((idxs, draws))
+            ON.train_step(onet, adam, torch.from_numpy(x), torch.from_numpy(y), 1e-4, 1, E)
+            times.append(time.time() - t0)
+    finally:
+        if pool is not None:
+            pool.terminate()
     return times
+
+
+def cpu_arm(ds, comp, mean, steps, warm):
+    """times the CPU restatement with ALL host cores and with 16 threads (torch-CPU convolutions on 8x8..64x64 maps
+    stop scaling somewhere in between) and reports the faster of the two - the reference arm gets every advantage"""
+    allc = cpu_threads()
+    tried = {}
+    for th in sorted(set([allc, min(allc, 16)]), reverse=True):
+        t = cpu_step_time(ds, comp, mean, steps + warm, th)[warm:]
+        tried[th] = B / float(np.mean(t))
+    best = max(tried, key=lambda k: tried[k])
+    return tried[best], best, tried
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = cpu_threads()
     ds, comp, mean = make_workload()
-    steps = max(1, min(args.steps, 6))
+    steps = max(1, min(args.steps, 4))
     warm = 1 if args.warmup > 0 else 0
-    times = cpu_step_time(ds, comp, mean, steps + warm, threads)[warm:]
-    ms = 1000. * float(np.mean(times))
-    val = B / (ms / 1000.)
-    sample = "%d step(s) of the batch-128 workload (cv2 augmentation + torch-CPU ResNet fwd/bwd/ADAM), %d thread(s)" % (
-        len(times), threads)
+    val, threads, tried = cpu_arm(ds, comp, mean, steps, warm)
+    ms = 1000. * B / val
+    sample = "%d step(s) of the batch-128 workload (cv2 augmentation in 8 worker processes + torch-CPU ResNet " \
+             "fwd/bwd/ADAM); frames/s by torch thread count: %s; host cores available: %d" % (
+                 steps, {k: round(v, 1) for k, v in tried.items()}, cpu_threads())
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "NYU posereg_embedding ResNet(type 0, 30-D embedding) training, batch 128, "
-                               "aug rot/com/none", "global_batch": B, "note": "CPU oracle restatement of the "
-                   "reference path (Theano cannot run here); host cores only"},
+        "config": {"workload": WORKLOADS['train'][4], "global_batch": B,
+                   "note": "CPU oracle restatement of the reference path (Theano cannot run here); host cores only"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -197,208 +266,367 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import ctypes as C
-    from dpp_b200.lib import lib, AUG_REC_DTYPE
-    from dpp_b200.engine import Engine
-    from net.resnet import ResNet, ResNetParams
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    dev = torch.device('cuda', local)
-    precision = int(os.environ.get('DPP_PRECISION', '1'))
-    ds, comp, mean = make_workload(seed=23455 + rank)
-    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=B, numJoints=1, nDims=E))
-    eng = Engine(net, precision=precision)
-    net._eng = eng
-    eng._alloc_training()
-    if world > 1:
-        eng.set_world(world, lambda g: dist.all_reduce(g))
-    total = args.warmup + args.steps
-    rng = np.random.RandomState(1234 + rank)
-    nrec = min(total, 64)                    # distinct record sets, cycled
-    recs_all, ys_all = [], []
-    for s in range(nrec):
-        idxs = rng.randint(0, N_RESIDENT, B)
-        r, y, _ = records_for(ds, comp, mean, idxs, rng)
-        recs_all.append(r); ys_all.append(y)
-    crops_dev = torch.from_numpy(ds['x'][:, 0].copy()).to(dev)
-    recs_np = np.concatenate(recs_all)
-    recs_dev = torch.from_numpy(recs_np.view(np.uint8).reshape(len(recs_np), -1).copy()).to(dev)
-    ys_dev = torch.from_numpy(np.concatenate(ys_all)).to(dev)
-    rec_bytes = np.dtype(AUG_REC_DTYPE).itemsize
-    eng.set_lr(1e-4)
-    launches = {'n': 0}
+class Ctx(object):
+    """device, ranks and the timing helper shared by the measurements of one run"""
 
-    def step_resident(s):
-        k = s % nrec
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        lib.dpp_augment_fwd(C.c_void_p(crops_dev.data_ptr()), C.c_void_p(recs_dev.data_ptr() + k * B * rec_bytes),
-                            C.c_void_p(eng.t_in.buf.data_ptr()), B, 128, 128, st)
-        eng.y_in.copy_(ys_dev[k * B:(k + 1) * B], non_blocking=True)
-        eng.train_step(None, use_graph=True)
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+            self.dist = dist
+        self.dev = torch.device('cuda', self.local)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(self, fn, steps, warmup):
+        """W untimed steps, then exactly `steps` timed ones between barrier + synchronize, CUDA events, max over ranks"""
+        torch = self.torch
         for s in range(warmup):
             fn(s)
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(steps):
             fn(warmup + s)
         e1.record()
-        barrier()
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if self.dist is not None:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             ms = float(t[0])
         return ms / steps
 
-    clocks = ClockSampler(local)
+
+class StepRunner(object):
+    """One training workload on this rank: engine, resident crops, pre-built record sets, the step functions."""
+
+    def __init__(self, ctx, dataset, aug_modes, batch, total_steps, syncbn=False, seed0=23455):
+        import ctypes as C
+        torch = ctx.torch
+        from dpp_b200.lib import lib, AUG_REC_DTYPE
+        from dpp_b200.engine import Engine
+        from net.resnet import ResNet, ResNetParams
+        self.C, self.lib, self.ctx, self.nb, self.aug_modes = C, lib, ctx, batch, aug_modes
+        self.precision = int(os.environ.get('DPP_PRECISION', '1'))
+        self.ds, self.comp, self.mean = make_workload(seed=seed0 + ctx.rank, dataset=dataset)
+        net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=batch, numJoints=1, nDims=E))
+        self.eng = eng = Engine(net, precision=self.precision)
+        net._eng = eng
+        eng._alloc_training()
+        if ctx.world > 1:
+            dist = ctx.dist
+            eng.set_world(ctx.world, lambda g: dist.all_reduce(g), rank=ctx.rank, syncbn=syncbn)
+        self.rng = np.random.RandomState(1234 + ctx.rank)
+        self.nrec = min(total_steps, 64)             # distinct record sets, cycled
+        self.recs_all, self.ys_all = [], []
+        for s in range(self.nrec):
+            idxs = self.rng.randint(0, N_RESIDENT, batch)
+            r, y, _ = records_for(self.ds, self.comp, self.mean, idxs, self.rng, aug_modes)
+            self.recs_all.append(r); self.ys_all.append(y)
+        dev = ctx.dev
+        self.crops_dev = torch.from_numpy(self.ds['x'][:, 0].copy()).to(dev)
+        recs_np = np.concatenate(self.recs_all)
+        self.recs_dev = torch.from_numpy(recs_np.view(np.uint8).reshape(len(recs_np), -1).copy()).to(dev)
+        self.ys_dev = torch.from_numpy(np.concatenate(self.ys_all)).to(dev)
+        self.rec_bytes = np.dtype(AUG_REC_DTYPE).itemsize
+        eng.set_lr(1e-4)
+
+    def augment(self, crops_ptr, recs_ptr):
+        C, torch = self.C, self.ctx.torch
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.lib.dpp_augment_fwd(C.c_void_p(crops_ptr), C.c_void_p(recs_ptr), C.c_void_p(self.eng.t_in.buf.data_ptr()),
+                                 self.nb, 128, 128, st)
+
+    def step_resident(self, s):
+        k = s % self.nrec
+        nb = self.nb
+        self.augment(self.crops_dev.data_ptr(), self.recs_dev.data_ptr() + k * nb * self.rec_bytes)
+        self.eng.y_in.copy_(self.ys_dev[k * nb:(k + 1) * nb], non_blocking=True)
+        self.eng.train_step(None, use_graph=True)
+
+    def cost_check(self):
+        """ONE step through the timed code path (CUDA graph, batch of the full size) on a fixed batch from the initial
+        weights, its cost compared with the float64 oracle's value for the same batch (tests/golden/bench_first_step.json,
+        written by tests/golden/make_bench_golden.py): the measured path is itself checked, not only its small-batch
+        relatives.  Only defined for the default workload on rank 0's data (seed 23455)."""
+        torch = self.ctx.torch
+        p = os.path.join(ROOT, 'tests', 'golden', 'bench_first_step.json')
+        if not os.path.exists(p):
+            return {"skipped": "no golden file"}
+        gold = json.load(open(p))
+        if gold.get('batch') != self.nb or gold.get('n_resident') != N_RESIDENT:
+            return {"skipped": "golden value is for batch %s of %s resident crops" % (gold.get('batch'), gold.get('n_resident'))}
+        idxs, r, y, _ = first_batch(self.ds, self.comp, self.mean, self.nb)
+        dev = self.ctx.dev
+        rd = torch.from_numpy(r.view(np.uint8).reshape(len(r), -1).copy()).to(dev)
+        self.augment(self.crops_dev.data_ptr(), rd.data_ptr())
+        self.eng.y_in.copy_(torch.from_numpy(y).to(dev))
+        cost = float(self.eng.train_step(None, use_graph=True).cpu()[0])
+        rel = abs(cost - gold['cost']) / abs(gold['cost'])
+        return {"engine": cost, "oracle": gold['cost'], "rel": rel, "ok": bool(rel < 1e-4), "tolerance": 1e-4,
+                "batch": self.nb, "golden": "tests/golden/bench_first_step.json"}
+
+
+def measure_e2e(run, ctx, steps, warmup, with_prep):
+    """host buffers in, cost out, every step.  with_prep: the draws, the augmentation records and the embedded labels of
+    batch s+1 are computed on the host (one thread) while step s runs on the device - all inside the timed region."""
+    import ctypes as C
+    torch = ctx.torch
+    eng, nb, dev = run.eng, run.nb, ctx.dev
+    rec_bytes = run.rec_bytes
+    stage_x = [torch.empty((nb, 128, 128), dtype=torch.float32, device=dev) for _ in range(2)]
+    stage_r = [torch.empty((nb, rec_bytes), dtype=torch.uint8, device=dev) for _ in range(2)]
+    stage_y = [torch.empty((nb, E), dtype=torch.float32, device=dev) for _ in range(2)]
+    cost_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    if with_prep:
+        rng2 = np.random.RandomState(777 + ctx.rank)
+        hx = [torch.empty((nb, 128, 128), dtype=torch.float32).pin_memory() for _ in range(2)]
+        hr = [torch.empty((nb, rec_bytes), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        hy = [torch.empty((nb, E), dtype=torch.float32).pin_memory() for _ in range(2)]
+        xs_host = run.ds['x'][:, 0]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        copy_stream = torch.cuda.Stream(device=dev)
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prep(b):
+            idxs = rng2.randint(0, N_RESIDENT, nb)
+            r, yv, _ = records_for(run.ds, run.comp, run.mean, idxs, rng2, run.aug_modes)
+            r = r.copy()
+            src = r['src_index'].copy()
+            r['src_index'] = np.arange(nb, dtype=np.int32)            # records index the staged batch
+            hx[b].numpy()[...] = xs_host[src]
+            hr[b].numpy()[...] = r.view(np.uint8).reshape(nb, -1)
+            hy[b].numpy()[...] = yv
+
+        def upload(b):
+            copy_stream.wait_event(consumed[b])                       # the step that read staging set b is done with it
+            with torch.cuda.stream(copy_stream):
+                stage_x[b].copy_(hx[b], non_blocking=True)
+                stage_r[b].copy_(hr[b], non_blocking=True)
+                stage_y[b].copy_(hy[b], non_blocking=True)
+                copied[b].record(copy_stream)
+
+        state = {'ready': None}
+
+        def step(s):
+            b = s & 1
+            main = torch.cuda.current_stream()
+            if state['ready'] != s:                                   # first step of a run: nothing prepared yet
+                prep(b); upload(b)
+            main.wait_event(copied[b])
+            run.augment(stage_x[b].data_ptr(), stage_r[b].data_ptr())
+            eng.y_in.copy_(stage_y[b], non_blocking=True)
+            consumed[b].record(main)
+            cost = eng.train_step(None, use_graph=True)
+            copied[b ^ 1].synchronize()                               # pinned set b^1 has been read by its last upload
+            prep(b ^ 1)                                               # host work of the NEXT batch, under this step
+            upload(b ^ 1)
+            state['ready'] = s + 1
+            cost_host.copy_(cost, non_blocking=False)                 # the float train_model() returns
+        for e in copied + consumed:
+            e.record()
+        note = "per step, inside the timed region: random draws + augmentation records + label embedding on one host " \
+               "thread (overlapping the previous step), crops + records + labels copied from pinned host memory, cost read back"
+    else:
+        host_batches = []
+        for k in range(run.nrec):
+            r = run.recs_all[k].copy()
+            src = r['src_index'].copy()
+            r['src_index'] = np.arange(nb, dtype=np.int32)
+            host_batches.append((torch.from_numpy(run.ds['x'][src, 0].copy()).pin_memory(),
+                                 torch.from_numpy(r.view(np.uint8).reshape(nb, -1).copy()).pin_memory(),
+                                 torch.from_numpy(run.ys_all[k].copy()).pin_memory()))
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {'next': None}
+
+        def upload(s):
+            b = s & 1
+            hx_, hr_, hy_ = host_batches[s % run.nrec]
+            copy_stream.wait_event(consumed[b])
+            with torch.cuda.stream(copy_stream):
+                stage_x[b].copy_(hx_, non_blocking=True)
+                stage_r[b].copy_(hr_, non_blocking=True)
+                stage_y[b].copy_(hy_, non_blocking=True)
+                copied[b].record(copy_stream)
+
+        def step(s):
+            b = s & 1
+            main = torch.cuda.current_stream()
+            if state['next'] != s:
+                upload(s)
+            upload(s + 1)
+            state['next'] = s + 1
+            main.wait_event(copied[b])
+            run.augment(stage_x[b].data_ptr(), stage_r[b].data_ptr())
+            eng.y_in.copy_(stage_y[b], non_blocking=True)
+            consumed[b].record(main)
+            cost = eng.train_step(None, use_graph=True)
+            cost_host.copy_(cost, non_blocking=False)
+        note = "records built on the host BEFORE the timed region; per step crops + records + labels copied from pinned " \
+               "host memory, cost read back"
+    ms = ctx.timed(step, steps, warmup)
+    return ms, note
+
+
+def measure_trainer_api(ctx, epochs=3, n_train=2048):
+    """frames/s of PoseRegNetTrainer.train() - the call the reference's entry scripts make - on a resident synthetic NYU
+    set: per epoch 16 minibatches of 128, the augmented set regenerated on the device from fresh host records
+    (force_macrobatch_reload, as main_nyu_posereg_embedding.py:112 sets it), the cost returned to the host every
+    minibatch; validation switched off inside the timed epochs (validation_frequency beyond the run)."""
+    import contextlib
+    import io
+    from data import synthetic
+    from net.resnet import ResNet, ResNetParams
+    from trainer.poseregnettrainer import PoseRegNetTrainer, PoseRegNetTrainerParams
+    ds, comp, mean = make_workload(seed=4242, n=n_train)
+    y = np.dot(ds['gt3Dcrop'].reshape(n_train, -1).astype(np.float64) - mean, comp.T).astype(np.float32)
+    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=B, numJoints=1, nDims=E))
+    p = PoseRegNetTrainerParams()
+    p.batch_size, p.learning_rate, p.weightreg_factor = B, 1e-4, 0.0
+    p.force_macrobatch_reload, p.para_augment, p.para_num_proc = True, True, 1
+    p.validation_frequency = 10 ** 9
+    p.snapshot_last = 10 ** 9
+
+    class _Proj(object):
+        def transform(self, lab):
+            return np.dot(np.asarray(lab, np.float64) - mean, comp.T)
+    p.augment_fun_params = {'fun': 'augment_poses', 'args': {'normZeroOne': False, 'di': ds['importer'], 'hd': ds['hd'],
+                                                              'aug_modes': AUG_MODES, 'proj': _Proj()}}
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = PoseRegNetTrainer(net, p, np.random.RandomState(23455), './')
+        tr.verbose = False
+        tr.setData(ds['x'], y, ds['x'][:B], y[:B])
+        tr.addStaticData({'val_data_y3D': ds['gt3D'][:B], 'pca_data': comp.astype(np.float32), 'mean_data': mean.astype(np.float32)})
+        tr.addManagedData({'train_data_cube': ds['cube'], 'train_data_com': ds['com3D'], 'train_data_M': ds['M'],
+                           'train_gt3Dcrop': ds['gt3Dcrop']})
+        tr.compileFunctions()
+        tr.poseNet.save = lambda *a, **k: None               # no snapshot files from a benchmark
+        tr.train(n_epochs=1)                                  # warm-up epoch: graph capture, first augmentation
+        ctx.torch.cuda.synchronize()
+        t0 = time.time()
+        tr.train(n_epochs=epochs)
+        ctx.torch.cuda.synchronize()
+        dt = time.time() - t0
+    frames = epochs * tr.getNumFullMiniBatches() * B
+    net._eng.release()
+    return {"value": frames / dt, "unit": UNIT, "epochs": epochs, "minibatches_per_epoch": tr.getNumFullMiniBatches(),
+            "wall_s": dt,
+            "note": "PoseRegNetTrainer.train() on %d resident crops: per epoch new draws + records on the host, the "
+                    "augmented set regenerated on the device, one train_model() call and one cost read-back per "
+                    "minibatch, plus the initial validation pass of each train() call" % n_train}
+
+
+def run_b200(args):
+    ctx = Ctx()
+    torch = ctx.torch
+    rank, world = ctx.rank, ctx.world
+    dataset, aug_modes, per_gpu, global_b, descr = WORKLOADS[args.workload]
+    per_gpu = B if per_gpu == 'B' else per_gpu
+    global_b = STRONG_GLOBAL_B if global_b == 'STRONG' else global_b
+    if per_gpu is None:
+        if global_b % world:
+            raise SystemExit("global batch %d does not divide over %d ranks" % (global_b, world))
+        nb, scaling = global_b // world, "strong"
+    else:
+        nb, scaling = per_gpu, "weak"
+    warm = max(args.warmup, 3)
+    total = warm + args.steps
+    run = StepRunner(ctx, dataset, aug_modes, nb, total, syncbn=args.syncbn)
+    eng = run.eng
+    check = None
+    if args.workload == 'train' and rank == 0 and not args.no_cost_check:
+        check = run.cost_check()
+    clocks = ClockSampler(ctx.local)
     if rank == 0:
         clocks.start()
-    ms_step = timed(step_resident, args.steps, max(args.warmup, 3))
-    value = B * world / (ms_step / 1000.)
+    ms_step = ctx.timed(run.step_resident, args.steps, warm)
+    value = nb * world / (ms_step / 1000.)
 
-    # ---- e2e: host buffers in, cost out, every step
-    # two staging sets: the host->device copies of batch s+1 run on a copy stream underneath the compute of batch s
-    stage_x = [torch.empty((B, 128, 128), dtype=torch.float32, device=dev) for _ in range(2)]
-    stage_r = [torch.empty((B, rec_bytes), dtype=torch.uint8, device=dev) for _ in range(2)]
-    stage_y = [torch.empty((B, E), dtype=torch.float32, device=dev) for _ in range(2)]
-    host_batches = []
-    for k in range(nrec):
-        r = recs_all[k].copy()
-        src = r['src_index'].copy()
-        r['src_index'] = np.arange(B, dtype=np.int32)        # records index the staged batch
-        host_batches.append((torch.from_numpy(ds['x'][src, 0].copy()).pin_memory(),
-                             torch.from_numpy(r.view(np.uint8).reshape(B, -1).copy()).pin_memory(),
-                             torch.from_numpy(ys_all[k].copy()).pin_memory()))
-    cost_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event(), torch.cuda.Event()]        # staging set b holds a complete batch
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]      # the step that read staging set b has consumed it
-    state = {'next': None}
-
-    def upload(s):
-        b = s & 1
-        hx, hr, hy = host_batches[s % nrec]
-        copy_stream.wait_event(consumed[b])
-        with torch.cuda.stream(copy_stream):
-            stage_x[b].copy_(hx, non_blocking=True)
-            stage_r[b].copy_(hr, non_blocking=True)
-            stage_y[b].copy_(hy, non_blocking=True)
-            copied[b].record(copy_stream)
-
-    def step_e2e(s):
-        b = s & 1
-        main = torch.cuda.current_stream()
-        if state['next'] != s:               # first step of a run: nothing was prefetched
-            upload(s)
-        upload(s + 1)                        # the next batch travels while this one is computed
-        state['next'] = s + 1
-        main.wait_event(copied[b])
-        st = C.c_void_p(main.cuda_stream)
-        lib.dpp_augment_fwd(C.c_void_p(stage_x[b].data_ptr()), C.c_void_p(stage_r[b].data_ptr()),
-                            C.c_void_p(eng.t_in.buf.data_ptr()), B, 128, 128, st)
-        eng.y_in.copy_(stage_y[b], non_blocking=True)
-        consumed[b].record(main)
-        cost = eng.train_step(None, use_graph=True)
-        cost_host.copy_(cost, non_blocking=False)            # the float train_model() returns
-
-    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3)) if not args.no_e2e else float('nan')
-    e2e_val = B * world / (ms_e2e / 1000.)
-
+    ms_e2e, e2e_note, ms_pre = float('nan'), "", None
+    if not args.no_e2e:
+        ms_e2e, e2e_note = measure_e2e(run, ctx, args.steps, warm, with_prep=True)
+        ms_pre, _ = measure_e2e(run, ctx, args.steps, warm, with_prep=False)
+    e2e_val = nb * world / (ms_e2e / 1000.)
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel class, timed live with CUDA events on this stream
     roof = measure_dominant_kernel(eng, torch) if not args.no_roofline else None
-    # ---- kernel launches per step (counted from the engine's op list)
     n_launch = count_launches(eng) + 1
 
-    # ---- e2e again, with the host-side record preparation INSIDE the timed region (single GPU only: an exception on
-    # one rank must not leave the others waiting in a collective).  Extra evidence, never the headline: it runs after
-    # every contract measurement has been taken, and any failure is reported in the key instead of breaking the line.
-    e2e_prep = None
-    if world == 1 and not args.no_e2e:
+    # strong-scaling sample inside the default run: BASELINE config 3 (global batch 512 split over the ranks)
+    strong = None
+    if args.workload == 'train' and not args.no_strong:
         try:
-            rng2 = np.random.RandomState(777)
-            hx = torch.empty((B, 128, 128), dtype=torch.float32).pin_memory()
-            hr = torch.empty((B, rec_bytes), dtype=torch.uint8).pin_memory()
-            hy = torch.empty((B, E), dtype=torch.float32).pin_memory()
-            xs_host = ds['x'][:, 0]
-            copied2 = torch.cuda.Event()
+            gb = STRONG_GLOBAL_B
+            if gb % world == 0:
+                eng._graphs.clear()
+                r2 = StepRunner(ctx, 'ICVL', ['com', 'rot', 'none'], gb // world, 3 + min(args.steps, 10))
+                ms2 = ctx.timed(r2.step_resident, min(args.steps, 10), 3)
+                strong = {"workload": WORKLOADS['icvl512'][4], "global_batch": gb, "per_gpu_batch": gb // world,
+                          "n_gpus": world, "ms_per_step": ms2, "value": gb / (ms2 / 1000.), "unit": UNIT,
+                          "scaling": "strong", "batchnorm": "per-replica statistics",
+                          "buckets": [list(b) for b in sorted(getattr(r2.eng, '_exchanged', []))]}
+                r2.eng._graphs.clear()
+                if world > 1:
+                    r3 = StepRunner(ctx, 'ICVL', ['com', 'rot', 'none'], gb // world, 3 + min(args.steps, 10), syncbn=True)
+                    ms3 = ctx.timed(r3.step_resident, min(args.steps, 10), 3)
+                    strong["syncbn_ms_per_step"] = ms3
+                    strong["syncbn_value"] = gb / (ms3 / 1000.)
+                    r3.eng._graphs.clear()
+        except Exception as exc:                 # pragma: no cover - extra evidence must not break the contract line
+            if world > 1:
+                raise
+            strong = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
 
-            def prep():
-                idxs = rng2.randint(0, N_RESIDENT, B)
-                r, yv, _ = records_for(ds, comp, mean, idxs, rng2)
-                r = r.copy()
-                src = r['src_index'].copy()
-                r['src_index'] = np.arange(B, dtype=np.int32)
-                hx.numpy()[...] = xs_host[src]
-                hr.numpy()[...] = r.view(np.uint8).reshape(B, -1)
-                hy.numpy()[...] = yv
-
-            def step_prep(s):
-                main = torch.cuda.current_stream()
-                stage_x[0].copy_(hx, non_blocking=True)
-                stage_r[0].copy_(hr, non_blocking=True)
-                stage_y[0].copy_(hy, non_blocking=True)
-                copied2.record(main)
-                st = C.c_void_p(main.cuda_stream)
-                lib.dpp_augment_fwd(C.c_void_p(stage_x[0].data_ptr()), C.c_void_p(stage_r[0].data_ptr()),
-                                    C.c_void_p(eng.t_in.buf.data_ptr()), B, 128, 128, st)
-                eng.y_in.copy_(stage_y[0], non_blocking=True)
-                cost = eng.train_step(None, use_graph=True)
-                copied2.synchronize()            # the pinned buffers have been read: the next batch may overwrite them
-                prep()                           # host: draws + records + labels of the NEXT batch, under this step
-                cost_host.copy_(cost, non_blocking=False)
-            prep()
-            ms_prep = timed(step_prep, args.steps, max(args.warmup, 3))
-            e2e_prep = {"value": B / (ms_prep / 1000.), "unit": UNIT, "ms_per_step": ms_prep,
-                        "note": "as e2e, plus the random draws, augmentation records and embedded labels of every batch "
-                                "computed on one host thread inside the timed region (overlapping the previous step)"}
+    trainer_api = None
+    if world == 1 and args.workload == 'train' and not args.no_e2e and not args.no_trainer_api:
+        try:
+            eng._graphs.clear()
+            trainer_api = measure_trainer_api(ctx)
         except Exception as exc:                 # pragma: no cover
-            e2e_prep = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+            trainer_api = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+
     if rank != 0:
-        if dist is not None:
-            shutdown_distributed(dist, eng)
+        if ctx.dist is not None:
+            shutdown_distributed(ctx.dist, [eng])
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = cpu_threads()
-        t = cpu_step_time(ds, comp, mean, 3, threads)[1:]
-        v = B / float(np.mean(t))
+        v, threads, tried = cpu_arm(run.ds, run.comp, run.mean, 2, 1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "2 steps of the batch-128 workload (cv2 augmentation + torch-CPU ResNet fwd/bwd/ADAM) after "
-                         "1 warm-up step"}
-    h2d = B * 128 * 128 * 4 + B * rec_bytes + B * E * 4
+               "sample": "2 steps of the batch-128 workload (cv2 augmentation in 8 worker processes + torch-CPU ResNet "
+                         "fwd/bwd/ADAM) after 1 warm-up step; frames/s by torch thread count: %s; host cores "
+                         "available: %d" % ({k: round(x, 1) for k, x in tried.items()}, cpu_threads())}
+    h2d = nb * 128 * 128 * 4 + nb * run.rec_bytes + nb * E * 4
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {0: "f32", 1: "tf32x3", 2: "tf32"}[precision], "data": "synthetic",
-        "config": {"workload": "NYU posereg_embedding ResNet(type 0, 30-D embedding) training, batch 128/GPU, "
-                               "aug rot/com/none, %d resident crops" % N_RESIDENT,
-                   "global_batch": B * world, "parallelism": "dp%d" % world,
+        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": {0: "f32", 1: "tf32x3", 2: "tf32"}[run.precision], "data": "synthetic",
+        "config": {"workload": "%s, %d resident crops" % (descr, N_RESIDENT),
+                   "global_batch": nb * world, "per_gpu_batch": nb, "parallelism": "dp%d" % world,
+                   "batchnorm": "SyncBN (statistics summed over the ranks)" if (args.syncbn and world > 1) else
+                                ("per-replica statistics" if world > 1 else "single device"),
                    "l2": "inputs (134 MB of crops + 0.9 GB of activations per step) exceed the 126 MB L2",
-                   "precision_mode": precision},
+                   "precision_mode": run.precision},
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4,
-                "note": "per step: crops + augmentation records + labels copied from pinned host memory, cost read "
-                        "back; the records are built on the host BEFORE the timed region (vectorised, ~2 ms per batch "
-                        "on one thread, i.e. less than a step); e2e_with_host_prep times them too"},
-        "e2e_with_host_prep": e2e_prep,
+                "d2h_bytes_per_step": 4, "note": e2e_note},
+        "e2e_records_prebuilt": None if ms_pre is None else {"value": nb * world / (ms_pre / 1000.), "unit": UNIT,
+                                                               "ms_per_step": ms_pre},
+        "trainer_api": trainer_api,
+        "cost_check": check,
+        "strong": strong,
         "gpu_launches": n_launch * args.steps,
         "clocks": clk,
         "roofline": roof,
@@ -406,14 +634,19 @@ def run_b200(args):
         "tensor_fraction_whole_step": value / world * TRAIN_GFLOP_PER_FRAME / 1000. / peaks()[1],
     }
     print(json.dumps(out))
-    if dist is not None:
-        shutdown_distributed(dist, eng)
+    if check is not None and check.get('ok') is False:
+        print("bench.py: the timed path's first-step cost differs from the oracle: %r" % (check,), file=sys.stderr)
+        if ctx.dist is not None:
+            shutdown_distributed(ctx.dist, [eng])
+        sys.exit(3)
+    if ctx.dist is not None:
+        shutdown_distributed(ctx.dist, [eng])
 
 
 def count_launches(eng):
-    """kernels of OUR library launched per training step (checked against the ncu launch list: 275 for the ResNet)"""
+    """kernels of OUR library launched per training step (checked against the ncu launch list)"""
     n = 1 + 2 + 1 + 1      # loss, adam + tick, weight-image pack, ema (the two arena fills are memset nodes)
-    n += len(eng.bns)      # one BN-backward apply per BatchNorm
+    n += eng.launches_bn_bwd() if hasattr(eng, 'launches_bn_bwd') else len(eng.bns)
     for op in eng.ops:
         k = op['kind']
         if k == 'conv':
@@ -431,7 +664,7 @@ def measure_dominant_kernel(eng, torch):
     """Roofline of the dominant kernel, timed live with CUDA events on the launching stream.
 
     The dominant kernel of the step is the implicit-GEMM convolution (k_conv_tc in precision 1/2, k_igemm in
-    precision 0: 126 of the ~285 launches and ~half of the GPU time, see profiles/).  All 63 ConvLayer forward
+    precision 0: 126 of the launches and ~40 % of the GPU time, see profiles/).  All 63 ConvLayer forward
     launches of the batch-128 net are issued back to back between two events (their 0.9 GB of activations exceed
     the 126 MB L2, so no flush is needed) and the average launch is compared with HBM speed: per launch the
     ALGORITHMIC bytes are 4 * (input + output [+ residual]) elements - at ~20 FLOP/B the
@@ -472,16 +705,20 @@ def measure_dominant_kernel(eng, torch):
     per_launch_bytes = bytes_alg / len(calls)
     gbs = per_launch_bytes / (ms * 1e-3) / 1e9
     tflops = 2.0 * macs / len(calls) / (ms * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get('conv_fwd_avg_bytes_per_launch')
+            tj = json.load(open(tp))
+            traffic = tj.get('conv_fwd_avg_bytes_per_launch')
+            traffic_src = "COMMITTED figure, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per " \
+                          "launch from the ncu pass recorded in profiles/ncu_traffic.json (%s)" % tj.get('source', 'see profiles/README.md')
         except Exception:
             traffic = None
     kname = {0: 'k_igemm', 1: 'k_conv_tc<*,2>', 2: 'k_conv_tc<*,1>'}[eng.precision]
     return {"bound": "hbm", "kernel": "%s: the %d ConvLayer forward launches of the step, back to back" % (kname, len(calls)),
             "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": "%s HBM copy bandwidth (MEASURED_PEAKS.json)" % how,
             "ms_per_launch": ms, "launches_timed": reps * len(calls), "alg_bytes_per_launch": per_launch_bytes,
             "tensor_tflops": tflops, "tensor_peak_tflops_tf32": burst / 2.0,
@@ -497,9 +734,14 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true', help='skip the live kernel timing (profiler runs)')
-    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiler runs)')
-    ap.add_argument('--workload', default='train', choices=['train', 'cascade'],
-                    help="train = BASELINE configs[1] (the headline); cascade = configs[4], tools/bench_cascade.py")
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arms (profiler runs)')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling sample of the default workload')
+    ap.add_argument('--no-trainer-api', action='store_true', help='skip the PoseRegNetTrainer.train() measurement')
+    ap.add_argument('--no-cost-check', action='store_true')
+    ap.add_argument('--syncbn', action='store_true', help='N > 1: sum the BatchNorm statistics over the ranks')
+    ap.add_argument('--workload', default='train', choices=['train', 'icvl512', 'msra15', 'cascade'],
+                    help="train = BASELINE configs[1] (the headline); icvl512 = configs[2]; msra15 = configs[3]; "
+                         "cascade = configs[4], tools/bench_cascade.py")
     args, rest = ap.parse_known_args()
     if args.workload == 'cascade':
         sys.path.insert(0, os.path.join(ROOT, 'tools'))

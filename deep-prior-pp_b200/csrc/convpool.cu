@@ -374,7 +374,7 @@ int make_dims(CPDims &d, int N, int H, int W, int Cin, int Cout, int k, int pad,
 
 }  // namespace
 
-// convpool8.cu: opt-in specialised kernels for the 8-filter 'valid' towers (DPP_CONVPOOL_FAST=1)
+// convpool8.cu: specialised kernels for the 8-filter 'valid' towers (default; DPP_CONVPOOL_FAST=0 switches them off)
 int dpp_convpool8_try(const float *x, const float *w, const float *bias, float *y, uint8_t *argmax, double *stats, int N,
                       int H, int W, int Cin, int Cout, int k, int pad, int pool, int relu, void *stream);
 

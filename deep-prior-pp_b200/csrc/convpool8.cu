@@ -6,10 +6,10 @@
 // loop bounds are template parameters (fully unrolled FMAs out of registers), the pooled tile is 16 x 16 so every
 // thread owns one pooled pixel x 8 channels, and the weights are read as broadcast shared-memory vectors.
 //
-// STATUS (round 1): OPT-IN via DPP_CONVPOOL_FAST=1 - written after the round's GPU budget was spent, so it has run
-// on the CPU only (tests/test_host_convpool8.py executes the shared per-thread code convpool8.cuh on the host against
-// an independent reference) and NOT yet on a B200; the default path is unchanged.  tests/test_gpu_zz_convpool8.py
-// (run with DPP_TEST_CONVPOOL_FAST=1) compares it bit for bit with the generic kernel.
+// STATUS: default path since round 2 (DPP_CONVPOOL_FAST=0 selects the generic kernel).  Verified on a B200:
+// tests/test_gpu_convpool8.py - outputs and arg-max cells bit for bit equal to the generic kernel for every tower
+// shape; cascade batch of 1024 frames 11.15 -> 7.98 ms (profiles/README.md, round 2).  tests/test_host_convpool8.py
+// runs the shared per-thread code (convpool8.cuh) on the host against an independent reference.
 #include <stdlib.h>
 #include "common.cuh"
 #include "convpool8.cuh"
@@ -75,7 +75,7 @@ int launch8(const float *x, const float *w, const float *bias, float *y, uint8_t
 int dpp_convpool8_try(const float *x, const float *w, const float *bias, float *y, uint8_t *argmax, double *stats, int N,
                       int H, int W, int Cin, int Cout, int k, int pad, int pool, int relu, void *stream) {
     const char *e = getenv("DPP_CONVPOOL_FAST");
-    if (e == nullptr || e[0] != '1') return DPP_ENOTSUP;
+    if (e != nullptr && e[0] == '0') return DPP_ENOTSUP;
     if (Cout != 8 || pad != 0 || stats != nullptr) return DPP_ENOTSUP;
     cudaStream_t st = S(stream);
     int rc = DPP_ENOTSUP;

@@ -74,3 +74,27 @@ def make_allreduce(dist, group=None, bucket_elems=8 * 1024 * 1024):
         for lo, hi in bucket_bounds(g.numel(), bucket_elems):
             dist.all_reduce(g[lo:hi], group=group)
     return fn
+
+
+def plan_buckets(slot_offsets, n_elems, events, min_elems):
+    """Exchange plan of the flat gradient arena for the backward pass.
+
+    The arena holds the parameter slots in layer order (``slot_offsets``, ``n_elems`` floats in total); the
+    backward pass fills it from the END: ``events[i] = (offsets of the slots whose gradient kernels have been issued
+    once step i of the reverse walk is done, force)``.  After every step the longest fully issued SUFFIX [lo, n) of
+    the arena is known; a bucket [lo, hi) is cut there as soon as it holds >= ``min_elems`` floats, or at once when
+    ``force`` is set (end of the FC tail: 90 % of the bytes, complete when the backward pass has barely begun).
+    The bucket that reaches offset 0 is returned separately: it trails the last backward kernel.
+    Returns ({step index: (lo, hi)}, (0, hi) or None)."""
+    order = sorted(slot_offsets)
+    done = set()
+    cuts, hi, k = {}, n_elems, len(order)
+    for i, (offs, force) in enumerate(events):
+        done.update(offs)
+        while k > 0 and order[k - 1] in done:
+            k -= 1
+        lo = order[k] if 0 < k < len(order) else (0 if k == 0 else n_elems)
+        if lo > 0 and hi > lo and (hi - lo >= min_elems or force):
+            cuts[i] = (lo, hi)
+            hi = lo
+    return cuts, ((0, hi) if hi > 0 else None)

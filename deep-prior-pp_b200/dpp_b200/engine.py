@@ -627,36 +627,21 @@ class Engine(object):
         return out
 
     def _plan_buckets(self, min_elems):
-        """Data-parallel exchange plan: the gradient arena is in layer order and the backward pass completes it from
-        the END (FC tail first, stem last).  Walk the reverse op list, track the longest fully-issued suffix of the
-        arena and cut a bucket [lo, hi) after the op that completes it once it holds >= min_elems parameters - the FC
-        tail (90 % of the bytes) becomes the first bucket as soon as the FC backward is issued, the deep conv stages
-        follow, and only the small remainder (first stage + stem) trails the last backward kernel.
-        Returns {index in reversed(self.ops): (lo, hi)} plus the trailing (lo, hi) or None."""
+        """Data-parallel exchange plan (dp.plan_buckets): which slices of the gradient arena can be summed over the
+        ranks after which op of the reverse walk.  Returns ({index in reversed(self.ops): (lo, hi)}, trailing)."""
+        from . import dp
         pending = {id(bn): len(self.bn_consumers.get(id(bn), [])) for bn in self.bns}
-        done = set()
-        order = sorted(self.w_slots, key=lambda sl: sl.offset)
-        cuts, hi, k_suffix = {}, self.n_w, len(order)
-        for i, op in enumerate(reversed(self.ops)):
+        events, rev = [], list(reversed(self.ops))
+        for i, op in enumerate(rev):
             finished = []
             bn = op.get('in_bn') if op['kind'] == 'conv' else (op.get('bn') if op['kind'] == 'bn_apply' else None)
             if bn is not None:
                 pending[id(bn)] -= 1
                 if pending[id(bn)] == 0:
                     finished.append(bn)
-            for sl in self._grad_slots_of(op, finished):
-                done.add(id(sl))
-            while k_suffix > 0 and id(order[k_suffix - 1]) in done:
-                k_suffix -= 1
-            lo = order[k_suffix].offset if k_suffix < len(order) else self.n_w
-            if k_suffix == 0:
-                lo = 0
-            is_fc_tail_end = op['kind'] == 'fc' and (i + 1 == len(self.ops) or list(reversed(self.ops))[i + 1]['kind'] != 'fc')
-            if hi - lo >= min_elems or (is_fc_tail_end and hi > lo):
-                if lo > 0:                       # the bucket that reaches offset 0 is the trailing one
-                    cuts[i] = (lo, hi)
-                    hi = lo
-        return cuts, ((0, hi) if hi > 0 else None)
+            force = op['kind'] == 'fc' and (i + 1 == len(rev) or rev[i + 1]['kind'] != 'fc')    # end of the FC tail
+            events.append(([sl.offset for sl in self._grad_slots_of(op, finished)], force))
+        return dp.plan_buckets([sl.offset for sl in self.w_slots], self.n_w, events, min_elems)
 
     def _run_backward(self):
         """Reverse walk.  t.grad of the output tensor must hold dCost/dOut on entry."""

@@ -125,7 +125,7 @@ class NetBase(object):
         if eng is None or eng.output_sym is not self.output:
             if eng is not None:
                 eng.release()
-            eng = Engine(self)
+            eng = Engine(self, **getattr(self, '_engine_opts', {}))     # a data-parallel trainer sets {'batch': B / world}
             self._eng = eng
         return eng
 
@@ -143,27 +143,30 @@ class NetBase(object):
         padSize = int(batch_size * numpy.ceil(nSamp / float(batch_size)))
         eng = self._engine()
         multi_out = isinstance(self.output, list)
-        outdims = self.cfgParams.outputDim if multi_out else [self.cfgParams.outputDim]
+        if multi_out:
+            raise NotImplementedError("networks with several outputs (none of the reference's nets has more than one)")
+        outdims = [self.cfgParams.outputDim]
         out = [numpy.zeros((padSize,) + tuple(od[1:]), dtype='float32') for od in outdims]
-        n_test_batches = padSize // batch_size
+        # the device executor may hold a share of the batch only (data-parallel training): walk the padded sample
+        # range in ITS batch size - in deterministic mode every sample is independent, so the result is the same
+        dev_batch = eng.B
+        assert padSize % dev_batch == 0
         start = time.time()
-        for i in range(n_test_batches):
+        for i in range(padSize // dev_batch):
             batch = []
             for k in range(len(inputs)):
-                chunk = inputs[k][i * batch_size:(i + 1) * batch_size]
-                if chunk.shape[0] < batch_size:
-                    pad = numpy.zeros((batch_size,) + chunk.shape[1:], dtype=inputs[k].dtype)
+                chunk = inputs[k][i * dev_batch:(i + 1) * dev_batch]
+                if chunk.shape[0] < dev_batch:
+                    pad = numpy.zeros((dev_batch,) + chunk.shape[1:], dtype=inputs[k].dtype)
                     pad[0:chunk.shape[0]] = chunk
                     pad[chunk.shape[0]:] = inputs[k][-1]
                     chunk = pad
                 batch.append(numpy.ascontiguousarray(chunk, dtype='float32'))
             o = eng.forward_host(batch)
-            out[0][i * batch_size:(i + 1) * batch_size] = o.reshape((batch_size,) + tuple(outdims[0][1:]))
+            out[0][i * dev_batch:(i + 1) * dev_batch] = o.reshape((dev_batch,) + tuple(outdims[0][1:]))
         end = time.time()
         if timeit:
             print("{} in {}s, {}ms per frame".format(padSize, end - start, (end - start) * 1000. / padSize))
-        if multi_out:
-            return [o[0:nSamp] for o in out]
         return out[0][0:nSamp]
 
     # -- train/test switch (netbase.py:318-358) ------------------------------------------
@@ -212,6 +215,12 @@ class NetBase(object):
 
     # -- checkpoints (netbase.py:405-477) --------------------------------------------------
     def save(self, filename):
+        try:                                    # data-parallel job: the replicas are identical, rank 0 writes
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+                return
+        except ImportError:
+            pass
         state = dict([('class', self.__class__.__name__), ('network', self.__str__())])
         for layer in self.layers:
             key = '{}-values'.format(layer.layerNum)

@@ -12,6 +12,7 @@ rule with ``RandomState(N)`` (:365-413), fresh augmentation per epoch swapped in
 minibatch of an epoch is requested (:528-529), ``lr_of_ep`` (:54), validation every
 ``validation_frequency`` iterations on full batches only (:796,859), ``net_last.pkl`` snapshots,
 NaN abort, best-weights restore."""
+import os
 import time
 import multiprocessing
 import numpy
@@ -50,14 +51,18 @@ class NetTrainerParams(object):
 def _records_chunk(args):
     """worker: build augmentation records + labels for a slice of samples (one vectorised pass,
     ``HandDetector.aug_records_batch``: bit-identical to the per-sample ``aug_record``)"""
-    trainer_state, idxs, draws = args
+    trainer_state, idxs, draws = args[:3]
+    src_rows = args[3] if len(args) > 3 else idxs
     hd, di, aug_modes, comDB, cubeDB, MDB, gtDB, proj = trainer_state
     idxs = numpy.asarray(idxs, dtype=numpy.int64)
     if len(idxs) == 0:
         from dpp_b200.lib import AUG_REC_DTYPE
         return numpy.zeros(0, dtype=AUG_REC_DTYPE), numpy.zeros((0, 0), dtype='float32')
     com = hd._toimg(numpy.asarray(comDB, dtype='float32')[idxs])           # di.joint3DToImg, vectorised
-    recs, labels = hd.aug_records_batch(idxs, [aug_modes[d[0]] for d in draws], numpy.array([d[1] for d in draws]),
+    # idxs index the host arrays (global rows); src_rows are the rows of the device-resident crops the records read
+    # (the same numbers on one device, this rank's local rows in a data-parallel job)
+    recs, labels = hd.aug_records_batch(numpy.asarray(src_rows, dtype=numpy.int64),
+                                        [aug_modes[d[0]] for d in draws], numpy.array([d[1] for d in draws]),
                                         numpy.array([d[2] for d in draws]), numpy.array([d[3] for d in draws]), com,
                                         numpy.asarray(cubeDB)[idxs], numpy.asarray(MDB)[idxs], numpy.asarray(gtDB)[idxs])
     labels = labels.reshape(len(idxs), -1)
@@ -98,6 +103,17 @@ class NetTrainer(object):
         self.validation_observer = []
         self._pool = None
         self._dev = {}
+        # record workers (nettrainer.py:666-689 starts para_num_proc augmentation processes): forked HERE, from a
+        # process that has neither a CUDA context nor NCCL threads yet - the workers are plain NumPy processes
+        if cfgParams.para_augment and cfgParams.para_num_proc > 1:
+            self._pool = multiprocessing.get_context('fork').Pool(cfgParams.para_num_proc)
+        # data parallelism (not in the single-device reference): under torchrun the global minibatch of
+        # cfgParams.batch_size samples is split over the ranks (strong scaling, SURVEY 8e / BASELINE config 3)
+        from dpp_b200 import dp
+        self._dist, self.rank, self.world = dp.init_process_group()
+        self.local_batch = dp.local_batch(cfgParams.batch_size, self.world)
+        self.syncbn = os.environ.get('DPP_SYNCBN', '0') == '1'
+        self.verbose = getattr(self, 'verbose', True) and self.rank == 0
 
     # -- data registration ------------------------------------------------------------------
     def setData(self, train_data, train_y, val_data, val_y, max_train_size=0):
@@ -120,10 +136,14 @@ class NetTrainer(object):
         self.trainingVar += ['train_data_x', 'train_data_y']
         self.val_data_xDB = val_data
         self.val_data_yDB = val_y
-        print("{} train samples, {} val samples, batch size {}".format(train_data.shape[0], val_data.shape[0],
-                                                                       self.cfgParams.batch_size))
-        print("{} macro batches, {} mini batches per macro, {} full mini batches total".format(
-            self.getNumMacroBatches(), self.getNumMiniBatchesPerMacroBatch(), self.getNumMiniBatches()))
+        if self.rank == 0:
+            print("{} train samples, {} val samples, batch size {}".format(train_data.shape[0], val_data.shape[0],
+                                                                           self.cfgParams.batch_size))
+            print("{} macro batches, {} mini batches per macro, {} full mini batches total".format(
+                self.getNumMacroBatches(), self.getNumMiniBatchesPerMacroBatch(), self.getNumMiniBatches()))
+            if self.world > 1:
+                print("data parallel: {} ranks x {} samples per minibatch{}".format(
+                    self.world, self.local_batch, ", SyncBN" if self.syncbn else ", per-replica BatchNorm statistics"))
         self._dev_dirty = True
 
     def addData(self, data):
@@ -211,29 +231,65 @@ class NetTrainer(object):
         import torch
         if not getattr(self, '_dev_dirty', True):
             return
-        dev = self.poseNet._engine().dev
+        from dpp_b200 import dp
+        dev = self._engine().dev
         f = lambda a: torch.from_numpy(numpy.ascontiguousarray(a, dtype='float32')).to(dev)
         d = self._dev
-        d['train_x_orig'] = f(self.train_data_xDB.reshape((self.train_data_xDB.shape[0],) + self.train_data_xDB.shape[-2:])) \
-            if self.train_data_xDB.shape[1] == 1 else None
-        if d['train_x_orig'] is None:
+        if self.train_data_xDB.shape[1] != 1:
             raise NotImplementedError("multi-channel training crops")
+        B = self.cfgParams.batch_size
+        # rows of the aligned set that live on this rank: slice [rank*b, (rank+1)*b) of every global minibatch
+        rows = dp.local_rows(self.train_data_xDB.shape[0], B, self.rank, self.world)
+        self._rows = rows
+        d['train_x_orig'] = f(self.train_data_xDB[rows].reshape((len(rows),) + self.train_data_xDB.shape[-2:]))
         d['train_x'] = d['train_x_orig'].clone()
-        d['train_y'] = f(self.train_data_yDB.reshape(self.train_data_yDB.shape[0], -1))
-        nb = self.val_data_xDB.shape[0] // self.cfgParams.batch_size * self.cfgParams.batch_size
-        d['val_x'] = f(self.val_data_xDB[:nb].reshape((nb,) + self.val_data_xDB.shape[-2:]))
-        flat = lambda a: a[:nb].reshape(nb, int(numpy.prod(a.shape[1:])))      # nb may be 0: fewer validation samples than a batch
+        d['train_y'] = f(self.train_data_yDB[rows].reshape(len(rows), -1))
+        nb = self.val_data_xDB.shape[0] // B * B
+        vrows = dp.local_rows(nb, B, self.rank, self.world) if nb else numpy.zeros(0, dtype=numpy.int64)
+        d['val_x'] = f(self.val_data_xDB[:nb][vrows].reshape((len(vrows),) + self.val_data_xDB.shape[-2:]))
+        flat = lambda a: a[:nb][vrows].reshape(len(vrows), int(numpy.prod(a.shape[1:])))   # nb may be 0: fewer validation samples than a batch
         d['val_y'] = f(flat(self.val_data_yDB))
         if hasattr(self, 'val_data_y3DDB'):
             d['val_y3D'] = f(flat(self.val_data_y3DDB))
         self._dev_dirty = False
 
+    def _engine(self):
+        """the net's device executor; in a data-parallel job it is built for this rank's share of the minibatch and
+        joined to the gradient (and, with DPP_SYNCBN=1, BatchNorm-statistics) exchange"""
+        net = self.poseNet
+        if self.world > 1:
+            net._engine_opts = {'batch': self.local_batch}
+        eng = net._engine()
+        if self.world > 1 and (eng.world != self.world or eng.allreduce_fn is None):
+            dist = self._dist
+            eng.set_world(self.world, lambda t: dist.all_reduce(t), rank=self.rank, syncbn=self.syncbn)
+        return eng
+
+    def _allreduce_scalar(self, value, op='mean'):
+        """combine a per-rank scalar (cost / error of this rank's share of a minibatch) into the global figure"""
+        if self.world == 1:
+            return value
+        import torch
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self._engine().dev)
+        if op == 'max':
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+            return float(t[0])
+        self._dist.all_reduce(t)
+        return float(t[0]) / self.world
+
+    def _sync_running_stats(self):
+        """per-replica BatchNorm: the running mean / inv_std of the ranks differ slightly; average them before they
+        are used (validation) or stored (snapshots), so that every rank evaluates and saves the same network"""
+        if self.world > 1 and not self.syncbn:
+            eng = self._engine()
+            self._dist.all_reduce(eng.R)
+            eng.R.mul_(1.0 / self.world)
+
     # -- augmentation pipeline ----------------------------------------------------------------------
     def setupDataLoading(self):
         """nettrainer.py:666-699: start the record workers and prepare the first augmented set."""
         if self.cfgParams.para_augment and self.cfgParams.para_num_proc > 1 and self._pool is None:
-            ctx = multiprocessing.get_context('fork')
-            self._pool = ctx.Pool(self.cfgParams.para_num_proc)
+            self._pool = multiprocessing.get_context('fork').Pool(self.cfgParams.para_num_proc)   # a second train() call
         self._pending = self._request_augmentation()
         self._swap_augmentation()
         self._pending = self._request_augmentation()
@@ -246,9 +302,10 @@ class NetTrainer(object):
 
     def _draw(self, n):
         a = self.cfgParams.augment_fun_params['args']
-        sigma_com = a.get('sigma_com') or 5.
-        sigma_sc = a.get('sigma_sc') or 0.02
-        rot_range = a.get('rot_range') or 180.
+        none_or = lambda v, default: default if v is None else v        # nettrainer.py:942-947 tests `is None`
+        sigma_com = none_or(a.get('sigma_com'), 5.)
+        sigma_sc = none_or(a.get('sigma_sc'), 0.02)
+        rot_range = none_or(a.get('rot_range'), 180.)
         draws = []
         for _ in range(n):                                    # nettrainer.py:954-957 draw order
             mode = self.rng.randint(0, len(a['aug_modes']))
@@ -261,16 +318,24 @@ class NetTrainer(object):
     def _request_augmentation(self):
         a = self.cfgParams.augment_fun_params['args']
         n = self.train_data_xDB.shape[0]
-        draws = self._draw(n)
-        state = (a['hd'], a['di'], a['aug_modes'], self.train_data_comDB, self.train_data_cubeDB,
-                 self.train_data_MDB, self.train_gt3DcropDB, a.get('proj'))
-        idxs = list(range(n))
+        draws = self._draw(n)                 # every rank draws for ALL samples: the stream of the single-device run
+        self._to_device()
+        idxs = [int(i) for i in self._rows]   # ... and builds records only for the rows it holds
+        draws = [draws[i] for i in idxs]
+        src = list(range(len(idxs)))
+        n = len(idxs)
+        # the side arrays travel as the rows a job needs (a few hundred bytes per sample), not as whole arrays
+        def job(sl):
+            ii = numpy.asarray(idxs[sl], dtype=numpy.int64)
+            g = lambda arr: numpy.asarray(arr)[ii]
+            state = (a['hd'], a['di'], a['aug_modes'], g(self.train_data_comDB), g(self.train_data_cubeDB),
+                     g(self.train_data_MDB), g(self.train_gt3DcropDB), a.get('proj'))
+            return (state, list(range(len(ii))), draws[sl], src[sl])
         if self._pool is not None:
             k = self.cfgParams.para_num_proc
             step = (n + k - 1) // k
-            jobs = [(state, idxs[s:s + step], draws[s:s + step]) for s in range(0, n, step)]
-            return ('async', self._pool.map_async(_records_chunk, jobs))
-        return ('sync', [_records_chunk((state, idxs, draws))])
+            return ('async', self._pool.map_async(_records_chunk, [job(slice(s, s + step)) for s in range(0, n, step)]))
+        return ('sync', [_records_chunk(job(slice(0, n)))])
 
     def _swap_augmentation(self):
         """wait for the records, regenerate train_x/train_y on the device (one kernel launch)"""
@@ -318,9 +383,11 @@ class NetTrainer(object):
         self.poseNet.unsetDeterministic()
         while self.epoch < n_epochs:
             if self.epoch % self.cfgParams.snapshot_last == 0:
-                self.poseNet.save(self.subfolder + '/net_last.pkl')
+                self._sync_running_stats()
+                self.poseNet.save(self.subfolder + '/net_last.pkl')        # rank 0 writes (NetBase.save)
             if self.cfgParams.snapshot_freq is not None:
                 if self.epoch % self.cfgParams.snapshot_freq == 0:
+                    self._sync_running_stats()
                     self.poseNet.save(self.subfolder + '/net_{}.pkl'.format(self.epoch))
             if self.cfgParams.pre_epoch_fn is not None:
                 getattr(self, self.cfgParams.pre_epoch_fn)()
@@ -346,28 +413,34 @@ class NetTrainer(object):
                         for lay in self.poseNet.layers:
                             if isinstance(lay, (ConvPoolLayer, ConvLayer)):
                                 wvals.append(lay.W.get_value())
+                    self._sync_running_stats()
                     self.poseNet.setDeterministic()
                     this_validation_loss = numpy.nanmean([self.validation_observer[0](i) for i in range(n_val_batches)])
                     for vi in range(1, len(self.validation_observer)):
                         validation_obs[vi - 1].append(
                             numpy.nanmean([self.validation_observer[vi](i) for i in range(n_val_batches)]))
                     self.poseNet.unsetDeterministic()
-                    print("{}: epoch {}, LR {}, minibatch {}/{}, validation cost {} error {}".format(
-                        time.ctime(), self.epoch, learning_rate, minibatch_index + 1, self.getNumFullMiniBatches(),
-                        this_validation_loss, [vo[-1] for vo in validation_obs]))
+                    if self.rank == 0:
+                        print("{}: epoch {}, LR {}, minibatch {}/{}, validation cost {} error {}".format(
+                            time.ctime(), self.epoch, learning_rate, minibatch_index + 1, self.getNumFullMiniBatches(),
+                            this_validation_loss, [vo[-1] for vo in validation_obs]))
                     if this_validation_loss < best_validation_loss:
                         best_validation_loss = this_validation_loss
-                        print("Best validation loss so far, store network weights!")
+                        if self.rank == 0:
+                            print("Best validation loss so far, store network weights!")
                         bestParams = self.poseNet.weightVals
                         bestParamsEp = self.epoch
             if self.cfgParams.post_epoch_fn is not None:
                 getattr(self, self.cfgParams.post_epoch_fn)()
         end_time = time.time()
-        print('Optimization complete with best validation score of %f,' % best_validation_loss)
-        print('The code run for %d epochs, with %f epochs/sec' % (self.epoch, self.epoch / (end_time - start_time)))
+        self._sync_running_stats()
+        if self.rank == 0:
+            print('Optimization complete with best validation score of %f,' % best_validation_loss)
+            print('The code run for %d epochs, with %f epochs/sec' % (self.epoch, self.epoch / (end_time - start_time)))
         if bestParams is not None and self.cfgParams.use_early_stopping is True:
             self.poseNet.weightVals = bestParams
-            print('Best params at epoch %d' % bestParamsEp)
+            if self.rank == 0:
+                print('Best params at epoch %d' % bestParamsEp)
         if self.cfgParams.augment_fun_params['fun'] is not None:
             self.unsetDataLoading()
         return train_costs, wvals, validation_obs[0] if len(validation_obs) == 1 else validation_obs

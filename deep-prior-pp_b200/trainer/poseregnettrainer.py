@@ -39,8 +39,9 @@ class PoseRegNetTrainer(NetTrainer):
 
     # -- helpers ---------------------------------------------------------------------------------
     def _load_batch(self, xsrc, index):
-        eng = self.poseNet._engine()
-        B = self.cfgParams.batch_size
+        """minibatch ``index`` of a device-resident set (this rank's rows of it in a data-parallel job)"""
+        eng = self._engine()
+        B = eng.B
         eng.t_in.buf.view(B, -1).copy_(xsrc[index * B:(index + 1) * B].reshape(B, -1))
         return eng
 
@@ -52,10 +53,11 @@ class PoseRegNetTrainer(NetTrainer):
             self._to_device()
             eng = self._load_batch(self._dev['train_x'], index)
             eng._alloc_training()
-            B = self.cfgParams.batch_size
+            B = eng.B
             eng.y_in.copy_(self._dev['train_y'][index * B:(index + 1) * B])
             cost = eng.train_step(float(learning_rate), use_graph=getattr(self, 'use_graph', True))
-            return numpy.float32(cost.cpu()[0])
+            # the mean over the GLOBAL minibatch (poseregnettrainer.py:92-99): equal shares, so the mean of the means
+            return numpy.float32(self._allreduce_scalar(float(cost.cpu()[0])))
         self.train_model = train_model
 
         def test_model_on_train(index):
@@ -68,25 +70,27 @@ class PoseRegNetTrainer(NetTrainer):
         self._to_device()
         eng = self._load_batch(xsrc, index)
         out = eng.forward_device(deterministic=self.poseNet.isDeterministic())
-        B = self.cfgParams.batch_size
+        B = eng.B
         y = ysrc[index * B:(index + 1) * B]
         if what == 'cost':
-            return float(((out - y) ** 2).sum(dim=1).mean().cpu())
+            return self._allreduce_scalar(float(((out - y) ** 2).sum(dim=1).mean().cpu()))
         if what == 'errors':
-            return float(torch.sqrt(((out - y) ** 2).sum(dim=1)).mean().cpu())
+            return self._allreduce_scalar(float(torch.sqrt(((out - y) ** 2).sum(dim=1)).mean().cpu()))
         pca = self._static('pca_data')
         mean = self._static('mean_data')
         y3 = self._dev['val_y3D'][index * B:(index + 1) * B]
         j = (out @ pca + mean).reshape(B, -1, 3) - y3.reshape(B, -1, 3)
         e = torch.sqrt((j ** 2).sum(dim=2))
-        return float(e.mean(dim=1).mean().cpu()) if what == 'avg' else float(e.max(dim=1)[0].max().cpu())
+        if what == 'avg':
+            return self._allreduce_scalar(float(e.mean(dim=1).mean().cpu()))
+        return self._allreduce_scalar(float(e.max(dim=1)[0].max().cpu()), op='max')
 
     def _static(self, key):
         import torch
         k = '_st_' + key
         if k not in self._dev:
             self._dev[k] = torch.from_numpy(numpy.ascontiguousarray(getattr(self, key + 'DB'), dtype='float32')).to(
-                self.poseNet._engine().dev)
+                self._engine().dev)
         return self._dev[k]
 
     def setupValidate(self):

@@ -49,14 +49,14 @@ import dpp_b200.engine as ENG                                  # noqa: E402
 
 
 class BenchEngine(FakeEngine):                                 # noqa: F821
-    def __init__(self, net, precision=None):
+    def __init__(self, net, precision=None, **kw):
         FakeEngine.__init__(self, net)                         # noqa: F821
         self.precision, self.bns, self._graphs, self._lr = precision, [], {}, 1e-4
 
     def set_lr(self, lr):
         self._lr = lr
 
-    def set_world(self, *a):
+    def set_world(self, *a, **k):
         pass
 
     def train_step(self, lr=None, use_graph=True):
@@ -64,11 +64,11 @@ class BenchEngine(FakeEngine):                                 # noqa: F821
 
 
 ENG.Engine = BenchEngine
-sys.argv = ['bench.py', '--steps', '1', '--warmup', '1', '--no-roofline', '--no-cpu-baseline']
+sys.argv = ['bench.py', '--steps', '1', '--warmup', '1', '--no-roofline', '--no-cpu-baseline', '--no-trainer-api']
 sys.path.insert(0, os.path.dirname(HERE))
 import bench                                                   # noqa: E402
 
-bench.B, bench.N_RESIDENT = 8, 32                              # a batch the CPU oracle steps through in a second
+bench.B, bench.N_RESIDENT, bench.STRONG_GLOBAL_B = 8, 32, 8                              # a batch the CPU oracle steps through in a second
 
 
 class _NoClocks(object):

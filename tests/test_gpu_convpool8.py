@@ -1,7 +1,7 @@
-"""OPT-IN GPU check of the specialised 8-filter conv+pool kernels (csrc/convpool8.cu, DPP_CONVPOOL_FAST=1): outputs
-and arg-max cells must equal the generic kernel's bit for bit (same accumulation order), for every layer shape of the
-ScaleNet / PoseRegNet towers.  The kernels were written after round 1's GPU budget was spent, so this test is skipped
-unless DPP_TEST_CONVPOOL_FAST=1 is set; round 2 runs it first, then flips the default."""
+"""The specialised 8-filter conv+pool kernels (csrc/convpool8.cu, the default path; DPP_CONVPOOL_FAST=0 selects the
+generic kernel): outputs and arg-max cells must equal the generic kernel's bit for bit (same accumulation order), for
+every layer shape of the ScaleNet / PoseRegNet towers.  The generic kernel is anchored to torch fp32 in
+test_gpu_convpool_fc.py."""
 import ctypes as C
 import os
 
@@ -9,9 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('DPP_TEST_CONVPOOL_FAST') != '1',
-                                 reason="opt-in kernel, not yet verified on hardware (set DPP_TEST_CONVPOOL_FAST=1)")]
+pytestmark = pytest.mark.gpu
 
 CASES = [(128, 1, 5, 4), (31, 8, 5, 2), (13, 8, 3, 1), (64, 1, 5, 2), (30, 8, 5, 2), (32, 1, 5, 2), (14, 8, 5, 1),
          (10, 8, 3, 1)]

@@ -2,7 +2,7 @@
 the device kernel and the host) executed on the CPU: tests/convpool8_host_test.cpp emulates the kernel's tile loop
 and compares outputs and arg-max cells bit for bit with an independent direct convolution + max-pool, for every
 (filter, channels, pool) combination of the ScaleNet / PoseRegNet towers.  The device kernel itself is compared with
-the generic kernel on the GPU by tests/test_gpu_zz_convpool8.py."""
+the generic kernel on the GPU by tests/test_gpu_convpool8.py."""
 import os
 import shutil
 import subprocess

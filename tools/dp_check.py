@@ -25,23 +25,37 @@ from dpp_b200.engine import Engine  # noqa: E402
 from net.resnet import ResNet, ResNetParams  # noqa: E402
 
 
+def inputs_of(rank, B):
+    g = torch.Generator(device='cuda').manual_seed(100 + rank)
+    x = torch.randn((B, 128, 128, 1), device='cuda', generator=g)
+    y = torch.randn((B, 30), device='cuda', generator=g)
+    return x, y
+
+
 def run(mode, rank, world, B=16):
+    """mode: local | early | late | syncbn (DP with BatchNorm statistics summed over the ranks) | full (ONE device
+    computing the global batch of world * B samples: what the single-device reference does)"""
     os.environ['DPP_EARLY_ALLREDUCE'] = '0' if mode == 'late' else '1'
-    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=B, numJoints=1, nDims=30))
+    nb = B * world if mode == 'full' else B
+    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=nb, numJoints=1, nDims=30))
     eng = Engine(net, precision=1)
     eng._alloc_training()
-    if mode != 'local':
-        eng.set_world(world, lambda g: dist.all_reduce(g))
+    if mode not in ('local', 'full'):
+        eng.set_world(world, lambda g: dist.all_reduce(g), rank=rank, syncbn=(mode == 'syncbn'))
     eng.set_lr(1e-3)
-    g = torch.Generator(device='cuda').manual_seed(100 + rank)
-    eng.t_in.buf.copy_(torch.randn(eng.t_in.buf.shape, device='cuda', generator=g))
-    eng.y_in.copy_(torch.randn(eng.y_in.shape, device='cuda', generator=g))
-    eng.train_step(None, use_graph=True)
+    if mode == 'full':
+        xs, ys = zip(*[inputs_of(r, B) for r in range(world)])
+        x, y = torch.cat(xs), torch.cat(ys)
+    else:
+        x, y = inputs_of(rank, B)
+    eng.t_in.buf.copy_(x)
+    eng.y_in.copy_(y)
+    cost = eng.train_step(None, use_graph=True)
     torch.cuda.synchronize()
-    G, W = eng.G.clone(), eng.W.clone()
+    G, W, R, c = eng.G.clone(), eng.W.clone(), eng.R.clone(), float(cost.cpu()[0])
     eng._graphs.clear()
     eng.release()
-    return G, W
+    return G, W, R, c
 
 
 def same_on_all_ranks(t):
@@ -56,20 +70,39 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    g_local, _ = run('local', rank, world)
+    g_local = run('local', rank, world)[0]
     g_sum = g_local.clone()
     dist.all_reduce(g_sum)
-    g_early, w_early = run('early', rank, world)
-    g_late, _ = run('late', rank, world)
+    g_early, w_early = run('early', rank, world)[:2]
+    g_late = run('late', rank, world)[0]
     scale = float(g_sum.abs().max())
     d_sum = float((g_early - g_sum).abs().max()) / scale
     d_late = float((g_early - g_late).abs().max()) / scale
     sync_g, sync_w = same_on_all_ranks(g_early), same_on_all_ranks(w_early)
+    # SyncBN: world ranks x B samples against ONE device with the global batch (the single-device reference,
+    # net/batchnormlayer.py:154-159).  The exchanged arena holds the SUM of the per-rank gradients of the per-rank
+    # MEAN costs = world x the gradient of the global mean cost (ADAM folds the 1/world in).
+    g_sbn, w_sbn, r_sbn, c_sbn = run('syncbn', rank, world)
+    g_full, w_full, r_full, c_full = run('full', rank, world)
+    c_mean = torch.tensor([c_sbn], dtype=torch.float64, device='cuda')
+    dist.all_reduce(c_mean)
+    c_mean = float(c_mean[0]) / world
+    gs = float(g_full.abs().max())
+    d_sbn = float((g_sbn / world - g_full).abs().max()) / gs
+    l2_sbn = float((g_sbn / world - g_full).norm() / g_full.norm())
+    d_run = float((r_sbn - r_full).abs().max() / r_full.abs().max())
+    d_cost = abs(c_mean - c_full) / abs(c_full)
+    sync_sbn = same_on_all_ranks(g_sbn) and same_on_all_ranks(w_sbn) and same_on_all_ranks(r_sbn)
     if rank == 0:
         print("dp_check world=%d  |G_early - sum(G_local)|/max|G| = %.2e   |G_early - G_late|/max|G| = %.2e   "
               "replicas identical: G %s, W %s" % (world, d_sum, d_late, sync_g, sync_w))
+        print("dp_check SyncBN vs one device with the global batch of %d: cost %.3e, gradient max %.2e / rel-L2 %.2e, "
+              "running statistics %.2e, replicas identical %s" % (16 * world, d_cost, d_sbn, l2_sbn, d_run, sync_sbn))
         ok = d_sum < 2e-5 and d_late < 2e-5 and sync_g and sync_w
-        print("DP_CHECK", "PASS" if ok else "FAIL")
+        # a handful of roundoff-level ReLU decisions may differ between the two runs (different summation order of the
+        # statistics): bound the gradient by what such flips allow, the cost and statistics tightly
+        ok_sbn = d_cost < 1e-5 and d_run < 1e-5 and l2_sbn < 2e-2 and sync_sbn
+        print("DP_CHECK", "PASS" if (ok and ok_sbn) else "FAIL")
         sys.stdout.flush()
     timer = threading.Timer(30.0, lambda: os._exit(0))
     timer.daemon = True
