@@ -20,10 +20,11 @@
 // Warp roles: warps 0-3 producers, warps 4-7 epilogue (TMEM lane quarter = warp%4), warp 8 MMA issuer +
 // TMEM allocator.  Persistent CTAs (<= 1 per SM) walk the tile list, so per-channel fp64 statistics
 // leave the CTA once.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 using namespace dpp;
+using namespace dpp::tc;
 
 namespace {
 
@@ -49,111 +50,7 @@ __device__ int g_dbg = 0;     // experiment knobs: 1 no global loads, 2 no trans
 
 constexpr int TM = 128;          // pixels per tile (TMEM lanes)
 constexpr int KC = 32;           // floats of K per stage: 128-byte rows
-constexpr int NSTAGE = 3;           // stages of the wgrad kernel (k_conv_tc uses SmemLayout::NS)
-constexpr int NTHREADS = 288;
 constexpr int NTHREADS_CONV = 576;  // k_conv_tc: 8 producer + 2 x 4 epilogue warps, MMA issuer, weight-image (TMA) loader
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// TF32 operand = fp32 with the low 13 mantissa bits cleared (truncation).  hi = trunc(x), lo = trunc(x - hi):
-// x - hi is exact in fp32, so hi + lo reproduces x to 2^-21 relative - the 3xTF32 split in 3 ALU ops per value
-// (cvt.rna.tf32.f32 expands to a ~10-instruction sequence on sm_100a and dominated the producer loop).
-__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (LBO = 16 B, SBO = 1024 B, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// Elected-lane variants: executed by a CONVERGED warp; elect.sync inside the asm lets ptxas emit bare
-// UTCHMMA / UTCBAR instructions (a lane-0 branch around tcgen05.mma costs an ELECT/BRA.U.ANY loop of
-// ~50 stall cycles per instruction, which dominates when the MMAs are small).
-__device__ __forceinline__ void mma_tf32_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
-        "elect.sync r|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit_e(uint32_t bar) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
-        "elect.sync r|q, 0xffffffff;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
-        : "memory");
-}
-
-__device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// L1-allocating variant: the taps of a 3x3 window re-read every input pixel 9 times (and the 64-byte row
-// pieces of narrow layers share 32-byte sectors); with .ca those re-reads hit L1 instead of L2
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct TCArgs {
     const float *in;      // gathered tensor [N, Hin, Win, Cin]
@@ -170,6 +67,9 @@ struct TCArgs {
     dpp_bn_ref in_bn; int has_in_bn;
     const float *bias; const float *residual; double *out_stats;
     int accumulate; dpp_bn_ref mask_bn; int has_mask; const float *x_pre; double *dz_stats;
+    // fused BatchNorm backward behind a grid-wide barrier (dgrad of the LAST consumer of a normalised tensor):
+    // after every CTA has written its dz tiles and added its statistics, dx = bn_bwd(dz, x_pre) [+ skip]
+    int tail; const float *tail_skip; float *tail_out; float *dgamma; float *dbeta; float pscale; unsigned int *gbar;
     // per k-chunk gather table (host-built): the chunk's 8 16-byte pieces come from tap A (pieces 0-3) and
     // tap B (pieces 4-7; same tap as A when Cin >= 32): {dr, ds (tap offset incl. -pad), element offset, channel}
     int tab[18][8];
@@ -215,59 +115,6 @@ struct SmemLayout {
     static constexpr int STAT_OFF = COEF_OFF + COEF_BYTES;
     static constexpr int TOTAL = STAT_OFF + 8 * 2 * BN * 8 + 1024;
 };
-
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// A operand from tensor memory, B from shared memory
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
-        "elect.sync r|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
-// relaxed wait for the non-critical roles (epilogue, weight loader): back off between polls so the
-// spinning warp does not steal issue slots from the producers on the same scheduler
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        __nanosleep(40);
-    }
-}
 
 constexpr int NPROD_WARPS = 8;
 constexpr int W_EPI = 8, W_MMA = 16, W_LOAD = 17;      // warps 8-11 / 12-15: epilogue warpgroups 0 / 1
@@ -404,13 +251,12 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         const int Tg = (T - grp + 1) / 2;             // chunks of this group: grp, grp + 2, ...
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
         const float *const gin = a.in;
-        const bool use_ca = (a.knobs & 1) && a.k > 1;
-        const bool coalesced = !(a.knobs & 2);
-        // raw slot layout: [8 pieces][128 rows][16 B] -> conflict-free for cp.async writes and LDS.128 reads
-        const uint32_t raw_u32 = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
-        const unsigned char *raw_ptr = smem + L::RAW_OFF + grp * RDG * (TM * 128) + row * 16;
+        // The warp's 32 rows x 8 pieces are fetched with lane = (row t*4 + lane/8, piece lane%8), t = 0..7: the 8 lanes of
+        // a row read its two 64-byte tap segments, so one instruction touches 8 lines instead of 32 (the L1 tag stage
+        // handles one line per cycle and was the serial resource of the gather).
+        const int pcs = lane & 7, lsub = lane >> 3;
         int i_tile = blockIdx.x, i_kc = grp;
-        int r_off, r_h0, r_w0;        // element offset of the row's pixel (-1: row beyond M)
+        int r_off, r_h0, r_w0;        // this thread's own row: element offset (-1: beyond M), top-left input pixel
         auto set_tile = [&]() {
             const int m = (i_tile / ntiles) * TM + row;
             int n, ho, wo;
@@ -424,44 +270,30 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         uint32_t cring = 0;           // (kc & 0xff) per in-flight chunk, 8 bits each (RDG <= 3)
         uint32_t stage = grp, phase = 0;
         int islot = 0, pslot = 0;
+        // landing slot: [row][piece ^ (row & 7)] (16-byte pieces): conflict-free for the cp.async writes and the LDS.128 reads
+        const uint32_t grp_u32 = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + q * 32 * 128;
+        const unsigned char *const grp_ptr = smem + L::RAW_OFF + grp * RDG * (TM * 128) + row * 128;
 #pragma unroll 1
         for (int i = -D; i < Tg; ++i) {
             if (i + D < Tg) {
                 const int4 e0 = s_tab[i_kc * 2], e1 = s_tab[i_kc * 2 + 1];
                 const bool v0 = r_off >= 0 && (unsigned)(r_h0 + e0.x) < (unsigned)Hin && (unsigned)(r_w0 + e0.y) < (unsigned)Win;
                 const bool v1 = r_off >= 0 && (unsigned)(r_h0 + e1.x) < (unsigned)Hin && (unsigned)(r_w0 + e1.y) < (unsigned)Win;
-                const float *p0 = gin + (v0 ? r_off + e0.z : 0), *p1 = gin + (v1 ? r_off + e1.z : 0);
-                const uint32_t dst = raw_u32 + islot * (TM * 128);
-                const uint32_t z0 = v0 ? 16u : 0u, z1 = v1 ? 16u : 0u;
-                if (coalesced) {
-                    // The warp's 32 rows x 8 pieces are fetched with lane = (row t*4 + lane/8, piece lane%8): the 8 lanes
-                    // of a row read its two 64-byte tap segments, so one instruction touches 8 lines instead of 32
-                    // (the L1 tag stage handles one line per cycle and was the serial resource of the gather).
-                    // Row geometry comes from the owning lane by shuffle; the slot is [row][piece ^ (row & 7)].
-                    const int pcs = lane & 7;
-                    const int4 e = pcs < 4 ? e0 : e1;
-                    const uint32_t sbuf = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + islot * (TM * 128) + q * 32 * 128;
+                const int4 e = pcs < 4 ? e0 : e1;
+                const int ez = e.z + (pcs & 3) * 4;
+                const uint32_t sbuf = grp_u32 + islot * (TM * 128);
+                if (!DBG(1)) {
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
-                        const int lrow = t * 4 + (lane >> 3);
+                        // row geometry comes from the owning lane by shuffle (decoding the 8 rows per tile into registers
+                        // was measured slower on the B200: 31.7 vs 28.8 us on the 3x3 16->16 layer)
+                        const int lrow = t * 4 + lsub;
                         const int o_off = __shfl_sync(0xffffffffu, r_off, lrow);
                         const int o_h0 = __shfl_sync(0xffffffffu, r_h0, lrow);
                         const int o_w0 = __shfl_sync(0xffffffffu, r_w0, lrow);
                         const bool v = o_off >= 0 && (unsigned)(o_h0 + e.x) < (unsigned)Hin && (unsigned)(o_w0 + e.y) < (unsigned)Win;
-                        const float *src = gin + (v ? o_off + e.z + (pcs & 3) * 4 : 0);
+                        const float *src = gin + (v ? o_off + ez : 0);
                         cp_async16(sbuf + lrow * 128 + ((pcs ^ (lrow & 7)) << 4), src, v ? 16u : 0u);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (DBG(1)) break;
-                        if (use_ca) {
-                            cp_async16_ca(dst + j * 2048, p0 + j * 4, z0);
-                            cp_async16_ca(dst + (j + 4) * 2048, p1 + j * 4, z1);
-                        } else {
-                            cp_async16(dst + j * 2048, p0 + j * 4, z0);
-                            cp_async16(dst + (j + 4) * 2048, p1 + j * 4, z1);
-                        }
                     }
                 }
                 const uint32_t sh2 = 2 * islot, sh8 = 8 * islot;
@@ -479,11 +311,29 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
             cp_async_wait<D>();       // this thread's copies of chunk i have landed
             const uint32_t vb = (vring >> (2 * pslot)) & 3u;
             const int kc = (int)((cring >> (8 * pslot)) & 0xffu);
-            const unsigned char *rp = raw_ptr + pslot * (TM * 128);
-            const unsigned char *rpc = smem + L::RAW_OFF + grp * RDG * (TM * 128) + pslot * (TM * 128) + row * 128;   // [row][piece ^ (row & 7)]
+            const unsigned char *rpc = grp_ptr + pslot * (TM * 128);
             if (++pslot == RDG) pslot = 0;
-            const int4 e0 = s_tab[kc * 2], e1 = s_tab[kc * 2 + 1];
             PROF(11);
+            // the row's 32 floats leave the landing slot before the stage wait: the loads overlap the wait and nothing in
+            // the arithmetic below depends on shared memory any more
+            float4 xr[8];
+#pragma unroll
+            for (int pj = 0; pj < 8; ++pj) xr[pj] = *reinterpret_cast<const float4 *>(rpc + ((pj ^ (lane & 7)) << 4));
+            if (pro) {
+                const int4 e0 = s_tab[kc * 2], e1 = s_tab[kc * 2 + 1];
+#pragma unroll
+                for (int pj = 0; pj < 8; ++pj) {
+                    const int chan = (pj < 4 ? e0.w : e1.w) + (pj & 3) * 4;
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
+                    const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
+                    float4 x = xr[pj];
+                    x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
+                    x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
+                    if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    if (!((vb >> (pj >> 2)) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);      // padding is zero AFTER BN + ReLU
+                    xr[pj] = x;
+                }
+            }
             if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);
             __syncwarp();
             tc_fence_after();
@@ -495,17 +345,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int pj = hh * 2 + j;         // piece 0-3: tap A, 4-7: tap B
-                    float4 x = *reinterpret_cast<const float4 *>(coalesced ? rpc + ((pj ^ (lane & 7)) << 4) : rp + pj * 2048);
-                    if (pro) {
-                        const int chan = (pj < 4 ? e0.w : e1.w) + (pj & 3) * 4;
-                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
-                        const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
-                        x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
-                        x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
-                        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                        if (!((vb >> (pj >> 2)) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    const float4 x = xr[hh * 2 + j];   // piece 0-3: tap A, 4-7: tap B
                     hi[4 * j] = to_tf32(x.x); hi[4 * j + 1] = to_tf32(x.y); hi[4 * j + 2] = to_tf32(x.z); hi[4 * j + 3] = to_tf32(x.w);
                     lo[4 * j] = to_tf32(x.x - __uint_as_float(hi[4 * j])); lo[4 * j + 1] = to_tf32(x.y - __uint_as_float(hi[4 * j + 1]));
                     lo[4 * j + 2] = to_tf32(x.z - __uint_as_float(hi[4 * j + 2])); lo[4 * j + 3] = to_tf32(x.w - __uint_as_float(hi[4 * j + 3]));
@@ -524,43 +364,46 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         }
     } else if (warp == W_MMA) {
         // =========================== MMA issuer ===========================
-        // the whole warp runs the loop converged; one elected lane issues (see mma_tf32_ts)
-        {
+        // ONE elected thread runs the whole role (waits, tcgen05.mma, commits): inside a single-thread region ptxas keeps
+        // descriptors and tensor-memory addresses in uniform registers and issues the 12 MMAs of a k-chunk back to back
+        // (the per-instruction elect.sync of round 1 cost ~55 cycles per MMA: ELECT / VOTEU / R2UR chains).
+        if (elect_one()) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            constexpr uint32_t LO_OFF = (BN * 128) >> 4;        // descriptor units (16 B) from the hi to the lo weight plane
             uint32_t acc = 0, aphase = 0;
             uint32_t stage = 0, phase = 0, bslot = 0, bphase = 0;
+            const int kchunks = a.kchunks;
             for (int t = 0; t < my_tiles; ++t) {
                 mbar_wait(bar(2 * NS + 2 + acc), aphase ^ 1);
                 tc_fence_after();
                 PROF(20);
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kc = 0; kc < a.kchunks; ++kc) {
+                for (int kc = 0; kc < kchunks; ++kc) {
                     if (resident) { bslot = kc; bphase = 0; }
                     mbar_wait(bar(2 * NS + 4 + bslot), bphase);
                     PROF(21);
                     mbar_wait(bar(stage), phase);
-                    __syncwarp();
                     tc_fence_after();
                     PROF(22);
                     const uint32_t ta = tmem_base + L::A_COL0 + stage * L::A_COLS;
-                    const uint32_t sb = sbase + L::B_OFF + bslot * L::B_BYTES;
+                    const uint64_t b0 = make_desc(sbase + L::B_OFF + bslot * L::B_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
                         if (DBG(4)) break;
-                        const uint64_t bh = make_desc(sb + ks * 32);
+                        const uint64_t bh = b0 + 2 * ks;       // + ks * 32 bytes along K inside the swizzled row
                         const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
                         if (PASSES > 1) {
-                            const uint64_t bl = make_desc(sb + BN * 128 + ks * 32);
-                            mma_tf32_ts(d_tmem, ta + ks * 8, bl, IDESC, first);
-                            mma_tf32_ts(d_tmem, ta + 32 + ks * 8, bh, IDESC, 1u);
-                            mma_tf32_ts(d_tmem, ta + ks * 8, bh, IDESC, 1u);
+                            const uint64_t bl = bh + LO_OFF;
+                            mma_tf32_ts_1t(d_tmem, ta + ks * 8, bl, IDESC, first);
+                            mma_tf32_ts_1t(d_tmem, ta + 32 + ks * 8, bh, IDESC, 1u);
+                            mma_tf32_ts_1t(d_tmem, ta + ks * 8, bh, IDESC, 1u);
                         } else {
-                            mma_tf32_ts(d_tmem, ta + ks * 8, bh, IDESC, first);
+                            mma_tf32_ts_1t(d_tmem, ta + ks * 8, bh, IDESC, first);
                         }
                     }
-                    mma_commit_e(bar(NS + stage));                              // frees the A stage when the MMAs retire
-                    if (!resident) mma_commit_e(bar(2 * NS + 4 + RB + bslot));  // ... and the weight slot
-                    if (kc == a.kchunks - 1) mma_commit_e(bar(2 * NS + acc));   // accumulator ready
+                    mma_commit_1t(bar(NS + stage));                              // frees the A stage when the MMAs retire
+                    if (!resident) mma_commit_1t(bar(2 * NS + 4 + RB + bslot));  // ... and the weight slot
+                    if (kc == kchunks - 1) mma_commit_1t(bar(2 * NS + acc));     // accumulator ready
                     PROF(23);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                     if (!resident && ++bslot == RB) { bslot = 0; bphase ^= 1; }
@@ -568,6 +411,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 if (++acc == 2) { acc = 0; aphase ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp == W_LOAD) {
         // =========================== weight-image loader ===========================
         // TMA bulk copies of the packed weight images: once per CTA when the n-tile's image fits the ring,
@@ -744,268 +588,64 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
     PROF(4);
-}
-
-// -------------------------------------------------------------------------------------------------
-// Backward-weights on tcgen05:  dW[(r,s,c)][o] += sum_p a[p*stride - pad + (r,s)][c] * dy[p][o]
-// GEMM with the PIXELS as the reduction dimension: D[128 rows (r,s,c)][BN cols o], K = pixels.
-// Both operands are K-major with K = pixel, i.e. transposed w.r.t. NHWC memory: the producers load
-// channel-contiguous 16-byte pieces (BN+ReLU prologue recomputed on the activations), split hi/lo and
-// scatter 4-byte elements into the swizzled rows (a warp = 32 consecutive pixels = one 128-byte row
-// segment per store instruction, conflict-free).  Each CTA reduces a slice of the pixels into TMEM and
-// its epilogue adds the tile to dW with fp32 reductions (red.global.add); db rides on the dy loads.
-// -------------------------------------------------------------------------------------------------
-struct WGTArgs {
-    const float *x; const float *dy; float *dw; float *db;
-    int N, H, W, Cin, Cout, k, stride, pad, Ho, Wo;
-    dpp_bn_ref in_bn; int has_in_bn;
-    int mtiles, ntiles, splits, chunks_per_split;   // pixel chunks of 32
-};
-
-// wgrad shared-memory plan: 2 MMA tile stages + RD private raw slots per producer thread
-template <int BN, int PASSES>
-struct WgSmem {
-    static constexpr int A_BYTES = PASSES * TM * 128;
-    static constexpr int B_BYTES = PASSES * BN * 128;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NST = 2;
-    static constexpr int SLOT = (8 + BN / 16) * 16 + 16;       // bytes per thread per raw stage (+16: bank spread)
-    static constexpr int RAW_BYTES = 128 * SLOT;
-    static constexpr int RD = (NST * STAGE_BYTES + 3 * RAW_BYTES + 4096 <= 225 * 1024) ? 3 : 2;
-    static constexpr int RAW_OFF = NST * STAGE_BYTES;
-    static constexpr int BAR_OFF = RAW_OFF + RD * RAW_BYTES;
-    static constexpr int COEF_OFF = BAR_OFF + 256;
-    static constexpr int TOTAL = COEF_OFF + 2 * 256 * 4 + 1024;
-};
-
-template <int BN, int PASSES>
-__global__ void __launch_bounds__(NTHREADS, 1)
-k_wgrad_tc(WGTArgs a) {
-    using L = WgSmem<BN, PASSES>;
-    constexpr int NST = L::NST, RD = L::RD, D = RD - 1;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
-    const uint32_t sbase = smem_u32(smem);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };      // full[s]=s, empty[s]=NST+s, done=2*NST
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
-    float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);
-    float *s_shift = s_scale + 256;
-    constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
-
-    const int tile = blockIdx.x % (a.mtiles * a.ntiles), split = blockIdx.x / (a.mtiles * a.ntiles);
-    const int mt = tile / a.ntiles, nt = tile % a.ntiles;
-    const int kd0 = mt * TM, o0 = nt * BN;
-    const int Kw = a.k * a.k * a.Cin;
-    const int P = a.N * a.Ho * a.Wo;
-    const int total_chunks = (P + 31) / 32;
-    const int c_begin = split * a.chunks_per_split;
-    int c_end = c_begin + a.chunks_per_split; if (c_end > total_chunks) c_end = total_chunks;
-    const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
-
-    if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), 128); mbar_init(bar(NST + s), 1); }
-        mbar_init(bar(2 * NST), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (a.has_in_bn)
-        for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < 4) {
-        // producers: thread = (pixel j of the chunk, row quarter q).  cp.async lands the raw activation /
-        // dy pieces of chunk ch+D in this thread's private slot while chunk ch is transposed into the tiles.
-        const int j = tid & 31, q = tid >> 5;
-        float dbp[BN / 4];
-#pragma unroll
-        for (int i = 0; i < BN / 4; ++i) dbp[i] = 0.f;
-        // per-thread invariants: piece g covers rows kd0 + q*32 + g*4 .. +3 = (tap, 4 channels)
-        int g_r[8], g_s[8], g_ch[8];
-        bool g_ok[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const int kd = kd0 + q * 32 + g * 4;
-            g_ok[g] = kd < Kw;
-            const int tap = g_ok[g] ? kd / a.Cin : 0;
-            g_ch[g] = g_ok[g] ? kd - tap * a.Cin : 0;
-            g_r[g] = tap / a.k; g_s[g] = tap - g_r[g] * a.k;
+    if (a.tail) {
+        // ---- BatchNorm backward of the tensor this dgrad completes (net/batchnormlayer.py:154-192 through T.grad).
+        // The statistics {sum dz, sum dz * xhat} are complete only when EVERY CTA has added its share: grid-wide
+        // barrier (the grid is at most one CTA per SM and every CTA is resident or will be without waiting for this
+        // one, see launch_tc), then each CTA turns its own dz tiles - still in L2 - into dx.  Same arithmetic, in the
+        // same order, as k_bn_bwd_apply (bn.cu): the two paths are bit-identical.
+        if (tid == 0) {
+            __threadfence();                                   // this CTA's dz tiles and statistics before its arrival
+            atomicAdd(a.gbar, 1u);
+            unsigned int seen = 0, polls = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.gbar) : "memory");
+                if (seen >= gridDim.x) break;
+                __nanosleep(64);
+            } while (++polls < (1u << 24));                    // ~1 s: never reached unless a CTA of this grid died
+            if (seen < gridDim.x) atomicExch(a.gbar + 1, 0xDEADu);   // leave a mark instead of hanging the device
         }
-        struct Pix { int wo, ho; const float *img; bool ok; };
-        auto decode = [&](int p) {
-            Pix px;
-            px.ok = p < P;
-            const int pp = px.ok ? p : 0;
-            px.wo = pp % a.Wo; px.ho = (pp / a.Wo) % a.Ho;
-            px.img = a.x + (size_t)(pp / (a.Wo * a.Ho)) * a.H * a.W * a.Cin;
-            return px;
-        };
-        auto a_src = [&](const Pix &px, int g) -> const float * {
-            if (!px.ok || !g_ok[g]) return nullptr;
-            const int hi = px.ho * a.stride - a.pad + g_r[g], wi = px.wo * a.stride - a.pad + g_s[g];
-            if (hi < 0 || hi >= a.H || wi < 0 || wi >= a.W) return nullptr;
-            return px.img + ((size_t)hi * a.W + wi) * a.Cin + g_ch[g];
-        };
-        auto issue = [&](int ch) {
-            const int p = (c_begin + ch) * 32 + j;
-            const uint32_t slot = sbase + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
-            const Pix px = decode(p);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const float *src = a_src(px, g);
-                cp_async16(slot + g * 16, src ? src : a.x, src ? 16u : 0u);
+        __syncthreads();
+        float *s_k1 = s_msc, *s_mdz = s_msh, *s_mdzx = s_bias;     // reuse: [BN] each (mask scale stays, shift / bias are done)
+        if (tid < BN) {
+            const int cg = cta_n0 + tid;
+            const double cnt = a.mask_bn.count;
+            const double sdz = __ldcg(a.dz_stats + cg), sdzx = __ldcg(a.dz_stats + a.Cn + cg);
+            s_mdz[tid] = (float)(sdz / cnt);
+            s_mdzx[tid] = (float)(sdzx / cnt);
+            if ((int)blockIdx.x < ntiles) {                        // one CTA per n-tile owns the parameter gradients
+                if (a.dbeta) a.dbeta[cg] += a.pscale * (float)sdz;
+                if (a.dgamma) a.dgamma[cg] += a.pscale * (float)sdzx;
             }
+        }
+        __syncthreads();
+        constexpr int Q = BN / 4;                                  // float4 per row of the n-tile
+        const float *dzp = a.out, *xp = a.x_pre, *skp = a.tail_skip;
+        float *dxp = a.tail_out;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int mt = (blockIdx.x + t * gridDim.x) / ntiles;
+            for (int idx = tid; idx < TM * Q; idx += NTHREADS_CONV) {
+                const int r = idx / Q, c = (idx - r * Q) * 4;
+                const int m = mt * TM + r;
+                if (m >= M) break;
+                const size_t o = (size_t)m * a.Cn + cta_n0 + c;    // out_stride == 1: GEMM row m is pixel m
+                const float4 g = __ldcg(reinterpret_cast<const float4 *>(dzp + o));
+                const float4 xv = __ldg(reinterpret_cast<const float4 *>(xp + o));
+                const float gr[4] = {g.x, g.y, g.z, g.w}, xr[4] = {xv.x, xv.y, xv.z, xv.w};
+                float rr[4];
 #pragma unroll
-            for (int g = 0; g < BN / 16; ++g) {
-                const bool ok = p < P;
-                cp_async16(slot + (8 + g) * 16, ok ? a.dy + (size_t)p * a.Cout + o0 + q * (BN / 4) + g * 4 : a.dy, ok ? 16u : 0u);
-            }
-            cp_async_commit();
-        };
-        auto process = [&](int ch) {
-            const int p = (c_begin + ch) * 32 + j;
-            const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
-            const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
-            mbar_wait(bar(NST + stage), phase ^ 1);
-            unsigned char *sA = smem + stage * L::STAGE_BYTES;
-            unsigned char *sB = sA + L::A_BYTES;
-            const Pix px = decode(p);
-            // element (row, col j): row block (row>>3)*1024 + (row&7)*128, 16B chunk (j>>2)^(row&7), + (j&3)*4
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const int chan = g_ch[g];
-                const bool valid = a_src(px, g) != nullptr;
-                float4 xv = *reinterpret_cast<const float4 *>(slot + g * 16);
-                if (!valid) xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                else if (a.has_in_bn) {
-                    xv.x = fmaf(xv.x, s_scale[chan], s_shift[chan]);
-                    xv.y = fmaf(xv.y, s_scale[chan + 1], s_shift[chan + 1]);
-                    xv.z = fmaf(xv.z, s_scale[chan + 2], s_shift[chan + 2]);
-                    xv.w = fmaf(xv.w, s_scale[chan + 3], s_shift[chan + 3]);
-                    if (a.in_bn.relu) {
-                        xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const float xh = (xr[j] - s_mmean[c + j]) * s_mistd[c + j];
+                    rr[j] = s_k1[c + j] * (gr[j] - s_mdz[c + j] - xh * s_mdzx[c + j]);
                 }
-                const float e[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int row = q * 32 + g * 4 + t;
-                    const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((j >> 2) ^ (row & 7)) << 4) + ((j & 3) << 2);
-                    const uint32_t h = to_tf32(e[t]);
-                    *reinterpret_cast<uint32_t *>(sA + off) = h;
-                    if (PASSES > 1) *reinterpret_cast<uint32_t *>(sA + TM * 128 + off) = to_tf32(e[t] - __uint_as_float(h));
+                if (skp != nullptr) {
+                    const float4 sk = __ldg(reinterpret_cast<const float4 *>(skp + o));
+                    rr[0] += sk.x; rr[1] += sk.y; rr[2] += sk.z; rr[3] += sk.w;
                 }
-            }
-#pragma unroll
-            for (int g = 0; g < BN / 16; ++g) {
-                const float4 bv = *reinterpret_cast<const float4 *>(slot + (8 + g) * 16);
-                const float e[4] = {bv.x, bv.y, bv.z, bv.w};
-                dbp[g * 4] += bv.x; dbp[g * 4 + 1] += bv.y; dbp[g * 4 + 2] += bv.z; dbp[g * 4 + 3] += bv.w;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int row = q * (BN / 4) + g * 4 + t;
-                    const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((j >> 2) ^ (row & 7)) << 4) + ((j & 3) << 2);
-                    const uint32_t h = to_tf32(e[t]);
-                    *reinterpret_cast<uint32_t *>(sB + off) = h;
-                    if (PASSES > 1) *reinterpret_cast<uint32_t *>(sB + BN * 128 + off) = to_tf32(e[t] - __uint_as_float(h));
-                }
-            }
-            fence_proxy_async();
-            mbar_arrive(bar(stage));
-        };
-        for (int i = 0; i < D && i < nchunks; ++i) issue(i);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            if (ch + D < nchunks) { issue(ch + D); cp_async_wait<D>(); }
-            else cp_async_wait<0>();
-            process(ch);
-        }
-        if (a.db != nullptr && mt == 0) {
-#pragma unroll
-            for (int i = 0; i < BN / 4; ++i) {
-                float t = warp_sum(dbp[i]);
-                if (j == 0) atomicAdd(&a.db[o0 + q * (BN / 4) + i], t);
-            }
-        }
-    } else if (warp == 8) {
-        if (nchunks > 0) {      // converged warp, elected issue
-            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
-                mbar_wait(bar(stage), phase);
-                __syncwarp();
-                tc_fence_after();
-                const uint32_t sa = sbase + stage * L::STAGE_BYTES;
-                const uint32_t sb = sa + L::A_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < KC / 8; ++ks) {
-                    const uint64_t ah = make_desc(sa + ks * 32), bh = make_desc(sb + ks * 32);
-                    const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
-                    if (PASSES > 1) {
-                        const uint64_t al = make_desc(sa + TM * 128 + ks * 32), bl = make_desc(sb + BN * 128 + ks * 32);
-                        mma_tf32_e(tmem_base, ah, bl, IDESC, first);
-                        mma_tf32_e(tmem_base, al, bh, IDESC, 1u);
-                        mma_tf32_e(tmem_base, ah, bh, IDESC, 1u);
-                    } else {
-                        mma_tf32_e(tmem_base, ah, bh, IDESC, first);
-                    }
-                }
-                mma_commit_e(bar(NST + stage));
-                if (ch == nchunks - 1) mma_commit_e(bar(2 * NST));
-            }
-        }
-    } else if (nchunks > 0) {
-        // epilogue: row = (tap, c) index, columns = output channels
-        const int ew = warp - 4;
-        const int kd = kd0 + ew * 32 + lane;
-        mbar_wait(bar(2 * NST), 0);
-        tc_fence_after();
-#pragma unroll
-        for (int cb = 0; cb < BN; cb += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + cb, v);
-            if (kd < Kw) {
-                float *dst = a.dw + (size_t)kd * a.Cout + o0 + cb;
-#pragma unroll
-                for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
+                *reinterpret_cast<float4 *>(dxp + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
             }
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
-    }
-}
-
-template <int BN, int PASSES>
-int launch_wgrad_tc(WGTArgs &a, cudaStream_t st) {
-    using L = WgSmem<BN, PASSES>;
-    static bool done = false;
-    if (!done) {
-        if (cudaFuncSetAttribute(k_wgrad_tc<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
-            return -1;
-        done = true;
-    }
-    const int Kw = a.k * a.k * a.Cin;
-    a.mtiles = (Kw + TM - 1) / TM;
-    a.ntiles = a.Cout / BN;
-    const int tiles = a.mtiles * a.ntiles;
-    const int P = a.N * a.Ho * a.Wo;
-    const int total_chunks = (P + 31) / 32;
-    int splits = 148 / tiles; if (splits < 1) splits = 1;
-    if (splits > total_chunks) splits = total_chunks;
-    a.chunks_per_split = (total_chunks + splits - 1) / splits;
-    a.splits = (total_chunks + a.chunks_per_split - 1) / a.chunks_per_split;
-    k_wgrad_tc<BN, PASSES><<<tiles * a.splits, NTHREADS, L::TOTAL, st>>>(a);
-    return 0;
 }
 
 // ---- weight packing: KC fp32 weights -> per-(n-tile, k-chunk) shared-memory images (hi/lo, swizzled)
@@ -1077,7 +717,6 @@ int tc_knobs() {
 }
 
 int dispatch_tc(TCArgs &a, int passes, cudaStream_t st) {
-    if (a.kchunks > 18) return -1;
     a.knobs = tc_knobs();
     const int KK = a.k * a.k;
     for (int kc = 0; kc < a.kchunks; ++kc)
@@ -1096,8 +735,6 @@ int dispatch_tc(TCArgs &a, int passes, cudaStream_t st) {
         a.wsh = 0; while ((1 << a.wsh) < a.Wg) ++a.wsh;
         a.hsh = 0; while ((1 << a.hsh) < a.Hg) ++a.hsh;
     }
-    // the kernel indexes both tensors with 32-bit element offsets
-    if ((int64_t)a.N * a.Hin * a.Win * a.Cin >= (1ll << 31) || (int64_t)a.N * a.Hout * a.Wout * a.Cn >= (1ll << 31)) return -1;
     const int bn = a.Cn > 128 ? 128 : a.Cn;
 #define DPP_TC_CASE(B_)                                                    \
     if (bn == B_) return passes > 1 ? launch_tc<B_, 2>(a, st) : launch_tc<B_, 1>(a, st);
@@ -1127,16 +764,21 @@ extern "C" int dpp_conv_pack_all(const void *items_dev, int n_items, void *strea
     return DPP_OK;
 }
 
-static int tc_supported(const dpp_conv_desc *d, int nout) {
+// nout / kin: channels of the produced / gathered tensor (Cout / Cin forward, Cin / Cout backward-data)
+static int tc_supported(const dpp_conv_desc *d, int nout, int kin) {
     if (d->precision != 1 && d->precision != 2) return 0;
     if (nout % 16 || nout > 256 || (nout > 128 && nout % 128)) return 0;
+    if (kin % 16 || kin > 256) return 0;                               // 64-byte tap segments, BN table of 256 channels
+    if ((d->k * d->k * kin + 31) / 32 > 18) return 0;                  // chunk table of the kernel
+    // the kernel indexes both tensors with 32-bit element offsets
+    if ((int64_t)d->N * d->H * d->W * d->Cin >= (1ll << 31) || (int64_t)d->N * d->Ho * d->Wo * d->Cout >= (1ll << 31)) return 0;
     return 1;
 }
 
 int dpp_conv2d_fwd_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *w,
                       const float *bias, const float *residual, float *y, double *out_stats, void *stream) {
     (void)w;
-    if (!tc_supported(d, d->Cout) || d->wpack_fwd == nullptr) return DPP_ENOTSUP;
+    if (!tc_supported(d, d->Cout, d->Cin) || d->wpack_fwd == nullptr) return DPP_ENOTSUP;
     TCArgs a;
     memset(&a, 0, sizeof(a));
     a.in = x; a.wimg = d->wpack_fwd; a.out = y;
@@ -1151,9 +793,10 @@ int dpp_conv2d_fwd_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *
     return DPP_OK;
 }
 
-int dpp_conv2d_dgrad_tc(const dpp_conv_desc *d, const float *dy, float *dx, int accumulate, const dpp_bn_ref *mask_bn,
-                        const float *x_pre, double *dz_stats, void *stream) {
-    if (!tc_supported(d, d->Cin) || d->wpack_dgrad == nullptr) return DPP_ENOTSUP;
+static int dgrad_tc_impl(const dpp_conv_desc *d, const float *dy, float *dx, int accumulate, const dpp_bn_ref *mask_bn,
+                         const float *x_pre, double *dz_stats, const float *skip, float *bn_dx, float *dgamma, float *dbeta,
+                         float pscale, unsigned int *gbar, void *stream) {
+    if (!tc_supported(d, d->Cin, d->Cout) || d->wpack_dgrad == nullptr) return DPP_ENOTSUP;
     TCArgs a;
     memset(&a, 0, sizeof(a));
     a.in = dy; a.wimg = d->wpack_dgrad; a.out = dx;
@@ -1165,9 +808,28 @@ int dpp_conv2d_dgrad_tc(const dpp_conv_desc *d, const float *dy, float *dx, int 
     a.wmode = 1; a.kchunks = (d->k * d->k * d->Cout + 31) / 32;
     a.accumulate = accumulate;
     if (mask_bn) { a.mask_bn = *mask_bn; a.has_mask = 1; a.x_pre = x_pre; a.dz_stats = dz_stats; }
+    if (bn_dx != nullptr) {
+        a.tail = 1; a.tail_skip = skip; a.tail_out = bn_dx; a.dgamma = dgamma; a.dbeta = dbeta; a.pscale = pscale; a.gbar = gbar;
+    }
     if (dispatch_tc(a, d->precision == 1 ? 2 : 1, S(stream)) != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
     DPP_LAUNCH_CHECK();
     return DPP_OK;
+}
+
+int dpp_conv2d_dgrad_tc(const dpp_conv_desc *d, const float *dy, float *dx, int accumulate, const dpp_bn_ref *mask_bn,
+                        const float *x_pre, double *dz_stats, void *stream) {
+    return dgrad_tc_impl(d, dy, dx, accumulate, mask_bn, x_pre, dz_stats, nullptr, nullptr, nullptr, nullptr, 1.f, nullptr, stream);
+}
+
+extern "C" int dpp_conv2d_dgrad_bn_bwd(const dpp_conv_desc *d, const float *dy, const float *w, float *dz, int accumulate,
+                                       const dpp_bn_ref *mask_bn, const float *x_pre, double *dz_stats, const float *skip,
+                                       float *dx, float *dgamma, float *dbeta, float param_grad_scale, unsigned int *gbar,
+                                       void *stream) {
+    (void)w;
+    DPP_CHECK_ARG(d && dy && dz && mask_bn && x_pre && dz_stats && dx && gbar);
+    // the fused tail walks GEMM rows as pixels (stride 1) and needs batch statistics
+    if (d->stride != 1 || mask_bn->sums == nullptr) return DPP_ENOTSUP;
+    return dgrad_tc_impl(d, dy, dz, accumulate, mask_bn, x_pre, dz_stats, skip, dx, dgamma, dbeta, param_grad_scale, gbar, stream);
 }
 
 int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
@@ -1175,27 +837,8 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
 
 int dpp_conv2d_wgrad_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
                         float *db, void *stream) {
-    if (!tc_supported(d, d->Cout)) return DPP_ENOTSUP;
-    {   // MN-major operand layout (wgrad_tc_mn.cu, SWIZZLE_128B_BASE32B) unless DPP_WGRAD_MN=0 selects the K-major transposing kernel
-        const char *e = getenv("DPP_WGRAD_MN");
-        if (!e || e[0] != '0') return dpp_conv2d_wgrad_tc_mn(d, x, in_bn, dy, dw, db, stream);
-    }
-    WGTArgs a;
-    memset(&a, 0, sizeof(a));
-    a.x = x; a.dy = dy; a.dw = dw; a.db = db;
-    a.N = d->N; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout;
-    a.k = d->k; a.stride = d->stride; a.pad = d->pad; a.Ho = d->Ho; a.Wo = d->Wo;
-    if (in_bn) { a.in_bn = *in_bn; a.has_in_bn = 1; }
-    const int bn = d->Cout > 128 ? 128 : d->Cout;
-    const bool p3 = d->precision == 1;
-    int rc = -1;
-    if (bn == 16) rc = p3 ? launch_wgrad_tc<16, 2>(a, S(stream)) : launch_wgrad_tc<16, 1>(a, S(stream));
-    else if (bn == 32) rc = p3 ? launch_wgrad_tc<32, 2>(a, S(stream)) : launch_wgrad_tc<32, 1>(a, S(stream));
-    else if (bn == 64) rc = p3 ? launch_wgrad_tc<64, 2>(a, S(stream)) : launch_wgrad_tc<64, 1>(a, S(stream));
-    else if (bn == 128) rc = p3 ? launch_wgrad_tc<128, 2>(a, S(stream)) : launch_wgrad_tc<128, 1>(a, S(stream));
-    if (rc != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
-    DPP_LAUNCH_CHECK();
-    return DPP_OK;
+    if (!tc_supported(d, d->Cout, d->Cin)) return DPP_ENOTSUP;
+    return dpp_conv2d_wgrad_tc_mn(d, x, in_bn, dy, dw, db, stream);     // MN-major operand tiles (wgrad_tc_mn.cu)
 }
 
 #ifdef DPP_PROFILE

@@ -7,9 +7,10 @@
 //   backward dW = x^T dpre   : A(m,k) = x[k][m]   transposed, B(n,k) = dpre[k][n] transposed
 // FC0 (16384 x 1024) is a 67 MB weight stream per GEMM at batch 128: split-K keeps >= 128 CTAs busy
 // and the epilogue adds partial tiles with red.global.add.f32 (outputs are pre-zeroed by the caller).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 using namespace dpp;
+using namespace dpp::tc;
 
 namespace {
 
@@ -17,66 +18,6 @@ constexpr int TM = 128;
 constexpr int KC = 32;
 constexpr int NSTAGE = 3;
 constexpr int NTHREADS = 288;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// TF32 operand = fp32 with the low 13 mantissa bits cleared (truncation).  hi = trunc(x), lo = trunc(x - hi):
-// x - hi is exact in fp32, so hi + lo reproduces x to 2^-21 relative - the 3xTF32 split in 3 ALU ops per value
-// (cvt.rna.tf32.f32 expands to a ~10-instruction sequence on sm_100a and dominated the producer loop).
-__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// executed by a CONVERGED warp: elect.sync inside the asm lets ptxas emit a bare UTCHMMA (a lane-0 branch
-// around tcgen05.mma costs an ELECT/BRA.U.ANY loop of ~50 stall cycles per instruction)
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
-        "elect.sync r|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
-        "elect.sync r|q, 0xffffffff;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 struct GTArgs {
     const float *A; const float *B; float *C;
@@ -217,32 +158,33 @@ k_gemm_tc(GTArgs a) {
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 8) {
-        if (nchunks > 0) {      // converged warp, elected issue
+        if (nchunks > 0 && elect_one()) {      // ONE thread runs the role (see tc_common.cuh)
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t stage = 0, phase = 0;
             for (int ch = 0; ch < nchunks; ++ch) {
                 mbar_wait(bar(stage), phase);
-                __syncwarp();
                 tc_fence_after();
-                const uint32_t sa = sbase + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                const uint32_t sa = sbase + stage * STAGE_BYTES;
+                const uint64_t a0 = make_desc(sa), b0 = make_desc(sa + A_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
-                    const uint64_t ah = make_desc(sa + ks * 32), bh = make_desc(sb + ks * 32);
+                    const uint64_t ah = a0 + 2 * ks, bh = b0 + 2 * ks;
                     const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
                     if (PASSES > 1) {
-                        const uint64_t al = make_desc(sa + TM * 128 + ks * 32), bl = make_desc(sb + BN * 128 + ks * 32);
-                        mma_tf32(tmem_base, ah, bl, IDESC, first);
-                        mma_tf32(tmem_base, al, bh, IDESC, 1u);
-                        mma_tf32(tmem_base, ah, bh, IDESC, 1u);
+                        const uint64_t al = ah + ((TM * 128) >> 4), bl = bh + ((BN * 128) >> 4);
+                        mma_tf32_ss_1t(tmem_base, ah, bl, IDESC, first);
+                        mma_tf32_ss_1t(tmem_base, al, bh, IDESC, 1u);
+                        mma_tf32_ss_1t(tmem_base, ah, bh, IDESC, 1u);
                     } else {
-                        mma_tf32(tmem_base, ah, bh, IDESC, first);
+                        mma_tf32_ss_1t(tmem_base, ah, bh, IDESC, first);
                     }
                 }
-                mma_commit(bar(NSTAGE + stage));
-                if (ch == nchunks - 1) mma_commit(bar(2 * NSTAGE));
+                mma_commit_1t(bar(NSTAGE + stage));
+                if (ch == nchunks - 1) mma_commit_1t(bar(2 * NSTAGE));
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
+        __syncwarp();
     } else if (nchunks > 0) {
         const int ew = warp - 4;
         const int m = m0 + ew * 32 + lane;

@@ -20,10 +20,11 @@
 //     swizzled columns = every bank group 4 times, the minimum 4 wavefronts.  Pieces beyond K are skipped, so a
 //     layer with few rows (1x1 16->64: 4 pieces) spreads them over 4 warps instead of loading one warp.
 //   dy: thread = (pixel t/16, piece t%16 (+16 for 128 channels)).
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 using namespace dpp;
+using namespace dpp::tc;
 
 namespace {
 
@@ -48,94 +49,6 @@ constexpr size_t WS_TILE_FLOATS = (size_t)WS_R * 16 * 128 * 128;   // [16 tiles]
 constexpr int NPROD = 16;                   // producer warps
 constexpr int W_MMA = NPROD;                // MMA issuer warp
 constexpr int NTHREADS = 32 * (NPROD + 1);
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// polling variant: mbarrier.test_wait returns at once, so the hand-off latency is one poll period
-__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// TF32 operand = fp32 with the low 13 mantissa bits cleared (truncation).  hi = trunc(x), lo = trunc(x - hi):
-// x - hi is exact in fp32, so hi + lo reproduces x to 2^-21 relative - the 3xTF32 split in 3 ALU ops per value
-// (cvt.rna.tf32.f32 expands to a ~10-instruction sequence on sm_100a and dominated the producer loop).
-__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
-// MN-major SWIZZLE_128B descriptor: LBO = 4096 B (next 32-channel block), SBO = 1024 B (next 8 pixels)
-// MN-major tf32 operands accept only the SWIZZLE_128B_BASE32B layout (type 1): atoms of 4 K-rows x 128 B,
-// 32-byte chunk index XOR (K-row & 3); LBO = stride between 32-element MN blocks, SBO = between 4-row K atoms.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo16 = 256, uint32_t sbo16 = 32, uint32_t lt = 1) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46) | ((uint64_t)lt << 61);
-}
-// executed by a CONVERGED warp: elect.sync inside the asm lets ptxas emit a bare UTCHMMA (a lane-0 branch
-// around tcgen05.mma costs an ELECT/BRA.U.ANY loop of ~50 stall cycles per instruction)
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b32 r;\n\t"
-        "elect.sync r|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t.reg .b32 r;\n\t"
-        "elect.sync r|q, 0xffffffff;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 struct WArgs {
     const float *x; const float *dy; float *dw; float *db;
@@ -384,37 +297,39 @@ k_wgrad_mn(WArgs a) {
             }
         }
     } else if (warp == W_MMA) {
-        if (nchunks > 0) {      // converged warp, elected issue
+        if (nchunks > 0 && elect_one()) {      // ONE thread runs the role: back-to-back UTCHMMA out of uniform registers
             // c_format F32, a/b TF32, a_major = b_major = MN (bits 15, 16), N = BNP, M = 128
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                        ((uint32_t)(BNP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t kstep16 = (uint32_t)a.kstep >> 4;
             for (int ch = 0; ch < nchunks; ++ch) {
                 const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
                 if (a.knobs & 2) mbar_spin(bar(stage), phase); else mbar_wait(bar(stage), phase);
-                __syncwarp();
                 tc_fence_after();
                 PROF(22);
                 const uint32_t sa = sbase + stage * L::STAGE_BYTES;
-                const uint32_t sb = sa + L::A_BYTES;
+                const uint64_t a0 = make_desc_mn(sa, a.lbo16, a.sbo16), b0 = make_desc_mn(sa + L::A_BYTES, a.lbo16, a.sbo16);
 #pragma unroll
-                for (int ks = 0; ks < ((a.knobs & 4) ? 1 : 4); ++ks) {            // 4 groups of 8 pixels (knob 4: timing ablation)
-                    const uint64_t ah = make_desc_mn(sa + ks * a.kstep, a.lbo16, a.sbo16), bh = make_desc_mn(sb + ks * a.kstep, a.lbo16, a.sbo16);
+                for (int ks = 0; ks < 4; ++ks) {            // 4 groups of 8 pixels
+                    if ((a.knobs & 4) && ks > 0) break;     // knob 4: timing ablation
+                    const uint64_t ah = a0 + ks * kstep16, bh = b0 + ks * kstep16;
                     const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
                     if (PASSES > 1) {
-                        const uint64_t al = make_desc_mn(sa + 4 * 4096 + ks * a.kstep, a.lbo16, a.sbo16);
-                        const uint64_t bl = make_desc_mn(sb + (BNP / 32) * 4096 + ks * a.kstep, a.lbo16, a.sbo16);
-                        mma_tf32(tmem_base, ah, bl, IDESC, first);
-                        mma_tf32(tmem_base, al, bh, IDESC, 1u);
-                        mma_tf32(tmem_base, ah, bh, IDESC, 1u);
+                        const uint64_t al = ah + ((4 * 4096) >> 4);
+                        const uint64_t bl = bh + (((BNP / 32) * 4096) >> 4);
+                        mma_tf32_ss_1t(tmem_base, ah, bl, IDESC, first);
+                        mma_tf32_ss_1t(tmem_base, al, bh, IDESC, 1u);
+                        mma_tf32_ss_1t(tmem_base, ah, bh, IDESC, 1u);
                     } else {
-                        mma_tf32(tmem_base, ah, bh, IDESC, first);
+                        mma_tf32_ss_1t(tmem_base, ah, bh, IDESC, first);
                     }
                 }
-                mma_commit(bar(NST + stage));
-                if (ch == nchunks - 1) mma_commit(bar(2 * NST));
+                mma_commit_1t(bar(NST + stage));
+                if (ch == nchunks - 1) mma_commit_1t(bar(2 * NST));
                 PROF(23);
             }
         }
+        __syncwarp();
     }
     PROF(32);
     tc_fence_before();

@@ -22,7 +22,7 @@ import ctypes as C
 import os
 import numpy as np
 
-from .lib import lib, BnRef, ConvDesc, BnEmaItem, PackItem, DppError
+from .lib import lib, BnRef, ConvDesc, BnEmaItem, PackItem, DppError, DPP_ENOTSUP
 
 
 def _torch():
@@ -373,6 +373,11 @@ class Engine(object):
             soff += 4 * c
         self.n_stats = max(soff, 2)
         self.STATS = torch.zeros(self.n_stats, dtype=torch.float64, device=self.dev)
+        # two 32-bit words per BN for the grid-wide barrier of the fused dgrad + BN-backward kernel (zeroed per step)
+        self.GBAR = torch.zeros(2 * max(len(self.bns), 1), dtype=torch.int32, device=self.dev)
+        self.bn_index = {id(bn): i for i, bn in enumerate(self.bns)}
+        self.fuse_bn_bwd = os.environ.get('DPP_FUSE_BN_BWD', '1') != '0'
+        self._n_bn_bwd_launches = None
 
     def release(self):
         """Detach variables from the device arenas (values are pulled back to the host)."""
@@ -688,6 +693,7 @@ class Engine(object):
             if self._comm_stream is None:
                 self._comm_stream = torch.cuda.Stream(device=self.dev)
         self._exchanged = []
+        n_fused = [0]
 
         def exchange(lo, hi):
             comm = self._comm_stream
@@ -744,11 +750,29 @@ class Engine(object):
                     dzbuf = self.dz[id(bn)]
                     if first and d.stride != 1:
                         lib.dpp_fill_f32(_ptr(dzbuf), 0.0, dzbuf.numel(), st)
-                    lib.dpp_conv2d_dgrad(C.byref(d), _ptr(dy), _ptr(self.pview(L.W)), _ptr(dzbuf), 0 if first else 1,
-                                         C.byref(bnref) if last else None, _ptr(raw.buf) if last else None,
-                                         self._stats_ptr(bn, 1) if last else None, st)
+                    fused = False
+                    if last and self.fuse_bn_bwd and not self.syncbn and d.stride == 1 and not op.get('no_tail'):
+                        # the LAST dgrad into a normalised tensor also applies that BatchNorm's backward, behind a
+                        # grid-wide barrier: one launch instead of two, dz re-read from L2
+                        sk = skip_of.get(id(raw))
+                        gb = C.c_void_p(self.GBAR.data_ptr() + 8 * self.bn_index[id(bn)])
+                        rc = lib.raw('dpp_conv2d_dgrad_bn_bwd')(
+                            C.byref(d), _ptr(dy), _ptr(self.pview(L.W)), _ptr(dzbuf), 0 if first else 1, C.byref(bnref),
+                            _ptr(raw.buf), self._stats_ptr(bn, 1), _ptr(sk.grad) if sk is not None else None, _ptr(raw.grad),
+                            _ptr(self.pview(bn.gamma, G)), _ptr(self.pview(bn.beta, G)), pscale, gb, st)
+                        if rc == 0:
+                            fused = True
+                            n_fused[0] += 1
+                        elif rc == DPP_ENOTSUP:
+                            op['no_tail'] = True
+                        else:
+                            raise DppError("dpp_conv2d_dgrad_bn_bwd failed (%d): %s" % (rc, lib.raw('dpp_last_error')().decode()))
+                    if not fused:
+                        lib.dpp_conv2d_dgrad(C.byref(d), _ptr(dy), _ptr(self.pview(L.W)), _ptr(dzbuf), 0 if first else 1,
+                                             C.byref(bnref) if last else None, _ptr(raw.buf) if last else None,
+                                             self._stats_ptr(bn, 1) if last else None, st)
                     pending[id(bn)] -= 1
-                    if last:
+                    if last and not fused:
                         finish_bn(bn, raw)
                 elif not raw.is_input:
                     lib.dpp_conv2d_dgrad(C.byref(d), _ptr(dy), _ptr(self.pview(L.W)), _ptr(raw.grad), 0, None, None,
@@ -774,6 +798,17 @@ class Engine(object):
             main.wait_stream(side)                  # join: the gradient arena is complete
         if exchanging:
             main.wait_stream(self._comm_stream)     # ... and summed over the ranks
+        self._n_bn_bwd_launches = len(self.bns) - n_fused[0]
+
+    def check_barriers(self):
+        """raises if a grid-wide barrier of the fused dgrad + BN-backward kernels gave up waiting (synchronises)"""
+        marks = self.GBAR[1::2].cpu().numpy()
+        if (marks != 0).any():
+            raise DppError("grid barrier timed out in %d fused BatchNorm-backward launch(es)" % int((marks != 0).sum()))
+
+    def launches_bn_bwd(self):
+        """separate BatchNorm-backward launches of the last step (the others ran fused behind their dgrad)"""
+        return len(self.bns) if self._n_bn_bwd_launches is None else self._n_bn_bwd_launches
 
     # ---------------------------------------------------------------------------------
     # public API
@@ -832,6 +867,7 @@ class Engine(object):
         st = self._stream()
         lib.dpp_fill_f64(_ptr(self.STATS), 0.0, self.STATS.numel(), st)
         lib.dpp_fill_f32(_ptr(self.G), 0.0, self.G.numel(), st)
+        lib.dpp_fill_f32(_ptr(self.GBAR), 0.0, self.GBAR.numel(), st)      # all-zero words
         self._run_forward(train=True)
         d = int(self.y_in.shape[1])
         lib.dpp_loss_sqerr(_ptr(self.t_out.buf), _ptr(self.y_in), _ptr(self.t_out.grad), _ptr(self.cost), self.B, d, st)

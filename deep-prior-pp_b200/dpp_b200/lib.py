@@ -66,6 +66,8 @@ CROP_REC_DTYPE = [('src_index', '<i4'), ('xstart', '<i4'), ('ystart', '<i4'), ('
                   ('reserved', '<f4'), ('ifx', '<f8'), ('ify', '<f8')]
 CROP_NORMALISE, CROP_CLAMP, CROP_MIRROR = 1, 2, 4
 
+DPP_ENOTSUP = -3
+
 P = C.c_void_p
 _SIGS = {
     'dpp_abi_version': (C.c_int, []),
@@ -83,6 +85,8 @@ _SIGS = {
     'dpp_conv_pack_all': (C.c_int, [P, C.c_int, P]),
     'dpp_conv2d_fwd': (C.c_int, [C.POINTER(ConvDesc), P, C.POINTER(BnRef), P, P, P, P, P, P]),
     'dpp_conv2d_dgrad': (C.c_int, [C.POINTER(ConvDesc), P, P, P, C.c_int, C.POINTER(BnRef), P, P, P]),
+    'dpp_conv2d_dgrad_bn_bwd': (C.c_int, [C.POINTER(ConvDesc), P, P, P, C.c_int, C.POINTER(BnRef), P, P, P, P, P, P,
+                                          C.c_float, P, P]),
     'dpp_conv2d_wgrad': (C.c_int, [C.POINTER(ConvDesc), P, C.POINTER(BnRef), P, P, P, P]),
     'dpp_bn_bwd_apply': (C.c_int, [P, P, C.POINTER(BnRef), P, P, P, P, P, P, C.c_int64, C.c_int, C.c_float, P]),
     'dpp_bn_apply': (C.c_int, [P, C.POINTER(BnRef), P, C.c_int64, C.c_int, P]),

@@ -39,7 +39,7 @@ extern "C" {
 #define DPP_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
 #define DPP_ENOTSUP (-3)  /* configuration not implemented by this build */
 
-#define DPP_ABI_VERSION 1
+#define DPP_ABI_VERSION 2
 
 int dpp_abi_version(void);
 const char *dpp_last_error(void);
@@ -214,6 +214,18 @@ int dpp_conv2d_fwd(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_
 int dpp_conv2d_dgrad(const dpp_conv_desc *d, const float *dy, const float *w, float *dx,
                      int accumulate, const dpp_bn_ref *mask_bn, const float *x_pre,
                      double *dz_stats, void *stream);
+
+/* Backward data of the LAST consumer of a normalised tensor with that BatchNorm's backward apply fused in behind a
+ * grid-wide barrier (one launch instead of dpp_conv2d_dgrad + dpp_bn_bwd_apply; same arithmetic):
+ *   dz = (dz +) dgrad(dy) * [bn(x_pre) > 0], dz_stats += {sum dz, sum dz*xhat}, then
+ *   dx = gamma*inv_std*(dz - mean(dz) - xhat*mean(dz*xhat)) [+ skip], dgamma/dbeta += param_grad_scale * sums.
+ * gbar: two zeroed 32-bit words (device) private to this call within a step (arrival counter, error mark).
+ * Returns DPP_ENOTSUP when the tcgen05 kernel does not cover the layer (stride 2, precision 0, unsupported widths,
+ * deterministic statistics): the caller then issues the two separate calls.                                    */
+int dpp_conv2d_dgrad_bn_bwd(const dpp_conv_desc *d, const float *dy, const float *w, float *dz,
+                            int accumulate, const dpp_bn_ref *mask_bn, const float *x_pre,
+                            double *dz_stats, const float *skip, float *dx, float *dgamma,
+                            float *dbeta, float param_grad_scale, unsigned int *gbar, void *stream);
 
 /* Backward weights: dw [(k*k*Cin)][Cout] += a^T dy with a = in_bn(x) recomputed on the
  * fly; db [Cout] += sum_p dy.  dw/db must be zeroed by the caller at step start.        */

@@ -343,3 +343,33 @@ def test_block0_backward_matches_torch_gpu_autograd_and_oracle():
     assert ea < 1e-4                      # stem kernels vs torch-GPU autograd on the same upstream gradient
     assert eb2 < 3e-2                     # vs the oracle: bounded by ReLU-flip noise (see test_train_step)
 
+
+
+@pytest.mark.parametrize("B", [16, 128])
+def test_fused_bn_backward_equals_separate_kernels(B, monkeypatch):
+    """The last backward-data kernel into a normalised tensor applies that BatchNorm's backward behind a grid-wide
+    barrier (dpp_conv2d_dgrad_bn_bwd); DPP_FUSE_BN_BWD=0 issues dpp_conv2d_dgrad + dpp_bn_bwd_apply instead.  Same
+    arithmetic in the same order: the gradient arenas of the two schedules must agree to float32 roundoff (the
+    backward-weights kernels accumulate with atomics, whose order varies from run to run)."""
+    D = 30
+    x, y = _data(B, D)
+    res = {}
+    for fuse in ('1', '0'):
+        monkeypatch.setenv('DPP_FUSE_BN_BWD', fuse)
+        net, onet, eng = _build(0, B, 1, D, precision=1)
+        eng.set_input_nchw(x)
+        eng._alloc_training()
+        eng.y_in.copy_(torch.from_numpy(y))
+        for use_graph in (False, True):
+            cost = float(eng.train_step(0.0, use_graph=use_graph).cpu()[0])
+        eng.check_barriers()
+        res[fuse] = (cost, eng.G.clone(), eng.launches_bn_bwd())
+        eng.release()
+    (c1, g1, n1), (c0, g0, n0) = res['1'], res['0']
+    print("batch", B, "separate BN-backward launches: fused schedule", n1, "unfused", n0)
+    assert n0 == 61 and n1 <= 4                       # 57 of the 61 run fused (3 stride-2 projections + the FC-side BN stay)
+    assert c1 == c0
+    err = float((g1 - g0).abs().max() / g0.abs().max())
+    l2 = float((g1 - g0).norm() / g0.norm())
+    print("gradient arena fused vs separate: max %.2e rel-L2 %.2e" % (err, l2))
+    assert err < 2e-5 and l2 < 2e-5

@@ -132,7 +132,7 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(dll, name), name
     assert set(EXPORTED_SYMBOLS) == set(declared)
     dll.dpp_abi_version.restype = ctypes.c_int
-    assert dll.dpp_abi_version() == 1
+    assert dll.dpp_abi_version() == 2
 
 
 def test_engine_refuses_to_run_without_cuda():
