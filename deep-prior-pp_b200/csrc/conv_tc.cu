@@ -21,6 +21,7 @@
 // TMEM allocator.  Persistent CTAs (<= 1 per SM) walk the tile list, so per-channel fp64 statistics
 // leave the CTA once.
 #include "tc_common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 
 using namespace dpp;
@@ -53,6 +54,10 @@ constexpr int KC = 32;           // floats of K per stage: 128-byte rows
 constexpr int NTHREADS_CONV = 576;  // k_conv_tc: 8 producer + 2 x 4 epilogue warps, MMA issuer, weight-image (TMA) loader
 
 struct TCArgs {
+    // TMA descriptor of the gathered tensor: rank 4 {C, W, H, N}, box = {min(Cin, 32) channels, the tile's pixel
+    // rectangle}, traversal strides = the convolution stride, zero fill outside the image ('half' padding for free)
+    alignas(64) CUtensorMap tmap;
+    int box_h, box_n;     // the 128 GEMM rows of a tile = box_n images x box_h rows x Wg pixels
     const float *in;      // gathered tensor [N, Hin, Win, Cin]
     const float *wimg;    // packed weight image for this mode
     float *out;           // [N, Hout, Wout, Cn]
@@ -63,7 +68,7 @@ struct TCArgs {
     int wmode;            // 0 forward, 1 dgrad
     int kchunks;          // ceil(k*k*Cin / 32)
     int wsh, hsh;         // log2(Wg), log2(Hg) when both are powers of two, else -1 (generic division)
-    int knobs;            // tuning bits (DPP_TC_KNOBS): 1 = L1-allocating gathers for k > 1, 2 = lane-per-row gather (old mapping)
+    int knobs;            // tuning bits (DPP_TC_KNOBS): 4 = skip the statistics atomics (timing ablation)
     dpp_bn_ref in_bn; int has_in_bn;
     const float *bias; const float *residual; double *out_stats;
     int accumulate; dpp_bn_ref mask_bn; int has_mask; const float *x_pre; double *dz_stats;
@@ -104,12 +109,12 @@ struct SmemLayout {
     static constexpr int B_BYTES = PASSES * BN * 128;
     static constexpr int NS = 4;                                   // A stages (TMEM)
     static constexpr int RB = (B_BYTES >= 32768) ? 3 : (B_BYTES >= 16384 ? 4 : 6);   // weight-image ring slots
-    static constexpr int RDG = (B_BYTES >= 32768) ? 2 : 3;         // raw landing slots (16 KB chunks) per producer group
+    static constexpr int NSLOT = (B_BYTES >= 32768) ? 4 : 6;       // landing slots of the gathered operand (16 KB k-chunks, TMA)
     static constexpr int A_COL0 = 256, A_COLS = 32 * PASSES;
     static constexpr int B_OFF = 0;
-    static constexpr int RAW_OFF = B_OFF + RB * B_BYTES;
-    static constexpr int BAR_OFF = RAW_OFF + 2 * RDG * TM * 128;
-    static constexpr int STG_OFF = BAR_OFF + 256;
+    static constexpr int RAW_OFF = B_OFF + RB * B_BYTES;           // multiple of 1024: the swizzled TMA boxes land here
+    static constexpr int BAR_OFF = RAW_OFF + NSLOT * TM * 128;
+    static constexpr int STG_OFF = BAR_OFF + 512;
     static constexpr int COEF_OFF = STG_OFF + 8 * EpiGeo<BN>::WARP_BYTES;
     static constexpr int COEF_BYTES = 2 * 256 * 4 + 5 * 128 * 4 + 18 * 32;   // in-BN scale/shift, n-tile coefficients, chunk table
     static constexpr int STAT_OFF = COEF_OFF + COEF_BYTES;
@@ -142,9 +147,12 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     PROF(1);
     DBG_DECL;
     // bar index: full[s] = s, empty[s] = NS + s, tfull[a] = 2*NS + a, tempty[a] = 2*NS + 2 + a,
-    //            bfull[b] = 2*NS + 4 + b, bempty[b] = 2*NS + 4 + RB + b
+    //            bfull[b] = 2*NS + 4 + b, bempty[b] = 2*NS + 4 + RB + b,
+    //            rfull[r] = RBAR + r, rempty[r] = RBAR + NSLOT + r   (landing ring of the gathered operand)
+    constexpr int NSLOT = L::NSLOT, RBAR = 2 * NS + 4 + 2 * RB;
+    static_assert(8 * (RBAR + 2 * NSLOT) <= 480, "barrier region");
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 224);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 480);
     float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);   // [256] input-BN scale
     float *s_shift = s_scale + 256;              // [256]
     float *s_msc = s_shift + 256;                // [BN] mask-BN scale   (this CTA's n-tile)
@@ -171,6 +179,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         for (int s = 0; s < NS; ++s) { mbar_init(bar(s), NPROD_WARPS / 2); mbar_init(bar(NS + s), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(2 * NS + i), 1); mbar_init(bar(2 * NS + 2 + i), 4); }
         for (int b = 0; b < RB; ++b) { mbar_init(bar(2 * NS + 4 + b), 1); mbar_init(bar(2 * NS + 4 + RB + b), 1); }
+        for (int r = 0; r < NSLOT; ++r) { mbar_init(bar(RBAR + r), 1); mbar_init(bar(RBAR + NSLOT + r), NPROD_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) {
@@ -235,14 +244,15 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     PROF(2);
 
     if (warp < NPROD_WARPS) {
-        // =========================== producers ===========================
-        // Two independent groups of 4 warps; group g owns the chunks with (chunk index % 2) == g, so the
-        // synchronisation latencies of the two groups overlap.  warp % 4 = TMEM lane quarter; a thread owns
-        // one GEMM row (pixel).  Per chunk it copies the row's 128 bytes (two taps of 64 B) with cp.async into
-        // a private raw slot RDG-1 chunks ahead (exact wait_group tracking, no registers tied up), reads them
-        // back, applies BN+ReLU, splits into TF32 hi/lo and writes 32 + 32 columns of its TMEM lane
-        // (tcgen05.st): the MMA reads A from tensor memory, A never goes through the swizzled smem layout.
-        constexpr int RDG = L::RDG, D = RDG - 1;
+        // =========================== transform warps ===========================
+        // Two independent groups of 4 warps; group g owns the k-chunks with (chunk index % 2) == g, so the
+        // synchronisation latencies of the two groups overlap.  warp % 4 = TMEM lane quarter; a thread owns one GEMM
+        // row (pixel).  The loader warp stages every chunk - the tile's 128 pixels x 32 K-values of one or two filter
+        // taps - with TMA tensor loads (cp.async.bulk.tensor, zero fill outside the image) into a landing ring.  A
+        // thread reads its row (8 x 16 bytes, hardware-swizzled: conflict-free), applies BN + ReLU, splits into TF32
+        // hi / lo and writes 32 + 32 columns of its TMEM lane (tcgen05.st): the MMA reads A from tensor memory.
+        // No address arithmetic and no load instructions per element are left in these warps (round 1 gathered
+        // with 1024 cp.async per chunk, a third of the chunk period).
         const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + L::A_COL0;
@@ -250,91 +260,62 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         const int T = my_tiles * kchunks;
         const int Tg = (T - grp + 1) / 2;             // chunks of this group: grp, grp + 2, ...
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
-        const float *const gin = a.in;
-        // The warp's 32 rows x 8 pieces are fetched with lane = (row t*4 + lane/8, piece lane%8), t = 0..7: the 8 lanes of
-        // a row read its two 64-byte tap segments, so one instruction touches 8 lines instead of 32 (the L1 tag stage
-        // handles one line per cycle and was the serial resource of the gather).
-        const int pcs = lane & 7, lsub = lane >> 3;
+        // where the row's 8 pieces lie in a landing slot.  Cin >= 32: one box of 32 channels, 128-byte rows,
+        // SWIZZLE_128B (piece ^ (row & 7)).  Cin == 16: two boxes of 16 channels (tap A, tap B) of 8 KB each, 64-byte
+        // rows, SWIZZLE_64B (piece ^ ((row >> 1) & 3)).
+        const bool c16 = a.Cin == 16;
+        uint32_t poff[8];
+#pragma unroll
+        for (int pj = 0; pj < 8; ++pj)
+            poff[pj] = c16 ? (uint32_t)((pj >> 2) * 8192 + row * 64 + (((pj & 3) ^ ((row >> 1) & 3)) << 4))
+                           : (uint32_t)(row * 128 + ((pj ^ (row & 7)) << 4));
         int i_tile = blockIdx.x, i_kc = grp;
-        int r_off, r_h0, r_w0;        // this thread's own row: element offset (-1: beyond M), top-left input pixel
+        int r_h0, r_w0; bool r_ok;    // this thread's own row: top-left input pixel, row inside M
         auto set_tile = [&]() {
             const int m = (i_tile / ntiles) * TM + row;
             int n, ho, wo;
             decode_pix(a, m < M ? m : 0, n, ho, wo);
             r_h0 = ho * a.in_stride; r_w0 = wo * a.in_stride;
-            r_off = m < M ? ((n * Hin + r_h0) * Win + r_w0) * a.Cin : -1;
+            r_ok = m < M;
         };
         while (i_kc >= kchunks) { i_kc -= kchunks; i_tile += gstride; }
         set_tile();
-        uint32_t vring = 0;           // 2 validity bits per in-flight chunk
-        uint32_t cring = 0;           // (kc & 0xff) per in-flight chunk, 8 bits each (RDG <= 3)
-        uint32_t stage = grp, phase = 0;
-        int islot = 0, pslot = 0;
-        // landing slot: [row][piece ^ (row & 7)] (16-byte pieces): conflict-free for the cp.async writes and the LDS.128 reads
-        const uint32_t grp_u32 = sbase + L::RAW_OFF + grp * RDG * (TM * 128) + q * 32 * 128;
-        const unsigned char *const grp_ptr = smem + L::RAW_OFF + grp * RDG * (TM * 128) + row * 128;
+        uint32_t stage = grp, phase = 0;              // A stage in TMEM (NS stages, this group uses grp, grp + 2)
+        uint32_t slot = grp, sphase = 0;              // landing slot (NSLOT slots, this group uses grp, grp + 2, ...)
 #pragma unroll 1
-        for (int i = -D; i < Tg; ++i) {
-            if (i + D < Tg) {
-                const int4 e0 = s_tab[i_kc * 2], e1 = s_tab[i_kc * 2 + 1];
-                const bool v0 = r_off >= 0 && (unsigned)(r_h0 + e0.x) < (unsigned)Hin && (unsigned)(r_w0 + e0.y) < (unsigned)Win;
-                const bool v1 = r_off >= 0 && (unsigned)(r_h0 + e1.x) < (unsigned)Hin && (unsigned)(r_w0 + e1.y) < (unsigned)Win;
-                const int4 e = pcs < 4 ? e0 : e1;
-                const int ez = e.z + (pcs & 3) * 4;
-                const uint32_t sbuf = grp_u32 + islot * (TM * 128);
-                if (!DBG(1)) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        // row geometry comes from the owning lane by shuffle (decoding the 8 rows per tile into registers
-                        // was measured slower on the B200: 31.7 vs 28.8 us on the 3x3 16->16 layer)
-                        const int lrow = t * 4 + lsub;
-                        const int o_off = __shfl_sync(0xffffffffu, r_off, lrow);
-                        const int o_h0 = __shfl_sync(0xffffffffu, r_h0, lrow);
-                        const int o_w0 = __shfl_sync(0xffffffffu, r_w0, lrow);
-                        const bool v = o_off >= 0 && (unsigned)(o_h0 + e.x) < (unsigned)Hin && (unsigned)(o_w0 + e.y) < (unsigned)Win;
-                        const float *src = gin + (v ? o_off + ez : 0);
-                        cp_async16(sbuf + lrow * 128 + ((pcs ^ (lrow & 7)) << 4), src, v ? 16u : 0u);
-                    }
-                }
-                const uint32_t sh2 = 2 * islot, sh8 = 8 * islot;
-                vring = (vring & ~(3u << sh2)) | (((uint32_t)v0 | ((uint32_t)v1 << 1)) << sh2);
-                cring = (cring & ~(0xffu << sh8)) | ((uint32_t)i_kc << sh8);
-                if (++islot == RDG) islot = 0;
-                i_kc += 2;
-                if (i_kc >= kchunks) {
-                    do { i_kc -= kchunks; i_tile += gstride; } while (i_kc >= kchunks);
-                    set_tile();
-                }
+        for (int i = 0; i < Tg; ++i) {
+            const int kc = i_kc;
+            const int4 e0 = s_tab[kc * 2], e1 = s_tab[kc * 2 + 1];
+            // taps outside the image (and K-values beyond k*k*Cin) are zero AFTER BN + ReLU
+            const bool v0 = r_ok && (unsigned)(r_h0 + e0.x) < (unsigned)Hin && (unsigned)(r_w0 + e0.y) < (unsigned)Win;
+            const bool v1 = r_ok && (unsigned)(r_h0 + e1.x) < (unsigned)Hin && (unsigned)(r_w0 + e1.y) < (unsigned)Win;
+            i_kc += 2;
+            if (i_kc >= kchunks) {
+                do { i_kc -= kchunks; i_tile += gstride; } while (i_kc >= kchunks);
+                set_tile();
             }
-            cp_async_commit();        // (possibly empty) group: keeps the wait_group arithmetic uniform
-            if (i < 0) continue;
-            cp_async_wait<D>();       // this thread's copies of chunk i have landed
-            const uint32_t vb = (vring >> (2 * pslot)) & 3u;
-            const int kc = (int)((cring >> (8 * pslot)) & 0xffu);
-            const unsigned char *rpc = grp_ptr + pslot * (TM * 128);
-            if (++pslot == RDG) pslot = 0;
+            if (lane == 0) mbar_wait(bar(RBAR + slot), sphase);       // the chunk has landed
+            __syncwarp();
             PROF(11);
-            // the row's 32 floats leave the landing slot before the stage wait: the loads overlap the wait and nothing in
-            // the arithmetic below depends on shared memory any more
+            const unsigned char *rp = smem + L::RAW_OFF + slot * (TM * 128);
             float4 xr[8];
 #pragma unroll
-            for (int pj = 0; pj < 8; ++pj) xr[pj] = *reinterpret_cast<const float4 *>(rpc + ((pj ^ (lane & 7)) << 4));
-            if (pro) {
-                const int4 e0 = s_tab[kc * 2], e1 = s_tab[kc * 2 + 1];
+            for (int pj = 0; pj < 8; ++pj) xr[pj] = *reinterpret_cast<const float4 *>(rp + poff[pj]);
 #pragma unroll
-                for (int pj = 0; pj < 8; ++pj) {
+            for (int pj = 0; pj < 8; ++pj) {
+                float4 x = xr[pj];
+                if (pro) {
                     const int chan = (pj < 4 ? e0.w : e1.w) + (pj & 3) * 4;
                     const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
                     const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
-                    float4 x = xr[pj];
                     x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
                     x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
                     if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                    if (!((vb >> (pj >> 2)) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);      // padding is zero AFTER BN + ReLU
-                    xr[pj] = x;
                 }
+                if (!(pj < 4 ? v0 : v1)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                xr[pj] = x;
             }
-            if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);
+            if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);     // the MMAs that read this A stage have retired
             __syncwarp();
             tc_fence_after();
             PROF(12);
@@ -357,10 +338,15 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
             PROF(14);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(stage));
+            if (lane == 0) {
+                mbar_arrive(bar(stage));                      // A stage written
+                mbar_arrive(bar(RBAR + NSLOT + slot));        // landing slot consumed (every lane's row went through registers)
+            }
             PROF(13);
             stage += 2;
             if (stage >= NS) { stage -= NS; phase ^= 1; }
+            slot += 2;
+            if (slot >= NSLOT) { slot -= NSLOT; sphase ^= 1; }
         }
     } else if (warp == W_MMA) {
         // =========================== MMA issuer ===========================
@@ -413,21 +399,47 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         }
         __syncwarp();
     } else if (warp == W_LOAD) {
-        // =========================== weight-image loader ===========================
-        // TMA bulk copies of the packed weight images: once per CTA when the n-tile's image fits the ring,
-        // otherwise streamed up to RB chunks ahead of the MMAs for every tile
+        // =========================== loader (TMA) ===========================
+        // One thread feeds both operands.  Weights: bulk copies of the packed images - once per CTA when the n-tile's
+        // image fits the ring, otherwise streamed up to RB chunks ahead of the MMAs for every tile.  Gathered operand:
+        // per k-chunk one tensor load (Cin >= 32: 32 channels of one filter tap) or two (Cin == 16: 16 channels of two
+        // taps) of the tile's pixel rectangle, shifted by the tap offset; pixels outside the image arrive as zeros.
         if (lane == 0) {
             const int nt = blockIdx.x % ntiles;
-            uint32_t b = 0, bphase = 0;
-            const int rounds = resident ? (my_tiles > 0 ? 1 : 0) : my_tiles;
-            for (int t = 0; t < rounds; ++t)
+            const uint64_t tmap = reinterpret_cast<uint64_t>(&a.tmap);
+            const bool c16 = a.Cin == 16;
+            const uint32_t box_bytes = c16 ? 8192u : 16384u;
+            const int KK = a.k * a.k;
+            uint32_t b = 0, bphase = 0, rs = 0, rphase = 0;
+            if (resident && my_tiles > 0)
                 for (int kc = 0; kc < a.kchunks; ++kc) {
-                    if (!resident) mbar_wait_relaxed(bar(2 * NS + 4 + RB + b), bphase ^ 1);
                     const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
-                    mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
-                    bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
-                    if (++b == RB) { b = 0; bphase ^= 1; }
+                    mbar_expect_tx(bar(2 * NS + 4 + kc), L::B_BYTES);
+                    bulk_g2s(sbase + L::B_OFF + kc * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + kc));
                 }
+            for (int t = 0; t < my_tiles; ++t) {
+                const int m0 = ((blockIdx.x + t * gridDim.x) / ntiles) * TM;
+                int n0, h0, w0;
+                decode_pix(a, m0, n0, h0, w0);                     // w0 == 0: a tile starts at the beginning of an image row
+                const int ch0 = h0 * a.in_stride;
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    if (!resident) {
+                        mbar_wait_relaxed(bar(2 * NS + 4 + RB + b), bphase ^ 1);
+                        const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
+                        mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
+                        bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
+                        if (++b == RB) { b = 0; bphase ^= 1; }
+                    }
+                    mbar_wait(bar(RBAR + NSLOT + rs), rphase ^ 1);         // landing slot free
+                    const uint32_t dst = sbase + L::RAW_OFF + rs * (TM * 128), fb = bar(RBAR + rs);
+                    const int *e = a.tab[kc];
+                    const bool two = c16 && (kc * 2 + 1) < KK;           // Cin == 16: is the chunk's second tap inside K?
+                    mbar_expect_tx(fb, two ? 2 * box_bytes : box_bytes);
+                    tma_load_4d(dst, tmap, e[3], e[1], ch0 + e[0], n0, fb);
+                    if (two) tma_load_4d(dst + 8192, tmap, e[7], e[5], ch0 + e[4], n0, fb);
+                    if (++rs == NSLOT) { rs = 0; rphase ^= 1; }
+                }
+            }
         }
     } else {
         // =========================== epilogue ===========================
@@ -716,8 +728,58 @@ int tc_knobs() {
     return v;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Tensor map of the gathered operand.  A tile's 128 GEMM rows must form a rectangle of the gather grid: whole image
+// rows (128 % Wg == 0), either box_h = 128 / Wg rows of one image or box_n = 128 / (Hg * Wg) whole images.
+// Returns DPP_ENOTSUP for other geometries (the fp32 SIMT kernels take them).
+int make_tmap(TCArgs &a) {
+    if (a.Cin != 16 && a.Cin % 32 != 0) return DPP_ENOTSUP;
+    if (a.Wg > TM || TM % a.Wg != 0) return DPP_ENOTSUP;
+    const int rows = TM / a.Wg;
+    if (a.Hg >= rows) {
+        if (a.Hg % rows != 0) return DPP_ENOTSUP;
+        a.box_h = rows; a.box_n = 1;
+    } else {
+        if (rows % a.Hg != 0) return DPP_ENOTSUP;
+        a.box_h = a.Hg; a.box_n = rows / a.Hg;
+    }
+    if ((reinterpret_cast<uintptr_t>(a.in) & 15) != 0) return DPP_ENOTSUP;
+    EncodeTiledFn enc = encode_tiled();
+    if (enc == nullptr) return -1;
+    const int cbox = a.Cin == 16 ? 16 : 32, s = a.in_stride;
+    if (a.Wg * s > 256 || a.box_h * s > 256 || s > 8) return DPP_ENOTSUP;
+    cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)a.N};
+    cuuint64_t gstr[3] = {(cuuint64_t)a.Cin * 4, (cuuint64_t)a.Win * a.Cin * 4, (cuuint64_t)a.Hin * a.Win * a.Cin * 4};
+    cuuint32_t box[4] = {(cuuint32_t)cbox, (cuuint32_t)(a.Wg * s), (cuuint32_t)(a.box_h * s), (cuuint32_t)a.box_n};
+    cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    const CUresult r = enc(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(a.in), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, cbox == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 int dispatch_tc(TCArgs &a, int passes, cudaStream_t st) {
     a.knobs = tc_knobs();
+    {
+        const int rc = make_tmap(a);
+        if (rc != 0) return rc;
+    }
     const int KK = a.k * a.k;
     for (int kc = 0; kc < a.kchunks; ++kc)
         for (int half = 0; half < 2; ++half) {
@@ -788,7 +850,11 @@ int dpp_conv2d_fwd_tc(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *
     a.wmode = 0; a.kchunks = (d->k * d->k * d->Cin + 31) / 32;
     if (in_bn) { a.in_bn = *in_bn; a.has_in_bn = 1; }
     a.bias = bias; a.residual = residual; a.out_stats = out_stats;
-    if (dispatch_tc(a, d->precision == 1 ? 2 : 1, S(stream)) != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
+    {
+        const int rc = dispatch_tc(a, d->precision == 1 ? 2 : 1, S(stream));
+        if (rc == DPP_ENOTSUP) return DPP_ENOTSUP;
+        if (rc != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
+    }
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }
@@ -811,7 +877,11 @@ static int dgrad_tc_impl(const dpp_conv_desc *d, const float *dy, float *dx, int
     if (bn_dx != nullptr) {
         a.tail = 1; a.tail_skip = skip; a.tail_out = bn_dx; a.dgamma = dgamma; a.dbeta = dbeta; a.pscale = pscale; a.gbar = gbar;
     }
-    if (dispatch_tc(a, d->precision == 1 ? 2 : 1, S(stream)) != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
+    {
+        const int rc = dispatch_tc(a, d->precision == 1 ? 2 : 1, S(stream));
+        if (rc == DPP_ENOTSUP) return DPP_ENOTSUP;
+        if (rc != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
+    }
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }
