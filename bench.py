@@ -647,10 +647,11 @@ def count_launches(eng):
     """kernels of OUR library launched per training step (checked against the ncu launch list)"""
     n = 1 + 2 + 1 + 1      # loss, adam + tick, weight-image pack, ema (the two arena fills are memset nodes)
     n += eng.launches_bn_bwd() if hasattr(eng, 'launches_bn_bwd') else len(eng.bns)
+    n += eng.launches_wgrad() if hasattr(eng, 'launches_wgrad') else len([o for o in eng.ops if o['kind'] == 'conv'])
     for op in eng.ops:
         k = op['kind']
         if k == 'conv':
-            n += 3                  # fwd, wgrad, dgrad
+            n += 2                  # fwd, dgrad (backward-weights: counted above, grouped or per layer)
         elif k == 'convpool':
             n += 2
         elif k == 'fc':

@@ -366,7 +366,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kc = 0; kc < kchunks; ++kc) {
                     if (resident) { bslot = kc; bphase = 0; }
-                    mbar_wait(bar(2 * NS + 4 + bslot), bphase);
+                    if (!resident || t == 0) mbar_wait(bar(2 * NS + 4 + bslot), bphase);   // resident images are complete after the first tile
                     PROF(21);
                     mbar_wait(bar(stage), phase);
                     tc_fence_after();

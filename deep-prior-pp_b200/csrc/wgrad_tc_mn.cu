@@ -22,6 +22,7 @@
 //   dy: thread = (pixel t/16, piece t%16 (+16 for 128 channels)).
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <vector>
 
 using namespace dpp;
 using namespace dpp::tc;
@@ -85,60 +86,24 @@ struct Lay {
     static constexpr int TOTAL = COEF_OFF + 2 * 256 * 4 + 1024;
 };
 
+// One work item: the pixel chunks [c_begin, c_begin + nchunks) of (m-tile mt, n-tile nt) of one layer.  Called by every
+// thread of the CTA with barriers and tensor memory set up, the MMA stages zeroed and the BN coefficients in shared
+// memory.  gch0 = chunks this CTA has pushed through the stage ring before (ring position and barrier parities carry
+// over from item to item), done_parity = parity of the "accumulator complete" barrier for this item.
+// direct: the epilogue reduces straight into dW (grouped launches: few CTAs per tile at any one time).
 template <int BN, int PASSES, int NST>
-__global__ void __launch_bounds__(NTHREADS, 1)
-k_wgrad_mn(WArgs a) {
+__device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int nt, const int split, const int c_begin,
+                                         const int nchunks, const bool direct, const uint32_t gch0, const uint32_t done_parity,
+                                         unsigned char *smem, const uint32_t sbase, const uint32_t tmem_base,
+                                         const float *s_scale, const float *s_shift, float *s_db) {
     using L = Lay<BN, PASSES, NST>;
     constexpr int RD = L::RD, D = RD - 1, BNP = L::BNP, NDY = L::NDY, NDYH = L::NDYH;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
-    const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     PROF_DECL(lane == 0 ? (warp == 0 ? 0 : warp == W_MMA ? 1000 : warp == 4 ? 2000 : warp == 7 ? 3000 : 4000) : 4000);
-    PROF(1);
     auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };      // full[s]=s, empty[s]=NST+s, done=2*NST
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
-    float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);
-    float *s_shift = s_scale + 256;
-    constexpr uint32_t TCOLS = BNP <= 32 ? 32 : (BNP <= 64 ? 64 : 128);
-
-    const int nt = blockIdx.x % a.ntiles;
-    int split = blockIdx.x / a.ntiles, mt = 0;
-    while (mt + 1 < a.mtiles && split >= a.splits[mt]) { split -= a.splits[mt]; ++mt; }
     const int kd0 = mt * TM, o0 = nt * BN;
     const int Kw = a.k * a.k * a.Cin;
     const int P = a.N * a.Ho * a.Wo;
-    const int total_chunks = (P + 31) / 32;
-    const int c_begin = split * a.cps[mt];
-    int c_end = c_begin + a.cps[mt]; if (c_end > total_chunks) c_end = total_chunks;
-    const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
-
-    __shared__ float s_db[128];      // this CTA's bias-gradient partial (m-tile 0 only)
-    __shared__ int s_last;
-    if (tid < 128) s_db[tid] = 0.f;
-    pdl_trigger();      // private set-up first (see common.cuh: programmatic dependent launch)
-    if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), NPROD); mbar_init(bar(NST + s), 1); }   // full: one arrival per producer warp
-        mbar_init(bar(2 * NST), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == W_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // zero the MMA stages once: padded dy columns (BN = 16) and rows beyond Kw stay zero
-    for (int i = tid; i < NST * L::STAGE_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    pdl_wait();
-    if (a.has_in_bn)
-        for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    PROF(2);
-
     if (warp < NPROD) {
         const bool pro = a.has_in_bn != 0, relu = a.in_bn.relu != 0;
         const bool use_ca = (a.knobs & 1) && a.k > 1;
@@ -213,7 +178,7 @@ k_wgrad_mn(WArgs a) {
             cp_async_wait<D>();
             PROF(11);
             const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
-            const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
+            const uint32_t stage = (gch0 + ch) % NST, phase = ((gch0 + ch) / NST) & 1;
             const uint32_t vm = (vbits >> (2 * (ch % RD))) & 3u;
             if (lane == 0) { if (kspin) mbar_spin(bar(NST + stage), phase ^ 1); else mbar_wait(bar(NST + stage), phase ^ 1); }
             __syncwarp();
@@ -280,7 +245,7 @@ k_wgrad_mn(WArgs a) {
             // epilogue (warps 4-7: TMEM lane quarter = warp % 4): row = (tap, c) index, columns = output channels
             const int ew = warp - 4;
             const int kd = kd0 + ew * 32 + lane;
-            if (lane == 0) mbar_wait(bar(2 * NST), 0);
+            if (lane == 0) mbar_wait(bar(2 * NST), done_parity);
             __syncwarp();
             tc_fence_after();
             PROF(31);
@@ -289,7 +254,7 @@ k_wgrad_mn(WArgs a) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + cb, v);
                 if (kd < Kw) {
-                    float *dst = a.splits[mt] == 1 ? a.dw + (size_t)kd * a.Cout + o0 + cb      // sole contributor: straight into dW
+                    float *dst = (direct || a.splits[mt] == 1) ? a.dw + (size_t)kd * a.Cout + o0 + cb      // straight into dW
                                                    : a.ws + ((size_t)((mt * a.ntiles + nt) * a.R + split % a.R) * TM + ew * 32 + lane) * BN + cb;
 #pragma unroll
                     for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
@@ -303,7 +268,7 @@ k_wgrad_mn(WArgs a) {
                                        ((uint32_t)(BNP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             const uint32_t kstep16 = (uint32_t)a.kstep >> 4;
             for (int ch = 0; ch < nchunks; ++ch) {
-                const uint32_t stage = ch % NST, phase = (ch / NST) & 1;
+                const uint32_t stage = (gch0 + ch) % NST, phase = ((gch0 + ch) / NST) & 1;
                 if (a.knobs & 2) mbar_spin(bar(stage), phase); else mbar_wait(bar(stage), phase);
                 tc_fence_after();
                 PROF(22);
@@ -331,6 +296,62 @@ k_wgrad_mn(WArgs a) {
         }
         __syncwarp();
     }
+}
+
+template <int BN, int PASSES, int NST>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_wgrad_mn(WArgs a) {
+    using L = Lay<BN, PASSES, NST>;
+    constexpr int BNP = L::BNP;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still in the shared window
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    PROF_DECL(lane == 0 ? (warp == 0 ? 0 : warp == W_MMA ? 1000 : warp == 4 ? 2000 : warp == 7 ? 3000 : 4000) : 4000);
+    PROF(1);
+    auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };      // full[s]=s, empty[s]=NST+s, done=2*NST
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
+    float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);
+    float *s_shift = s_scale + 256;
+    constexpr uint32_t TCOLS = BNP <= 32 ? 32 : (BNP <= 64 ? 64 : 128);
+
+    const int nt = blockIdx.x % a.ntiles;
+    int split = blockIdx.x / a.ntiles, mt = 0;
+    while (mt + 1 < a.mtiles && split >= a.splits[mt]) { split -= a.splits[mt]; ++mt; }
+    const int kd0 = mt * TM, o0 = nt * BN;
+    const int Kw = a.k * a.k * a.Cin;
+    const int P = a.N * a.Ho * a.Wo;
+    const int total_chunks = (P + 31) / 32;
+    const int c_begin = split * a.cps[mt];
+    int c_end = c_begin + a.cps[mt]; if (c_end > total_chunks) c_end = total_chunks;
+    const int nchunks = c_end > c_begin ? c_end - c_begin : 0;
+
+    __shared__ float s_db[128];      // this CTA's bias-gradient partial (m-tile 0 only)
+    __shared__ int s_last;
+    if (tid < 128) s_db[tid] = 0.f;
+    pdl_trigger();      // private set-up first (see common.cuh: programmatic dependent launch)
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), NPROD); mbar_init(bar(NST + s), 1); }   // full: one arrival per producer warp
+        mbar_init(bar(2 * NST), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // zero the MMA stages once: padded dy columns (BN = 16) and rows beyond Kw stay zero
+    for (int i = tid; i < NST * L::STAGE_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    pdl_wait();
+    if (a.has_in_bn)
+        for (int c = tid; c < a.Cin; c += NTHREADS) bn_scale_shift(a.in_bn, c, a.Cin, s_scale[c], s_shift[c]);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    PROF(2);
+    item_run<BN, PASSES, NST>(a, mt, nt, split, c_begin, nchunks, false, 0u, 0u, smem, sbase, tmem_base, s_scale, s_shift, s_db);
     PROF(32);
     tc_fence_before();
     __syncthreads();
@@ -376,6 +397,90 @@ k_wgrad_mn(WArgs a) {
             a.db[o0 + tid] += acc;
         }
         if (tid == 0) a.ctr[tile_id] = 0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Grouped launch: the backward-weights GEMMs of MANY layers in one persistent kernel.  A step has 63 of them, most far
+// too small to fill the device for longer than their own fixed cost (launch, set-up, pipeline fill, split reduction:
+// ~9 us each, a third of their total time); their results are needed only by the optimiser.  The work of all layers with
+// the same n-tile width is cut into items of `nchunks` pixel chunks of one (layer, m-tile, n-tile); CTAs (one per SM)
+// take items from a list - the first statically, the rest through an atomic counter - and reduce each item's tile
+// straight into dW (the list interleaves the tiles, so only a handful of CTAs work on the same tile at any time).
+// -------------------------------------------------------------------------------------------------------------------
+struct WItem { int layer, mt, nt, c_begin, nchunks, pad0, pad1, pad2; };
+struct WGroupArgs { const WArgs *layers; const WItem *items; int n_items; unsigned int *sched; };
+
+template <int BN, int PASSES, int NST>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_wgrad_group(const WGroupArgs g) {
+    using L = Lay<BN, PASSES, NST>;
+    constexpr int BNP = L::BNP;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    auto bar = [&](int i) { return sbase + L::BAR_OFF + 8 * i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
+    float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);
+    float *s_shift = s_scale + 256;
+    constexpr uint32_t TCOLS = BNP <= 32 ? 32 : (BNP <= 64 ? 64 : 128);
+    __shared__ WArgs s_a;
+    __shared__ float s_db[128];
+    __shared__ int s_next;
+
+    pdl_trigger();
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(bar(s), NPROD); mbar_init(bar(NST + s), 1); }
+        mbar_init(bar(2 * NST), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    uint32_t gch = 0, done_parity = 0;
+    int item = blockIdx.x;
+    while (item < g.n_items) {
+        const WItem it = g.items[item];
+        if (tid == 0) s_next = (int)(atomicAdd(g.sched, 1u) + gridDim.x);          // the item after this one
+        {   // the layer's arguments -> shared memory
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(g.layers + it.layer);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&s_a);
+            for (int i = tid; i < (int)(sizeof(WArgs) / 4); i += NTHREADS) dst[i] = src[i];
+        }
+        if (tid < 128) s_db[tid] = 0.f;
+        // zero the MMA stages: rows beyond K and padded dy columns of THIS layer must be zero (the previous item's MMAs
+        // have retired: its epilogue waited for them before the barrier at the end of the loop)
+        for (int i = tid; i < NST * L::STAGE_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        if (s_a.has_in_bn)
+            for (int c = tid; c < s_a.Cin; c += NTHREADS) bn_scale_shift(s_a.in_bn, c, s_a.Cin, s_scale[c], s_shift[c]);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        item_run<BN, PASSES, NST>(s_a, it.mt, it.nt, 0, it.c_begin, it.nchunks, true, gch, done_parity, smem, sbase, tmem_base,
+                                  s_scale, s_shift, s_db);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (s_a.db != nullptr && it.mt == 0 && tid < BN) atomicAdd(s_a.db + it.nt * BN + tid, s_db[tid]);
+        gch += (uint32_t)it.nchunks;
+        done_parity ^= 1u;
+        item = s_next;
+        __syncthreads();                // s_next / s_a / s_db are rewritten by the next round
+    }
+    if (warp == W_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
 }
 
@@ -452,11 +557,8 @@ int launch(WArgs &a, cudaStream_t st) {
 
 }  // namespace
 
-int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
-                           float *db, void *stream) {
-    if (d->precision != 1 && d->precision != 2) return DPP_ENOTSUP;
-    if (d->Cout % 16 || d->Cout > 256 || (d->Cout > 128 && d->Cout % 128)) return DPP_ENOTSUP;
-    WArgs a;
+static void fill_args(WArgs &a, const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
+                      float *db) {
     memset(&a, 0, sizeof(a));
     a.x = x; a.dy = dy; a.dw = dw; a.db = db;
     a.N = d->N; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout;
@@ -470,6 +572,20 @@ int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_
         a.wsh = 0; while ((1 << a.wsh) < a.Wo) ++a.wsh;
         a.hsh = 0; while ((1 << a.hsh) < a.Ho) ++a.hsh;
     }
+}
+
+static int wgrad_mn_supported(const dpp_conv_desc *d) {
+    if (d->precision != 1 && d->precision != 2) return 0;
+    if (d->Cout % 16 || d->Cout > 256 || (d->Cout > 128 && d->Cout % 128)) return 0;
+    if (d->Cin % 4 || d->Cin > 256 || (d->k * d->k * d->Cin + TM - 1) / TM > 8) return 0;
+    return 1;
+}
+
+int dpp_conv2d_wgrad_tc_mn(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn, const float *dy, float *dw,
+                           float *db, void *stream) {
+    if (!wgrad_mn_supported(d)) return DPP_ENOTSUP;
+    WArgs a;
+    fill_args(a, d, x, in_bn, dy, dw, db);
     const int bn = d->Cout > 128 ? 128 : d->Cout;
     const bool p3 = d->precision == 1;
     // MMA stages: two by default.  A third stage (DPP_WG_NST=3, BN <= 64) was measured on B200 and changes nothing
@@ -496,6 +612,137 @@ extern "C" int dpp_debug_set_prof_wg(void *buf) {
     return DPP_OK;
 }
 #endif
+
+// ---- grouped backward-weights ------------------------------------------------------------------------------------------
+namespace {
+
+struct WGroupLaunch { int bn; WGroupArgs args; int grid; };
+struct WGroup {
+    std::vector<WGroupLaunch> launches;
+    std::vector<void *> allocs;
+    int passes;
+};
+
+template <int BN, int PASSES>
+int launch_group(const WGroupLaunch &l, cudaStream_t st) {
+    using L = Lay<BN, PASSES, 2>;
+    static bool done = false;
+    if (!done) {
+        if (cudaFuncSetAttribute(k_wgrad_group<BN, PASSES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return -1;
+        done = true;
+    }
+    if (cudaMemsetAsync(l.args.sched, 0, sizeof(unsigned int), st) != cudaSuccess) return -1;
+    if (launch_pdl(2, k_wgrad_group<BN, PASSES, 2>, dim3(l.grid), dim3(NTHREADS), L::TOTAL, st, l.args) != cudaSuccess) return -1;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layers, void **handle_out) {
+    DPP_CHECK_ARG(layers && n_layers > 0 && handle_out);
+    for (int i = 0; i < n_layers; ++i) {
+        DPP_CHECK_ARG(layers[i].x && layers[i].dy && layers[i].dw);
+        if (!wgrad_mn_supported(&layers[i].d)) return DPP_ENOTSUP;
+        DPP_CHECK_ARG(layers[i].d.precision == layers[0].d.precision);
+    }
+    WGroup *grp = new WGroup();
+    grp->passes = layers[0].d.precision == 1 ? 2 : 1;
+    const int widths[4] = {16, 32, 64, 128};
+    for (int wi = 0; wi < 4; ++wi) {
+        const int bn = widths[wi];
+        std::vector<WArgs> la;
+        for (int i = 0; i < n_layers; ++i) {
+            const int lbn = layers[i].d.Cout > 128 ? 128 : layers[i].d.Cout;
+            if (lbn != bn) continue;
+            WArgs a;
+            fill_args(a, &layers[i].d, layers[i].x, layers[i].has_in_bn ? &layers[i].in_bn : nullptr, layers[i].dy, layers[i].dw,
+                      layers[i].db);
+            la.push_back(a);
+        }
+        if (la.empty()) continue;
+        // items: every (layer, m-tile, n-tile) cut into runs of `cpi` pixel chunks; cpi such that a CTA sees ~6 items
+        long long total = 0;
+        for (const WArgs &a : la) {
+            const int Kw = a.k * a.k * a.Cin;
+            total += (long long)((Kw + TM - 1) / TM) * (a.Cout / bn) * ((a.N * a.Ho * a.Wo + 31) / 32);
+        }
+        long long cpi = (total + 148 * 6 - 1) / (148 * 6);
+        if (cpi < 8) cpi = 8;
+        if (cpi > 64) cpi = 64;
+        // list order: round s of every tile, then round s + 1, ... so that neighbouring items (which run at the same
+        // time) belong to different tiles and do not pile their reductions onto the same addresses
+        std::vector<WItem> items;
+        for (int s = 0;; ++s) {
+            bool any = false;
+            for (size_t li = 0; li < la.size(); ++li) {
+                const WArgs &a = la[li];
+                const int Kw = a.k * a.k * a.Cin, mtiles = (Kw + TM - 1) / TM, ntiles = a.Cout / bn;
+                const int chunks = (a.N * a.Ho * a.Wo + 31) / 32;
+                const int c0 = (int)(s * cpi);
+                if (c0 >= chunks) continue;
+                any = true;
+                const int n = chunks - c0 < cpi ? chunks - c0 : (int)cpi;
+                for (int mt = 0; mt < mtiles; ++mt)
+                    for (int nt = 0; nt < ntiles; ++nt) {
+                        WItem it;
+                        memset(&it, 0, sizeof(it));
+                        it.layer = (int)li; it.mt = mt; it.nt = nt; it.c_begin = c0; it.nchunks = n;
+                        items.push_back(it);
+                    }
+            }
+            if (!any) break;
+        }
+        WGroupLaunch l;
+        l.bn = bn;
+        void *dl = nullptr, *di = nullptr, *ds = nullptr;
+        if (cudaMalloc(&dl, la.size() * sizeof(WArgs)) != cudaSuccess || cudaMalloc(&di, items.size() * sizeof(WItem)) != cudaSuccess ||
+            cudaMalloc(&ds, 64) != cudaSuccess ||
+            cudaMemcpy(dl, la.data(), la.size() * sizeof(WArgs), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(di, items.data(), items.size() * sizeof(WItem), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemset(ds, 0, 64) != cudaSuccess) {
+            delete grp;
+            return dpp::fail(DPP_ECUDA, "%s: device table allocation failed", __func__);
+        }
+        grp->allocs.push_back(dl); grp->allocs.push_back(di); grp->allocs.push_back(ds);
+        l.args.layers = reinterpret_cast<const WArgs *>(dl);
+        l.args.items = reinterpret_cast<const WItem *>(di);
+        l.args.n_items = (int)items.size();
+        l.args.sched = reinterpret_cast<unsigned int *>(ds);
+        l.grid = l.args.n_items < 148 ? l.args.n_items : 148;
+        grp->launches.push_back(l);
+    }
+    *handle_out = grp;
+    return DPP_OK;
+}
+
+extern "C" int dpp_wgrad_group_run(void *handle, void *stream) {
+    DPP_CHECK_ARG(handle);
+    WGroup *grp = reinterpret_cast<WGroup *>(handle);
+    for (const WGroupLaunch &l : grp->launches) {
+        int rc = -1;
+        const bool p3 = grp->passes == 2;
+        if (l.bn == 16) rc = p3 ? launch_group<16, 2>(l, S(stream)) : launch_group<16, 1>(l, S(stream));
+        else if (l.bn == 32) rc = p3 ? launch_group<32, 2>(l, S(stream)) : launch_group<32, 1>(l, S(stream));
+        else if (l.bn == 64) rc = p3 ? launch_group<64, 2>(l, S(stream)) : launch_group<64, 1>(l, S(stream));
+        else if (l.bn == 128) rc = p3 ? launch_group<128, 2>(l, S(stream)) : launch_group<128, 1>(l, S(stream));
+        if (rc != 0) return dpp::fail(DPP_ECUDA, "%s: launch setup failed", __func__);
+        DPP_LAUNCH_CHECK();
+    }
+    return DPP_OK;
+}
+
+extern "C" int dpp_wgrad_group_launches(void *handle) {
+    return handle ? (int)reinterpret_cast<WGroup *>(handle)->launches.size() : 0;
+}
+
+extern "C" int dpp_wgrad_group_destroy(void *handle) {
+    if (handle) {
+        WGroup *grp = reinterpret_cast<WGroup *>(handle);
+        for (void *p : grp->allocs) cudaFree(p);
+        delete grp;
+    }
+    return DPP_OK;
+}
 
 // Allocates the library-owned workspace of the backward-weights split reduction (idempotent).  Must be called
 // outside CUDA-graph capture (Engine does it at construction); dpp_conv2d_wgrad allocates lazily otherwise.

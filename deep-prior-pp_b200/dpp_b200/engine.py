@@ -22,7 +22,7 @@ import ctypes as C
 import os
 import numpy as np
 
-from .lib import lib, BnRef, ConvDesc, BnEmaItem, PackItem, DppError, DPP_ENOTSUP
+from .lib import lib, BnRef, ConvDesc, BnEmaItem, PackItem, WgradLayer, DppError, DPP_ENOTSUP
 
 
 def _torch():
@@ -377,6 +377,10 @@ class Engine(object):
         self.GBAR = torch.zeros(2 * max(len(self.bns), 1), dtype=torch.int32, device=self.dev)
         self.bn_index = {id(bn): i for i, bn in enumerate(self.bns)}
         self.fuse_bn_bwd = os.environ.get('DPP_FUSE_BN_BWD', '1') != '0'
+        # the backward-weights GEMMs of all ConvLayers in a few persistent launches at the end of the backward pass
+        # (dpp_wgrad_group_*) instead of one launch per layer on a second stream
+        self.group_wgrad = self.precision != 0 and os.environ.get('DPP_WGRAD_GROUP', '1') != '0'
+        self._wgroup = None
         self._n_bn_bwd_launches = None
 
     def release(self):
@@ -386,6 +390,10 @@ class Engine(object):
                 s.var._host = self.download_param(s)
                 s.var._binding = None
         self._graphs = {}
+        if getattr(self, '_wgroup', None) is not None:
+            self.torch.cuda.synchronize()
+            lib.dpp_wgrad_group_destroy(self._wgroup)
+            self._wgroup = None
 
     def _arena(self, slot):
         return self.W if slot.arena == 'w' else self.R
@@ -624,9 +632,9 @@ class Engine(object):
     def _grad_slots_of(self, op, bn_done):
         """arena slots whose gradients are issued by the backward kernels of ``op`` (+ the BNs it completes)"""
         out = []
-        if op['kind'] in ('conv', 'convpool', 'fc'):
+        if op['kind'] in ('convpool', 'fc') or (op['kind'] == 'conv' and not self.group_wgrad):
             L = op['layer']
-            out += [self.slots[id(L.W)], self.slots[id(L.b)]]
+            out += [self.slots[id(L.W)], self.slots[id(L.b)]]     # (grouped backward-weights: complete only at the very end)
         for bn in bn_done:
             out += [self.slots[id(bn.gamma)], self.slots[id(bn.beta)]]
         return out
@@ -694,6 +702,7 @@ class Engine(object):
                 self._comm_stream = torch.cuda.Stream(device=self.dev)
         self._exchanged = []
         n_fused = [0]
+        wlayers = []
 
         def exchange(lo, hi):
             comm = self._comm_stream
@@ -738,11 +747,23 @@ class Engine(object):
                 dy = skip_of[id(dst)].grad if (id(dst) in skip_of and dst.bn is None) else dst.grad
                 bn, raw = op['in_bn'], op['src']
                 bnref = self._bnref(bn, raw, True) if bn is not None else None
-                if side is not None:
-                    side.wait_stream(main)          # dy (and everything before it) is complete
-                    forked = True
-                lib.dpp_conv2d_wgrad(C.byref(d), _ptr(raw.buf), C.byref(bnref) if bnref else None, _ptr(dy),
-                                     _ptr(self.pview(L.W, G)), _ptr(self.pview(L.b, G)), side_ptr if side is not None else st)
+                if self.group_wgrad:
+                    if self._wgroup is None:
+                        wl = WgradLayer()
+                        wl.d = d
+                        wl.x = raw.buf.data_ptr()
+                        if bnref is not None:
+                            wl.in_bn, wl.has_in_bn = bnref, 1
+                        wl.dy = dy.data_ptr()
+                        wl.dw = self.pview(L.W, G).data_ptr()
+                        wl.db = self.pview(L.b, G).data_ptr()
+                        wlayers.append(wl)
+                else:
+                    if side is not None:
+                        side.wait_stream(main)          # dy (and everything before it) is complete
+                        forked = True
+                    lib.dpp_conv2d_wgrad(C.byref(d), _ptr(raw.buf), C.byref(bnref) if bnref else None, _ptr(dy),
+                                         _ptr(self.pview(L.W, G)), _ptr(self.pview(L.b, G)), side_ptr if side is not None else st)
                 if bn is not None:
                     total = len(self.bn_consumers[id(bn)])
                     first = (pending[id(bn)] == total)
@@ -792,6 +813,21 @@ class Engine(object):
                 raise NotImplementedError(k)
             if i in cuts:
                 exchange(*cuts[i])
+        if self.group_wgrad:
+            if self._wgroup is None and wlayers:
+                if torch.cuda.is_current_stream_capturing():
+                    raise DppError("the grouped backward-weights tables must be built outside graph capture "
+                                   "(Engine.train_step runs one eager step first)")
+                arr = (WgradLayer * len(wlayers))(*wlayers)
+                h = C.c_void_p()
+                rc = lib.raw('dpp_wgrad_group_create')(arr, len(wlayers), C.byref(h))
+                if rc == DPP_ENOTSUP:
+                    raise DppError("grouped backward-weights: a ConvLayer lies outside the tcgen05 path; set DPP_WGRAD_GROUP=0")
+                if rc != 0:
+                    raise DppError("dpp_wgrad_group_create failed (%d): %s" % (rc, lib.raw('dpp_last_error')().decode()))
+                self._wgroup = h
+            if self._wgroup is not None:
+                lib.dpp_wgrad_group_run(self._wgroup, st)
         if exchanging and trailing is not None:
             exchange(*trailing)
         if forked:
@@ -805,6 +841,13 @@ class Engine(object):
         marks = self.GBAR[1::2].cpu().numpy()
         if (marks != 0).any():
             raise DppError("grid barrier timed out in %d fused BatchNorm-backward launch(es)" % int((marks != 0).sum()))
+
+    def launches_wgrad(self):
+        """backward-weights launches per step: one per ConvLayer, or the grouped launches"""
+        convs = len([o for o in self.ops if o['kind'] == 'conv'])
+        if self.group_wgrad and self._wgroup is not None:
+            return int(lib.dpp_wgrad_group_launches(self._wgroup))
+        return convs
 
     def launches_bn_bwd(self):
         """separate BatchNorm-backward launches of the last step (the others ran fused behind their dgrad)"""

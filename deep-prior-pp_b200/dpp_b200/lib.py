@@ -49,6 +49,11 @@ class PackItem(C.Structure):
                 ('Cout', C.c_int), ('k', C.c_int), ('bn_fwd', C.c_int), ('bn_dgrad', C.c_int), ('passes', C.c_int)]
 
 
+class WgradLayer(C.Structure):
+    _fields_ = [('d', ConvDesc), ('x', C.c_void_p), ('in_bn', BnRef), ('has_in_bn', C.c_int), ('dy', C.c_void_p),
+                ('dw', C.c_void_p), ('db', C.c_void_p)]
+
+
 class BnEmaItem(C.Structure):
     _fields_ = [('sums', C.c_void_p), ('mean', C.c_void_p), ('inv_std', C.c_void_p),
                 ('count', C.c_double), ('C', C.c_int), ('eps', C.c_float)]
@@ -88,6 +93,10 @@ _SIGS = {
     'dpp_conv2d_dgrad_bn_bwd': (C.c_int, [C.POINTER(ConvDesc), P, P, P, C.c_int, C.POINTER(BnRef), P, P, P, P, P, P,
                                           C.c_float, P, P]),
     'dpp_conv2d_wgrad': (C.c_int, [C.POINTER(ConvDesc), P, C.POINTER(BnRef), P, P, P, P]),
+    'dpp_wgrad_group_create': (C.c_int, [P, C.c_int, C.POINTER(C.c_void_p)]),
+    'dpp_wgrad_group_run': (C.c_int, [P, P]),
+    'dpp_wgrad_group_launches': (C.c_int, [P]),
+    'dpp_wgrad_group_destroy': (C.c_int, [P]),
     'dpp_bn_bwd_apply': (C.c_int, [P, P, C.POINTER(BnRef), P, P, P, P, P, P, C.c_int64, C.c_int, C.c_float, P]),
     'dpp_bn_apply': (C.c_int, [P, C.POINTER(BnRef), P, C.c_int64, C.c_int, P]),
     'dpp_bn_relu_bwd_reduce': (C.c_int, [P, P, C.POINTER(BnRef), P, P, C.c_int64, C.c_int, P]),
@@ -134,7 +143,7 @@ class _Lib(object):
         if name.startswith('_'):
             raise AttributeError(name)
         fn = getattr(self.load(), name)
-        if name in ('dpp_last_error', 'dpp_abi_version'):
+        if name in ('dpp_last_error', 'dpp_abi_version', 'dpp_wgrad_group_launches'):
             return fn
 
         def call(*a):

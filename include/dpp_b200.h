@@ -232,6 +232,27 @@ int dpp_conv2d_dgrad_bn_bwd(const dpp_conv_desc *d, const float *dy, const float
 int dpp_conv2d_wgrad(const dpp_conv_desc *d, const float *x, const dpp_bn_ref *in_bn,
                      const float *dy, float *dw, float *db, void *stream);
 
+/* Grouped backward weights: the dpp_conv2d_wgrad work of MANY layers in a few persistent launches (one per n-tile
+ * width 16 / 32 / 64 / 128).  A training step has 63 of these GEMMs, most too small to amortise their own launch,
+ * set-up and split-reduction cost; their results are only needed by the optimiser, so they can run together once all
+ * dy tensors exist.  create() copies the layer table to the device (allocates: call it outside graph capture; every
+ * pointer - activations, gradients, statistics, dw / db - must stay valid while the handle lives); run() is
+ * asynchronous and capturable.  dw / db are ACCUMULATED with floating-point reductions (zero them at step start).
+ * create() returns DPP_ENOTSUP if a layer is outside the tcgen05 path (precision 0, unsupported widths).          */
+typedef struct dpp_wgrad_layer {
+    dpp_conv_desc d;
+    const float *x;       /* input activations of the layer (before its BN + ReLU prologue) */
+    dpp_bn_ref in_bn;     /* prologue, used when has_in_bn != 0 */
+    int has_in_bn;
+    const float *dy;      /* gradient w.r.t. the layer's output */
+    float *dw;            /* [(k*k*Cin)][Cout] */
+    float *db;            /* [Cout] or NULL */
+} dpp_wgrad_layer;
+int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layers, void **handle_out);
+int dpp_wgrad_group_run(void *handle, void *stream);
+int dpp_wgrad_group_launches(void *handle);     /* kernels one run() launches */
+int dpp_wgrad_group_destroy(void *handle);
+
 /* ---- BatchNorm backward apply (full BN backward through batch statistics) -------------
  * dx = gamma*inv_std*(dz - mean(dz) - xhat*mean(dz*xhat)) [+ skip]; dgamma += sum dz*xhat,
  * dbeta += sum dz.  `bn` must be in train mode (sums != NULL).  dz and dx may alias.

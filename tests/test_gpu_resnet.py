@@ -373,3 +373,31 @@ def test_fused_bn_backward_equals_separate_kernels(B, monkeypatch):
     l2 = float((g1 - g0).norm() / g0.norm())
     print("gradient arena fused vs separate: max %.2e rel-L2 %.2e" % (err, l2))
     assert err < 2e-5 and l2 < 2e-5
+
+
+@pytest.mark.parametrize("B", [16, 128])
+def test_grouped_backward_weights_equal_per_layer_launches(B, monkeypatch):
+    """dpp_wgrad_group_* runs the 63 backward-weights GEMMs in four persistent launches (items of pixel chunks taken
+    from a list, reduced straight into dW); DPP_WGRAD_GROUP=0 launches dpp_conv2d_wgrad per layer on a second stream.
+    Same products, different summation order: gradient arenas agree to float32 roundoff."""
+    D = 30
+    x, y = _data(B, D)
+    res = {}
+    for grp in ('1', '0'):
+        monkeypatch.setenv('DPP_WGRAD_GROUP', grp)
+        net, onet, eng = _build(0, B, 1, D, precision=1)
+        eng.set_input_nchw(x)
+        eng._alloc_training()
+        eng.y_in.copy_(torch.from_numpy(y))
+        for use_graph in (False, True, True):
+            cost = float(eng.train_step(0.0, use_graph=use_graph).cpu()[0])
+        res[grp] = (cost, eng.G.clone(), eng.launches_wgrad())
+        eng.release()
+    (c1, g1, n1), (c0, g0, n0) = res['1'], res['0']
+    print("batch", B, "backward-weights launches: grouped", n1, "per layer", n0)
+    assert n0 == 63 and n1 == 4
+    assert c1 == c0
+    err = float((g1 - g0).abs().max() / g0.abs().max())
+    l2 = float((g1 - g0).norm() / g0.norm())
+    print("gradient arena grouped vs per-layer: max %.2e rel-L2 %.2e" % (err, l2))
+    assert err < 2e-5 and l2 < 2e-5
