@@ -547,8 +547,12 @@ def run_b200(args):
     run = StepRunner(ctx, dataset, aug_modes, nb, total, syncbn=args.syncbn)
     eng = run.eng
     check = None
-    if args.workload == 'train' and rank == 0 and not args.no_cost_check:
+    if args.workload == 'train' and not args.no_cost_check:
+        # every rank steps (the training step of a data-parallel job contains collectives: all ranks or none); the
+        # golden value is that of rank 0's data, and the cost is taken before the gradient exchange
         check = run.cost_check()
+        if rank != 0:
+            check = None
     clocks = ClockSampler(ctx.local)
     if rank == 0:
         clocks.start()

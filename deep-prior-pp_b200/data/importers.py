@@ -2,8 +2,10 @@
 :51-150, ICVLImporter :186-210, MSRA15Importer :536-570 + :756-793, NYUImporter :880-920 +
 :1187-1224).  Only the pin-hole projections and per-dataset constants are on the hot path
 (augmentation label math); the file readers are out of scope (datasets are absent):
-``loadSequence`` keeps its signature and returns a deterministic synthetic ``NamedImgSequence``
-(``data.synthetic``) so that the entry scripts' data preparation runs unchanged.
+``loadSequence`` keeps its signature; with ``basepath=None`` - or with a basepath and the explicit
+opt-in DPP_SYNTHETIC=1 (a loud warning names the directory that is NOT read) - it returns a
+deterministic synthetic ``NamedImgSequence`` (``data.synthetic``) so that the entry scripts' data
+preparation runs unchanged; with a basepath and no opt-in it raises.
 
 dtype discipline: the reference ran on NumPy 1.x value-based casting, where
 ``np.float32 scalar (op) python float`` is computed in float64 and only the store into the
@@ -79,6 +81,20 @@ class DepthImporter(object):
         import zlib
         from data import synthetic
         from data.basetypes import NamedImgSequence
+        # A caller that names a dataset directory expects ITS frames.  The readers are not part of this package, so
+        # never hand back synthetic frames silently: with a basepath the caller must opt in (DPP_SYNTHETIC=1), and
+        # even then every call says what it returns.  ``basepath=None`` (data.synthetic, tests) is the explicit
+        # synthetic importer and stays quiet.
+        if self.basepath is not None:
+            if os.environ.get('DPP_SYNTHETIC', '0') != '1':
+                raise NotImplementedError(
+                    "%s.loadSequence(%r): the dataset file readers of the reference (src/data/importers.py) are not part "
+                    "of this package - basepath=%r is NOT read.  Set DPP_SYNTHETIC=1 to run on deterministic synthetic "
+                    "frames instead (results then say nothing about the real dataset), or construct the importer with "
+                    "basepath=None." % (type(self).__name__, seqName, self.basepath))
+            print("WARNING: %s.loadSequence(%r) returns SYNTHETIC frames (DPP_SYNTHETIC=1); basepath %r is not read%s"
+                  % (type(self).__name__, seqName, self.basepath,
+                     " although it exists" if os.path.exists(self.basepath) else ""))
         if cube is None:
             cube = self.default_cubes[seqName]
         else:

@@ -287,6 +287,7 @@ if __name__ == '__main__' or True:
         # 40 frames: fewer validation samples than a batch (the observers average over zero batches, like the reference)
         for script, frames in (('main_nyu_posereg_embedding.py', '130'), ('main_icvl_posereg_embedding.py', '40')):
             os.environ['DPP_SYNTH_FRAMES'] = frames
+            os.environ['DPP_SYNTHETIC'] = '1'          # the reference's scripts name ../data/<set>/: explicit opt-in to synthetic frames
             with tempfile.TemporaryDirectory() as d:
                 ended, calls, g, hpe = run_reference_entry_script(script, d)
             joints = g['joints']

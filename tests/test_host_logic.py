@@ -232,13 +232,19 @@ def test_trainer_record_worker_matches_per_sample_path():
     assert len(empty[0]) == 0
 
 
-def test_importers_load_synthetic_sequences_with_reference_signature():
+def test_importers_load_synthetic_sequences_with_reference_signature(monkeypatch, capsys):
     """data/importers.py ``loadSequence`` (reference importers.py:233, :597, :943 signatures) without dataset files."""
     from data.importers import NYUImporter, ICVLImporter, MSRA15Importer
     from data.basetypes import NamedImgSequence, DepthFrame
     rng = np.random.RandomState(23455)
     di = NYUImporter('../data/NYU/', refineNet=None)
+    # a dataset directory is named but its readers are not part of the package: refuse unless the caller opts in
+    monkeypatch.delenv('DPP_SYNTHETIC', raising=False)
+    with pytest.raises(NotImplementedError, match="DPP_SYNTHETIC=1"):
+        di.loadSequence('train', Nmax=6)
+    monkeypatch.setenv('DPP_SYNTHETIC', '1')
     s1 = di.loadSequence('train', Nmax=6, shuffle=True, rng=rng, docom=False)
+    assert "SYNTHETIC" in capsys.readouterr().out               # ... and says so on every call
     s2 = di.loadSequence('test_1', Nmax=4, docom=False)
     assert isinstance(s1, NamedImgSequence) and s1.name == 'train' and len(s1.data) == 6 and len(s2.data) == 4
     assert s1.config == {'cube': (300, 300, 300)} and isinstance(s1.data[0], DepthFrame)
