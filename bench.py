@@ -10,6 +10,7 @@ Workloads (BASELINE.json configs):
           N > 1: every rank runs the same per-GPU batch (weak scaling, global batch 128*N).
   icvl512 configs[2]: ICVL 16-joint, GLOBAL batch 512 split over the N ranks (strong scaling), gradient exchange in
           stage-ordered buckets; --syncbn sums the BatchNorm statistics over the ranks as well.
+  poseregnet  the network the reference's entry scripts actually train (PoseRegNet type 0), batch 128 per GPU.
   msra15  configs[3]: MSRA15 21-joint (y-flipped projection, per-subject cubes), aug com/rot/sc/none, batch 128 per GPU.
   cascade configs[4]: tools/bench_cascade.py.
 
@@ -55,6 +56,10 @@ WORKLOADS = {
     'icvl512': ('ICVL', ['com', 'rot', 'none'], None, 'STRONG',
                 "ICVL 16-joint posereg_embedding ResNet(type 0, 30-D embedding) training, GLOBAL batch 512 split over "
                 "the ranks, aug rot/com/none"),
+    'poseregnet': ('NYU', ['com', 'rot', 'none'], 'B', None,
+                   "NYU posereg_embedding PoseRegNet(type 0: 3 x 8-filter conv+pool, FC 1024 - dropout - FC 1024 - dropout - 30-D "
+                   "embedding) training - the network the reference's main_*_posereg_embedding.py scripts build -, batch "
+                   "128/GPU, aug rot/com/none"),
     'msra15': ('MSRA15', ['com', 'rot', 'sc', 'none'], 'B', None,
                "MSRA15 21-joint crossval config, ResNet(type 0, 30-D embedding) training, batch 128/GPU, "
                "aug rot/scale/com/none on the device"),
@@ -311,7 +316,7 @@ class Ctx(object):
 class StepRunner(object):
     """One training workload on this rank: engine, resident crops, pre-built record sets, the step functions."""
 
-    def __init__(self, ctx, dataset, aug_modes, batch, total_steps, syncbn=False, seed0=23455):
+    def __init__(self, ctx, dataset, aug_modes, batch, total_steps, syncbn=False, seed0=23455, net_kind='resnet'):
         import ctypes as C
         torch = ctx.torch
         from dpp_b200.lib import lib, AUG_REC_DTYPE
@@ -320,7 +325,12 @@ class StepRunner(object):
         self.C, self.lib, self.ctx, self.nb, self.aug_modes = C, lib, ctx, batch, aug_modes
         self.precision = int(os.environ.get('DPP_PRECISION', '1'))
         self.ds, self.comp, self.mean = make_workload(seed=seed0 + ctx.rank, dataset=dataset)
-        net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=batch, numJoints=1, nDims=E))
+        if net_kind == 'poseregnet':
+            from net.poseregnet import PoseRegNet, PoseRegNetParams
+            net = PoseRegNet(np.random.RandomState(23455), cfgParams=PoseRegNetParams(type=0, nChan=1, wIn=128, hIn=128,
+                                                                                      batchSize=batch, numJoints=1, nDims=E))
+        else:
+            net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=batch, numJoints=1, nDims=E))
         self.eng = eng = Engine(net, precision=self.precision)
         net._eng = eng
         eng._alloc_training()
@@ -544,7 +554,8 @@ def run_b200(args):
         nb, scaling = per_gpu, "weak"
     warm = max(args.warmup, 3)
     total = warm + args.steps
-    run = StepRunner(ctx, dataset, aug_modes, nb, total, syncbn=args.syncbn)
+    run = StepRunner(ctx, dataset, aug_modes, nb, total, syncbn=args.syncbn,
+                     net_kind='poseregnet' if args.workload == 'poseregnet' else 'resnet')
     eng = run.eng
     check = None
     if args.workload == 'train' and not args.no_cost_check:
@@ -566,7 +577,7 @@ def run_b200(args):
     e2e_val = nb * world / (ms_e2e / 1000.)
     clk = clocks.stop() if rank == 0 else None
 
-    roof = measure_dominant_kernel(eng, torch) if not args.no_roofline else None
+    roof = measure_dominant_kernel(eng, torch) if (not args.no_roofline and args.workload != 'poseregnet') else None
     n_launch = count_launches(eng) + 1
 
     # strong-scaling sample inside the default run: BASELINE config 3 (global batch 512 split over the ranks)
@@ -635,7 +646,7 @@ def run_b200(args):
         "clocks": clk,
         "roofline": roof,
         "cpu_baseline": cpu,
-        "tensor_fraction_whole_step": value / world * TRAIN_GFLOP_PER_FRAME / 1000. / peaks()[1],
+        "tensor_fraction_whole_step": (value / world * TRAIN_GFLOP_PER_FRAME / 1000. / peaks()[1]) if args.workload != 'poseregnet' else None,
     }
     print(json.dumps(out))
     if check is not None and check.get('ok') is False:
@@ -744,7 +755,7 @@ def main():
     ap.add_argument('--no-trainer-api', action='store_true', help='skip the PoseRegNetTrainer.train() measurement')
     ap.add_argument('--no-cost-check', action='store_true')
     ap.add_argument('--syncbn', action='store_true', help='N > 1: sum the BatchNorm statistics over the ranks')
-    ap.add_argument('--workload', default='train', choices=['train', 'icvl512', 'msra15', 'cascade'],
+    ap.add_argument('--workload', default='train', choices=['train', 'icvl512', 'msra15', 'poseregnet', 'cascade'],
                     help="train = BASELINE configs[1] (the headline); icvl512 = configs[2]; msra15 = configs[3]; "
                          "cascade = configs[4], tools/bench_cascade.py")
     args, rest = ap.parse_known_args()

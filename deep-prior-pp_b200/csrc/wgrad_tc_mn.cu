@@ -68,12 +68,16 @@ struct WArgs {
 template <int BN, int PASSES, int NST>
 struct Lay {
     static constexpr int BNP = BN < 32 ? 32 : BN;                 // MMA N (padded to one 32-channel block)
-    static constexpr int A_BYTES = PASSES * 4 * 4096;             // 4 column blocks of 32 (tap,c) rows x 32 pixels
+    // 4 column blocks of 32 (tap,c) rows x 32 pixels + a 5th block for the "tail" rows of the layer's last, nearly empty
+    // m-tile (K = 144 -> 128 + 16, K = 288 -> 256 + 32), which ride along with the m-tile before it (second accumulator)
+    static constexpr int A_BLOCKS = BN <= 32 ? 5 : 4;             // (only the 16- and 32-channel layers have such tails)
+    static constexpr int A_BYTES = PASSES * A_BLOCKS * 4096;
     static constexpr int B_BYTES = PASSES * (BNP / 32) * 4096;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NDY = BNP / 32;                          // 32-channel column blocks of the dy tile
     static constexpr int NDYH = BNP >= 64 ? BNP / 64 : 1;         // dy pieces (16 B) per producer thread per chunk
-    static constexpr int UNITS = (2 + NDYH) | 1;                  // 16-byte units per thread slot, odd: conflict-free LDS.128
+    static constexpr int AP = A_BLOCKS > 4 ? 3 : 2;               // activation pieces per transform thread and chunk
+    static constexpr int UNITS = (AP + NDYH) | 1;                 // 16-byte units per thread slot, odd: conflict-free LDS.128
     static constexpr int SLOT = UNITS * 16;
     static constexpr int RAW_BYTES = 32 * NPROD * SLOT;
     // raw landing slots = prefetch distance + 1: as many as fit next to the two MMA stages (the loop is bound by
@@ -93,7 +97,7 @@ struct Lay {
 // direct: the epilogue reduces straight into dW (grouped launches: few CTAs per tile at any one time).
 template <int BN, int PASSES, int NST>
 __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int nt, const int split, const int c_begin,
-                                         const int nchunks, const bool direct, const uint32_t gch0, const uint32_t done_parity,
+                                         const int nchunks, const int tail, const bool direct, const uint32_t gch0, const uint32_t done_parity,
                                          unsigned char *smem, const uint32_t sbase, const uint32_t tmem_base,
                                          const float *s_scale, const float *s_shift, float *s_db) {
     using L = Lay<BN, PASSES, NST>;
@@ -113,15 +117,16 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
         const int j = (tid >> 2) & 31;
         const int gq = (tid & 3) + 4 * (tid >> 7);
         const uint32_t a_sw = (uint32_t)(j & 3) << 1;
-        bool g_ok[2];
-        int g_dr[2], g_ds[2], g_ch[2];
-        uint32_t a_off[2];
-        float4 sc[2], sf[2];
+        // (third piece: the tail rows kd0 + 128 .. kd0 + 128 + tail - 1 in column block 4, threads with gq < tail / 4)
+        bool g_ok[3];
+        int g_dr[3], g_ds[3], g_ch[3];
+        uint32_t a_off[3];
+        float4 sc[3], sf[3];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 3; ++k) {
             const int piece = gq + 16 * k;
             const int kd = kd0 + piece * 4;
-            g_ok[k] = kd < Kw;                       // rows beyond K are never written: the stage stays zero there
+            g_ok[k] = k < 2 ? kd < Kw : (L::A_BLOCKS > 4 && gq * 4 < tail);   // rows beyond K are never written: the stage stays zero there
             const int tap = g_ok[k] ? kd / Cin : 0;
             g_ch[k] = g_ok[k] ? kd - tap * Cin : 0;
             g_dr[k] = tap / a.k - a.pad; g_ds[k] = tap % a.k - a.pad;
@@ -136,7 +141,7 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
         float dbp[NDYH * 4];
 #pragma unroll
         for (int i = 0; i < NDYH * 4; ++i) dbp[i] = 0.f;
-        uint32_t vbits = 0;       // 2 validity bits per in-flight chunk
+        uint32_t vbits = 0;       // 3 validity bits per in-flight chunk
         for (int ch = -D; ch < nchunks; ++ch) {
             const int ci = ch + D;
             if (ci < nchunks) {
@@ -151,7 +156,7 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
                     const float *img = a.x + (size_t)n * H * W * Cin;
                     const int h0 = ho * stride, w0 = wo * stride;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
+                    for (int k = 0; k < 3; ++k) {
                         if (!g_ok[k]) continue;
                         const int hi = h0 + g_dr[k], wi = w0 + g_ds[k];
                         const bool v = p < P && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
@@ -167,10 +172,10 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
 #pragma unroll
                     for (int m = 0; m < NDYH; ++m)
                         if ((p16 + 16 * m) * 4 < BN)
-                            cp_async16(slot + (2 + m) * 16, pok ? a.dy + (size_t)pd * Cout + o0 + (p16 + 16 * m) * 4 : a.dy, pok ? 16u : 0u);
+                            cp_async16(slot + (L::AP + m) * 16, pok ? a.dy + (size_t)pd * Cout + o0 + (p16 + 16 * m) * 4 : a.dy, pok ? 16u : 0u);
                 }
-                const uint32_t sh = 2 * (ci % RD);
-                vbits = (vbits & ~(3u << sh)) | (vm << sh);
+                const uint32_t sh = 3 * (ci % RD);
+                vbits = (vbits & ~(7u << sh)) | (vm << sh);
             }
             cp_async_commit();
             if (ch < 0) continue;
@@ -179,14 +184,14 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
             PROF(11);
             const unsigned char *slot = smem + L::RAW_OFF + (ch % RD) * L::RAW_BYTES + tid * L::SLOT;
             const uint32_t stage = (gch0 + ch) % NST, phase = ((gch0 + ch) / NST) & 1;
-            const uint32_t vm = (vbits >> (2 * (ch % RD))) & 3u;
+            const uint32_t vm = (vbits >> (3 * (ch % RD))) & 7u;
             if (lane == 0) { if (kspin) mbar_spin(bar(NST + stage), phase ^ 1); else mbar_wait(bar(NST + stage), phase ^ 1); }
             __syncwarp();
             PROF(12);
             unsigned char *st = smem + stage * L::STAGE_BYTES;
             if (any_a && !kskip_p) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < 3; ++k) {
                     if (!g_ok[k]) continue;
                     float4 xv = *reinterpret_cast<const float4 *>(slot + k * 16);
                     if (pro) {
@@ -203,7 +208,7 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
                         uint4 l;
                         l.x = to_tf32(xv.x - __uint_as_float(h.x)); l.y = to_tf32(xv.y - __uint_as_float(h.y));
                         l.z = to_tf32(xv.z - __uint_as_float(h.z)); l.w = to_tf32(xv.w - __uint_as_float(h.w));
-                        *reinterpret_cast<uint4 *>(dst + 4 * 4096) = l;
+                        *reinterpret_cast<uint4 *>(dst + L::A_BLOCKS * 4096) = l;
                     }
                 }
             }
@@ -211,7 +216,7 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
             for (int m = 0; m < NDYH; ++m) {
                 const int pcm = p16 + 16 * m;
                 if (pcm * 4 >= BN || kskip_p) continue;
-                const float4 bv = *reinterpret_cast<const float4 *>(slot + (2 + m) * 16);
+                const float4 bv = *reinterpret_cast<const float4 *>(slot + (L::AP + m) * 16);
                 dbp[m * 4] += bv.x; dbp[m * 4 + 1] += bv.y; dbp[m * 4 + 2] += bv.z; dbp[m * 4 + 3] += bv.w;
                 unsigned char *dst = st + L::A_BYTES + (pcm >> 3) * 4096 + jb * 128 + ((((uint32_t)pcm & 7) ^ b_sw) << 4);
                 uint4 h;
@@ -249,6 +254,18 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
             __syncwarp();
             tc_fence_after();
             PROF(31);
+            if (L::A_BLOCKS > 4 && tail > 0 && ew == 0) {               // the tail rows: second accumulator, TMEM columns [BNP, 2 * BNP), lanes 0 .. tail - 1
+#pragma unroll
+                for (int cb = 0; cb < BN; cb += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + BNP + cb, v);
+                    if (lane < tail) {
+                        float *dst = a.dw + (size_t)(kd0 + TM + lane) * a.Cout + o0 + cb;
+#pragma unroll
+                        for (int t = 0; t < 16; t += 4) red_add_v4(dst + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
+                    }
+                }
+            }
 #pragma unroll
             for (int cb = 0; cb < BN; cb += 16) {
                 float v[16];
@@ -280,13 +297,21 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
                     const uint64_t ah = a0 + ks * kstep16, bh = b0 + ks * kstep16;
                     const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
                     if (PASSES > 1) {
-                        const uint64_t al = ah + ((4 * 4096) >> 4);
+                        const uint64_t al = ah + ((L::A_BLOCKS * 4096) >> 4);
                         const uint64_t bl = bh + (((BNP / 32) * 4096) >> 4);
                         mma_tf32_ss_1t(tmem_base, ah, bl, IDESC, first);
                         mma_tf32_ss_1t(tmem_base, al, bh, IDESC, 1u);
                         mma_tf32_ss_1t(tmem_base, ah, bh, IDESC, 1u);
+                        if (L::A_BLOCKS > 4 && tail > 0) {     // column block 4 (the tail rows) against the same dy tile; rows >= 32 of this
+                                            // accumulator read whatever follows block 4 and are never looked at
+                            const uint64_t th = ah + ((4 * 4096) >> 4), tl = al + ((4 * 4096) >> 4);
+                            mma_tf32_ss_1t(tmem_base + BNP, th, bl, IDESC, first);
+                            mma_tf32_ss_1t(tmem_base + BNP, tl, bh, IDESC, 1u);
+                            mma_tf32_ss_1t(tmem_base + BNP, th, bh, IDESC, 1u);
+                        }
                     } else {
                         mma_tf32_ss_1t(tmem_base, ah, bh, IDESC, first);
+                        if (L::A_BLOCKS > 4 && tail > 0) mma_tf32_ss_1t(tmem_base + BNP, ah + ((4 * 4096) >> 4), bh, IDESC, first);
                     }
                 }
                 mma_commit_1t(bar(NST + stage));
@@ -351,7 +376,7 @@ k_wgrad_mn(WArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     PROF(2);
-    item_run<BN, PASSES, NST>(a, mt, nt, split, c_begin, nchunks, false, 0u, 0u, smem, sbase, tmem_base, s_scale, s_shift, s_db);
+    item_run<BN, PASSES, NST>(a, mt, nt, split, c_begin, nchunks, 0, false, 0u, 0u, smem, sbase, tmem_base, s_scale, s_shift, s_db);
     PROF(32);
     tc_fence_before();
     __syncthreads();
@@ -408,7 +433,7 @@ k_wgrad_mn(WArgs a) {
 // take items from a list - the first statically, the rest through an atomic counter - and reduce each item's tile
 // straight into dW (the list interleaves the tiles, so only a handful of CTAs work on the same tile at any time).
 // -------------------------------------------------------------------------------------------------------------------
-struct WItem { int layer, mt, nt, c_begin, nchunks, pad0, pad1, pad2; };
+struct WItem { int layer, mt, nt, c_begin, nchunks, tail, pad1, pad2; };   // tail: rows of the layer's last m-tile merged into this one
 struct WGroupArgs { const WArgs *layers; const WItem *items; int n_items; unsigned int *sched; };
 
 template <int BN, int PASSES, int NST>
@@ -424,7 +449,7 @@ k_wgrad_group(const WGroupArgs g) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR_OFF + 128);
     float *s_scale = reinterpret_cast<float *>(smem + L::COEF_OFF);
     float *s_shift = s_scale + 256;
-    constexpr uint32_t TCOLS = BNP <= 32 ? 32 : (BNP <= 64 ? 64 : 128);
+    constexpr uint32_t TCOLS = 2 * (BNP <= 32 ? 32 : (BNP <= 64 ? 64 : 128));     // two accumulators (m-tile + merged tail rows)
     __shared__ WArgs s_a;
     __shared__ float s_db[128];
     __shared__ int s_next;
@@ -467,8 +492,8 @@ k_wgrad_group(const WGroupArgs g) {
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        item_run<BN, PASSES, NST>(s_a, it.mt, it.nt, 0, it.c_begin, it.nchunks, true, gch, done_parity, smem, sbase, tmem_base,
-                                  s_scale, s_shift, s_db);
+        item_run<BN, PASSES, NST>(s_a, it.mt, it.nt, 0, it.c_begin, it.nchunks, it.tail, true, gch, done_parity, smem, sbase,
+                                  tmem_base, s_scale, s_shift, s_db);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -623,6 +648,14 @@ struct WGroup {
     int passes;
 };
 
+// A layer whose last m-tile holds at most 32 rows (K = 144 -> 128 + 16, K = 288 -> 256 + 32) does not get a pass over all
+// pixels for those rows alone: they ride with the m-tile before (WItem::tail, second accumulator in item_run)
+void merged_tail(int bn, int Kw, int &mtiles, int &tail) {
+    tail = 0;
+    const int last = Kw - (mtiles - 1) * TM;
+    if (bn <= 32 && mtiles >= 2 && last <= 32 && last % 4 == 0) { tail = last; --mtiles; }
+}
+
 template <int BN, int PASSES>
 int launch_group(const WGroupLaunch &l, cudaStream_t st) {
     using L = Lay<BN, PASSES, 2>;
@@ -664,7 +697,9 @@ extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layer
         long long total = 0;
         for (const WArgs &a : la) {
             const int Kw = a.k * a.k * a.Cin;
-            total += (long long)((Kw + TM - 1) / TM) * (a.Cout / bn) * ((a.N * a.Ho * a.Wo + 31) / 32);
+            int mtiles = (Kw + TM - 1) / TM, tail = 0;
+            merged_tail(bn, Kw, mtiles, tail);
+            total += (long long)mtiles * (a.Cout / bn) * ((a.N * a.Ho * a.Wo + 31) / 32);
         }
         long long cpi = (total + 148 * 6 - 1) / (148 * 6);
         if (cpi < 8) cpi = 8;
@@ -676,7 +711,9 @@ extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layer
             bool any = false;
             for (size_t li = 0; li < la.size(); ++li) {
                 const WArgs &a = la[li];
-                const int Kw = a.k * a.k * a.Cin, mtiles = (Kw + TM - 1) / TM, ntiles = a.Cout / bn;
+                const int Kw = a.k * a.k * a.Cin, ntiles = a.Cout / bn;
+                int mtiles = (Kw + TM - 1) / TM, tail = 0;
+                merged_tail(bn, Kw, mtiles, tail);
                 const int chunks = (a.N * a.Ho * a.Wo + 31) / 32;
                 const int c0 = (int)(s * cpi);
                 if (c0 >= chunks) continue;
@@ -687,6 +724,7 @@ extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layer
                         WItem it;
                         memset(&it, 0, sizeof(it));
                         it.layer = (int)li; it.mt = mt; it.nt = nt; it.c_begin = c0; it.nchunks = n;
+                        it.tail = mt == mtiles - 1 ? tail : 0;
                         items.push_back(it);
                     }
             }
