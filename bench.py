@@ -336,7 +336,7 @@ class StepRunner(object):
         eng._alloc_training()
         if ctx.world > 1:
             dist = ctx.dist
-            eng.set_world(ctx.world, lambda g: dist.all_reduce(g), rank=ctx.rank, syncbn=syncbn)
+            eng.set_world(ctx.world, lambda g: dist.all_reduce(g), rank=ctx.rank, syncbn=syncbn, dist=dist)
         self.rng = np.random.RandomState(1234 + ctx.rank)
         self.nrec = min(total_steps, 64)             # distinct record sets, cycled
         self.recs_all, self.ys_all = [], []
@@ -600,6 +600,14 @@ def run_b200(args):
                     strong["syncbn_ms_per_step"] = ms3
                     strong["syncbn_value"] = gb / (ms3 / 1000.)
                     r3.eng._graphs.clear()
+                    r4 = StepRunner(ctx, 'ICVL', ['com', 'rot', 'none'], gb // world, 3 + min(args.steps, 10), syncbn='p2p')
+                    ms4 = ctx.timed(r4.step_resident, min(args.steps, 10), 3)
+                    r4.eng.check_barriers()
+                    strong["syncbn_p2p_ms_per_step"] = ms4
+                    strong["syncbn_p2p_value"] = gb / (ms4 / 1000.)
+                    strong["syncbn_note"] = "syncbn: one NCCL all-reduce per BatchNorm and direction (122 per step); " \
+                                            "syncbn_p2p: dpp_stats_exchange, a one-shot exchange over NVLink peer memory"
+                    r4.eng._graphs.clear()
         except Exception as exc:                 # pragma: no cover - extra evidence must not break the contract line
             if world > 1:
                 raise
@@ -631,7 +639,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": {0: "f32", 1: "tf32x3", 2: "tf32"}[run.precision], "data": "synthetic",
         "config": {"workload": "%s, %d resident crops" % (descr, N_RESIDENT),
                    "global_batch": nb * world, "per_gpu_batch": nb, "parallelism": "dp%d" % world,
-                   "batchnorm": "SyncBN (statistics summed over the ranks)" if (args.syncbn and world > 1) else
+                   "batchnorm": ("SyncBN (statistics summed over the ranks, %s)" % ('peer memory' if args.syncbn == 'p2p' else 'NCCL')) if (args.syncbn and world > 1) else
                                 ("per-replica statistics" if world > 1 else "single device"),
                    "l2": "inputs (134 MB of crops + 0.9 GB of activations per step) exceed the 126 MB L2",
                    "precision_mode": run.precision},
@@ -754,7 +762,8 @@ def main():
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling sample of the default workload')
     ap.add_argument('--no-trainer-api', action='store_true', help='skip the PoseRegNetTrainer.train() measurement')
     ap.add_argument('--no-cost-check', action='store_true')
-    ap.add_argument('--syncbn', action='store_true', help='N > 1: sum the BatchNorm statistics over the ranks')
+    ap.add_argument('--syncbn', nargs='?', const=True, default=False, choices=[True, 'nccl', 'p2p'],
+                    help="N > 1: sum the BatchNorm statistics over the ranks (NCCL per BatchNorm, or 'p2p': peer-memory exchange)")
     ap.add_argument('--workload', default='train', choices=['train', 'icvl512', 'msra15', 'poseregnet', 'cascade'],
                     help="train = BASELINE configs[1] (the headline); icvl512 = configs[2]; msra15 = configs[3]; "
                          "cascade = configs[4], tools/bench_cascade.py")

@@ -126,6 +126,7 @@ class Engine(object):
         self.rank = 0
         self.allreduce_fn = None
         self.syncbn = False
+        self._peer = None
         self._graphs = {}
         self._masks_injected = None
         # backward-weights kernels run on a second stream (forked/joined inside the step, also under graph
@@ -394,6 +395,12 @@ class Engine(object):
             self.torch.cuda.synchronize()
             lib.dpp_wgrad_group_destroy(self._wgroup)
             self._wgroup = None
+        if getattr(self, '_peer', None) is not None:
+            self.torch.cuda.synchronize()
+            for p in self._peer['opened']:
+                lib.dpp_peer_close(p)
+            lib.dpp_peer_free(self._peer['local'])
+            self._peer = None
 
     def _arena(self, slot):
         return self.W if slot.arena == 'w' else self.R
@@ -570,7 +577,42 @@ class Engine(object):
         takes the statistics over the whole minibatch)."""
         f0, b0, c = self.bn_stat_off[id(bn)]
         lo = f0 if which == 0 else b0
-        self.stats_allreduce_fn(self.STATS[lo:lo + 2 * c])
+        if self._peer is not None:
+            # one-shot exchange over peer memory (NVLink P2P): one small kernel in stream order instead of a collective
+            pr = self._peer
+            lib.dpp_stats_exchange(C.c_void_p(self.STATS.data_ptr() + 8 * lo), 2 * c, _ptr(pr['ptrs']),
+                                   pr['regions'][(id(bn), which)], self.rank, self.world, _ptr(pr['seq']), _ptr(pr['err']),
+                                   self._stream())
+        else:
+            self.stats_allreduce_fn(self.STATS[lo:lo + 2 * c])
+
+    def _setup_peer_exchange(self, dist):
+        """exchange buffers of the SyncBN statistics, mapped into every rank over CUDA IPC (same node, NVLink)"""
+        torch = self.torch
+        regions, off = {}, 0
+        for bn in self.bns:
+            c = self.bn_stat_off[id(bn)][2]
+            for which in (0, 1):
+                regions[(id(bn), which)] = off
+                off += ((self.world * (2 * c + 1) * 8 + 15) // 16) * 16
+        local, handle = C.c_void_p(), C.create_string_buffer(64)
+        lib.dpp_peer_alloc(max(off, 16), C.byref(local), handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        ptrs, opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(local.value)
+            else:
+                p = C.c_void_p()
+                lib.dpp_peer_open(handles[r], C.byref(p))
+                ptrs.append(p.value)
+                opened.append(p)
+        self._peer = dict(regions=regions, local=local, opened=opened,
+                          ptrs=torch.tensor(ptrs, dtype=torch.int64, device=self.dev),
+                          seq=torch.zeros(1, dtype=torch.int64, device=self.dev),
+                          err=torch.zeros(1, dtype=torch.int32, device=self.dev))
+        dist.barrier()          # every rank has mapped every buffer before the first exchange is issued
 
     def _run_forward(self, train):
         st = self._stream()
@@ -837,10 +879,13 @@ class Engine(object):
         self._n_bn_bwd_launches = len(self.bns) - n_fused[0]
 
     def check_barriers(self):
-        """raises if a grid-wide barrier of the fused dgrad + BN-backward kernels gave up waiting (synchronises)"""
+        """raises if a grid-wide barrier of the fused dgrad + BN-backward kernels, or a wait of the peer-memory
+        statistics exchange, gave up (synchronises)"""
         marks = self.GBAR[1::2].cpu().numpy()
         if (marks != 0).any():
             raise DppError("grid barrier timed out in %d fused BatchNorm-backward launch(es)" % int((marks != 0).sum()))
+        if self._peer is not None and int(self._peer['err'].cpu()[0]) != 0:
+            raise DppError("peer-memory statistics exchange timed out waiting for another rank")
 
     def launches_wgrad(self):
         """backward-weights launches per step: one per ConvLayer, or the grouped launches"""
@@ -925,17 +970,22 @@ class Engine(object):
     def set_lr(self, lr):
         self.hyper[0:1].fill_(float(lr))
 
-    def set_world(self, world, allreduce_fn, rank=0, syncbn=False, stats_allreduce_fn=None, bucket_elems=None):
+    def set_world(self, world, allreduce_fn, rank=0, syncbn=False, stats_allreduce_fn=None, bucket_elems=None, dist=None):
         """Data-parallel mode (the reference is single-device).  ``allreduce_fn(t)`` sums a float32 slice
         of the gradient arena over the ranks in place, on the CURRENT stream (torch.distributed.all_reduce).
         ``syncbn``: also sum every BatchNorm's fp64 statistics (forward and backward) with ``stats_allreduce_fn``
         (default: the same function), which makes ``world`` ranks x B/world samples compute the single-device
-        function of the global minibatch."""
+        function of the global minibatch.  ``syncbn='p2p'`` (needs ``dist`` = torch.distributed, all ranks on one
+        node) exchanges the statistics with dpp_stats_exchange over peer memory instead of a collective per BN."""
         self.world = int(world)
         self.rank = int(rank)
         self.allreduce_fn = allreduce_fn
         self.syncbn = bool(syncbn) and self.world > 1
         self.stats_allreduce_fn = stats_allreduce_fn or allreduce_fn
+        if self.syncbn and syncbn == 'p2p' and self._peer is None:
+            if dist is None:
+                raise DppError("syncbn='p2p' needs dist=torch.distributed to exchange the IPC handles")
+            self._setup_peer_exchange(dist)
         self._graphs = {}
         self._alloc_training()
         self._build_ema_items()                      # the counts behind the statistics depend on world / syncbn

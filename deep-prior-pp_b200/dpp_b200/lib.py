@@ -98,6 +98,11 @@ _SIGS = {
     'dpp_wgrad_group_launches': (C.c_int, [P]),
     'dpp_wgrad_group_destroy': (C.c_int, [P]),
     'dpp_bn_bwd_apply': (C.c_int, [P, P, C.POINTER(BnRef), P, P, P, P, P, P, C.c_int64, C.c_int, C.c_float, P]),
+    'dpp_peer_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    'dpp_peer_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'dpp_peer_close': (C.c_int, [P]),
+    'dpp_peer_free': (C.c_int, [P]),
+    'dpp_stats_exchange': (C.c_int, [P, C.c_int, P, C.c_int64, C.c_int, C.c_int, P, P, P]),
     'dpp_bn_apply': (C.c_int, [P, C.POINTER(BnRef), P, C.c_int64, C.c_int, P]),
     'dpp_bn_relu_bwd_reduce': (C.c_int, [P, P, C.POINTER(BnRef), P, P, C.c_int64, C.c_int, P]),
     'dpp_bn_ema_update': (C.c_int, [P, C.c_int, C.c_float, P]),

@@ -112,7 +112,7 @@ class NetTrainer(object):
         from dpp_b200 import dp
         self._dist, self.rank, self.world = dp.init_process_group()
         self.local_batch = dp.local_batch(cfgParams.batch_size, self.world)
-        self.syncbn = os.environ.get('DPP_SYNCBN', '0') == '1'
+        self.syncbn = {'1': True, 'nccl': True, 'p2p': 'p2p'}.get(os.environ.get('DPP_SYNCBN', '0'), False)
         self.verbose = getattr(self, 'verbose', True) and self.rank == 0
 
     # -- data registration ------------------------------------------------------------------
@@ -262,7 +262,7 @@ class NetTrainer(object):
         eng = net._engine()
         if self.world > 1 and (eng.world != self.world or eng.allreduce_fn is None):
             dist = self._dist
-            eng.set_world(self.world, lambda t: dist.all_reduce(t), rank=self.rank, syncbn=self.syncbn)
+            eng.set_world(self.world, lambda t: dist.all_reduce(t), rank=self.rank, syncbn=self.syncbn, dist=dist)
         return eng
 
     def _allreduce_scalar(self, value, op='mean'):

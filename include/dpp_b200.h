@@ -267,6 +267,25 @@ int dpp_bn_bwd_apply(const float *dz, const float *x, const dpp_bn_ref *bn,
                      float *dbeta, double *dbias_stats, int64_t pixels, int C,
                      float param_grad_scale, void *stream);
 
+/* ---- SyncBN statistics exchange over peer memory (NVLink P2P) -------------------------------------------------
+ * Data-parallel training with BatchNorm statistics of the GLOBAL minibatch (what the single-device reference
+ * computes, net/batchnormlayer.py:154-159): the 2*C fp64 sums of every BN are summed over the ranks, forward and
+ * backward.  dpp_stats_exchange is a one-shot all-reduce written for this size (a few KB, latency-bound, on the
+ * critical chain): one single-CTA kernel stores the local sums into every rank's exchange buffer over NVLink,
+ * publishes a sequence number, waits for the other ranks' numbers and overwrites `stats` with the sum taken in rank
+ * order (bit-identical on all ranks).  Asynchronous, capturable; every rank must issue the same sequence of calls.
+ *   dpp_peer_alloc / dpp_peer_open: a zeroed device buffer with its 64-byte CUDA IPC handle / the mapping of another
+ *   rank's buffer (same node).  Exchange-buffer layout per sync point at `region_off` (16-byte aligned):
+ *   [world][n] doubles, then [world] 64-bit flags - i.e. world * (n + 1) * 8 bytes.
+ *   peers_dev: DEVICE array of `world` pointers (entry `rank` = the local buffer).  seq_counter: device u64, zero at
+ *   start, advanced by the kernel.  err_flag: device u32 set to 0xDEAD if a wait gave up (a rank died).          */
+int dpp_peer_alloc(int64_t bytes, void **ptr_out, unsigned char *ipc_handle_out64);
+int dpp_peer_open(const unsigned char *ipc_handle64, void **ptr_out);
+int dpp_peer_close(void *ptr);
+int dpp_peer_free(void *ptr);
+int dpp_stats_exchange(double *stats, int n, void *const *peers_dev, int64_t region_off, int rank,
+                       int world, unsigned long long *seq_counter, unsigned int *err_flag, void *stream);
+
 /* materialise a = bn(x) (+relu): used for the last BN+ReLU in front of the FC stack      */
 int dpp_bn_apply(const float *x, const dpp_bn_ref *bn, float *y, int64_t pixels, int C,
                  void *stream);

@@ -41,7 +41,8 @@ def run(mode, rank, world, B=16):
     eng = Engine(net, precision=1)
     eng._alloc_training()
     if mode not in ('local', 'full'):
-        eng.set_world(world, lambda g: dist.all_reduce(g), rank=rank, syncbn=(mode == 'syncbn'))
+        eng.set_world(world, lambda g: dist.all_reduce(g), rank=rank,
+                      syncbn={'syncbn': True, 'syncbn_p2p': 'p2p'}.get(mode, False), dist=dist)
     eng.set_lr(1e-3)
     if mode == 'full':
         xs, ys = zip(*[inputs_of(r, B) for r in range(world)])
@@ -52,6 +53,7 @@ def run(mode, rank, world, B=16):
     eng.y_in.copy_(y)
     cost = eng.train_step(None, use_graph=True)
     torch.cuda.synchronize()
+    eng.check_barriers()
     G, W, R, c = eng.G.clone(), eng.W.clone(), eng.R.clone(), float(cost.cpu()[0])
     eng._graphs.clear()
     eng.release()
@@ -93,6 +95,12 @@ def main():
     d_run = float((r_sbn - r_full).abs().max() / r_full.abs().max())
     d_cost = abs(c_mean - c_full) / abs(c_full)
     sync_sbn = same_on_all_ranks(g_sbn) and same_on_all_ranks(w_sbn) and same_on_all_ranks(r_sbn)
+    # the same with the statistics exchanged over peer memory (dpp_stats_exchange) instead of NCCL
+    g_p2p, w_p2p, r_p2p, c_p2p = run('syncbn_p2p', rank, world)
+    d_p2p = float((g_p2p / world - g_full).abs().max()) / gs
+    l2_p2p = float((g_p2p / world - g_full).norm() / g_full.norm())
+    d_run_p2p = float((r_p2p - r_full).abs().max() / r_full.abs().max())
+    sync_p2p = same_on_all_ranks(g_p2p) and same_on_all_ranks(w_p2p) and same_on_all_ranks(r_p2p)
     if rank == 0:
         print("dp_check world=%d  |G_early - sum(G_local)|/max|G| = %.2e   |G_early - G_late|/max|G| = %.2e   "
               "replicas identical: G %s, W %s" % (world, d_sum, d_late, sync_g, sync_w))
@@ -102,7 +110,10 @@ def main():
         # a handful of roundoff-level ReLU decisions may differ between the two runs (different summation order of the
         # statistics): bound the gradient by what such flips allow, the cost and statistics tightly
         ok_sbn = d_cost < 1e-5 and d_run < 1e-5 and l2_sbn < 2e-2 and sync_sbn
-        print("DP_CHECK", "PASS" if (ok and ok_sbn) else "FAIL")
+        print("dp_check SyncBN over peer memory vs one device: gradient max %.2e / rel-L2 %.2e, running statistics %.2e, "
+              "replicas identical %s" % (d_p2p, l2_p2p, d_run_p2p, sync_p2p))
+        ok_p2p = d_run_p2p < 1e-5 and l2_p2p < 2e-2 and sync_p2p
+        print("DP_CHECK", "PASS" if (ok and ok_sbn and ok_p2p) else "FAIL")
         sys.stdout.flush()
     timer = threading.Timer(30.0, lambda: os._exit(0))
     timer.daemon = True
