@@ -643,8 +643,8 @@ def run_b200(args):
                                 ("per-replica statistics" if world > 1 else "single device"),
                    "l2": "inputs (134 MB of crops + 0.9 GB of activations per step) exceed the 126 MB L2",
                    "precision_mode": run.precision},
-        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "note": e2e_note},
+        "e2e": None if args.no_e2e else {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                                         "d2h_bytes_per_step": 4, "note": e2e_note},
         "e2e_records_prebuilt": None if ms_pre is None else {"value": nb * world / (ms_pre / 1000.), "unit": UNIT,
                                                                "ms_per_step": ms_pre},
         "trainer_api": trainer_api,

@@ -18,7 +18,7 @@ def test_roofline_traffic_matches_the_committed_launch_list():
     got = json.loads(r.stdout)
     assert got['launches'] == want['launches'] == 63
     assert abs(got['conv_fwd_avg_bytes_per_launch'] - want['conv_fwd_avg_bytes_per_launch']) < 1.0
-    bench = json.load(open(os.path.join(ROOT, 'profiles', 'r1_final_bench.json')))
+    bench = json.load(open(os.path.join(ROOT, 'profiles', 'r2_final_bench.json')))
     assert abs(bench['roofline']['traffic'] - want['conv_fwd_avg_bytes_per_launch']) < 0.01 * want['conv_fwd_avg_bytes_per_launch']
     assert abs(bench['roofline']['frac'] - bench['roofline']['achieved'] / bench['roofline']['peak']) < 1e-9
 
@@ -29,6 +29,15 @@ def test_launch_list_names_the_kernels_of_the_step():
     names = set(n.split('<')[0] for n, _, _, _ in load(os.path.join(ROOT, 'profiles', 'r1_final_launches.csv')))
     for k in ('k_conv_tc', 'k_wgrad_mn', 'k_bn_bwd_apply', 'k_stem_fwd', 'k_gemm_tc', 'k_adam', 'k_augment', 'k_loss_sqerr'):
         assert k in names, k
+    rows = load(os.path.join(ROOT, 'profiles', 'r2_final_launches.csv'))
+    names2 = set(n.split('<')[0] for n, _, _, _ in rows)
+    for k in ('k_conv_tc', 'k_wgrad_group', 'k_bn_bwd_apply', 'k_stem_fwd', 'k_gemm_tc', 'k_adam', 'k_augment', 'k_loss_sqerr'):
+        assert k in names2, k
+    assert 'k_wgrad_mn' not in names2                  # round 2: the backward-weights GEMMs run grouped
+    # ... and between two k_augment launches (one step) only the 4 un-fusable BatchNorm-backward launches are left
+    aug = [i for i, r in enumerate(rows) if r[0].startswith('k_augment')]
+    step = [r[0].split('<')[0] for r in rows[aug[0]:aug[1]]]
+    assert step.count('k_bn_bwd_apply') == 4 and step.count('k_wgrad_group') == 4 and step.count('k_conv_tc') == 126
     casc = set(n.split('<')[0] for n, _, _, _ in load(os.path.join(ROOT, 'profiles', 'r1_cascade_launches.csv')))
     assert {'k_recrop', 'k_convpool_fwd', 'k_conv_tc', 'k_stem_fwd'} <= casc
 
@@ -36,12 +45,14 @@ def test_launch_list_names_the_kernels_of_the_step():
 def test_committed_bench_lines_follow_the_contract():
     keys = ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
             'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches')
-    for path in glob.glob(os.path.join(ROOT, 'profiles', 'r1_*bench*.json')):
+    for path in glob.glob(os.path.join(ROOT, 'profiles', 'r1_*bench*.json')) + glob.glob(os.path.join(ROOT, 'profiles', 'r2_*bench*.json*')):
         for line in open(path).read().strip().splitlines():
             d = json.loads(line)
             for k in keys:
                 assert k in d, (os.path.basename(path), k)
-            assert 'workload' in d['config'] and d['e2e']['value'] > 0
+            assert 'workload' in d['config']
+            if d['e2e'] is not None:                 # profiler / multi-variant runs skip the host-buffer arm (--no-e2e)
+                assert d['e2e']['value'] > 0
             if d.get('impl') != 'reference':
                 assert d['gpu_launches'] > 0
                 if d.get('roofline'):            # multi-GPU and early lines were taken with --no-roofline
