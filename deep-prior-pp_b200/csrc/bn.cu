@@ -182,7 +182,10 @@ extern "C" int dpp_bn_apply(const float *x, const dpp_bn_ref *bn, float *y, int6
 extern "C" int dpp_bn_relu_bwd_reduce(const float *dy, const float *x, const dpp_bn_ref *bn, float *dz,
                                       double *dz_stats, int64_t pixels, int C, void *stream) {
     DPP_CHECK_ARG(dy && x && bn && dz && dz_stats && pixels > 0 && C % 4 == 0 && C <= 256 && 256 % (C / 4) == 0);
-    k_bn_relu_bwd_reduce<<<ew_grid(pixels, C), BT, 0, S(stream)>>>(dy, x, *bn, dz, dz_stats, pixels, C);
+    // every block ends with 2*C fp64 atomics onto the same 2*C addresses: few, long-running blocks
+    int grid = ew_grid(pixels, C);
+    if (grid > 148) grid = 148;
+    k_bn_relu_bwd_reduce<<<grid, BT, 0, S(stream)>>>(dy, x, *bn, dz, dz_stats, pixels, C);
     DPP_LAUNCH_CHECK();
     return DPP_OK;
 }

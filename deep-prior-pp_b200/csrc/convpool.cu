@@ -211,156 +211,239 @@ __global__ void k_convpool_bwd_x(const float *__restrict__ w, const float *__res
 
 // -------------------------------------------------------------------------------------------------
 // ResNet stem specialisation: 5x5 'half' conv, Cin = 1, Cout = 32, 2x2 max-pool (net/resnet.py:128-133).
-// Everything is compile-time: a thread owns one pooled pixel x 8 channels, keeps its 6x6 input window
-// in registers and runs 25 taps x 4 pool cells x 8 channels of FMAs against broadcast weight reads.
+// fp32 FMA-bound (K = 25, one input channel: no GEMM shape worth the tensor pipe), so the kernels are built around
+// FMA density.  Forward: a CTA owns an 8 x 16 region of pooled pixels; a thread owns TWO horizontally adjacent
+// pooled pixels x 8 channels = 64 accumulators, keeps a sliding 2 x 8 input window in registers and runs 25 taps x
+// 8 conv pixels x 8 channels of FMAs against broadcast weight vectors (64 FMAs per two 16-byte weight loads);
+// BatchNorm statistics stay in registers until the end of the CTA.  The next region's input patch is loaded
+// while the current one is computed (one barrier per region).
 // -------------------------------------------------------------------------------------------------
-constexpr int SP = 20;   // stem input patch edge: 8*2 + 5 - 1
+constexpr int SPH = 20, SPW = 36;   // forward input patch: 8*2 + 4 rows, 16*2 + 4 columns
 
-__global__ void __launch_bounds__(256)
+// a thread's share of a region's input patch (3 of the 720 values): global loads into registers ...
+__device__ __forceinline__ void stem_fetch_fwd(float (&v)[3], const float *__restrict__ x, int n, int ty0, int tx0, int H, int W) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int i = threadIdx.x + j * 256;
+        const int py = i / SPW, px = i - py * SPW;
+        const int yy = ty0 * 16 - 2 + py, xx = tx0 * 32 - 2 + px;
+        v[j] = (i < SPH * SPW && yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * H + yy) * W + xx] : 0.f;
+    }
+}
+// ... and, after the arithmetic that hides their latency, into shared memory
+__device__ __forceinline__ void stem_put_fwd(float *patch, const float (&v)[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int i = threadIdx.x + j * 256;
+        if (i < SPH * SPW) patch[i] = v[j];
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
 k_stem_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
            float *__restrict__ y, uint8_t *__restrict__ argmax, double *__restrict__ stats, int N, int H, int W) {
     __shared__ __align__(16) float ws[25 * 32];
-    __shared__ float patch[SP * SP];
+    __shared__ __align__(16) float patch[2][SPH * SPW];
     __shared__ double ssum[64];
     const int tid = threadIdx.x;
     for (int i = tid; i < 25 * 32; i += 256) ws[i] = w[i];
     if (tid < 64) ssum[tid] = 0.0;
     const int Hp = H / 2, Wp = W / 2;
-    const int tilesY = (Hp + 7) / 8, tilesX = (Wp + 7) / 8;
+    const int tilesY = (Hp + 7) / 8, tilesX = (Wp + 15) / 16;
     const int tiles = N * tilesY * tilesX;
-    const int pix = tid & 63, grp = tid >> 6;
-    const int ly = pix >> 3, lx = pix & 7;
+    const int pair = tid & 63, grp = tid >> 6;     // grp is warp-uniform: weight reads are broadcasts
+    const int ly = pair >> 3, lxp = pair & 7;
     const int o0 = grp * 8;
-    float bq[8];
+    float bq[8], st1[8], st2[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) bq[q] = bias[o0 + q];
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int q = 0; q < 8; ++q) { bq[q] = bias[o0 + q]; st1[q] = 0.f; st2[q] = 0.f; }
+    int buf = 0;
+    float pf[3];
+    if ((int)blockIdx.x < tiles) {
+        const int t = blockIdx.x;
+        stem_fetch_fwd(pf, x, t / (tilesY * tilesX), (t % (tilesY * tilesX)) / tilesX, t % tilesX, H, W);
+        stem_put_fwd(patch[0], pf);
+    }
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
         const int n = tile / (tilesY * tilesX), tr = tile % (tilesY * tilesX);
         const int ty0 = tr / tilesX, tx0 = tr % tilesX;
-        __syncthreads();
-        for (int i = tid; i < SP * SP; i += 256) {
-            int py = i / SP, px = i - py * SP;
-            int yy = ty0 * 16 - 2 + py, xx = tx0 * 16 - 2 + px;
-            patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * H + yy) * W + xx] : 0.f;
+        __syncthreads();            // patch[buf] complete; everybody is done with patch[buf ^ 1]
+        const int t2 = tile + gridDim.x;
+        if (t2 < tiles) stem_fetch_fwd(pf, x, t2 / (tilesY * tilesX), (t2 % (tilesY * tilesX)) / tilesX, t2 % tilesX, H, W);
+        const float *pw0 = patch[buf] + (ly * 2) * SPW + lxp * 4;
+        float acc[2][4][8];         // [pooled pixel][pool cell cy*2+cx][channel]
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[p][c][q] = 0.f;
+        float rowa[8], rowb[8];     // window rows r and r + 1
+        {
+            const float4 a0 = *reinterpret_cast<const float4 *>(pw0), a1 = *reinterpret_cast<const float4 *>(pw0 + 4);
+            rowa[0] = a0.x; rowa[1] = a0.y; rowa[2] = a0.z; rowa[3] = a0.w; rowa[4] = a1.x; rowa[5] = a1.y; rowa[6] = a1.z; rowa[7] = a1.w;
         }
-        __syncthreads();
-        float win[6][6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int s = 0; s < 6; ++s) win[r][s] = patch[(ly * 2 + r) * SP + lx * 2 + s];
-        float acc[4][8];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[c][q] = 0.f;
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
+        for (int r = 0; r < 5; ++r) {
+            {
+                const float4 b0 = *reinterpret_cast<const float4 *>(pw0 + (r + 1) * SPW);
+                const float4 b1 = *reinterpret_cast<const float4 *>(pw0 + (r + 1) * SPW + 4);
+                rowb[0] = b0.x; rowb[1] = b0.y; rowb[2] = b0.z; rowb[3] = b0.w; rowb[4] = b1.x; rowb[5] = b1.y; rowb[6] = b1.z; rowb[7] = b1.w;
+            }
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 const float4 w0 = *reinterpret_cast<const float4 *>(&ws[(r * 5 + s) * 32 + o0]);
                 const float4 w1 = *reinterpret_cast<const float4 *>(&ws[(r * 5 + s) * 32 + o0 + 4]);
                 const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float xv = win[(c >> 1) + r][(c & 1) + s];
+                for (int p = 0; p < 2; ++p)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[c][q] = fmaf(xv, wq[q], acc[c][q]);
-                }
+                    for (int c = 0; c < 4; ++c) {
+                        const float xv = (c >> 1) ? rowb[p * 2 + (c & 1) + s] : rowa[p * 2 + (c & 1) + s];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[p][c][q] = fmaf(xv, wq[q], acc[p][c][q]);
+                    }
             }
-        const int ph = ty0 * 8 + ly, pw = tx0 * 8 + lx;
-        const bool valid = ph < Hp && pw < Wp;
-        float v[8];
-        uint8_t am[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float b = acc[0][q];
-            uint8_t bi = 0;
+            for (int j = 0; j < 8; ++j) rowa[j] = rowb[j];
+        }
+        if (t2 < tiles) stem_put_fwd(patch[buf ^ 1], pf);
+        const int ph = ty0 * 8 + ly;
 #pragma unroll
-            for (int c = 1; c < 4; ++c)
-                if (acc[c][q] > b) { b = acc[c][q]; bi = (uint8_t)c; }       // first max wins
-            v[q] = b + bq[q];
-            am[q] = bi;
-        }
-        if (valid) {
-            size_t ob = (((size_t)n * Hp + ph) * Wp + pw) * 32 + o0;
-            *reinterpret_cast<float4 *>(y + ob) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4 *>(y + ob + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            if (argmax) {
-                uint2 pk;
-                pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
-                pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
-                *reinterpret_cast<uint2 *>(argmax + ob) = pk;
-            }
-        }
-        if (stats) {
+        for (int p = 0; p < 2; ++p) {
+            const int pw = tx0 * 16 + lxp * 2 + p;
+            const bool valid = ph < Hp && pw < Wp;
+            float v[8];
+            uint32_t am[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                float s0 = warp_sum(valid ? v[q] : 0.f), s1 = warp_sum(valid ? v[q] * v[q] : 0.f);
-                if ((tid & 31) == 0) { atomicAdd(&ssum[o0 + q], (double)s0); atomicAdd(&ssum[32 + o0 + q], (double)s1); }
+                float b = acc[p][0][q];
+                uint32_t bi = 0;
+#pragma unroll
+                for (int c = 1; c < 4; ++c)
+                    if (acc[p][c][q] > b) { b = acc[p][c][q]; bi = (uint32_t)c; }       // first max wins
+                v[q] = b + bq[q];
+                am[q] = bi;
+            }
+            if (valid) {
+                const size_t ob = (((size_t)n * Hp + ph) * Wp + pw) * 32 + o0;
+                *reinterpret_cast<float4 *>(y + ob) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(y + ob + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                if (argmax) {
+                    uint2 pk;
+                    pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+                    pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+                    *reinterpret_cast<uint2 *>(argmax + ob) = pk;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { st1[q] += v[q]; st2[q] = fmaf(v[q], v[q], st2[q]); }
             }
         }
     }
     if (stats) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const double s0 = warp_sum_d((double)st1[q]), s1 = warp_sum_d((double)st2[q]);
+            if ((tid & 31) == 0) { atomicAdd(&ssum[o0 + q], s0); atomicAdd(&ssum[32 + o0 + q], s1); }
+        }
         __syncthreads();
         if (tid < 64) atomicAdd(&stats[tid], ssum[tid]);
     }
 }
 
-// stem weight/bias gradients.  Thread = (output channel o, tap group): it walks the tile's 64 pooled
-// pixels and accumulates g * x[argmax cell + tap] for its own taps in registers - no reductions until the
-// single atomicAdd per (tap, o) per CTA at the end.
+// stem weight / bias gradients.  Lane = output channel, warp = 8 of the tile's 64 pooled pixels: a thread reads
+// its own (pixel, channel) gradient and arg-max cell straight from global memory (128-byte rows per warp), turns
+// the cell into the patch offset of its 5x5 window and accumulates all 25 taps in registers (one shared-memory
+// read with an immediate offset + one FMA per tap).  The 8 warps meet in shared memory at the end of the CTA:
+// one atomicAdd per (tap, channel) per CTA.
+constexpr int SP = 20;   // backward input patch edge: 8*2 + 5 - 1
+
+__device__ __forceinline__ void stem_fetch_bwd(float (&v)[2], const float *__restrict__ x, int n, int ty0, int tx0, int H, int W) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = threadIdx.x + j * 256;
+        const int py = i / SP, px = i - py * SP;
+        const int yy = ty0 * 16 - 2 + py, xx = tx0 * 16 - 2 + px;
+        v[j] = (i < SP * SP && yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * H + yy) * W + xx] : 0.f;
+    }
+}
+__device__ __forceinline__ void stem_put_bwd(float *patch, const float (&v)[2]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = threadIdx.x + j * 256;
+        if (i < SP * SP) patch[i] = v[j];
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_stem_bwd_w(const float *__restrict__ x, const uint8_t *__restrict__ argmax, const float *__restrict__ dy,
              float *__restrict__ dw, float *__restrict__ db, int N, int H, int W) {
-    __shared__ float patch[SP * SP];
-    __shared__ float gs[64 * 32];
-    __shared__ uint8_t cs[64 * 32];
+    __shared__ float patch[2][SP * SP];
+    __shared__ float red[8][26][32];
     const int tid = threadIdx.x;
-    const int o = tid & 31, tg = tid >> 5;      // taps tg, tg+8, tg+16, tg+24
+    const int o = tid & 31, wq = tid >> 5;
     const int Hp = H / 2, Wp = W / 2;
     const int tilesY = (Hp + 7) / 8, tilesX = (Wp + 7) / 8;
     const int tiles = N * tilesY * tilesX;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
-    int toff[4];
+    float acc[25], accb = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int t = tg + 8 * j;
-        toff[j] = t < 25 ? (t / 5) * SP + (t % 5) : -1;
-    }
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int t = 0; t < 25; ++t) acc[t] = 0.f;
+    int buf = 0;
+    float g[8], gn[8], pf[2];
+    int base[8], cn[8];
+    // this warp's pooled row ty0*8 + wq, columns tx0*8 .. +7 of a tile: gradient and arg-max cell per (pixel, lane = channel)
+    auto fetch = [&](int tile) {
         const int n = tile / (tilesY * tilesX), tr = tile % (tilesY * tilesX);
         const int ty0 = tr / tilesX, tx0 = tr % tilesX;
-        __syncthreads();
-        for (int i = tid; i < SP * SP; i += 256) {
-            int py = i / SP, px = i - py * SP;
-            int yy = ty0 * 16 - 2 + py, xx = tx0 * 16 - 2 + px;
-            patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((size_t)n * H + yy) * W + xx] : 0.f;
-        }
-        for (int i = tid; i < 64 * 32; i += 256) {
-            int p = i >> 5, c = i & 31;
-            int ph = ty0 * 8 + (p >> 3), pw = tx0 * 8 + (p & 7);
-            bool valid = ph < Hp && pw < Wp;
-            size_t ob = (((size_t)n * Hp + (valid ? ph : 0)) * Wp + (valid ? pw : 0)) * 32 + c;
-            gs[i] = valid ? dy[ob] : 0.f;
-            cs[i] = valid ? argmax[ob] : 0;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int p = 0; p < 64; ++p) {
-            const float g = gs[p * 32 + o];
-            const int cell = cs[p * 32 + o];
-            const int base = ((p >> 3) * 2 + (cell >> 1)) * SP + (p & 7) * 2 + (cell & 1);
+        const int ph = ty0 * 8 + wq;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (toff[j] >= 0) acc[j] = fmaf(g, patch[base + toff[j]], acc[j]);
-            accb += g;
+        for (int j = 0; j < 8; ++j) {
+            const int pw = tx0 * 8 + j;
+            const bool valid = ph < Hp && pw < Wp;
+            const size_t ob = (((size_t)n * Hp + (valid ? ph : 0)) * Wp + (valid ? pw : 0)) * 32 + o;
+            gn[j] = valid ? dy[ob] : 0.f;
+            cn[j] = valid ? argmax[ob] : 0;
         }
+    };
+    if ((int)blockIdx.x < tiles) {
+        const int t = blockIdx.x;
+        stem_fetch_bwd(pf, x, t / (tilesY * tilesX), (t % (tilesY * tilesX)) / tilesX, t % tilesX, H, W);
+        stem_put_bwd(patch[0], pf);
+        fetch(t);
+    }
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            g[j] = gn[j];
+            base[j] = (wq * 2 + (cn[j] >> 1)) * SP + j * 2 + (cn[j] & 1);
+        }
+        __syncthreads();            // patch[buf] complete; everybody is done with patch[buf ^ 1]
+        const int t2 = tile + gridDim.x;
+        if (t2 < tiles) {
+            stem_fetch_bwd(pf, x, t2 / (tilesY * tilesX), (t2 % (tilesY * tilesX)) / tilesX, t2 % tilesX, H, W);
+            fetch(t2);
+        }
+        const float *pb = patch[buf];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float *pp = pb + base[j];
+#pragma unroll
+            for (int t = 0; t < 25; ++t) acc[t] = fmaf(g[j], pp[(t / 5) * SP + (t % 5)], acc[t]);
+            accb += g[j];
+        }
+        if (t2 < tiles) stem_put_bwd(patch[buf ^ 1], pf);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (toff[j] >= 0) atomicAdd(&dw[(tg + 8 * j) * 32 + o], acc[j]);
-    if (tg == 0) atomicAdd(&db[o], accb);
+    for (int t = 0; t < 25; ++t) red[wq][t][o] = acc[t];
+    red[wq][25][o] = accb;
+    __syncthreads();
+    for (int i = tid; i < 26 * 32; i += 256) {
+        const int t = i >> 5, oo = i & 31;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][t][oo];
+        if (t < 25) atomicAdd(&dw[t * 32 + oo], s); else atomicAdd(&db[oo], s);
+    }
 }
 
 int make_dims(CPDims &d, int N, int H, int W, int Cin, int Cout, int k, int pad, int pool) {
@@ -393,7 +476,8 @@ extern "C" int dpp_convpool_fwd(const float *x, const float *w, const float *bia
     DPP_CUDA(cudaFuncSetAttribute(k_convpool_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int tiles = N * d.tilesY * d.tilesX;
     if (k == 5 && pool == 2 && Cin == 1 && Cout == 32 && pad == 2 && !relu && H % 2 == 0 && W % 2 == 0) {
-        int g2 = tiles < 148 * 4 ? tiles : 148 * 4;
+        const int t2 = N * ((d.Hp + 7) / 8) * ((d.Wp + 15) / 16);     // 8 x 16 pooled regions
+        const int g2 = t2 < 148 * 2 ? t2 : 148 * 2;
         k_stem_fwd<<<g2, 256, 0, S(stream)>>>(x, w, bias, y, argmax, stats, N, H, W);
         DPP_LAUNCH_CHECK();
         return DPP_OK;

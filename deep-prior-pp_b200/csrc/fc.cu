@@ -111,20 +111,31 @@ __global__ void k_fc_epilogue(float *__restrict__ y, const float *__restrict__ b
 }
 
 // dpre = dy * mask * scale * [y > 0]; db[n] += sum_b dpre
-__global__ void k_fc_bwd_pre(const float *__restrict__ y, const float *__restrict__ dy, const float *__restrict__ mask,
-                             float scale, int relu, float *__restrict__ dpre, float *__restrict__ db, int B, int n_out) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_out) return;
+// block = 32 output columns x 16 row groups (coalesced 128-byte rows); the row groups meet in shared memory
+__global__ void __launch_bounds__(512)
+k_fc_bwd_pre(const float *__restrict__ y, const float *__restrict__ dy, const float *__restrict__ mask,
+             float scale, int relu, float *__restrict__ dpre, float *__restrict__ db, int B, int n_out) {
+    __shared__ float s_part[16][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) {
-        size_t i = (size_t)b * n_out + n;
-        float g = dy[i] * scale;
-        if (mask) g *= mask[i];
-        if (relu && !(y[i] > 0.f)) g = 0.f;
-        dpre[i] = g;
-        s += g;
+    if (n < n_out)
+        for (int b = ty; b < B; b += 16) {
+            size_t i = (size_t)b * n_out + n;
+            float g = dy[i] * scale;
+            if (mask) g *= mask[i];
+            if (relu && !(y[i] > 0.f)) g = 0.f;
+            dpre[i] = g;
+            s += g;
+        }
+    s_part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < n_out) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t += s_part[j][tx];
+        db[n] += t;
     }
-    db[n] += s;
 }
 
 }  // namespace
@@ -146,7 +157,7 @@ extern "C" int dpp_fc_bwd(const float *x, const float *w, const float *y, const 
                           float *dx, float *scratch, int B, int n_in, int n_out, int relu, const float *mask,
                           float scale_out, int precision, void *stream) {
     DPP_CHECK_ARG(x && w && y && dy && dw && db && scratch && B > 0);
-    k_fc_bwd_pre<<<cdiv(n_out, 128), 128, 0, S(stream)>>>(y, dy, mask, scale_out, relu, scratch, db, B, n_out);
+    k_fc_bwd_pre<<<cdiv(n_out, 32), 512, 0, S(stream)>>>(y, dy, mask, scale_out, relu, scratch, db, B, n_out);
     DPP_LAUNCH_CHECK();
     // dW[n_in][n_out] += x^T dpre : A(m=i,k=b) = x[b*n_in + i]
     run_gemm(x, scratch, dw, n_in, n_out, B, 1, n_in, n_out, 1, S(stream), precision);

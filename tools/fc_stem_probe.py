@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Kernel probe (development tool, GPU only): times the ResNet stem (dpp_convpool_fwd / _bwd, 5x5 1->32 + pool 2)
+and the HiddenLayer entry points (dpp_fc_fwd / dpp_fc_bwd) at the benchmarked batch-128 shapes, CUDA events over
+20 back-to-back calls with a 256 MB L2 flush write between rounds."""
+import ctypes as C
+import os
+import sys
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'deep-prior-pp_b200'))
+from dpp_b200.lib import lib  # noqa: E402
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def timed(fn, reps=20, rounds=3):
+    flush = torch.empty(64 * 1024 * 1024, device='cuda')
+    best = 1e9
+    for _ in range(rounds):
+        flush.fill_(1.0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+    return best
+
+
+def main():
+    B = int(os.environ.get('PROBE_B', '128'))
+    precision = int(os.environ.get('DPP_PRECISION', '1'))
+    g = torch.Generator(device='cuda').manual_seed(1)
+    # ---- stem
+    x = torch.randn(B, 128, 128, 1, device='cuda', generator=g)
+    w = torch.randn(25, 32, device='cuda', generator=g) * 0.2
+    b = torch.randn(32, device='cuda', generator=g) * 0.1
+    y = torch.zeros(B, 64, 64, 32, device='cuda')
+    am = torch.zeros(B, 64, 64, 32, dtype=torch.uint8, device='cuda')
+    stats = torch.zeros(64, dtype=torch.float64, device='cuda')
+    dy = torch.randn(B, 64, 64, 32, device='cuda', generator=g)
+    dw = torch.zeros(25, 32, device='cuda')
+    db = torch.zeros(32, device='cuda')
+    t = timed(lambda: lib.dpp_convpool_fwd(P(x), P(w), P(b), P(y), P(am), P(stats), B, 128, 128, 1, 32, 5, 2, 2, 0, None))
+    print("stem fwd   %7.1f us  (%.1f TFLOP/s fp32)" % (t, 2.0 * B * 128 * 128 * 25 * 32 / t * 1e-6))
+    t = timed(lambda: lib.dpp_convpool_bwd(P(x), P(w), P(y), P(am), P(dy), P(dw), P(db), None, B, 128, 128, 1, 32, 5, 2, 2, 0, None))
+    print("stem bwd_w %7.1f us" % t)
+    # ---- FC layers of the ResNet
+    for (n_in, n_out, relu) in ((16384, 1024, 1), (1024, 1024, 1), (1024, 30, 0)):
+        xx = torch.randn(B, n_in, device='cuda', generator=g)
+        ww = torch.randn(n_in, n_out, device='cuda', generator=g) * (1.0 / n_in) ** 0.5
+        bb = torch.randn(n_out, device='cuda', generator=g) * 0.1
+        yy = torch.zeros(B, n_out, device='cuda')
+        go = torch.randn(B, n_out, device='cuda', generator=g)
+        dww = torch.zeros(n_in, n_out, device='cuda')
+        dbb = torch.zeros(n_out, device='cuda')
+        dxx = torch.zeros(B, n_in, device='cuda')
+        scratch = torch.zeros(B, n_out, device='cuda')
+        tf = timed(lambda: lib.dpp_fc_fwd(P(xx), P(ww), P(bb), P(yy), B, n_in, n_out, relu, None, 1.0, precision, None))
+        tb = timed(lambda: lib.dpp_fc_bwd(P(xx), P(ww), P(yy), P(go), P(dww), P(dbb), P(dxx), P(scratch), B, n_in, n_out, relu,
+                                          None, 1.0, precision, None))
+        mb = n_in * n_out * 4e-6
+        print("fc %5d -> %4d: fwd %7.1f us (%.0f GB/s of weights)   bwd (pre + dW + dx) %7.1f us (%.0f GB/s over 2 weight-sized streams)"
+              % (n_in, n_out, tf, mb / tf * 1e3, tb, 2 * mb / tb * 1e3))
+
+
+if __name__ == '__main__':
+    main()
