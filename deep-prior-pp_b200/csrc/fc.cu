@@ -8,6 +8,12 @@ using namespace dpp;
 
 int dpp_gemm_tc(const float *A, const float *B, float *C, int M, int N, int K, int64_t lda, int64_t ldb, int a_trans,
                 int b_trans, int precision, void *stream);
+namespace dpp {
+// fc_stream.cu: TMA-fed streaming 3xTF32 GEMM, C[n*ldc + m] (+)= sum_k A(m,k) B(n,k); DPP_ENOTSUP when the layout rules it out
+struct FcEpilogue { const float *bias; const float *mask; float scale; int relu; };
+int fc_stream_gemm(const float *A, int a_mn, int64_t lda, const float *B, int b_mn, int64_t ldb, float *C, int64_t ldc, int M,
+                   int N, int K, int add, const FcEpilogue *epi, int *epi_done, cudaStream_t st);
+}
 
 namespace {
 
@@ -143,30 +149,60 @@ k_fc_bwd_pre(const float *__restrict__ y, const float *__restrict__ dy, const fl
 extern "C" int dpp_fc_fwd(const float *x, const float *w, const float *bias, float *y, int B, int n_in, int n_out,
                           int relu, const float *mask, float scale_out, int precision, void *stream) {
     DPP_CHECK_ARG(x && w && bias && y && B > 0 && n_in > 0 && n_out > 0);
-    DPP_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)B * n_out, S(stream)));
-    run_gemm(x, w, y, B, n_out, n_in, n_in, 1, n_out, 1, S(stream), precision);
+    // y[b][o] = sum_i W[i][o] x[b][i]: lanes = output units, columns = samples
+    const FcEpilogue epi{bias, mask, scale_out, relu};
+    int epi_done = 0;
+    int rc = precision == 1 ? fc_stream_gemm(w, 1, n_out, x, 0, n_in, y, n_out, n_out, B, n_in, 0, &epi, &epi_done, S(stream)) : DPP_ENOTSUP;
+    if (rc == DPP_ENOTSUP) {
+        DPP_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)B * n_out, S(stream)));
+        run_gemm(x, w, y, B, n_out, n_in, n_in, 1, n_out, 1, S(stream), precision);
+    } else if (rc != DPP_OK) {
+        return dpp::fail(rc, "%s: streaming GEMM launch failed", __func__);
+    }
     DPP_LAUNCH_CHECK();
-    int64_t total = (int64_t)B * n_out;
-    int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    k_fc_epilogue<<<blocks, 256, 0, S(stream)>>>(y, bias, mask, scale_out, relu, total, n_out);
+    if (!epi_done) {        // (the streaming GEMM's split reduction applies bias / activation / mask itself)
+        int64_t total = (int64_t)B * n_out;
+        int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+        k_fc_epilogue<<<blocks, 256, 0, S(stream)>>>(y, bias, mask, scale_out, relu, total, n_out);
+        DPP_LAUNCH_CHECK();
+    }
+    return DPP_OK;
+}
+
+extern "C" int dpp_fc_bwd_ex(const float *x, const float *w, const float *y, const float *dy, float *dw, float *db,
+                             float *dx, float *scratch, int B, int n_in, int n_out, int relu, const float *mask,
+                             float scale_out, int precision, int flags, void *stream) {
+    DPP_CHECK_ARG(x && w && y && dy && dw && db && scratch && B > 0);
+    const int assign = (flags & DPP_FC_DW_ASSIGN) ? 1 : 0;
+    k_fc_bwd_pre<<<cdiv(n_out, 32), 512, 0, S(stream)>>>(y, dy, mask, scale_out, relu, scratch, db, B, n_out);
     DPP_LAUNCH_CHECK();
+    // dW[i][o] (+)= sum_b x[b][i] dpre[b][o]: lanes = output units, columns = input units, reduction over the samples
+    int rc = precision == 1 ? fc_stream_gemm(scratch, 1, n_out, x, 1, n_in, dw, n_out, n_out, n_in, B, !assign, nullptr, nullptr, S(stream))
+                            : DPP_ENOTSUP;
+    if (rc == DPP_ENOTSUP) {
+        if (assign) DPP_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)n_in * n_out, S(stream)));
+        run_gemm(x, scratch, dw, n_in, n_out, B, 1, n_in, n_out, 1, S(stream), precision);
+    } else if (rc != DPP_OK) {
+        return dpp::fail(rc, "%s: streaming GEMM (dW) launch failed", __func__);
+    }
+    DPP_LAUNCH_CHECK();
+    if (dx) {
+        // dx[b][i] = sum_o W[i][o] dpre[b][o]: lanes = input units, columns = samples
+        rc = precision == 1 ? fc_stream_gemm(w, 0, n_out, scratch, 0, n_out, dx, n_in, n_in, B, n_out, 0, nullptr, nullptr, S(stream))
+                            : DPP_ENOTSUP;
+        if (rc == DPP_ENOTSUP) {
+            DPP_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * n_in, S(stream)));
+            run_gemm(scratch, w, dx, B, n_in, n_out, n_out, 1, 1, n_out, S(stream), precision);
+        } else if (rc != DPP_OK) {
+            return dpp::fail(rc, "%s: streaming GEMM (dx) launch failed", __func__);
+        }
+        DPP_LAUNCH_CHECK();
+    }
     return DPP_OK;
 }
 
 extern "C" int dpp_fc_bwd(const float *x, const float *w, const float *y, const float *dy, float *dw, float *db,
                           float *dx, float *scratch, int B, int n_in, int n_out, int relu, const float *mask,
                           float scale_out, int precision, void *stream) {
-    DPP_CHECK_ARG(x && w && y && dy && dw && db && scratch && B > 0);
-    k_fc_bwd_pre<<<cdiv(n_out, 32), 512, 0, S(stream)>>>(y, dy, mask, scale_out, relu, scratch, db, B, n_out);
-    DPP_LAUNCH_CHECK();
-    // dW[n_in][n_out] += x^T dpre : A(m=i,k=b) = x[b*n_in + i]
-    run_gemm(x, scratch, dw, n_in, n_out, B, 1, n_in, n_out, 1, S(stream), precision);
-    DPP_LAUNCH_CHECK();
-    if (dx) {
-        DPP_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * n_in, S(stream)));
-        // dx[B][n_in] = dpre W^T : B(k=o, n=i) = w[i*n_out + o]
-        run_gemm(scratch, w, dx, B, n_in, n_out, n_out, 1, 1, n_out, S(stream), precision);
-        DPP_LAUNCH_CHECK();
-    }
-    return DPP_OK;
+    return dpp_fc_bwd_ex(x, w, y, dy, dw, db, dx, scratch, B, n_in, n_out, relu, mask, scale_out, precision, 0, stream);
 }

@@ -109,6 +109,9 @@ _SIGS = {
     'dpp_fc_fwd': (C.c_int, [P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_float, C.c_int, P]),
     'dpp_fc_bwd': (C.c_int, [P, P, P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_float,
                              C.c_int, P]),
+    'dpp_fc_bwd_ex': (C.c_int, [P, P, P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_float,
+                                C.c_int, C.c_int, P]),
+    'dpp_fc_workspace_init': (C.c_int, []),
     'dpp_loss_sqerr': (C.c_int, [P, P, P, P, C.c_int, C.c_int, P]),
     'dpp_adam_step': (C.c_int, [P, P, P, P, P, C.c_int64, P]),
     'dpp_adam_tick': (C.c_int, [P, P]),

@@ -319,6 +319,17 @@ int dpp_fc_fwd(const float *x, const float *w, const float *bias, float *y, int 
 int dpp_fc_bwd(const float *x, const float *w, const float *y, const float *dy, float *dw,
                float *db, float *dx, float *scratch, int B, int n_in, int n_out, int relu,
                const float *mask, float scale_out, int precision, void *stream);
+/* Same with flags.  DPP_FC_DW_ASSIGN: dW = x^T dpre (plain stores: one 67 MB write for the ResNet's first HiddenLayer
+ * instead of a read-modify-write; the caller need not zero dw) - T.grad of a weight used once is an assignment
+ * (trainer/poseregnettrainer.py:110-111).  db is accumulated either way.                                        */
+#define DPP_FC_DW_ASSIGN 1
+int dpp_fc_bwd_ex(const float *x, const float *w, const float *y, const float *dy, float *dw,
+                  float *db, float *dx, float *scratch, int B, int n_in, int n_out, int relu,
+                  const float *mask, float scale_out, int precision, int flags, void *stream);
+/* Allocates the library-owned workspace of the k-split HiddenLayer GEMMs (9.7 MB, idempotent).  Call once outside
+ * CUDA-graph capture (an uncaptured dpp_fc_fwd / dpp_fc_bwd allocates it lazily; a captured one without it reduces
+ * with red.global.add instead).                                                                                 */
+int dpp_fc_workspace_init(void);
 
 /* ---- cost (trainer/poseregnettrainer.py:84-99) ----------------------------------------
  * out, target [B, D]; cost = mean_b sum_d (out-target)^2 (numJoints==1 branch) written to

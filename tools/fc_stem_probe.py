@@ -69,5 +69,60 @@ def main():
               % (n_in, n_out, tf, mb / tf * 1e3, tb, 2 * mb / tb * 1e3))
 
 
+TAGS = {1: 'entry', 2: 'setup done', 3: 'role done', 10: 'T slot free', 20: 'landed', 21: 'stage free', 22: 'stored + arrived',
+        40: 'M acc free', 41: 'M A full', 42: 'M B full', 43: 'M committed', 50: 'E acc full', 51: 'E done'}
+
+
+def timeline_fs(B, n_in, n_out, which, maxev=120):
+    """in-kernel timeline of CTA 0 of one k_fc_stream launch (prof build: make -C deep-prior-pp_b200/csrc prof)"""
+    try:
+        setp = lib.raw('dpp_debug_set_prof_fs')
+    except Exception:
+        print("(no dpp_debug_set_prof_fs in this build)")
+        return
+    setp.restype = C.c_int
+    setp.argtypes = [C.c_void_p]
+    g = torch.Generator(device='cuda').manual_seed(1)
+    xx = torch.randn(B, n_in, device='cuda', generator=g)
+    ww = torch.randn(n_in, n_out, device='cuda', generator=g)
+    bb = torch.zeros(n_out, device='cuda')
+    yy = torch.zeros(B, n_out, device='cuda')
+    go = torch.randn(B, n_out, device='cuda', generator=g)
+    dww = torch.zeros(n_in, n_out, device='cuda')
+    dbb = torch.zeros(n_out, device='cuda')
+    dxx = torch.zeros(B, n_in, device='cuda')
+    scratch = torch.zeros(B, n_out, device='cuda')
+    prof = torch.zeros(5000, dtype=torch.int64, device='cuda')
+    for _ in range(2):      # second run: warm instruction cache
+        prof.zero_()
+        torch.cuda.synchronize()
+        if which == 'fwd':
+            setp(prof.data_ptr())
+            lib.dpp_fc_fwd(P(xx), P(ww), P(bb), P(yy), B, n_in, n_out, 1, None, 1.0, 1, None)
+        else:
+            setp(prof.data_ptr())
+            lib.dpp_fc_bwd(P(xx), P(ww), P(yy), P(go), P(dww), P(dbb), P(dxx) if which == 'dx' else None, P(scratch), B, n_in, n_out, 1,
+                           None, 1.0, 1, None)
+        torch.cuda.synchronize()
+    setp(None)
+    pr = prof.cpu().numpy()
+    ev = []
+    for base, role in ((0, 'A'), (1000, 'B'), (2000, 'M'), (3000, 'E'), (4000, 'T')):
+        i = base
+        while i < base + 990 and pr[i] != 0:
+            ev.append((int(pr[i + 1]), role, int(pr[i])))
+            i += 2
+    ev.sort()
+    print("== timeline %s %d x %d -> %d (CTA 0; with dx the buffer holds the LAST launch = dx)" % (which, B, n_in, n_out))
+    t0 = ev[0][0]
+    for t, role, tag in ev[:maxev]:
+        print("  %7d  %s  %s" % (t - t0, role, TAGS.get(tag, tag)))
+    print("  ... %d events, last at %d" % (len(ev), ev[-1][0] - t0))
+
+
 if __name__ == '__main__':
+    if os.environ.get('PROBE_TIMELINE', '0') == '1':
+        for which in os.environ.get('PROBE_WHICH', 'fwd,dw,dx').split(','):
+            timeline_fs(128, 16384, 1024, which, int(os.environ.get('PROBE_EVENTS', '120')))
+        sys.exit(0)
     main()
