@@ -147,13 +147,17 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
             const Unit un = decode_unit(a, u);
             for (int c = un.c_begin; c < un.c_end; ++c, ++g) {
                 const uint32_t slot = g % NL, lph = (g / NL) & 1, stage = g & 1, sph = (g >> 1) & 1;
-                if (lane == 0) mbar_wait(bar(LF + slot), lph);
+                if (lane == 0) mbar_wait_hint(bar(LF + slot), lph);
                 __syncwarp();
                 PROF(20);
                 const unsigned char *tile = smem + slot * SLOT_BYTES + (isA ? 0 : 16384);
                 float v[32];
                 if (isA || b_live) read_row(tile, mn, row, v);
-                if (lane == 0) mbar_wait(bar(SE + stage), sph ^ 1);     // the MMAs that read this stage have retired
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(LE + slot));        // the row is in registers: the landing slot can be refilled
+                    mbar_wait_hint(bar(SE + stage), sph ^ 1);     // the MMAs that read this stage have retired
+                }
                 __syncwarp();
                 PROF(21);
                 if (isA) {
@@ -173,7 +177,7 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(bar(AF + stage)); mbar_arrive(bar(LE + slot)); }
+                    if (lane == 0) mbar_arrive(bar(AF + stage));
                     PROF(22);
                 } else {
                     unsigned char *bt_tile = smem + BT_OFF + stage * 32768;
@@ -191,7 +195,7 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(bar(BF + stage)); mbar_arrive(bar(LE + slot)); }
+                    if (lane == 0) mbar_arrive(bar(BF + stage));
                     PROF(22);
                 }
             }
@@ -205,11 +209,16 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
                 const Unit un = decode_unit(a, u);
                 for (int c = un.c_begin; c < un.c_end; ++c, ++g) {
                     const uint32_t slot = g % NL, lph = (g / NL) & 1;
-                    mbar_wait(bar(LE + slot), lph ^ 1);
+                    mbar_wait_hint(bar(LE + slot), lph ^ 1);
                     PROF(10);
                     mbar_expect_tx(bar(LF + slot), SLOT_BYTES);
                     const uint32_t dst = sbase + slot * SLOT_BYTES;
-                    const int k0 = c * 32;
+                    // every CTA walks its k-range from a different starting chunk: CTAs running in lock step would
+                    // otherwise all touch the same offset inside the (4 KB-strided) matrix rows at the same time
+                    const int nch = un.c_end - un.c_begin;
+                    int cr = c + (u * 5) % nch;
+                    if (cr >= un.c_end) cr -= nch;
+                    const int k0 = cr * 32;
                     if (a.a_mn) tma_load_2d(dst, tmA, un.m0, k0, bar(LF + slot)); else tma_load_2d(dst, tmA, k0, un.m0, bar(LF + slot));
                     if (a.b_mn) tma_load_2d(dst + 16384, tmB, un.n0, k0, bar(LF + slot)); else tma_load_2d(dst + 16384, tmB, k0, un.n0, bar(LF + slot));
                 }
@@ -224,15 +233,15 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
             for (int u = blockIdx.x; u < a.units; u += gstride, ++j) {
                 const Unit un = decode_unit(a, u);
                 const uint32_t acc = j & 1, aph = (j >> 1) & 1;
-                mbar_wait(bar(CE + acc), aph ^ 1);
+                mbar_wait_hint(bar(CE + acc), aph ^ 1);
                 tc_fence_after();
                 PROF(40);
                 const uint32_t d_tmem = tmem_base + acc * 128;
                 for (int c = un.c_begin; c < un.c_end; ++c, ++g) {
                     const uint32_t stage = g & 1, sph = (g >> 1) & 1;
-                    mbar_wait(bar(AF + stage), sph);
+                    mbar_wait_hint(bar(AF + stage), sph);
                     PROF(41);
-                    mbar_wait(bar(BF + stage), sph);
+                    mbar_wait_hint(bar(BF + stage), sph);
                     tc_fence_after();
                     PROF(42);
                     const uint32_t ta = tmem_base + A_COL0 + stage * 64;
@@ -259,33 +268,52 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
         for (int u = blockIdx.x; u < a.units; u += gstride, ++j) {
             const Unit un = decode_unit(a, u);
             const uint32_t acc = j & 1, aph = (j >> 1) & 1;
-            if (lane == 0) mbar_wait_relaxed(bar(CF + acc), aph);
+            if (lane == 0) mbar_wait_hint(bar(CF + acc), aph);
             __syncwarp();
             tc_fence_after();
             PROF(50);
             const int m = un.m0 + q * 32 + lane;
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
+            const int rot = ((u * 3) % (a.bt >> 4)) << 4;        // ... and its output columns from a different one
             if (a.ws != nullptr) {
                 float *dst = a.ws + (size_t)u * 16384 + q * 32 + lane;
-                for (int cb = 0; cb < a.bt; cb += 16) {
+                for (int cb0 = 0; cb0 < a.bt; cb0 += 16) {
+                    const int cb = cb0 + rot < a.bt ? cb0 + rot : cb0 + rot - a.bt;
                     float v[16];
                     tmem_ld16(t0 + cb, v);
+                    PROF(52);
 #pragma unroll
                     for (int t = 0; t < 16; ++t) dst[(cb + t) * 128] = v[t];
+                    PROF(53);
                 }
             } else {
-                for (int cb = 0; cb < a.bt; cb += 16) {
+                // interior tiles (the common case) take a branch-free path: 16 independent row stores per TMEM load
+                const bool full = un.n0 + a.bt <= a.N;
+                const bool red = a.use_red != 0;
+                const size_t ldc = (size_t)a.ldc;
+                for (int cb0 = 0; cb0 < a.bt; cb0 += 16) {
+                    const int cb = cb0 + rot < a.bt ? cb0 + rot : cb0 + rot - a.bt;
                     float v[16];
                     tmem_ld16(t0 + cb, v);
+                    PROF(52);
                     if (m < a.M) {
-                        float *dst = a.C + (size_t)(un.n0 + cb) * a.ldc + m;
+                        float *dst = a.C + (size_t)(un.n0 + cb) * ldc + m;
+                        if (full && !red) {
 #pragma unroll
-                        for (int t = 0; t < 16; ++t)
-                            if (un.n0 + cb + t < a.N) {
-                                if (a.use_red) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)t * a.ldc), "f"(v[t]) : "memory");
-                                else dst[(size_t)t * a.ldc] = v[t];
-                            }
+                            for (int t = 0; t < 16; ++t) dst[t * ldc] = v[t];
+                        } else if (full) {
+#pragma unroll
+                            for (int t = 0; t < 16; ++t) atomicAdd(dst + t * ldc, v[t]);
+                        } else {
+                            const int nleft = a.N - (un.n0 + cb);
+#pragma unroll
+                            for (int t = 0; t < 16; ++t)
+                                if (t < nleft) {
+                                    if (red) atomicAdd(dst + t * ldc, v[t]); else dst[t * ldc] = v[t];
+                                }
+                        }
                     }
+                    PROF(53);
                 }
             }
             tc_fence_before();

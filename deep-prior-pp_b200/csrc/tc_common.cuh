@@ -32,6 +32,21 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try(bar, parity)) {}
 }
+// wait with an explicit suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint, in ns,
+// expires) instead of re-issuing try_wait - every poll is a shared-memory operation that competes with the loads /
+// stores of the warps that do have work
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns = 20000u) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
 // relaxed wait for the non-critical roles (epilogue, weight loader): back off between polls so the
 // spinning warp does not steal issue slots from the producers on the same scheduler
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {

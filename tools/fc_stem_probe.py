@@ -17,7 +17,20 @@ def P(t):
 
 
 def timed(fn, reps=20, rounds=3):
+    """us per call; PROBE_COLD=1: a 256 MB write before EVERY call (weights come from HBM, as inside a training step)"""
     flush = torch.empty(64 * 1024 * 1024, device='cuda')
+    if os.environ.get('PROBE_COLD', '0') == '1':
+        tot = []
+        for _ in range(reps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot.append(e0.elapsed_time(e1) * 1e3)
+        tot.sort()
+        return tot[len(tot) // 2]
     best = 1e9
     for _ in range(rounds):
         flush.fill_(1.0)
@@ -62,15 +75,17 @@ def main():
         dxx = torch.zeros(B, n_in, device='cuda')
         scratch = torch.zeros(B, n_out, device='cuda')
         tf = timed(lambda: lib.dpp_fc_fwd(P(xx), P(ww), P(bb), P(yy), B, n_in, n_out, relu, None, 1.0, precision, None))
-        tb = timed(lambda: lib.dpp_fc_bwd(P(xx), P(ww), P(yy), P(go), P(dww), P(dbb), P(dxx), P(scratch), B, n_in, n_out, relu,
-                                          None, 1.0, precision, None))
+        tb = timed(lambda: lib.dpp_fc_bwd_ex(P(xx), P(ww), P(yy), P(go), P(dww), P(dbb), P(dxx), P(scratch), B, n_in, n_out, relu,
+                                             None, 1.0, precision, 1, None))
+        tw = timed(lambda: lib.dpp_fc_bwd_ex(P(xx), P(ww), P(yy), P(go), P(dww), P(dbb), None, P(scratch), B, n_in, n_out, relu,
+                                             None, 1.0, precision, 1, None))
         mb = n_in * n_out * 4e-6
         print("fc %5d -> %4d: fwd %7.1f us (%.0f GB/s of weights)   bwd (pre + dW + dx) %7.1f us (%.0f GB/s over 2 weight-sized streams)"
-              % (n_in, n_out, tf, mb / tf * 1e3, tb, 2 * mb / tb * 1e3))
+              "   pre + dW %7.1f us" % (n_in, n_out, tf, mb / tf * 1e3, tb, 2 * mb / tb * 1e3, tw))
 
 
 TAGS = {1: 'entry', 2: 'setup done', 3: 'role done', 10: 'T slot free', 20: 'landed', 21: 'stage free', 22: 'stored + arrived',
-        40: 'M acc free', 41: 'M A full', 42: 'M B full', 43: 'M committed', 50: 'E acc full', 51: 'E done'}
+        52: 'E ld16 done', 53: 'E 16 stores issued', 40: 'M acc free', 41: 'M A full', 42: 'M B full', 43: 'M committed', 50: 'E acc full', 51: 'E done'}
 
 
 def timeline_fs(B, n_in, n_out, which, maxev=120):
@@ -101,8 +116,8 @@ def timeline_fs(B, n_in, n_out, which, maxev=120):
             lib.dpp_fc_fwd(P(xx), P(ww), P(bb), P(yy), B, n_in, n_out, 1, None, 1.0, 1, None)
         else:
             setp(prof.data_ptr())
-            lib.dpp_fc_bwd(P(xx), P(ww), P(yy), P(go), P(dww), P(dbb), P(dxx) if which == 'dx' else None, P(scratch), B, n_in, n_out, 1,
-                           None, 1.0, 1, None)
+            lib.dpp_fc_bwd_ex(P(xx), P(ww), P(yy), P(go), P(dww), P(dbb), P(dxx) if which == 'dx' else None, P(scratch), B, n_in,
+                              n_out, 1, None, 1.0, 1, 1, None)
         torch.cuda.synchronize()
     setp(None)
     pr = prof.cpu().numpy()
@@ -115,6 +130,9 @@ def timeline_fs(B, n_in, n_out, which, maxev=120):
     ev.sort()
     print("== timeline %s %d x %d -> %d (CTA 0; with dx the buffer holds the LAST launch = dx)" % (which, B, n_in, n_out))
     t0 = ev[0][0]
+    only = os.environ.get('PROBE_ROLES')
+    if only:
+        ev = [e for e in ev if e[1] in only]
     for t, role, tag in ev[:maxev]:
         print("  %7d  %s  %s" % (t - t0, role, TAGS.get(tag, tag)))
     print("  ... %d events, last at %d" % (len(ev), ev[-1][0] - t0))
