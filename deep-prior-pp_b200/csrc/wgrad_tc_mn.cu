@@ -639,6 +639,22 @@ extern "C" int dpp_debug_set_prof_wg(void *buf) {
 #endif
 
 // ---- grouped backward-weights ------------------------------------------------------------------------------------------
+namespace dpp {
+// wgrad_simt3.cu: the 3x3 Cin = Cout = 16 / 32 layers run as an fp32 FMA kernel (faster than tcgen05 at N = 16 / 32)
+struct W3Layer {
+    const float *x; const float *dy; float *dw; float *db;
+    dpp_bn_ref in_bn; int has_in_bn;
+    int N, H, W, C;
+    int rblocks, item0;
+    unsigned wp_magic, w_magic;
+};
+bool wgrad3_supported(const dpp_conv_desc *d);
+int wgrad3_create(const std::vector<W3Layer> &layers, void **handle_out);
+int wgrad3_launches(void *handle);
+int wgrad3_run(void *handle, cudaStream_t st);
+void wgrad3_destroy(void *handle);
+}
+
 namespace {
 
 struct WGroupLaunch { int bn; WGroupArgs args; int grid; };
@@ -646,6 +662,7 @@ struct WGroup {
     std::vector<WGroupLaunch> launches;
     std::vector<void *> allocs;
     int passes;
+    void *w3 = nullptr;       // handle of the fp32 3x3 launches (wgrad_simt3.cu)
 };
 
 // A layer whose last m-tile holds at most 32 rows (K = 144 -> 128 + 16, K = 288 -> 256 + 32) does not get a pass over all
@@ -680,13 +697,30 @@ extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layer
     }
     WGroup *grp = new WGroup();
     grp->passes = layers[0].d.precision == 1 ? 2 : 1;
+    {
+        std::vector<dpp::W3Layer> l3;
+        for (int i = 0; i < n_layers; ++i)
+            if (dpp::wgrad3_supported(&layers[i].d)) {
+                dpp::W3Layer w;
+                memset(&w, 0, sizeof(w));
+                w.x = layers[i].x; w.dy = layers[i].dy; w.dw = layers[i].dw; w.db = layers[i].db;
+                w.has_in_bn = layers[i].has_in_bn;
+                if (w.has_in_bn) w.in_bn = layers[i].in_bn;
+                w.N = layers[i].d.N; w.H = layers[i].d.H; w.W = layers[i].d.W; w.C = layers[i].d.Cin;
+                l3.push_back(w);
+            }
+        if (!l3.empty() && dpp::wgrad3_create(l3, &grp->w3) != 0) {
+            delete grp;
+            return dpp::fail(DPP_ECUDA, "%s: set-up of the fp32 3x3 launches failed", __func__);
+        }
+    }
     const int widths[4] = {16, 32, 64, 128};
     for (int wi = 0; wi < 4; ++wi) {
         const int bn = widths[wi];
         std::vector<WArgs> la;
         for (int i = 0; i < n_layers; ++i) {
             const int lbn = layers[i].d.Cout > 128 ? 128 : layers[i].d.Cout;
-            if (lbn != bn) continue;
+            if (lbn != bn || dpp::wgrad3_supported(&layers[i].d)) continue;
             WArgs a;
             fill_args(a, &layers[i].d, layers[i].x, layers[i].has_in_bn ? &layers[i].in_bn : nullptr, layers[i].dy, layers[i].dw,
                       layers[i].db);
@@ -756,6 +790,7 @@ extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layer
 extern "C" int dpp_wgrad_group_run(void *handle, void *stream) {
     DPP_CHECK_ARG(handle);
     WGroup *grp = reinterpret_cast<WGroup *>(handle);
+    if (grp->w3 != nullptr && dpp::wgrad3_run(grp->w3, S(stream)) != 0) return dpp::fail(DPP_ECUDA, "%s: fp32 3x3 launch failed", __func__);
     for (const WGroupLaunch &l : grp->launches) {
         int rc = -1;
         const bool p3 = grp->passes == 2;
@@ -770,13 +805,16 @@ extern "C" int dpp_wgrad_group_run(void *handle, void *stream) {
 }
 
 extern "C" int dpp_wgrad_group_launches(void *handle) {
-    return handle ? (int)reinterpret_cast<WGroup *>(handle)->launches.size() : 0;
+    if (!handle) return 0;
+    WGroup *grp = reinterpret_cast<WGroup *>(handle);
+    return (int)grp->launches.size() + (grp->w3 ? dpp::wgrad3_launches(grp->w3) : 0);
 }
 
 extern "C" int dpp_wgrad_group_destroy(void *handle) {
     if (handle) {
         WGroup *grp = reinterpret_cast<WGroup *>(handle);
         for (void *p : grp->allocs) cudaFree(p);
+        if (grp->w3) dpp::wgrad3_destroy(grp->w3);
         delete grp;
     }
     return DPP_OK;

@@ -248,3 +248,53 @@ def test_bench_shapes_vs_torch_fp64(shape, precision, tol):
     assert e_y < tol and e_dz < tol
     assert e_s < 1e-5 and e_dzs < 1e-4        # fp32 tile partials summed in fp64
     assert e_dw < 5e-5 and e_db < 1e-5        # reduction over up to 5e5 pixels in fp32 partials
+
+
+GROUP_SHAPES = [  # the grouped launches: fp32 3x3 kernel (C = 16 / 32) next to the tcgen05 groups
+    (128, 32, 16, 16, 3, 1),      # fp32 3x3, 16 pixel lanes, 4 row blocks per image
+    (128, 16, 32, 32, 3, 1),      # fp32 3x3, 4 pixel lanes
+    (3, 20, 16, 16, 3, 1),        # fp32 3x3: ragged last row block (20 = 8 + 8 + 4), width not a power of two
+    (5, 8, 32, 32, 3, 1),         # fp32 3x3: one row block per image, fewer items than SMs
+    (128, 32, 64, 16, 1, 1),      # tcgen05 group, BN=16 (now without its 3x3 neighbours)
+    (128, 8, 64, 64, 3, 1),       # tcgen05 group, BN=64 (3x3 with 64 channels stays on the tensor cores)
+]
+
+
+@pytest.mark.parametrize("simt3", ["1", "0"])
+def test_wgrad_group_vs_torch_fp64(simt3, monkeypatch):
+    """dpp_wgrad_group_*: all layers of GROUP_SHAPES in one handle (two runs: dw / db accumulate), every dw / db against
+    float64 torch.  DPP_WGRAD_SIMT3=0 keeps the 3x3 16 / 32-channel layers on the tcgen05 kernels."""
+    monkeypatch.setenv("DPP_WGRAD_SIMT3", simt3)
+    from dpp_b200.lib import WgradLayer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    keepall, layers, refs = [], [], []
+    for i, (N, H, Cin, Cout, k, stride) in enumerate(GROUP_SHAPES):
+        d, x, w, bias, bn, Ho, keep = _setup(N, H, Cin, Cout, k, stride, 1, seed=40 + i)
+        gamma, beta = keep[-3], keep[-2]
+        g = torch.Generator(device='cuda').manual_seed(60 + i)
+        dy = torch.randn(N, Ho, Ho, Cout, device='cuda', generator=g)
+        dw = torch.zeros(k * k * Cin, Cout, device='cuda')
+        db = torch.zeros(Cout, device='cuda')
+        wl = WgradLayer()
+        wl.d, wl.x, wl.in_bn, wl.has_in_bn = d, x.data_ptr(), bn, 1
+        wl.dy, wl.dw, wl.db = dy.data_ptr(), dw.data_ptr(), db.data_ptr()
+        layers.append(wl)
+        ref = _ref_ops(N, H, Cin, Cout, k, stride, x, w, bias, gamma, beta, None, dy, None)
+        refs.append((dw, db, ref['dw'], ref['db']))
+        keepall += [x, w, bias, dy, keep]
+    arr = (WgradLayer * len(layers))(*layers)
+    h = C.c_void_p()
+    create = lib.raw('dpp_wgrad_group_create')
+    assert create(arr, len(layers), C.byref(h)) == 0
+    n_launch = int(lib.dpp_wgrad_group_launches(h))
+    lib.dpp_wgrad_group_run(h, None)
+    lib.dpp_wgrad_group_run(h, None)
+    torch.cuda.synchronize()
+    lib.dpp_wgrad_group_destroy(h)
+    print("launches per run:", n_launch)
+    assert n_launch == (4 if simt3 == "1" else 3)       # fp32: C = 16 and C = 32; tcgen05 widths: 16, 64 (+ 32 without the fp32 kernel)
+    for (shape, (dw, db, rdw, rdb)) in zip(GROUP_SHAPES, refs):
+        e_dw, e_db = _relmax(dw, 2 * rdw), _relmax(db, 2 * rdb)
+        print(shape, "simt3", simt3, "dw %.2e db %.2e" % (e_dw, e_db))
+        assert e_dw < 5e-5 and e_db < 1e-5

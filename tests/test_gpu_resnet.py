@@ -372,14 +372,18 @@ def test_fused_bn_backward_equals_separate_kernels(B, monkeypatch):
     err = float((g1 - g0).abs().max() / g0.abs().max())
     l2 = float((g1 - g0).norm() / g0.norm())
     print("gradient arena fused vs separate: max %.2e rel-L2 %.2e" % (err, l2))
-    assert err < 2e-5 and l2 < 2e-5
+    # (3xTF32 drops the lo x lo products and truncates: ~5e-7 per product, visible where a weight gradient is a small
+    #  difference of large sums; the fp32 launches of the grouped path are the more exact side - measured 1.8e-5 / 2.7e-5)
+    assert err < 5e-5 and l2 < 5e-5
 
 
 @pytest.mark.parametrize("B", [16, 128])
 def test_grouped_backward_weights_equal_per_layer_launches(B, monkeypatch):
-    """dpp_wgrad_group_* runs the 63 backward-weights GEMMs in four persistent launches (items of pixel chunks taken
-    from a list, reduced straight into dW); DPP_WGRAD_GROUP=0 launches dpp_conv2d_wgrad per layer on a second stream.
-    Same products, different summation order: gradient arenas agree to float32 roundoff."""
+    """dpp_wgrad_group_* runs the 63 backward-weights GEMMs in six persistent launches (four tcgen05 launches by
+    n-tile width: items of pixel chunks taken from a list, reduced straight into dW; two fp32 launches for the 3x3
+    16- and 32-channel layers, wgrad_simt3.cu); DPP_WGRAD_GROUP=0 launches dpp_conv2d_wgrad per layer on a second
+    stream.  Same products, different summation order (and fp32 instead of 3xTF32 products for ten layers): gradient
+    arenas agree to float32 roundoff."""
     D = 30
     x, y = _data(B, D)
     res = {}
@@ -395,9 +399,11 @@ def test_grouped_backward_weights_equal_per_layer_launches(B, monkeypatch):
         eng.release()
     (c1, g1, n1), (c0, g0, n0) = res['1'], res['0']
     print("batch", B, "backward-weights launches: grouped", n1, "per layer", n0)
-    assert n0 == 63 and n1 == 4
+    assert n0 == 63 and n1 == 6
     assert c1 == c0
     err = float((g1 - g0).abs().max() / g0.abs().max())
     l2 = float((g1 - g0).norm() / g0.norm())
     print("gradient arena grouped vs per-layer: max %.2e rel-L2 %.2e" % (err, l2))
-    assert err < 2e-5 and l2 < 2e-5
+    # (3xTF32 drops the lo x lo products and truncates: ~5e-7 per product, visible where a weight gradient is a small
+    #  difference of large sums; the fp32 launches of the grouped path are the more exact side - measured 1.8e-5 / 2.7e-5)
+    assert err < 5e-5 and l2 < 5e-5
