@@ -190,8 +190,13 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
     for (int c = tid; c < a.kchunks * 2; c += NTHREADS_CONV)
         s_tab[c] = make_int4(a.tab[c >> 1][(c & 1) * 4], a.tab[c >> 1][(c & 1) * 4 + 1], a.tab[c >> 1][(c & 1) * 4 + 2], a.tab[c >> 1][(c & 1) * 4 + 3]);
     for (int c = tid; c < 8 * 2 * BN; c += NTHREADS_CONV) s_stat[c] = 0.0;
+    __syncthreads();                             // barrier inits visible to every role (the loader starts right after the wait)
     // ---- everything below reads what the previous kernels wrote (statistics, activations, weight images)
     pdl_wait();
+    // The loader warp goes straight to its role: its first TMA round trip (~1 us) overlaps the coefficient phase of the
+    // other warps (statistics from L2 + fp64 arithmetic, ~1 us) instead of following it at the head of every launch of
+    // the chain.  The other 17 warps meet at a named barrier once the coefficients are in shared memory.
+    if (warp != W_LOAD) {
     // Three independent coefficient jobs on disjoint thread ranges, every job with all its global loads issued
     // before the fp64 arithmetic: one exposed memory latency instead of a chain of dependent ones.
     if (tid < 256) {                                   // input-BN scale / shift (Cin <= 256)
@@ -237,9 +242,10 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
         if (c < BN) s_bias[c] = (a.wmode == 0 && a.bias) ? a.bias[cta_n0 + c] : 0.f;
     }
     tc_fence_before();
-    __syncthreads();
+    asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS_CONV - 32) : "memory");
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    }
+    const uint32_t tmem_base = *tmem_slot;       // (the loader warp may read this before the allocation: it never uses it)
     const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
     PROF(2);
 
