@@ -24,6 +24,7 @@ struct W3Layer {
     int rblocks;       // ceil(H / 8)
     int item0;         // first item of this layer in the global item numbering
     unsigned wp_magic, w_magic;   // i / (W + 2) = (i * wp_magic) >> 16 and i / W = (i * w_magic) >> 16 over a tile's pixel indices
+    int cout;                     // 1x1 layers (k_wgrad1): Cout; there H = pixels, W = 1, C = Cin
 };
 }
 
@@ -263,16 +264,193 @@ k_wgrad3(const W3Args a) {
     flush(L, buf * bufsz);     // buf was flipped after the last item: this is the buffer NOT read last (the flush syncs first anyway)
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 1x1 stride-1 layers of the first residual stage (64 -> 16 and 16 -> 64 channels at 32 x 32, batch 128: 131072 pixels):
+//   dw[ci][co] += sum_p a[p][ci] * dy[p][co],  a = ReLU(BN(x)),  db[co] += sum_p dy[p][co]
+// a tall-skinny product (M x N = 16 x 64 or 64 x 16, K = pixels) that tcgen05 runs at N = 16 or M = 16 of 128 useful rows
+// (30 - 35 us per layer in wgrad_tc_mn.cu); here a thread owns an 8 x 8 block of dw in registers and walks every 16th
+// pixel of a 256-pixel tile: 4 x LDS.128 per 64 FMAs.  Same tile pipeline as k_wgrad3: cp.async double buffer,
+// BatchNorm + ReLU in place, a contiguous cost-balanced range of (layer, tile) items per CTA, one flush per layer.
+// W3Layer is reused: H = number of pixels, W = 1, C = Cin, rblocks = tiles, `cout` = Cout.
+constexpr int P1 = 256;          // pixels per tile
+
+template <int CI, int CO>
+__device__ __forceinline__ void stage_item1(const W3Layer &L, int tile, int bufo) {
+    float *buf = smem3 + bufo;
+    const int npix = L.H - tile * P1 < P1 ? L.H - tile * P1 : P1;
+    const float *xs = L.x + (size_t)tile * P1 * CI, *ds = L.dy + (size_t)tile * P1 * CO;
+    for (int i = threadIdx.x; i < P1 * CI / 4; i += W3_THREADS) cp16(buf + i * 4, xs + (size_t)i * 4, i * 4 < npix * CI);
+    float *dyb = buf + P1 * CI;
+    for (int i = threadIdx.x; i < P1 * CO / 4; i += W3_THREADS) cp16(dyb + i * 4, ds + (size_t)i * 4, i * 4 < npix * CO);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(W3_THREADS, 1)
+k_wgrad1(const W3Args a) {
+    constexpr int GI = CI / 8, GO = CO / 8, COMBOS = GI * GO, PL = W3_THREADS / COMBOS;
+    static_assert(COMBOS * PL == W3_THREADS && PL * COMBOS * 64 <= P1 * (CI + CO), "flush scratch must fit a staging buffer");
+    __shared__ float s_scale[CI], s_shift[CI];
+    const int tid = threadIdx.x;
+    const int combo = tid % COMBOS, ps = tid / COMBOS;
+    const int gi = combo / GO, go = combo % GO;
+    const int bufsz = a.buf_floats;
+    float acc[8][8], dbp[8];
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            dbp[i] = 0.f;
+        }
+    };
+    auto flush = [&](const W3Layer &L, int scro) {
+        float *scratch = smem3 + scro;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float *d = scratch + ((size_t)ps * COMBOS + combo) * 64 + i * 8;
+            *reinterpret_cast<float4 *>(d) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4 *>(d + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+        __syncthreads();
+        for (int o = tid; o < COMBOS * 64; o += W3_THREADS) {
+            float s = 0.f;
+#pragma unroll
+            for (int l = 0; l < PL; ++l) s += scratch[(size_t)l * (COMBOS * 64) + o];
+            const int cb = o >> 6, e = o & 63;
+            const int ci = (cb / GO) * 8 + (e >> 3), co = (cb % GO) * 8 + (e & 7);
+            atomicAdd(L.dw + (size_t)ci * CO + co, s);
+        }
+        __syncthreads();
+        if (L.db != nullptr) {
+            if (gi == 0) {
+                float *d = scratch + ((size_t)ps * GO + go) * 8;
+                *reinterpret_cast<float4 *>(d) = make_float4(dbp[0], dbp[1], dbp[2], dbp[3]);
+                *reinterpret_cast<float4 *>(d + 4) = make_float4(dbp[4], dbp[5], dbp[6], dbp[7]);
+            }
+            __syncthreads();
+            if (tid < CO) {
+                float s = 0.f;
+#pragma unroll
+                for (int l = 0; l < PL; ++l) s += scratch[(size_t)l * CO + tid];
+                atomicAdd(L.db + tid, s);
+            }
+            __syncthreads();
+        }
+    };
+    const int it_begin = a.cta_begin[blockIdx.x], it_end = a.cta_begin[blockIdx.x + 1];
+    if (it_begin >= it_end) return;
+    int li = 0;
+    while (li + 1 < a.n_layers && a.layers[li + 1].item0 <= it_begin) ++li;
+    W3Layer L = a.layers[li];
+    auto load_coef = [&]() {
+        if (tid < CI) {
+            float sc = 1.f, sh = 0.f;
+            if (L.has_in_bn) bn_scale_shift(L.in_bn, tid, CI, sc, sh);
+            s_scale[tid] = sc; s_shift[tid] = sh;
+        }
+    };
+    load_coef();
+    zero_acc();
+    int buf = 0;
+    stage_item1<CI, CO>(L, it_begin - L.item0, 0);
+    for (int it = it_begin; it < it_end; ++it, buf ^= 1) {
+        const int tile = it - L.item0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int npix = L.H - tile * P1 < P1 ? L.H - tile * P1 : P1;
+        if (L.has_in_bn) {
+            float *xb = smem3 + buf * bufsz;
+            const bool relu = L.in_bn.relu != 0;
+            for (int i = tid; i < npix * CI / 4; i += W3_THREADS) {
+                float4 v = *reinterpret_cast<float4 *>(xb + i * 4);
+                const int c = (i * 4) % CI;
+                v.x = fmaf(v.x, s_scale[c], s_shift[c]); v.y = fmaf(v.y, s_scale[c + 1], s_shift[c + 1]);
+                v.z = fmaf(v.z, s_scale[c + 2], s_shift[c + 2]); v.w = fmaf(v.w, s_scale[c + 3], s_shift[c + 3]);
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                *reinterpret_cast<float4 *>(xb + i * 4) = v;
+            }
+        }
+        const int nxt = it + 1;
+        const bool more = nxt < it_end;
+        const bool same = more && (li + 1 >= a.n_layers || a.layers[li + 1].item0 > nxt);
+        if (same) stage_item1<CI, CO>(L, nxt - L.item0, (buf ^ 1) * bufsz);
+        __syncthreads();
+        {
+            const int xo = buf * bufsz + gi * 8, dyo = buf * bufsz + P1 * CI + go * 8;
+#pragma unroll 2
+            for (int p = ps; p < npix; p += PL) {
+                const float4 x0 = *reinterpret_cast<const float4 *>(smem3 + xo + p * CI);
+                const float4 x1 = *reinterpret_cast<const float4 *>(smem3 + xo + p * CI + 4);
+                const float4 d0 = *reinterpret_cast<const float4 *>(smem3 + dyo + p * CO);
+                const float4 d1 = *reinterpret_cast<const float4 *>(smem3 + dyo + p * CO + 4);
+                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], dv[j], acc[i][j]);
+                if (gi == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dbp[j] += dv[j];
+                }
+            }
+        }
+        if (more && !same) {
+            flush(L, (buf ^ 1) * bufsz);
+            ++li;
+            L = a.layers[li];
+            load_coef();
+            zero_acc();
+            stage_item1<CI, CO>(L, nxt - L.item0, (buf ^ 1) * bufsz);
+        }
+    }
+    flush(L, buf * bufsz);
+}
+
 struct W3Group {
-    W3Args args16, args32;
-    int grid16, grid32, smem16, smem32;
+    W3Args args16, args32, args1a, args1b;        // 3x3 C = 16 / 32; 1x1 64 -> 16 / 16 -> 64
+    int grid16, grid32, smem16, smem32, grid1a, grid1b, smem1a, smem1b;
     std::vector<void *> allocs;
 };
+
+// 1x1 layers with (Cin, Cout) = (CI, CO): items = tiles of 256 pixels, equal cost
+template <int CI, int CO>
+int build1(const std::vector<dpp::W3Layer> &all, W3Args &args, int &grid, int &smem, std::vector<void *> &allocs) {
+    std::vector<dpp::W3Layer> ls;
+    for (const dpp::W3Layer &l : all) if (l.W == 1 && l.C == CI && l.cout == CO) ls.push_back(l);
+    grid = 0; smem = 0;
+    if (ls.empty()) return 0;
+    int items = 0;
+    for (dpp::W3Layer &l : ls) {
+        l.rblocks = (l.H + P1 - 1) / P1;
+        l.item0 = items;
+        items += l.rblocks;
+    }
+    const int bufmax = P1 * (CI + CO);
+    smem = 2 * bufmax * (int)sizeof(float);
+    grid = items < 148 ? items : 148;
+    std::vector<int> begin(grid + 1, 0);
+    for (int b = 0; b <= grid; ++b) begin[b] = (int)((long long)items * b / grid);
+    void *dl = nullptr, *db = nullptr;
+    if (cudaMalloc(&dl, ls.size() * sizeof(dpp::W3Layer)) != cudaSuccess || cudaMalloc(&db, begin.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(dl, ls.data(), ls.size() * sizeof(dpp::W3Layer), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(db, begin.data(), begin.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+        return -1;
+    allocs.push_back(dl); allocs.push_back(db);
+    args.layers = reinterpret_cast<const dpp::W3Layer *>(dl);
+    args.n_layers = (int)ls.size();
+    args.cta_begin = reinterpret_cast<const int *>(db);
+    args.buf_floats = bufmax;
+    if (cudaFuncSetAttribute(k_wgrad1<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    return 0;
+}
 
 template <int C>
 int build(const std::vector<dpp::W3Layer> &all, W3Args &args, int &grid, int &smem, std::vector<void *> &allocs) {
     std::vector<dpp::W3Layer> ls;
-    for (const dpp::W3Layer &l : all) if (l.C == C) ls.push_back(l);
+    for (const dpp::W3Layer &l : all) if (l.C == C && l.W > 1) ls.push_back(l);
     grid = 0; smem = 0;
     if (ls.empty()) return 0;
     // items and their cost (pixels of a full tile x C^2); ranges of equal cost per CTA
@@ -330,14 +508,23 @@ int build(const std::vector<dpp::W3Layer> &all, W3Args &args, int &grid, int &sm
 
 namespace dpp {
 
-int wgrad3_enabled() {      // read at every dpp_wgrad_group_create (tests switch it)
+int wgrad3_enabled() {      // read at every dpp_wgrad_group_create (tests switch it): bit 0 = 3x3 kernel, bit 1 = 1x1 kernel
     const char *e = getenv("DPP_WGRAD_SIMT3");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 3;
+}
+bool wgrad3_supported(const dpp_conv_desc *d);
+
+// which layers these kernels take out of the tensor-core groups: 1 = 3x3 (k_wgrad3), 2 = 1x1 (k_wgrad1), 0 = none
+int wgrad3_kind(const dpp_conv_desc *d) {
+    if (!wgrad3_enabled()) return 0;
+    if (d->k == 1 && d->stride == 1 && d->pad == 0 && ((d->Cin == 64 && d->Cout == 16) || (d->Cin == 16 && d->Cout == 64)) &&
+        (wgrad3_enabled() & 2))
+        return 2;
+    return wgrad3_supported(d) ? 1 : 0;
 }
 
-// which layers this kernel takes out of the tensor-core groups
 bool wgrad3_supported(const dpp_conv_desc *d) {
-    if (!wgrad3_enabled()) return false;
+    if (!(wgrad3_enabled() & 1)) return false;
     if (d->k != 3 || d->stride != 1 || d->pad != 1 || d->Cin != d->Cout || (d->Cin != 16 && d->Cin != 32)) return false;
     if (d->Ho != d->H || d->Wo != d->W) return false;
     const int bf = ((R3 + 2) * (d->W + 2) + R3 * d->W) * d->Cin;
@@ -347,7 +534,10 @@ bool wgrad3_supported(const dpp_conv_desc *d) {
 int wgrad3_create(const std::vector<W3Layer> &layers, void **handle_out) {
     W3Group *g = new W3Group();
     memset(&g->args16, 0, sizeof(W3Args)); memset(&g->args32, 0, sizeof(W3Args));
-    if (build<16>(layers, g->args16, g->grid16, g->smem16, g->allocs) != 0 || build<32>(layers, g->args32, g->grid32, g->smem32, g->allocs) != 0) {
+    memset(&g->args1a, 0, sizeof(W3Args)); memset(&g->args1b, 0, sizeof(W3Args));
+    if (build<16>(layers, g->args16, g->grid16, g->smem16, g->allocs) != 0 || build<32>(layers, g->args32, g->grid32, g->smem32, g->allocs) != 0 ||
+        build1<64, 16>(layers, g->args1a, g->grid1a, g->smem1a, g->allocs) != 0 ||
+        build1<16, 64>(layers, g->args1b, g->grid1b, g->smem1b, g->allocs) != 0) {
         for (void *p : g->allocs) cudaFree(p);
         delete g;
         return -1;
@@ -358,13 +548,15 @@ int wgrad3_create(const std::vector<W3Layer> &layers, void **handle_out) {
 
 int wgrad3_launches(void *handle) {
     W3Group *g = reinterpret_cast<W3Group *>(handle);
-    return (g->grid16 > 0) + (g->grid32 > 0);
+    return (g->grid16 > 0) + (g->grid32 > 0) + (g->grid1a > 0) + (g->grid1b > 0);
 }
 
 int wgrad3_run(void *handle, cudaStream_t st) {
     W3Group *g = reinterpret_cast<W3Group *>(handle);
     if (g->grid16 > 0) k_wgrad3<16><<<g->grid16, W3_THREADS, g->smem16, st>>>(g->args16);
     if (g->grid32 > 0) k_wgrad3<32><<<g->grid32, W3_THREADS, g->smem32, st>>>(g->args32);
+    if (g->grid1a > 0) k_wgrad1<64, 16><<<g->grid1a, W3_THREADS, g->smem1a, st>>>(g->args1a);
+    if (g->grid1b > 0) k_wgrad1<16, 64><<<g->grid1b, W3_THREADS, g->smem1b, st>>>(g->args1b);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

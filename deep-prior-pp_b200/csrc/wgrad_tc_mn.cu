@@ -647,8 +647,9 @@ struct W3Layer {
     int N, H, W, C;
     int rblocks, item0;
     unsigned wp_magic, w_magic;
+    int cout;
 };
-bool wgrad3_supported(const dpp_conv_desc *d);
+int wgrad3_kind(const dpp_conv_desc *d);        // 1 = 3x3 16 / 32 channels, 2 = 1x1 64 -> 16 / 16 -> 64, 0 = stays on tcgen05
 int wgrad3_create(const std::vector<W3Layer> &layers, void **handle_out);
 int wgrad3_launches(void *handle);
 int wgrad3_run(void *handle, cudaStream_t st);
@@ -700,13 +701,15 @@ extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layer
     {
         std::vector<dpp::W3Layer> l3;
         for (int i = 0; i < n_layers; ++i)
-            if (dpp::wgrad3_supported(&layers[i].d)) {
+            if (const int kind = dpp::wgrad3_kind(&layers[i].d)) {
                 dpp::W3Layer w;
                 memset(&w, 0, sizeof(w));
                 w.x = layers[i].x; w.dy = layers[i].dy; w.dw = layers[i].dw; w.db = layers[i].db;
                 w.has_in_bn = layers[i].has_in_bn;
                 if (w.has_in_bn) w.in_bn = layers[i].in_bn;
                 w.N = layers[i].d.N; w.H = layers[i].d.H; w.W = layers[i].d.W; w.C = layers[i].d.Cin;
+                w.cout = layers[i].d.Cout;
+                if (kind == 2) { w.H = layers[i].d.N * layers[i].d.H * layers[i].d.W; w.W = 1; w.N = 1; }   // a flat pixel range
                 l3.push_back(w);
             }
         if (!l3.empty() && dpp::wgrad3_create(l3, &grp->w3) != 0) {
@@ -720,7 +723,7 @@ extern "C" int dpp_wgrad_group_create(const dpp_wgrad_layer *layers, int n_layer
         std::vector<WArgs> la;
         for (int i = 0; i < n_layers; ++i) {
             const int lbn = layers[i].d.Cout > 128 ? 128 : layers[i].d.Cout;
-            if (lbn != bn || dpp::wgrad3_supported(&layers[i].d)) continue;
+            if (lbn != bn || dpp::wgrad3_kind(&layers[i].d) != 0) continue;
             WArgs a;
             fill_args(a, &layers[i].d, layers[i].x, layers[i].has_in_bn ? &layers[i].in_bn : nullptr, layers[i].dy, layers[i].dw,
                       layers[i].db);

@@ -255,15 +255,19 @@ GROUP_SHAPES = [  # the grouped launches: fp32 3x3 kernel (C = 16 / 32) next to 
     (128, 16, 32, 32, 3, 1),      # fp32 3x3, 4 pixel lanes
     (3, 20, 16, 16, 3, 1),        # fp32 3x3: ragged last row block (20 = 8 + 8 + 4), width not a power of two
     (5, 8, 32, 32, 3, 1),         # fp32 3x3: one row block per image, fewer items than SMs
-    (128, 32, 64, 16, 1, 1),      # tcgen05 group, BN=16 (now without its 3x3 neighbours)
+    (128, 32, 64, 16, 1, 1),      # fp32 1x1 (k_wgrad1<64, 16>): 512 tiles of 256 pixels
+    (128, 32, 16, 64, 1, 1),      # fp32 1x1 (k_wgrad1<16, 64>)
+    (3, 20, 64, 16, 1, 1),        # fp32 1x1: 1200 pixels = 4 full tiles + a ragged one
+    (128, 16, 128, 32, 1, 1),     # tcgen05 group, BN=32
     (128, 8, 64, 64, 3, 1),       # tcgen05 group, BN=64 (3x3 with 64 channels stays on the tensor cores)
 ]
 
 
-@pytest.mark.parametrize("simt3", ["1", "0"])
+@pytest.mark.parametrize("simt3", ["3", "1", "0"])
 def test_wgrad_group_vs_torch_fp64(simt3, monkeypatch):
     """dpp_wgrad_group_*: all layers of GROUP_SHAPES in one handle (two runs: dw / db accumulate), every dw / db against
-    float64 torch.  DPP_WGRAD_SIMT3=0 keeps the 3x3 16 / 32-channel layers on the tcgen05 kernels."""
+    float64 torch.  DPP_WGRAD_SIMT3: bit 0 = fp32 kernel for the 3x3 16 / 32-channel layers, bit 1 = fp32 kernel for the
+    1x1 64 -> 16 / 16 -> 64 layers (default 3); 0 keeps everything on the tcgen05 kernels."""
     monkeypatch.setenv("DPP_WGRAD_SIMT3", simt3)
     from dpp_b200.lib import WgradLayer
     torch.backends.cudnn.allow_tf32 = False
@@ -293,7 +297,8 @@ def test_wgrad_group_vs_torch_fp64(simt3, monkeypatch):
     torch.cuda.synchronize()
     lib.dpp_wgrad_group_destroy(h)
     print("launches per run:", n_launch)
-    assert n_launch == (4 if simt3 == "1" else 3)       # fp32: C = 16 and C = 32; tcgen05 widths: 16, 64 (+ 32 without the fp32 kernel)
+    # fp32 launches: 3x3 C = 16, C = 32 (bit 0), 1x1 64 -> 16, 16 -> 64 (bit 1); tcgen05 widths left: 32, 64 (+ 16 without bit 1)
+    assert n_launch == {"3": 6, "1": 5, "0": 3}[simt3]
     for (shape, (dw, db, rdw, rdb)) in zip(GROUP_SHAPES, refs):
         e_dw, e_db = _relmax(dw, 2 * rdw), _relmax(db, 2 * rdb)
         print(shape, "simt3", simt3, "dw %.2e db %.2e" % (e_dw, e_db))
