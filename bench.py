@@ -167,6 +167,60 @@ def records_for(ds, comp, mean, idxs, rng, aug_modes=None):
     return recs, np.asarray(ys, np.float32), draws
 
 
+# ---- host preparation in worker processes (the reference augments in 8 worker processes, trainer/nettrainer.py:59,666-689)
+_PREP = {}
+
+
+def _prep_init(dataset, n_resident, seed, aug_modes):
+    """worker initialiser: every worker rebuilds the (deterministic) synthetic set and the PCA stand-in once"""
+    global N_RESIDENT
+    N_RESIDENT = n_resident
+    _PREP['ds'], _PREP['comp'], _PREP['mean'] = make_workload(seed=seed, dataset=dataset, n=n_resident)
+    _PREP['aug'] = list(aug_modes)
+
+
+def _prep_job(job):
+    """one batch: random draws, augmentation records, embedded labels (the host work of one step).  job = (seed, nb) returns
+    the arrays; job = (seed, nb, shm name, slot, slot bytes) also gathers the batch's crops and writes crops | records |
+    labels into staging slot `slot` of the shared-memory ring (page-locked by the parent) and returns the slot number."""
+    seed, nb = job[:2]
+    rng = np.random.RandomState(seed)
+    idxs = rng.randint(0, _PREP['ds']['x'].shape[0], nb)
+    r, yv, _ = records_for(_PREP['ds'], _PREP['comp'], _PREP['mean'], idxs, rng, _PREP['aug'])
+    r = r.copy()
+    src = r['src_index'].astype(np.int64)
+    r['src_index'] = np.arange(nb, dtype=np.int32)                    # records index the staged batch
+    rb = r.view(np.uint8).reshape(nb, -1)
+    yv = np.ascontiguousarray(yv, np.float32)
+    if len(job) == 2:
+        return src, rb.copy(), yv
+    name, slot, slot_bytes = job[2:]
+    shm = _PREP.get('shm')
+    if shm is None or shm.name != name:
+        from multiprocessing import shared_memory
+        shm = _PREP['shm'] = shared_memory.SharedMemory(name=name)
+    base = slot * slot_bytes
+    xb = nb * 128 * 128 * 4
+    x = np.ndarray((nb, 128, 128), np.float32, buffer=shm.buf, offset=base)
+    np.take(_PREP['ds']['x'][:, 0], src, axis=0, out=x)
+    np.ndarray(rb.shape, np.uint8, buffer=shm.buf, offset=base + xb)[...] = rb
+    np.ndarray(yv.shape, np.float32, buffer=shm.buf, offset=base + xb + rb.size)[...] = yv
+    return slot
+
+
+def prep_workers():
+    """worker processes per rank for the e2e host preparation: DPP_PREP_WORKERS, default min(4, cores / ranks - 1)"""
+    e = os.environ.get('DPP_PREP_WORKERS')
+    if e is not None:
+        return max(0, int(e))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    return max(0, min(4, cores // max(world, 1) - 1))
+
+
 def first_batch(ds, comp, mean, nb, seed=1234):
     """the batch the cost check runs on: same recipe in bench.py (device) and tests/golden/make_bench_golden.py (oracle)"""
     rng = np.random.RandomState(seed)
@@ -324,6 +378,7 @@ class StepRunner(object):
         from net.resnet import ResNet, ResNetParams
         self.C, self.lib, self.ctx, self.nb, self.aug_modes = C, lib, ctx, batch, aug_modes
         self.precision = int(os.environ.get('DPP_PRECISION', '1'))
+        self.dataset, self.seed = dataset, seed0 + ctx.rank
         self.ds, self.comp, self.mean = make_workload(seed=seed0 + ctx.rank, dataset=dataset)
         if net_kind == 'poseregnet':
             from net.poseregnet import PoseRegNet, PoseRegNetParams
@@ -399,8 +454,38 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
     stage_r = [torch.empty((nb, rec_bytes), dtype=torch.uint8, device=dev) for _ in range(2)]
     stage_y = [torch.empty((nb, E), dtype=torch.float32, device=dev) for _ in range(2)]
     cost_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    pool = None
     if with_prep:
         rng2 = np.random.RandomState(777 + ctx.rank)
+        nwork = prep_workers()
+        if nwork > 0:
+            try:
+                import multiprocessing
+                pool = multiprocessing.get_context('spawn').Pool(
+                    nwork, initializer=_prep_init, initargs=(run.dataset, run.ds['x'].shape[0], run.seed, list(run.aug_modes)))
+                pool.map(_prep_job, [(1, nb)] * nwork)                # workers up and initialised before anything is timed
+            except Exception as ex:                                   # no worker processes on this box: one host thread
+                print("bench: host-preparation workers unavailable (%s); preparing on the main thread" % ex, file=sys.stderr)
+                pool = None
+        ring = None
+        if pool is not None:
+            try:
+                # staging ring in shared memory, page-locked here: the workers write a finished batch (crops gathered from
+                # their copy of the set, records, labels) straight into it; the parent only issues the copies
+                from multiprocessing import shared_memory
+                xb, rbts, ybts = nb * 128 * 128 * 4, nb * rec_bytes, nb * E * 4
+                slot_bytes = (xb + rbts + ybts + 4095) // 4096 * 4096
+                nslot = 2 * nwork + 2
+                shm = shared_memory.SharedMemory(create=True, size=nslot * slot_bytes)
+                whole = torch.frombuffer(shm.buf, dtype=torch.uint8)
+                rc = torch.cuda.cudart().cudaHostRegister(whole.data_ptr(), nslot * slot_bytes, 0)
+                if int(rc) != 0:
+                    raise RuntimeError("cudaHostRegister failed (%s)" % rc)
+                ring = {'shm': shm, 'whole': whole, 'slot_bytes': slot_bytes, 'nslot': nslot, 'free': list(range(nslot)),
+                        'inflight': [], 'xb': xb, 'rb': rbts, 'yb': ybts, 'busy': {}}
+            except Exception as ex:
+                print("bench: shared-memory staging unavailable (%s); gathering on the main thread" % ex, file=sys.stderr)
+                ring = None
         hx = [torch.empty((nb, 128, 128), dtype=torch.float32).pin_memory() for _ in range(2)]
         hr = [torch.empty((nb, rec_bytes), dtype=torch.uint8).pin_memory() for _ in range(2)]
         hy = [torch.empty((nb, E), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -409,7 +494,55 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
         copy_stream = torch.cuda.Stream(device=dev)
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+        xs_t = torch.from_numpy(xs_host)
+        pending = []                                                  # batches being prepared by the workers
+        jobno = [0]
+
+        def submit():
+            jobno[0] += 1
+            pending.append(pool.apply_async(_prep_job, ((1000003 * (ctx.rank + 1) + jobno[0], nb),)))
+
+        def ring_submit():
+            r_ = ring
+            while r_['free'] and len(r_['inflight']) < 2 * nwork:
+                slot = r_['free'].pop(0)
+                ev = r_['busy'].pop(slot, None)
+                if ev is not None:
+                    ev.synchronize()                                  # the copies out of this slot have completed
+                jobno[0] += 1
+                r_['inflight'].append(pool.apply_async(
+                    _prep_job, ((1000003 * (ctx.rank + 1) + jobno[0], nb, r_['shm'].name, slot, r_['slot_bytes']),)))
+
+        def ring_upload(b):
+            r_ = ring
+            ring_submit()
+            slot = r_['inflight'].pop(0).get()                        # a finished batch
+            o = slot * r_['slot_bytes']
+            w = r_['whole']
+            copy_stream.wait_event(consumed[b])
+            with torch.cuda.stream(copy_stream):
+                stage_x[b].view(torch.uint8).view(-1).copy_(w[o:o + r_['xb']], non_blocking=True)
+                stage_r[b].view(-1).copy_(w[o + r_['xb']:o + r_['xb'] + r_['rb']], non_blocking=True)
+                stage_y[b].view(torch.uint8).view(-1).copy_(w[o + r_['xb'] + r_['rb']:o + r_['xb'] + r_['rb'] + r_['yb']],
+                                                            non_blocking=True)
+                copied[b].record(copy_stream)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            r_['busy'][slot] = ev
+            r_['free'].append(slot)
+            ring_submit()
+
         def prep(b):
+            if ring is not None:
+                return                                                # the batch is prepared by a worker, see ring_upload
+            if pool is not None:
+                while len(pending) < 2 * nwork:                       # keep the workers busy a few batches ahead
+                    submit()
+                src, rbytes, yv = pending.pop(0).get()
+                torch.index_select(xs_t, 0, torch.from_numpy(src), out=hx[b])     # the batch's crops into pinned memory
+                hr[b].numpy()[...] = rbytes
+                hy[b].numpy()[...] = yv
+                return
             idxs = rng2.randint(0, N_RESIDENT, nb)
             r, yv, _ = records_for(run.ds, run.comp, run.mean, idxs, rng2, run.aug_modes)
             r = r.copy()
@@ -420,6 +553,8 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
             hy[b].numpy()[...] = yv
 
         def upload(b):
+            if ring is not None:
+                return ring_upload(b)
             copy_stream.wait_event(consumed[b])                       # the step that read staging set b is done with it
             with torch.cuda.stream(copy_stream):
                 stage_x[b].copy_(hx[b], non_blocking=True)
@@ -439,15 +574,22 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
             eng.y_in.copy_(stage_y[b], non_blocking=True)
             consumed[b].record(main)
             cost = eng.train_step(None, use_graph=True)
-            copied[b ^ 1].synchronize()                               # pinned set b^1 has been read by its last upload
+            if ring is None:
+                copied[b ^ 1].synchronize()                           # pinned set b^1 has been read by its last upload
             prep(b ^ 1)                                               # host work of the NEXT batch, under this step
             upload(b ^ 1)
             state['ready'] = s + 1
             cost_host.copy_(cost, non_blocking=False)                 # the float train_model() returns
         for e in copied + consumed:
             e.record()
-        note = "per step, inside the timed region: random draws + augmentation records + label embedding on one host " \
-               "thread (overlapping the previous step), crops + records + labels copied from pinned host memory, cost read back"
+        if pool is not None:
+            note = "per step, inside the timed region: random draws + augmentation records + label embedding of one batch in %d " \
+                   "worker processes (the reference augments in 8), the batch's crops gathered into %s, crops + " \
+                   "records + labels copied to the device, cost read back" % (
+                       nwork, "a page-locked shared-memory ring by the workers" if ring is not None else "pinned memory")
+        else:
+            note = "per step, inside the timed region: random draws + augmentation records + label embedding on one host " \
+                   "thread (overlapping the previous step), crops + records + labels copied from pinned host memory, cost read back"
     else:
         host_batches = []
         for k in range(run.nrec):
@@ -488,10 +630,32 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
         note = "records built on the host BEFORE the timed region; per step crops + records + labels copied from pinned " \
                "host memory, cost read back"
     ms = ctx.timed(step, steps, warmup)
+    if pool is not None:
+        torch.cuda.synchronize()
+        pool.terminate()
+        pool.join()
+        if ring is not None:
+            torch.cuda.cudart().cudaHostUnregister(ring['whole'].data_ptr())
+            whole = ring.pop('whole')
+            del whole
+            try:
+                ring['shm'].close()
+                ring['shm'].unlink()
+            except Exception:
+                pass
     return ms, note
 
 
-def measure_trainer_api(ctx, epochs=3, n_train=2048):
+class _PcaProj(object):
+    """sklearn-PCA stand-in handed to the trainer (module level: it travels to the record workers)"""
+    def __init__(self, comp, mean):
+        self.comp, self.mean = comp, mean
+
+    def transform(self, lab):
+        return np.dot(np.asarray(lab, np.float64) - self.mean, self.comp.T)
+
+
+def measure_trainer_api(ctx, epochs=6, n_train=2048):
     """frames/s of PoseRegNetTrainer.train() - the call the reference's entry scripts make - on a resident synthetic NYU
     set: per epoch 16 minibatches of 128, the augmented set regenerated on the device from fresh host records
     (force_macrobatch_reload, as main_nyu_posereg_embedding.py:112 sets it), the cost returned to the host every
@@ -506,15 +670,12 @@ def measure_trainer_api(ctx, epochs=3, n_train=2048):
     net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=B, numJoints=1, nDims=E))
     p = PoseRegNetTrainerParams()
     p.batch_size, p.learning_rate, p.weightreg_factor = B, 1e-4, 0.0
-    p.force_macrobatch_reload, p.para_augment, p.para_num_proc = True, True, 1
+    p.force_macrobatch_reload, p.para_augment, p.para_num_proc = True, True, 8        # the reference's default: 8 record workers
     p.validation_frequency = 10 ** 9
     p.snapshot_last = 10 ** 9
 
-    class _Proj(object):
-        def transform(self, lab):
-            return np.dot(np.asarray(lab, np.float64) - mean, comp.T)
     p.augment_fun_params = {'fun': 'augment_poses', 'args': {'normZeroOne': False, 'di': ds['importer'], 'hd': ds['hd'],
-                                                              'aug_modes': AUG_MODES, 'proj': _Proj()}}
+                                                              'aug_modes': AUG_MODES, 'proj': _PcaProj(comp, mean)}}
     with contextlib.redirect_stdout(io.StringIO()):
         tr = PoseRegNetTrainer(net, p, np.random.RandomState(23455), './')
         tr.verbose = False
@@ -534,7 +695,7 @@ def measure_trainer_api(ctx, epochs=3, n_train=2048):
     net._eng.release()
     return {"value": frames / dt, "unit": UNIT, "epochs": epochs, "minibatches_per_epoch": tr.getNumFullMiniBatches(),
             "wall_s": dt,
-            "note": "PoseRegNetTrainer.train() on %d resident crops: per epoch new draws + records on the host, the "
+            "note": "PoseRegNetTrainer.train() on %d resident crops: per epoch new draws + records in 8 worker processes, the "
                     "augmented set regenerated on the device, one train_model() call and one cost read-back per "
                     "minibatch, plus the initial validation pass of each train() call" % n_train}
 

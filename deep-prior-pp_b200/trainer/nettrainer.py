@@ -48,11 +48,41 @@ class NetTrainerParams(object):
         self.post_minibatch_fn = None
 
 
+def _draw_all(rng, n, n_modes, sigma_com, sigma_sc, rot_range):
+    """the n draws of one epoch in the reference's order (nettrainer.py:954-957): mode, CoM offset, rotation, scale"""
+    ri, rn, ru = rng.randint, rng.randn, rng.uniform
+    draws = []
+    for _ in range(n):
+        mode = ri(0, n_modes)
+        off = rn(3) * sigma_com
+        rot = ru(-rot_range, rot_range)
+        sc = abs(1. + rn() * sigma_sc)
+        draws.append((mode, off, rot, sc))
+    return draws
+
+
 def _records_chunk(args):
     """worker: build augmentation records + labels for a slice of samples (one vectorised pass,
-    ``HandDetector.aug_records_batch``: bit-identical to the per-sample ``aug_record``)"""
+    ``HandDetector.aug_records_batch``: bit-identical to the per-sample ``aug_record``).  ``draws`` is either the
+    slice's list of draws or ('replay', rng state, n, draw parameters, rows): the worker then replays the epoch's
+    WHOLE draw sequence from the trainer's generator state (the sequence is serial; replaying it in every worker in
+    parallel keeps its ~13 us per sample off the thread that launches the training steps) and takes its rows;
+    the generator state after the sequence travels back with the result."""
     trainer_state, idxs, draws = args[:3]
     src_rows = args[3] if len(args) > 3 else idxs
+    state_after = None
+    if isinstance(draws, tuple) and len(draws) == 5 and draws[0] == 'replay':
+        _, st, n_all, dpar, rows = draws
+        rng = numpy.random.RandomState()
+        rng.set_state(st)
+        alld = _draw_all(rng, n_all, *dpar)
+        state_after = rng.get_state()
+        draws = [alld[i] for i in rows]
+    out = _records_chunk_drawn(trainer_state, idxs, draws, src_rows)
+    return out if state_after is None else out + (state_after,)
+
+
+def _records_chunk_drawn(trainer_state, idxs, draws, src_rows):
     hd, di, aug_modes, comDB, cubeDB, MDB, gtDB, proj = trainer_state
     idxs = numpy.asarray(idxs, dtype=numpy.int64)
     if len(idxs) == 0:
@@ -306,35 +336,42 @@ class NetTrainer(object):
         sigma_com = none_or(a.get('sigma_com'), 5.)
         sigma_sc = none_or(a.get('sigma_sc'), 0.02)
         rot_range = none_or(a.get('rot_range'), 180.)
-        draws = []
-        for _ in range(n):                                    # nettrainer.py:954-957 draw order
-            mode = self.rng.randint(0, len(a['aug_modes']))
-            off = self.rng.randn(3) * sigma_com
-            rot = self.rng.uniform(-rot_range, rot_range)
-            sc = abs(1. + self.rng.randn() * sigma_sc)
-            draws.append((mode, off, rot, sc))
-        return draws
+        return _draw_all(self.rng, n, len(a['aug_modes']), sigma_com, sigma_sc, rot_range)      # nettrainer.py:954-957 draw order
+
+    def _draw_params(self):
+        a = self.cfgParams.augment_fun_params['args']
+        none_or = lambda v, default: default if v is None else v
+        return (len(a['aug_modes']), none_or(a.get('sigma_com'), 5.), none_or(a.get('sigma_sc'), 0.02),
+                none_or(a.get('rot_range'), 180.))
 
     def _request_augmentation(self):
         a = self.cfgParams.augment_fun_params['args']
-        n = self.train_data_xDB.shape[0]
-        draws = self._draw(n)                 # every rank draws for ALL samples: the stream of the single-device run
+        n_all = self.train_data_xDB.shape[0]
         self._to_device()
-        idxs = [int(i) for i in self._rows]   # ... and builds records only for the rows it holds
-        draws = [draws[i] for i in idxs]
-        src = list(range(len(idxs)))
+        idxs = [int(i) for i in self._rows]   # every rank draws for ALL samples (the stream of the single-device run)
+        src = list(range(len(idxs)))          # ... and builds records only for the rows it holds
         n = len(idxs)
+        replay = self._pool is not None
+        if replay:
+            # the draw sequence is replayed inside the workers from this generator state (see _records_chunk);
+            # _swap_augmentation installs the state after the sequence before the next request is made
+            st, dpar = self.rng.get_state(), self._draw_params()
+            draws_of = lambda sl: ('replay', st, n_all, dpar, idxs[sl])
+        else:
+            draws = self._draw(n_all)
+            draws = [draws[i] for i in idxs]
+            draws_of = lambda sl: draws[sl]
         # the side arrays travel as the rows a job needs (a few hundred bytes per sample), not as whole arrays
         def job(sl):
             ii = numpy.asarray(idxs[sl], dtype=numpy.int64)
             g = lambda arr: numpy.asarray(arr)[ii]
             state = (a['hd'], a['di'], a['aug_modes'], g(self.train_data_comDB), g(self.train_data_cubeDB),
                      g(self.train_data_MDB), g(self.train_gt3DcropDB), a.get('proj'))
-            return (state, list(range(len(ii))), draws[sl], src[sl])
-        if self._pool is not None:
+            return (state, list(range(len(ii))), draws_of(sl), src[sl])
+        if replay:
             k = self.cfgParams.para_num_proc
             step = (n + k - 1) // k
-            return ('async', self._pool.map_async(_records_chunk, [job(slice(s, s + step)) for s in range(0, n, step)]))
+            return ('async', self._pool.map_async(_records_chunk, [job(slice(s, s + step)) for s in range(0, max(n, 1), step)]))
         return ('sync', [_records_chunk(job(slice(0, n)))])
 
     def _swap_augmentation(self):
@@ -343,6 +380,8 @@ class NetTrainer(object):
         from dpp_b200.augment import run_records_device
         kind, res = self._pending
         parts = res.get() if kind == 'async' else res
+        if kind == 'async' and len(parts[0]) > 2:
+            self.rng.set_state(parts[0][2])          # the generator as the epoch's draw sequence leaves it
         recs = numpy.concatenate([p[0] for p in parts])
         labels = numpy.concatenate([p[1] for p in parts])
         self._to_device()

@@ -66,6 +66,7 @@ class BenchEngine(FakeEngine):                                 # noqa: F821
 ENG.Engine = BenchEngine
 sys.argv = ['bench.py', '--steps', '1', '--warmup', '1', '--no-roofline', '--no-cpu-baseline', '--no-trainer-api']
 sys.path.insert(0, os.path.dirname(HERE))
+os.environ['DPP_PREP_WORKERS'] = '0'       # this script has no __main__ guard: spawned workers would re-run it (the pool has its own test)
 import bench                                                   # noqa: E402
 
 bench.B, bench.N_RESIDENT, bench.STRONG_GLOBAL_B = 8, 32, 8                              # a batch the CPU oracle steps through in a second

@@ -230,6 +230,17 @@ def test_trainer_record_worker_matches_per_sample_path():
     assert labels.dtype == np.float32 and labels.shape == (16, 30)
     empty = _records_chunk(((hd, di, modes, ds['com3D'], ds['cube'], ds['M'], ds['gt3Dcrop'], None), [], []))
     assert len(empty[0]) == 0
+    # a worker that replays the epoch's draw sequence from the generator state builds the same records for its rows
+    # and reports the state the sequence leaves behind (NetTrainer._request_augmentation / _swap_augmentation)
+    rng2 = np.random.RandomState(1)
+    rows = [3, 4, 5, 9, 15]
+    state = (hd, di, modes, ds['com3D'][rows], ds['cube'][rows], ds['M'][rows], ds['gt3Dcrop'][rows], Proj())
+    out = _records_chunk((state, list(range(len(rows))), ('replay', rng2.get_state(), 16, (3, 5., 0.02, 180.), rows), rows))
+    assert len(out) == 3
+    for k, i in enumerate(rows):
+        assert out[0][k].tobytes() == recs[i].tobytes() and (out[1][k] == labels[i]).all()
+    a, b = out[2], rng.get_state()
+    assert a[0] == b[0] and (a[1] == b[1]).all() and a[2:] == b[2:]
 
 
 def test_importers_load_synthetic_sequences_with_reference_signature(monkeypatch, capsys):
