@@ -271,13 +271,16 @@ k_stem_fwd(const float *__restrict__ x, const float *__restrict__ w, const float
         const int t2 = tile + gridDim.x;
         if (t2 < tiles) stem_fetch_fwd(pf, x, t2 / (tilesY * tilesX), (t2 % (tilesY * tilesX)) / tilesX, t2 % tilesX, H, W);
         const float *pw0 = patch[buf] + (ly * 2) * SPW + lxp * 4;
-        float acc[2][4][8];         // [pooled pixel][pool cell cy*2+cx][channel]
+        // [pooled pixel][pool cell cy*2+cx][channel pair]: one FFMA2 (fma.rn.f32x2: two correctly rounded fp32 FMAs) per
+        // pair - a 3-register FFMA issues only every second cycle per scheduler, i.e. the scalar form caps this kernel at
+        // half the fp32 peak.  Same products, same order per channel: results are bit-identical to the scalar kernel.
+        float2 acc[2][4][4];
 #pragma unroll
         for (int p = 0; p < 2; ++p)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[p][c][q] = 0.f;
+                for (int q = 0; q < 4; ++q) acc[p][c][q] = make_float2(0.f, 0.f);
         float rowa[8], rowb[8];     // window rows r and r + 1
         {
             const float4 a0 = *reinterpret_cast<const float4 *>(pw0), a1 = *reinterpret_cast<const float4 *>(pw0 + 4);
@@ -294,14 +297,15 @@ k_stem_fwd(const float *__restrict__ x, const float *__restrict__ w, const float
             for (int s = 0; s < 5; ++s) {
                 const float4 w0 = *reinterpret_cast<const float4 *>(&ws[(r * 5 + s) * 32 + o0]);
                 const float4 w1 = *reinterpret_cast<const float4 *>(&ws[(r * 5 + s) * 32 + o0 + 4]);
-                const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float2 wq[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
                 for (int p = 0; p < 2; ++p)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float xv = (c >> 1) ? rowb[p * 2 + (c & 1) + s] : rowa[p * 2 + (c & 1) + s];
+                        const float xs = (c >> 1) ? rowb[p * 2 + (c & 1) + s] : rowa[p * 2 + (c & 1) + s];
+                        const float2 xv = make_float2(xs, xs);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) acc[p][c][q] = fmaf(xv, wq[q], acc[p][c][q]);
+                        for (int q = 0; q < 4; ++q) acc[p][c][q] = __ffma2_rn(xv, wq[q], acc[p][c][q]);
                     }
             }
 #pragma unroll
@@ -317,11 +321,13 @@ k_stem_fwd(const float *__restrict__ x, const float *__restrict__ w, const float
             uint32_t am[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                float b = acc[p][0][q];
+                const float a4[4] = {(q & 1) ? acc[p][0][q >> 1].y : acc[p][0][q >> 1].x, (q & 1) ? acc[p][1][q >> 1].y : acc[p][1][q >> 1].x,
+                                     (q & 1) ? acc[p][2][q >> 1].y : acc[p][2][q >> 1].x, (q & 1) ? acc[p][3][q >> 1].y : acc[p][3][q >> 1].x};
+                float b = a4[0];
                 uint32_t bi = 0;
 #pragma unroll
                 for (int c = 1; c < 4; ++c)
-                    if (acc[p][c][q] > b) { b = acc[p][c][q]; bi = (uint32_t)c; }       // first max wins
+                    if (a4[c] > b) { b = a4[c]; bi = (uint32_t)c; }       // first max wins
                 v[q] = b + bq[q];
                 am[q] = bi;
             }

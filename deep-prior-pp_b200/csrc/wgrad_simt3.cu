@@ -109,15 +109,18 @@ k_wgrad3(const W3Args a) {
     const int gi = combo / G, go = combo % G;
     const int bufsz = a.buf_floats;          // staging buffer b starts at float offset b * bufsz
 
-    float acc[9][4][4];
+    // accumulators as float2 pairs over the input channel: acc[t][ip][j] = {dw(ci = 2 ip, co = j), dw(ci = 2 ip + 1, co = j)}.
+    // One FFMA2 (fma.rn.f32x2, two correctly rounded fp32 FMAs) per pair: a 3-register FFMA issues every second cycle
+    // per scheduler on this architecture, so the scalar form caps an FMA-bound kernel at half the fp32 peak.
+    float2 acc[9][2][4];
     float dbp[4];
     auto zero_acc = [&]() {
 #pragma unroll
         for (int t = 0; t < 9; ++t)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+                for (int j = 0; j < 4; ++j) acc[t][i][j] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) dbp[j] = 0.f;
     };
@@ -130,7 +133,8 @@ k_wgrad3(const W3Args a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 *reinterpret_cast<float4 *>(scratch + ((size_t)ps * (G * G) + combo) * 16 + i * 4) =
-                    make_float4(acc[t][i][0], acc[t][i][1], acc[t][i][2], acc[t][i][3]);
+                    (i & 1) ? make_float4(acc[t][i >> 1][0].y, acc[t][i >> 1][1].y, acc[t][i >> 1][2].y, acc[t][i >> 1][3].y)
+                            : make_float4(acc[t][i >> 1][0].x, acc[t][i >> 1][1].x, acc[t][i >> 1][2].x, acc[t][i >> 1][3].x);
             __syncthreads();
             for (int o = tid; o < G * G * 16; o += W3_THREADS) {
                 float s = 0.f;
@@ -204,31 +208,28 @@ k_wgrad3(const W3Args a) {
             int p = ps * run;
             const int p_end = p + run < npix ? p + run : npix;
             int py = (int)(((unsigned)p * L.w_magic) >> 16), px = p - py * W;
-            float c0[3][4], c1[3][4], c2[3][4];
-            auto ldcol = [&](float (&c)[3][4], int base) {       // base = haloed column, tile row py (= image row py - 1)
+            float2 c0[3][2], c1[3][2], c2[3][2];      // a column: 3 rows x 4 channels as two channel pairs
+            auto ldcol = [&](float2 (&c)[3][2], int base) {       // base = haloed column, tile row py (= image row py - 1)
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float4 v = *reinterpret_cast<const float4 *>(smem3 + base + r * Wp * C);
-                    c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
+                    c[r][0] = make_float2(v.x, v.y); c[r][1] = make_float2(v.z, v.w);
                 }
             };
-            auto fma_px = [&](const float (&l)[3][4], const float (&m)[3][4], const float (&rr)[3][4], int dp) {
+            auto fma_px = [&](const float2 (&l)[3][2], const float2 (&m)[3][2], const float2 (&rr)[3][2], int dp) {
                 const float4 d4 = *reinterpret_cast<const float4 *>(smem3 + dp);
-                const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+                const float2 d[4] = {make_float2(d4.x, d4.x), make_float2(d4.y, d4.y), make_float2(d4.z, d4.z), make_float2(d4.w, d4.w)};
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 2; ++i)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            acc[r * 3 + 0][i][j] = fmaf(l[r][i], d[j], acc[r * 3 + 0][i][j]);
-                            acc[r * 3 + 1][i][j] = fmaf(m[r][i], d[j], acc[r * 3 + 1][i][j]);
-                            acc[r * 3 + 2][i][j] = fmaf(rr[r][i], d[j], acc[r * 3 + 2][i][j]);
+                            acc[r * 3 + 0][i][j] = __ffma2_rn(l[r][i], d[j], acc[r * 3 + 0][i][j]);
+                            acc[r * 3 + 1][i][j] = __ffma2_rn(m[r][i], d[j], acc[r * 3 + 1][i][j]);
+                            acc[r * 3 + 2][i][j] = __ffma2_rn(rr[r][i], d[j], acc[r * 3 + 2][i][j]);
                         }
-                if (gi == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dbp[j] += d[j];
-                }
+                if (gi == 0) { dbp[0] += d4.x; dbp[1] += d4.y; dbp[2] += d4.z; dbp[3] += d4.w; }
             };
 #pragma unroll 1
             while (p < p_end) {
@@ -295,12 +296,13 @@ k_wgrad1(const W3Args a) {
     const int combo = tid % COMBOS, ps = tid / COMBOS;
     const int gi = combo / GO, go = combo % GO;
     const int bufsz = a.buf_floats;
-    float acc[8][8], dbp[8];
+    float2 acc[4][8];       // pairs over the input channel: acc[ip][j] = {dw(2 ip, j), dw(2 ip + 1, j)}, one FFMA2 each
+    float dbp[8];
     auto zero_acc = [&]() {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 8; ++j) acc[i >> 1][j] = make_float2(0.f, 0.f);
             dbp[i] = 0.f;
         }
     };
@@ -310,8 +312,9 @@ k_wgrad1(const W3Args a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float *d = scratch + ((size_t)ps * COMBOS + combo) * 64 + i * 8;
-            *reinterpret_cast<float4 *>(d) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            *reinterpret_cast<float4 *>(d + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+            const float2 *ar = acc[i >> 1];
+            *reinterpret_cast<float4 *>(d) = (i & 1) ? make_float4(ar[0].y, ar[1].y, ar[2].y, ar[3].y) : make_float4(ar[0].x, ar[1].x, ar[2].x, ar[3].x);
+            *reinterpret_cast<float4 *>(d + 4) = (i & 1) ? make_float4(ar[4].y, ar[5].y, ar[6].y, ar[7].y) : make_float4(ar[4].x, ar[5].x, ar[6].x, ar[7].x);
         }
         __syncthreads();
         for (int o = tid; o < COMBOS * 64; o += W3_THREADS) {
@@ -385,12 +388,14 @@ k_wgrad1(const W3Args a) {
                 const float4 x1 = *reinterpret_cast<const float4 *>(smem3 + xo + p * CI + 4);
                 const float4 d0 = *reinterpret_cast<const float4 *>(smem3 + dyo + p * CO);
                 const float4 d1 = *reinterpret_cast<const float4 *>(smem3 + dyo + p * CO + 4);
-                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const float2 xv[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
                 const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int j = 0; j < 8; ++j) {
+                    const float2 dd = make_float2(dv[j], dv[j]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], dv[j], acc[i][j]);
+                    for (int i = 0; i < 4; ++i) acc[i][j] = __ffma2_rn(xv[i], dd, acc[i][j]);
+                }
                 if (gi == 0) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) dbp[j] += dv[j];
