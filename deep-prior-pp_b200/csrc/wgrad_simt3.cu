@@ -50,9 +50,11 @@ extern __shared__ __align__(16) float smem3[];     // all accesses go through th
                                                    // compile to LDS / STS rather than generic loads
 
 // issue the loads of one item into a staging buffer: x rows [h0-1, h0+R3] x cols [-1, W] x C (zero fill outside), dy rows [h0, h0+R3)
+template <int C>
 __device__ __forceinline__ void stage_item(const W3Layer &L, int n, int rb, int bufo) {
     float *buf = smem3 + bufo;
-    const int C = L.C, W = L.W, H = L.H, Wp = W + 2, q = C >> 2;      // q = 16-byte pieces per pixel
+    const int W = L.W, H = L.H, Wp = W + 2;
+    constexpr int q = C >> 2;      // 16-byte pieces per pixel (compile-time: the index arithmetic below is shifts, not divisions)
     const int h0 = rb * R3;
     const int xpieces = (R3 + 2) * Wp * q;
     for (int i = threadIdx.x; i < xpieces; i += W3_THREADS) {
@@ -77,9 +79,11 @@ __device__ __forceinline__ void stage_item(const W3Layer &L, int n, int rb, int 
 }
 
 // a = ReLU(x * scale + shift) in place, halo stays zero
+template <int C>
 __device__ __forceinline__ void bn_in_place(const W3Layer &L, int rb, int bufo, const float *s_scale, const float *s_shift) {
     float *buf = smem3 + bufo;
-    const int C = L.C, W = L.W, H = L.H, Wp = W + 2, q = C >> 2;
+    const int W = L.W, H = L.H, Wp = W + 2;
+    constexpr int q = C >> 2;
     const int h0 = rb * R3;
     const int xpieces = (R3 + 2) * Wp * q;
     const bool relu = L.in_bn.relu != 0;
@@ -177,21 +181,21 @@ k_wgrad3(const W3Args a) {
     int buf = 0;
     {
         const int r = it_begin - L.item0;
-        stage_item(L, r / L.rblocks, r % L.rblocks, 0);
+        stage_item<C>(L, r / L.rblocks, r % L.rblocks, 0);
     }
     for (int it = it_begin; it < it_end; ++it, buf ^= 1) {
         const int r = it - L.item0;
         const int rb = r % L.rblocks;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                    // tile `it` has landed; everybody is done with the other buffer
-        if (L.has_in_bn) bn_in_place(L, rb, buf * bufsz, s_scale, s_shift);
+        if (L.has_in_bn) bn_in_place<C>(L, rb, buf * bufsz, s_scale, s_shift);
         // next item: same layer -> prefetch now; a new layer starts after the flush below
         const int nxt = it + 1;
         const bool more = nxt < it_end;
         const bool same = more && (li + 1 >= a.n_layers || a.layers[li + 1].item0 > nxt);
         if (same) {
             const int r2 = nxt - L.item0;
-            stage_item(L, r2 / L.rblocks, r2 % L.rblocks, (buf ^ 1) * bufsz);
+            stage_item<C>(L, r2 / L.rblocks, r2 % L.rblocks, (buf ^ 1) * bufsz);
         }
         __syncthreads();                    // normalised tile visible
         {
@@ -259,7 +263,7 @@ k_wgrad3(const W3Args a) {
             load_coef();
             zero_acc();
             const int r2 = nxt - L.item0;
-            stage_item(L, r2 / L.rblocks, r2 % L.rblocks, (buf ^ 1) * bufsz);
+            stage_item<C>(L, r2 / L.rblocks, r2 % L.rblocks, (buf ^ 1) * bufsz);
         }
     }
     flush(L, buf * bufsz);     // buf was flipped after the last item: this is the buffer NOT read last (the flush syncs first anyway)
