@@ -220,6 +220,22 @@ __global__ void k_convpool_bwd_x(const float *__restrict__ w, const float *__res
 // -------------------------------------------------------------------------------------------------
 constexpr int SPH = 20, SPW = 36;   // forward input patch: 8*2 + 4 rows, 16*2 + 4 columns
 
+// tile index -> (image, tile row, tile column) without integer divisions in the per-tile path: magic multipliers
+// computed once per thread (exact while tile * divisor < 2^32, i.e. for any tensor this library addresses with ints)
+struct TileDiv {
+    unsigned m_img, m_row;
+    int per_img, per_row;
+    __device__ __forceinline__ TileDiv(int tilesY, int tilesX)
+        : m_img(0xFFFFFFFFu / (unsigned)(tilesY * tilesX) + 1u), m_row(0xFFFFFFFFu / (unsigned)tilesX + 1u),
+          per_img(tilesY * tilesX), per_row(tilesX) {}
+    __device__ __forceinline__ void operator()(int tile, int &n, int &ty, int &tx) const {
+        n = per_img == 1 ? tile : (int)__umulhi((unsigned)tile, m_img);
+        const int tr = tile - n * per_img;
+        ty = per_row == 1 ? tr : (int)__umulhi((unsigned)tr, m_row);
+        tx = tr - ty * per_row;
+    }
+};
+
 // a thread's share of a region's input patch (3 of the 720 values): global loads into registers ...
 __device__ __forceinline__ void stem_fetch_fwd(float (&v)[3], const float *__restrict__ x, int n, int ty0, int tx0, int H, int W) {
 #pragma unroll
@@ -251,6 +267,7 @@ k_stem_fwd(const float *__restrict__ x, const float *__restrict__ w, const float
     const int Hp = H / 2, Wp = W / 2;
     const int tilesY = (Hp + 7) / 8, tilesX = (Wp + 15) / 16;
     const int tiles = N * tilesY * tilesX;
+    const TileDiv tdiv(tilesY, tilesX);
     const int pair = tid & 63, grp = tid >> 6;     // grp is warp-uniform: weight reads are broadcasts
     const int ly = pair >> 3, lxp = pair & 7;
     const int o0 = grp * 8;
@@ -261,15 +278,21 @@ k_stem_fwd(const float *__restrict__ x, const float *__restrict__ w, const float
     float pf[3];
     if ((int)blockIdx.x < tiles) {
         const int t = blockIdx.x;
-        stem_fetch_fwd(pf, x, t / (tilesY * tilesX), (t % (tilesY * tilesX)) / tilesX, t % tilesX, H, W);
+        int n_, ty_, tx_;
+        tdiv(t, n_, ty_, tx_);
+        stem_fetch_fwd(pf, x, n_, ty_, tx_, H, W);
         stem_put_fwd(patch[0], pf);
     }
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
-        const int n = tile / (tilesY * tilesX), tr = tile % (tilesY * tilesX);
-        const int ty0 = tr / tilesX, tx0 = tr % tilesX;
+        int n, ty0, tx0;
+        tdiv(tile, n, ty0, tx0);
         __syncthreads();            // patch[buf] complete; everybody is done with patch[buf ^ 1]
         const int t2 = tile + gridDim.x;
-        if (t2 < tiles) stem_fetch_fwd(pf, x, t2 / (tilesY * tilesX), (t2 % (tilesY * tilesX)) / tilesX, t2 % tilesX, H, W);
+        if (t2 < tiles) {
+            int n_, ty_, tx_;
+            tdiv(t2, n_, ty_, tx_);
+            stem_fetch_fwd(pf, x, n_, ty_, tx_, H, W);
+        }
         const float *pw0 = patch[buf] + (ly * 2) * SPW + lxp * 4;
         // [pooled pixel][pool cell cy*2+cx][channel pair]: one FFMA2 (fma.rn.f32x2: two correctly rounded fp32 FMAs) per
         // pair - a 3-register FFMA issues only every second cycle per scheduler, i.e. the scalar form caps this kernel at
@@ -391,6 +414,7 @@ k_stem_bwd_w(const float *__restrict__ x, const uint8_t *__restrict__ argmax, co
     const int Hp = H / 2, Wp = W / 2;
     const int tilesY = (Hp + 7) / 8, tilesX = (Wp + 7) / 8;
     const int tiles = N * tilesY * tilesX;
+    const TileDiv tdiv(tilesY, tilesX);
     float acc[25], accb = 0.f;
 #pragma unroll
     for (int t = 0; t < 25; ++t) acc[t] = 0.f;
@@ -399,8 +423,8 @@ k_stem_bwd_w(const float *__restrict__ x, const uint8_t *__restrict__ argmax, co
     int base[8], cn[8];
     // this warp's pooled row ty0*8 + wq, columns tx0*8 .. +7 of a tile: gradient and arg-max cell per (pixel, lane = channel)
     auto fetch = [&](int tile) {
-        const int n = tile / (tilesY * tilesX), tr = tile % (tilesY * tilesX);
-        const int ty0 = tr / tilesX, tx0 = tr % tilesX;
+        int n, ty0, tx0;
+        tdiv(tile, n, ty0, tx0);
         const int ph = ty0 * 8 + wq;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -413,7 +437,9 @@ k_stem_bwd_w(const float *__restrict__ x, const uint8_t *__restrict__ argmax, co
     };
     if ((int)blockIdx.x < tiles) {
         const int t = blockIdx.x;
-        stem_fetch_bwd(pf, x, t / (tilesY * tilesX), (t % (tilesY * tilesX)) / tilesX, t % tilesX, H, W);
+        int n_, ty_, tx_;
+        tdiv(t, n_, ty_, tx_);
+        stem_fetch_bwd(pf, x, n_, ty_, tx_, H, W);
         stem_put_bwd(patch[0], pf);
         fetch(t);
     }
@@ -426,7 +452,9 @@ k_stem_bwd_w(const float *__restrict__ x, const uint8_t *__restrict__ argmax, co
         __syncthreads();            // patch[buf] complete; everybody is done with patch[buf ^ 1]
         const int t2 = tile + gridDim.x;
         if (t2 < tiles) {
-            stem_fetch_bwd(pf, x, t2 / (tilesY * tilesX), (t2 % (tilesY * tilesX)) / tilesX, t2 % tilesX, H, W);
+            int n_, ty_, tx_;
+            tdiv(t2, n_, ty_, tx_);
+            stem_fetch_bwd(pf, x, n_, ty_, tx_, H, W);
             fetch(t2);
         }
         const float *pb = patch[buf];

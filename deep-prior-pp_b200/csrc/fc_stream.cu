@@ -50,7 +50,7 @@ __device__ long long *g_prof_fs = nullptr;
 #endif
 
 constexpr int FS_THREADS = 448;
-constexpr int NL = 4;                       // landing slots (32 KB each)
+constexpr int NL = 5;                       // landing slots (32 KB each): as many as fit next to the operand tiles
 constexpr int SLOT_BYTES = 32768;           // A part 16 KB | B part 16 KB
 constexpr int BT_OFF = NL * SLOT_BYTES;     // B operand tiles: 2 stages x (hi 16 KB | lo 16 KB)
 constexpr int BAR_OFF = BT_OFF + 2 * 32768;
