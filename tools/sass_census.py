@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'deep-prior-pp_b200', 'csrc', 'libdpp_b200.so')
-OPS = ['UTCHMMA', 'LDTM', 'STTM', 'UTCBAR', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'LDGSTS', 'SYNCS', 'RED', 'HMMA', 'FFMA', 'DFMA']
+OPS = ['UTCHMMA', 'LDTM', 'STTM', 'UTCBAR', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'LDGSTS', 'SYNCS', 'RED', 'HMMA', 'FFMA2', 'FFMA', 'DFMA']
 
 
 def demangle(name):
@@ -37,7 +37,7 @@ def main():
             op = m.group(1)
             lines[cur] += 1
             for o in OPS:
-                if op == o or op.startswith(o + '.') or (o == 'RED' and op.startswith('REDG')):
+                if op == o or op.startswith(o + '.') or (o == 'RED' and op.startswith('REDG')):      # (the regex stops 'FFMA2' from counting as 'FFMA')
                     counts[cur][o] += 1
     print("SASS opcode census of %s (sm_100a), one row per kernel" % os.path.relpath(LIB, ROOT))
     print("%-58s %7s " % ("kernel", "instrs") + " ".join("%7s" % o for o in OPS))

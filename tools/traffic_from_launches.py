@@ -30,7 +30,7 @@ def main():
     tot_w = sum(wr[i][1] for i in idx)
     tot_t = sum(dur[i][1] for i in idx)
     print(json.dumps({
-        "source": path, "launches": len(idx),
+        "source": path, "step": step, "launches": len(idx),
         "conv_fwd_avg_bytes_per_launch": (tot_r + tot_w) / len(idx),
         "conv_fwd_dram_read_bytes": tot_r, "conv_fwd_dram_write_bytes": tot_w,
         "conv_fwd_avg_ns_per_launch_under_ncu": tot_t / len(idx),
