@@ -872,11 +872,22 @@ class Engine(object):
                 self._wgroup = h
             if self._wgroup is not None:
                 lib.dpp_wgrad_group_run(self._wgroup, st)
+        self._adam_tail = None
         if exchanging and trailing is not None:
+            split = (cuts and trailing[0] == 0 and 0 < trailing[1] < self.n_w and trailing[1] % 4 == 0
+                     and os.environ.get('DPP_SPLIT_ADAM', '1') != '0')
+            if split:
+                # everything above the trailing bucket has been handed to the comm stream already: the optimiser can
+                # take [hi, n) while the last, small bucket (conv / BN gradients) is still being exchanged
+                early_done = torch.cuda.Event()
+                early_done.record(self._comm_stream)
             exchange(*trailing)
+            if split:
+                main.wait_event(early_done)
+                self._adam_tail = trailing
         if forked:
             main.wait_stream(side)                  # join: the gradient arena is complete
-        if exchanging:
+        if exchanging and self._adam_tail is None:
             main.wait_stream(self._comm_stream)     # ... and summed over the ranks
         self._n_bn_bwd_launches = len(self.bns) - n_fused[0]
 
@@ -980,7 +991,18 @@ class Engine(object):
         d = int(self.y_in.shape[1])
         lib.dpp_loss_sqerr(_ptr(self.t_out.buf), _ptr(self.y_in), _ptr(self.t_out.grad), _ptr(self.cost), self.B, d, st)
         self._run_backward()
-        lib.dpp_adam_step(_ptr(self.W), _ptr(self.G), _ptr(self.M), _ptr(self.V), _ptr(self.hyper), self.n_w, st)
+        tail = getattr(self, '_adam_tail', None)
+        if tail is not None:
+            # data parallel: ADAM over the part of the arena whose exchange is complete (the HiddenLayers: 90 % of the
+            # parameters) hides the exchange of the trailing bucket; then the rest
+            lo, hi = tail
+            lib.dpp_adam_step(_ptr(self.W[hi:]), _ptr(self.G[hi:]), _ptr(self.M[hi:]), _ptr(self.V[hi:]), _ptr(self.hyper),
+                              self.n_w - hi, st)
+            self.torch.cuda.current_stream().wait_stream(self._comm_stream)
+            lib.dpp_adam_step(_ptr(self.W[lo:hi]), _ptr(self.G[lo:hi]), _ptr(self.M[lo:hi]), _ptr(self.V[lo:hi]),
+                              _ptr(self.hyper), hi - lo, st)
+        else:
+            lib.dpp_adam_step(_ptr(self.W), _ptr(self.G), _ptr(self.M), _ptr(self.V), _ptr(self.hyper), self.n_w, st)
         lib.dpp_adam_tick(_ptr(self.hyper), st)
         if self.pack_items is not None:
             lib.dpp_conv_pack_all(_ptr(self.pack_items), self.n_pack, st)
