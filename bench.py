@@ -516,7 +516,7 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
         def ring_upload(b):
             r_ = ring
             ring_submit()
-            slot = r_['inflight'].pop(0).get()                        # a finished batch
+            slot = r_['inflight'].pop(0).get(timeout=300)             # a finished batch (a dead worker must not hang the run)
             o = slot * r_['slot_bytes']
             w = r_['whole']
             copy_stream.wait_event(consumed[b])
@@ -538,7 +538,7 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
             if pool is not None:
                 while len(pending) < 2 * nwork:                       # keep the workers busy a few batches ahead
                     submit()
-                src, rbytes, yv = pending.pop(0).get()
+                src, rbytes, yv = pending.pop(0).get(timeout=300)
                 torch.index_select(xs_t, 0, torch.from_numpy(src), out=hx[b])     # the batch's crops into pinned memory
                 hr[b].numpy()[...] = rbytes
                 hy[b].numpy()[...] = yv

@@ -334,8 +334,8 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 for (int j = 0; j < 2; ++j) {
                     const float4 x = xr[hh * 2 + j];   // piece 0-3: tap A, 4-7: tap B
                     hi[4 * j] = to_tf32(x.x); hi[4 * j + 1] = to_tf32(x.y); hi[4 * j + 2] = to_tf32(x.z); hi[4 * j + 3] = to_tf32(x.w);
-                    lo[4 * j] = to_tf32(x.x - __uint_as_float(hi[4 * j])); lo[4 * j + 1] = to_tf32(x.y - __uint_as_float(hi[4 * j + 1]));
-                    lo[4 * j + 2] = to_tf32(x.z - __uint_as_float(hi[4 * j + 2])); lo[4 * j + 3] = to_tf32(x.w - __uint_as_float(hi[4 * j + 3]));
+                    lo[4 * j] = lo_tf32(x.x, hi[4 * j]); lo[4 * j + 1] = lo_tf32(x.y, hi[4 * j + 1]);
+                    lo[4 * j + 2] = lo_tf32(x.z, hi[4 * j + 2]); lo[4 * j + 3] = lo_tf32(x.w, hi[4 * j + 3]);
                 }
                 tmem_st8(ta + hh * 8, hi);
                 if (PASSES > 1) tmem_st8(ta + 32 + hh * 8, lo);
@@ -705,7 +705,7 @@ __global__ void k_pack(const PackItem *__restrict__ items) {
             const uint32_t h = to_tf32(v);
             float *dst = img + blk * per + row * 32 + pch * 4 + e;
             dst[0] = __uint_as_float(h);
-            if (it.passes > 1) dst[BN * 32] = __uint_as_float(to_tf32(v - __uint_as_float(h)));
+            if (it.passes > 1) dst[BN * 32] = __uint_as_float(lo_tf32(v, h));
         }
     }
 }

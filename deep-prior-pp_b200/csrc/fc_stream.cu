@@ -169,7 +169,7 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             hi[j] = to_tf32(v[hh * 8 + j]);
-                            lo[j] = to_tf32(v[hh * 8 + j] - __uint_as_float(hi[j]));
+                            lo[j] = lo_tf32(v[hh * 8 + j], hi[j]);
                         }
                         tmem_st8(ta + hh * 8, hi);
                         tmem_st8(ta + 32 + hh * 8, lo);
@@ -187,8 +187,8 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
                             const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4);
                             uint4 h, l;
                             h.x = to_tf32(v[4 * j]); h.y = to_tf32(v[4 * j + 1]); h.z = to_tf32(v[4 * j + 2]); h.w = to_tf32(v[4 * j + 3]);
-                            l.x = to_tf32(v[4 * j] - __uint_as_float(h.x)); l.y = to_tf32(v[4 * j + 1] - __uint_as_float(h.y));
-                            l.z = to_tf32(v[4 * j + 2] - __uint_as_float(h.z)); l.w = to_tf32(v[4 * j + 3] - __uint_as_float(h.w));
+                            l.x = lo_tf32(v[4 * j], h.x); l.y = lo_tf32(v[4 * j + 1], h.y);
+                            l.z = lo_tf32(v[4 * j + 2], h.z); l.w = lo_tf32(v[4 * j + 3], h.w);
                             *reinterpret_cast<uint4 *>(bt_tile + off) = h;
                             *reinterpret_cast<uint4 *>(bt_tile + 16384 + off) = l;
                         }

@@ -35,8 +35,8 @@ __device__ __forceinline__ void st_piece(unsigned char *tile, int row, int ch, f
     *reinterpret_cast<uint4 *>(tile + off) = h;
     if (PASSES > 1) {
         uint4 l;
-        l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
-        l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
+        l.x = lo_tf32(v.x, h.x); l.y = lo_tf32(v.y, h.y);
+        l.z = lo_tf32(v.z, h.z); l.w = lo_tf32(v.w, h.w);
         *reinterpret_cast<uint4 *>(tile + ROWS * 128 + off) = l;
     }
 }
@@ -46,7 +46,7 @@ __device__ __forceinline__ void st_elem(unsigned char *tile, int row, int j, flo
     const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((j >> 2) ^ (row & 7)) << 4) + ((j & 3) << 2);
     const uint32_t h = to_tf32(e);
     *reinterpret_cast<uint32_t *>(tile + off) = h;
-    if (PASSES > 1) *reinterpret_cast<uint32_t *>(tile + ROWS * 128 + off) = to_tf32(e - __uint_as_float(h));
+    if (PASSES > 1) *reinterpret_cast<uint32_t *>(tile + ROWS * 128 + off) = lo_tf32(e, h);
 }
 
 template <int BN, int PASSES, bool ATRANS, bool BTRANS>

@@ -106,6 +106,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // x - hi is exact in fp32, so hi + lo reproduces x to 2^-21 relative - the 3xTF32 split in 3 ALU ops per value
 // (cvt.rna.tf32.f32 expands to a ~10-instruction sequence on sm_100a and dominated the producer loops).
 __device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+// The lo plane needs no masking of its own: x - hi is exact, and whatever the tensor core does with the 13 low mantissa
+// bits of a tf32 operand (it ignores them) costs at most 2^-11 of |lo| <= 2^-11 |x|, i.e. 2^-22 of |x| - the order of the
+// lo x lo products 3xTF32 drops anyway.  One ALU operation less per value in every transform loop.
+#ifndef DPP_LO_MASK
+#define DPP_LO_MASK 0
+#endif
+__device__ __forceinline__ uint32_t lo_tf32(float x, uint32_t hi) {
+    const float l = x - __uint_as_float(hi);
+    return DPP_LO_MASK ? (__float_as_uint(l) & 0xFFFFE000u) : __float_as_uint(l);
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (LBO = 16 B, SBO = 1024 B, version 1).  The start address
 // sits in the low 14 bits (>> 4): advancing it by n bytes inside the tile is `desc + (n >> 4)`.

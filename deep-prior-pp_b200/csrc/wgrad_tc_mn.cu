@@ -206,8 +206,8 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
                     *reinterpret_cast<uint4 *>(dst) = h;
                     if (PASSES > 1) {
                         uint4 l;
-                        l.x = to_tf32(xv.x - __uint_as_float(h.x)); l.y = to_tf32(xv.y - __uint_as_float(h.y));
-                        l.z = to_tf32(xv.z - __uint_as_float(h.z)); l.w = to_tf32(xv.w - __uint_as_float(h.w));
+                        l.x = lo_tf32(xv.x, h.x); l.y = lo_tf32(xv.y, h.y);
+                        l.z = lo_tf32(xv.z, h.z); l.w = lo_tf32(xv.w, h.w);
                         *reinterpret_cast<uint4 *>(dst + L::A_BLOCKS * 4096) = l;
                     }
                 }
@@ -224,8 +224,8 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
                 *reinterpret_cast<uint4 *>(dst) = h;
                 if (PASSES > 1) {
                     uint4 l;
-                    l.x = to_tf32(bv.x - __uint_as_float(h.x)); l.y = to_tf32(bv.y - __uint_as_float(h.y));
-                    l.z = to_tf32(bv.z - __uint_as_float(h.z)); l.w = to_tf32(bv.w - __uint_as_float(h.w));
+                    l.x = lo_tf32(bv.x, h.x); l.y = lo_tf32(bv.y, h.y);
+                    l.z = lo_tf32(bv.z, h.z); l.w = lo_tf32(bv.w, h.w);
                     *reinterpret_cast<uint4 *>(dst + NDY * 4096) = l;
                 }
             }
