@@ -318,8 +318,12 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                     x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
                     if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                 }
-                if (!(pj < 4 ? v0 : v1)) x = make_float4(0.f, 0.f, 0.f, 0.f);
                 xr[pj] = x;
+            }
+            if (!__all_sync(0xffffffffu, v0 && v1)) {      // only warps that touch the image border (or the tail of M) pay for the zeroing
+#pragma unroll
+                for (int pj = 0; pj < 8; ++pj)
+                    if (!(pj < 4 ? v0 : v1)) xr[pj] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (lane == 0) mbar_wait(bar(NS + stage), phase ^ 1);     // the MMAs that read this A stage have retired
             __syncwarp();
