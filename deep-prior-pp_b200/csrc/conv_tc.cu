@@ -434,7 +434,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                 const int ch0 = h0 * a.in_stride;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     if (!resident) {
-                        mbar_wait_relaxed(bar(2 * NS + 4 + RB + b), bphase ^ 1);
+                        mbar_wait_hint(bar(2 * NS + 4 + RB + b), bphase ^ 1);
                         const float *src = a.wimg + ((size_t)(nt * a.kchunks + kc)) * (PASSES * BN * 32);
                         mbar_expect_tx(bar(2 * NS + 4 + b), L::B_BYTES);
                         bulk_g2s(sbase + L::B_OFF + b * L::B_BYTES, src, L::B_BYTES, bar(2 * NS + 4 + b));
@@ -495,7 +495,7 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
             side_round(0);
             if (NB > 1) side_round(1);
             PROF(30);
-            if (lane == 0) mbar_wait_relaxed(bar(2 * NS + acc), aphase);
+            if (lane == 0) mbar_wait_hint(bar(2 * NS + acc), aphase);
             __syncwarp();
             tc_fence_after();
             PROF(31);
