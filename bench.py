@@ -476,6 +476,12 @@ def measure_e2e(run, ctx, steps, warmup, with_prep):
                 xb, rbts, ybts = nb * 128 * 128 * 4, nb * rec_bytes, nb * E * 4
                 slot_bytes = (xb + rbts + ybts + 4095) // 4096 * 4096
                 nslot = 2 * nwork + 2
+                try:                                              # a small /dev/shm (container default: 64 MB) cannot hold the ring:
+                    vfs = os.statvfs('/dev/shm')                  # writing past it would kill the workers with SIGBUS
+                    if vfs.f_bavail * vfs.f_frsize < 2 * nslot * slot_bytes * max(ctx.world, 1):
+                        raise RuntimeError("/dev/shm has %d MB free" % (vfs.f_bavail * vfs.f_frsize >> 20))
+                except OSError:
+                    pass
                 shm = shared_memory.SharedMemory(create=True, size=nslot * slot_bytes)
                 whole = torch.frombuffer(shm.buf, dtype=torch.uint8)
                 rc = torch.cuda.cudart().cudaHostRegister(whole.data_ptr(), nslot * slot_bytes, 0)
