@@ -373,3 +373,31 @@ def test_parameter_layout_conversions_between_reference_and_device():
     b = rng.randn(7).astype(np.float32)
     s = Slot(shared(b), 'w', 0)
     assert np.array_equal(s.from_device_layout(s.to_device_layout(b)), b)
+
+
+def test_gradient_arena_zero_ranges_skip_the_assigned_hiddenlayer_weights():
+    """Engine._g_zero_ranges: the HiddenLayer weight gradients are ASSIGNED by dpp_fc_bwd_ex (DPP_FC_DW_ASSIGN), so the
+    per-step clear of the gradient arena covers exactly everything else - conv weights, biases, BatchNorm parameters,
+    HiddenLayer biases, slot padding - in sorted, disjoint ranges."""
+    import torch
+    from dpp_b200.engine import Engine
+    net = ResNet(np.random.RandomState(23455), cfgParams=ResNetParams(type=0, batchSize=4, numJoints=1, nDims=30))
+    eng = Engine.__new__(Engine)
+    eng.net, eng.output_sym, eng.B, eng.precision = net, net.output, 4, 1
+    eng.torch, eng.dev = torch, torch.device('cpu')
+    eng._lower()
+    eng._alloc_params()
+    ranges = eng._g_zero_ranges()
+    assert ranges == sorted(ranges) and all(lo < hi for lo, hi in ranges)
+    assert all(ranges[i][1] <= ranges[i + 1][0] for i in range(len(ranges) - 1))
+    cleared = np.zeros(eng.n_w, bool)
+    for lo, hi in ranges:
+        cleared[lo:hi] = True
+    fcw = [eng.slots[id(o['layer'].W)] for o in eng.ops if o['kind'] == 'fc']
+    assert len(fcw) == 3 and max(s.size for s in fcw) == 16384 * 1024
+    for s in fcw:
+        assert not cleared[s.offset:s.offset + s.size].any()          # assigned, never cleared
+        cleared[s.offset:s.offset + s.size] = True
+    assert cleared.all()                                               # ... and nothing else is left out
+    skipped = sum(s.size for s in fcw) / float(eng.n_w)
+    assert 0.9 < skipped < 0.99                                        # the HiddenLayers hold ~95 % of the parameters
