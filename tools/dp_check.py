@@ -10,6 +10,8 @@ mathematically zero gradient - into +-lr updates, so weights are not a usable co
   (a) G_early == sum over ranks of G_local            (the exchange computes the global sum)
   (b) G_early == G_late                               (the overlap changes the schedule, not the arithmetic)
   (c) all ranks hold identical G and identical weights after the step (replicas stay in sync)
+  (d) the weights after the step are one reference ADAM step from the weights before it, over the WHOLE arena (the
+      optimiser pass is split so that its first part hides the exchange of the trailing bucket)
 Tolerance 2e-5 of max|G|: the backward-weights kernels accumulate with floating-point atomics, whose order varies."""
 import os
 import sys
@@ -51,10 +53,12 @@ def run(mode, rank, world, B=16):
         x, y = inputs_of(rank, B)
     eng.t_in.buf.copy_(x)
     eng.y_in.copy_(y)
+    w_before = eng.W.clone()
     cost = eng.train_step(None, use_graph=True)
     torch.cuda.synchronize()
     eng.check_barriers()
     G, W, R, c = eng.G.clone(), eng.W.clone(), eng.R.clone(), float(cost.cpu()[0])
+    run.last_w_before, run.last_hyper = w_before, eng.hyper.clone()
     eng._graphs.clear()
     eng.release()
     return G, W, R, c
@@ -76,6 +80,17 @@ def main():
     g_sum = g_local.clone()
     dist.all_reduce(g_sum)
     g_early, w_early = run('early', rank, world)[:2]
+    # (d) the optimiser pass is split in data-parallel runs (everything above the trailing bucket first, the trailing
+    # bucket after its exchange): every parameter must have received exactly ONE first ADAM step with the exchanged
+    # gradient (trainer/optimizer.py:69-88 at t = 1: m = 0.1 g, v = 0.001 g^2, bias corrections 0.1 / 0.001)
+    w0, hyper = run.last_w_before, run.last_hyper
+    lr, gs = float(hyper[0]), float(hyper[3])
+    g1 = g_early * gs
+    c1 = 1.0 - torch.tensor(0.9, dtype=torch.float32).pow(1.0)
+    c2 = 1.0 - torch.tensor(0.999, dtype=torch.float32).pow(1.0)
+    mh, vh = (0.1 * g1) / c1.item(), (0.001 * (g1 * g1)) / c2.item()
+    w_ref = w0 - (lr * mh) / (vh.sqrt() + 1e-8)
+    d_adam = float((w_early - w_ref).abs().max()) / lr
     g_late = run('late', rank, world)[0]
     scale = float(g_sum.abs().max())
     d_sum = float((g_early - g_sum).abs().max()) / scale
@@ -103,10 +118,11 @@ def main():
     sync_p2p = same_on_all_ranks(g_p2p) and same_on_all_ranks(w_p2p) and same_on_all_ranks(r_p2p)
     if rank == 0:
         print("dp_check world=%d  |G_early - sum(G_local)|/max|G| = %.2e   |G_early - G_late|/max|G| = %.2e   "
-              "replicas identical: G %s, W %s" % (world, d_sum, d_late, sync_g, sync_w))
+              "replicas identical: G %s, W %s   split ADAM vs one reference step: max |dW| = %.1e lr"
+              % (world, d_sum, d_late, sync_g, sync_w, d_adam))
         print("dp_check SyncBN vs one device with the global batch of %d: cost %.3e, gradient max %.2e / rel-L2 %.2e, "
               "running statistics %.2e, replicas identical %s" % (16 * world, d_cost, d_sbn, l2_sbn, d_run, sync_sbn))
-        ok = d_sum < 2e-5 and d_late < 2e-5 and sync_g and sync_w
+        ok = d_sum < 2e-5 and d_late < 2e-5 and sync_g and sync_w and d_adam < 1e-3      # a missed or doubled range would be ~1 lr
         # a handful of roundoff-level ReLU decisions may differ between the two runs (different summation order of the
         # statistics): bound the gradient by what such flips allow, the cost and statistics tightly
         ok_sbn = d_cost < 1e-5 and d_run < 1e-5 and l2_sbn < 2e-2 and sync_sbn
