@@ -314,8 +314,9 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                     const int chan = (pj < 4 ? e0.w : e1.w) + (pj & 3) * 4;
                     const float4 sc = *reinterpret_cast<const float4 *>(s_scale + chan);
                     const float4 sf = *reinterpret_cast<const float4 *>(s_shift + chan);
-                    x.x = fmaf(x.x, sc.x, sf.x); x.y = fmaf(x.y, sc.y, sf.y);
-                    x.z = fmaf(x.z, sc.z, sf.z); x.w = fmaf(x.w, sc.w, sf.w);
+                    const float2 p0 = __ffma2_rn(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(sf.x, sf.y));
+                    const float2 p1 = __ffma2_rn(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(sf.z, sf.w));
+                    x = make_float4(p0.x, p0.y, p1.x, p1.y);         // (packed FMAs: same roundings, half the issue slots)
                     if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                 }
                 xr[pj] = x;
@@ -337,9 +338,8 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const float4 x = xr[hh * 2 + j];   // piece 0-3: tap A, 4-7: tap B
-                    hi[4 * j] = to_tf32(x.x); hi[4 * j + 1] = to_tf32(x.y); hi[4 * j + 2] = to_tf32(x.z); hi[4 * j + 3] = to_tf32(x.w);
-                    lo[4 * j] = lo_tf32(x.x, hi[4 * j]); lo[4 * j + 1] = lo_tf32(x.y, hi[4 * j + 1]);
-                    lo[4 * j + 2] = lo_tf32(x.z, hi[4 * j + 2]); lo[4 * j + 3] = lo_tf32(x.w, hi[4 * j + 3]);
+                    split_tf32x2(x.x, x.y, hi[4 * j], hi[4 * j + 1], lo[4 * j], lo[4 * j + 1]);
+                    split_tf32x2(x.z, x.w, hi[4 * j + 2], hi[4 * j + 3], lo[4 * j + 2], lo[4 * j + 3]);
                 }
                 tmem_st8(ta + hh * 8, hi);
                 if (PASSES > 1) tmem_st8(ta + 32 + hh * 8, lo);

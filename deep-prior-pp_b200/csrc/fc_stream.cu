@@ -167,10 +167,7 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
                     for (int hh = 0; hh < 4; ++hh) {
                         uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            hi[j] = to_tf32(v[hh * 8 + j]);
-                            lo[j] = lo_tf32(v[hh * 8 + j], hi[j]);
-                        }
+                        for (int j = 0; j < 8; j += 2) split_tf32x2(v[hh * 8 + j], v[hh * 8 + j + 1], hi[j], hi[j + 1], lo[j], lo[j + 1]);
                         tmem_st8(ta + hh * 8, hi);
                         tmem_st8(ta + 32 + hh * 8, lo);
                     }
@@ -186,9 +183,8 @@ k_fc_stream(const __grid_constant__ FSArgs a) {
                         for (int j = 0; j < 8; ++j) {
                             const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4);
                             uint4 h, l;
-                            h.x = to_tf32(v[4 * j]); h.y = to_tf32(v[4 * j + 1]); h.z = to_tf32(v[4 * j + 2]); h.w = to_tf32(v[4 * j + 3]);
-                            l.x = lo_tf32(v[4 * j], h.x); l.y = lo_tf32(v[4 * j + 1], h.y);
-                            l.z = lo_tf32(v[4 * j + 2], h.z); l.w = lo_tf32(v[4 * j + 3], h.w);
+                            split_tf32x2(v[4 * j], v[4 * j + 1], h.x, h.y, l.x, l.y);
+                            split_tf32x2(v[4 * j + 2], v[4 * j + 3], h.z, h.w, l.z, l.w);
                             *reinterpret_cast<uint4 *>(bt_tile + off) = h;
                             *reinterpret_cast<uint4 *>(bt_tile + 16384 + off) = l;
                         }

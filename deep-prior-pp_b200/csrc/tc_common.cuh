@@ -112,6 +112,15 @@ __device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x)
 #ifndef DPP_LO_MASK
 #define DPP_LO_MASK 0
 #endif
+// two values at once: hi by masking, lo = x - hi as ONE packed FMA (fma.rn.f32x2: hi * (-1) + x is exact, so the result is
+// the same as two subtractions) - the transform loops are bound by issue slots
+__device__ __forceinline__ void split_tf32x2(float a, float b, uint32_t &h0, uint32_t &h1, uint32_t &l0, uint32_t &l1) {
+    h0 = __float_as_uint(a) & 0xFFFFE000u;
+    h1 = __float_as_uint(b) & 0xFFFFE000u;
+    const float2 l = __ffma2_rn(make_float2(__uint_as_float(h0), __uint_as_float(h1)), make_float2(-1.f, -1.f), make_float2(a, b));
+    l0 = __float_as_uint(l.x);
+    l1 = __float_as_uint(l.y);
+}
 __device__ __forceinline__ uint32_t lo_tf32(float x, uint32_t hi) {
     const float l = x - __uint_as_float(hi);
     return DPP_LO_MASK ? (__float_as_uint(l) & 0xFFFFE000u) : __float_as_uint(l);
