@@ -195,21 +195,18 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
                     if (!g_ok[k]) continue;
                     float4 xv = *reinterpret_cast<const float4 *>(slot + k * 16);
                     if (pro) {
-                        xv.x = fmaf(xv.x, sc[k].x, sf[k].x); xv.y = fmaf(xv.y, sc[k].y, sf[k].y);
-                        xv.z = fmaf(xv.z, sc[k].z, sf[k].z); xv.w = fmaf(xv.w, sc[k].w, sf[k].w);
+                        const float2 p0 = __ffma2_rn(make_float2(xv.x, xv.y), make_float2(sc[k].x, sc[k].y), make_float2(sf[k].x, sf[k].y));
+                        const float2 p1 = __ffma2_rn(make_float2(xv.z, xv.w), make_float2(sc[k].z, sc[k].w), make_float2(sf[k].z, sf[k].w));
+                        xv = make_float4(p0.x, p0.y, p1.x, p1.y);        // packed FMAs: same roundings, half the issue slots
                         if (relu) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f); }
                     }
                     if (!((vm >> k) & 1u)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
                     unsigned char *dst = st + a_off[k];
-                    uint4 h;
-                    h.x = to_tf32(xv.x); h.y = to_tf32(xv.y); h.z = to_tf32(xv.z); h.w = to_tf32(xv.w);
+                    uint4 h, l;
+                    split_tf32x2(xv.x, xv.y, h.x, h.y, l.x, l.y);
+                    split_tf32x2(xv.z, xv.w, h.z, h.w, l.z, l.w);
                     *reinterpret_cast<uint4 *>(dst) = h;
-                    if (PASSES > 1) {
-                        uint4 l;
-                        l.x = lo_tf32(xv.x, h.x); l.y = lo_tf32(xv.y, h.y);
-                        l.z = lo_tf32(xv.z, h.z); l.w = lo_tf32(xv.w, h.w);
-                        *reinterpret_cast<uint4 *>(dst + L::A_BLOCKS * 4096) = l;
-                    }
+                    if (PASSES > 1) *reinterpret_cast<uint4 *>(dst + L::A_BLOCKS * 4096) = l;
                 }
             }
 #pragma unroll
@@ -219,15 +216,11 @@ __device__ __forceinline__ void item_run(const WArgs &a, const int mt, const int
                 const float4 bv = *reinterpret_cast<const float4 *>(slot + (L::AP + m) * 16);
                 dbp[m * 4] += bv.x; dbp[m * 4 + 1] += bv.y; dbp[m * 4 + 2] += bv.z; dbp[m * 4 + 3] += bv.w;
                 unsigned char *dst = st + L::A_BYTES + (pcm >> 3) * 4096 + jb * 128 + ((((uint32_t)pcm & 7) ^ b_sw) << 4);
-                uint4 h;
-                h.x = to_tf32(bv.x); h.y = to_tf32(bv.y); h.z = to_tf32(bv.z); h.w = to_tf32(bv.w);
+                uint4 h, l;
+                split_tf32x2(bv.x, bv.y, h.x, h.y, l.x, l.y);
+                split_tf32x2(bv.z, bv.w, h.z, h.w, l.z, l.w);
                 *reinterpret_cast<uint4 *>(dst) = h;
-                if (PASSES > 1) {
-                    uint4 l;
-                    l.x = lo_tf32(bv.x, h.x); l.y = lo_tf32(bv.y, h.y);
-                    l.z = lo_tf32(bv.z, h.z); l.w = lo_tf32(bv.w, h.w);
-                    *reinterpret_cast<uint4 *>(dst + NDY * 4096) = l;
-                }
+                if (PASSES > 1) *reinterpret_cast<uint4 *>(dst + NDY * 4096) = l;
             }
             PROF(14);
             fence_proxy_async();                 // every writer orders its own stores towards the async proxy ...
