@@ -532,35 +532,46 @@ k_conv_tc(const __grid_constant__ TCArgs a) {
                     cf0 = *reinterpret_cast<const float4 *>(s_msc + cl); cf1 = *reinterpret_cast<const float4 *>(s_msh + cl);
                     cf2 = *reinterpret_cast<const float4 *>(s_mmean + cl); cf3 = *reinterpret_cast<const float4 *>(s_mistd + cl);
                 }
-                float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                // packed fp32 arithmetic (add / mul / fma .f32x2: the same roundings as the scalar forms, half the issue slots -
+                // the epilogue warps share their schedulers with the transform warps that set the k-chunk rate)
+                float2 s0a = make_float2(0.f, 0.f), s0b = s0a, s1a = s0a, s1b = s0a;
+                const float2 m1 = make_float2(-1.f, -1.f);
 #pragma unroll
                 for (int i = 0; i < NIT; ++i) {
                     const float4 sd = sdq[b & 1][i];
                     float4 y = *reinterpret_cast<const float4 *>(stg + G::addr(i * RPI + rsub, c4));
+                    float2 ya = make_float2(y.x, y.y), yb = make_float2(y.z, y.w);
+                    const float2 sda = make_float2(sd.x, sd.y), sdb = make_float2(sd.z, sd.w);
                     const bool valid = ob[i] >= 0;
                     if (fwd) {
-                        y.x += cf0.x + sd.x; y.y += cf0.y + sd.y; y.z += cf0.z + sd.z; y.w += cf0.w + sd.w;
+                        ya = __fadd2_rn(ya, __fadd2_rn(make_float2(cf0.x, cf0.y), sda));
+                        yb = __fadd2_rn(yb, __fadd2_rn(make_float2(cf0.z, cf0.w), sdb));
                         if (valid) {
-                            s0.x += y.x; s0.y += y.y; s0.z += y.z; s0.w += y.w;
-                            s1.x = fmaf(y.x, y.x, s1.x); s1.y = fmaf(y.y, y.y, s1.y); s1.z = fmaf(y.z, y.z, s1.z); s1.w = fmaf(y.w, y.w, s1.w);
+                            s0a = __fadd2_rn(s0a, ya); s0b = __fadd2_rn(s0b, yb);
+                            s1a = __ffma2_rn(ya, ya, s1a); s1b = __ffma2_rn(yb, yb, s1b);
                         }
                     } else {
                         if (acc_out && valid) {
                             const float4 ex = *reinterpret_cast<const float4 *>(a.out + ob[i] + b * CB);
-                            y.x += ex.x; y.y += ex.y; y.z += ex.z; y.w += ex.w;
+                            ya = __fadd2_rn(ya, make_float2(ex.x, ex.y)); yb = __fadd2_rn(yb, make_float2(ex.z, ex.w));
                         }
                         if (a.has_mask) {
-                            y.x = (fmaf(sd.x, cf0.x, cf1.x) > 0.f && valid) ? y.x : 0.f;
-                            y.y = (fmaf(sd.y, cf0.y, cf1.y) > 0.f && valid) ? y.y : 0.f;
-                            y.z = (fmaf(sd.z, cf0.z, cf1.z) > 0.f && valid) ? y.z : 0.f;
-                            y.w = (fmaf(sd.w, cf0.w, cf1.w) > 0.f && valid) ? y.w : 0.f;
-                            s0.x += y.x; s0.y += y.y; s0.z += y.z; s0.w += y.w;
-                            s1.x += y.x * (sd.x - cf2.x) * cf3.x; s1.y += y.y * (sd.y - cf2.y) * cf3.y;
-                            s1.z += y.z * (sd.z - cf2.z) * cf3.z; s1.w += y.w * (sd.w - cf2.w) * cf3.w;
+                            const float2 pa = __ffma2_rn(sda, make_float2(cf0.x, cf0.y), make_float2(cf1.x, cf1.y));
+                            const float2 pb = __ffma2_rn(sdb, make_float2(cf0.z, cf0.w), make_float2(cf1.z, cf1.w));
+                            ya.x = (pa.x > 0.f && valid) ? ya.x : 0.f;
+                            ya.y = (pa.y > 0.f && valid) ? ya.y : 0.f;
+                            yb.x = (pb.x > 0.f && valid) ? yb.x : 0.f;
+                            yb.y = (pb.y > 0.f && valid) ? yb.y : 0.f;
+                            s0a = __fadd2_rn(s0a, ya); s0b = __fadd2_rn(s0b, yb);
+                            // s1 += (y * (sd - mean)) * inv_std
+                            const float2 ta = __ffma2_rn(make_float2(cf2.x, cf2.y), m1, sda), tb = __ffma2_rn(make_float2(cf2.z, cf2.w), m1, sdb);
+                            s1a = __ffma2_rn(__fmul2_rn(ya, ta), make_float2(cf3.x, cf3.y), s1a);
+                            s1b = __ffma2_rn(__fmul2_rn(yb, tb), make_float2(cf3.z, cf3.w), s1b);
                         }
                     }
-                    if (valid) *reinterpret_cast<float4 *>(a.out + ob[i] + b * CB) = y;
+                    if (valid) *reinterpret_cast<float4 *>(a.out + ob[i] + b * CB) = make_float4(ya.x, ya.y, yb.x, yb.y);
                 }
+                const float4 s0 = make_float4(s0a.x, s0a.y, s0b.x, s0b.y), s1 = make_float4(s1a.x, s1a.y, s1b.x, s1b.y);
                 if (b + 2 < NB) side_round(b + 2);     // in flight during the statistics and the whole next batch
                 PROF(35);
                 if (want_stats) {
